@@ -1,0 +1,202 @@
+/*
+ * b200trl.h — C-ABI of libb200trl.so: the B200 (sm_100a) implementation of
+ * TRL's per-token policy-loss hot path.
+ *
+ * The reference (shiwanghua/swh-trl, a fork of HF TRL 0.21.0.dev0) is pure
+ * Python/torch and has no FFI of its own; each entry point below replaces the
+ * torch-eager block cited next to it (paths relative to the reference root)
+ * and is what a ctypes/cffi binding on the reference side would load
+ * (INTEGRATION.md shows that stub).
+ *
+ * Conventions
+ *   - plain device pointers and sizes only; no torch types;
+ *   - every call is asynchronous on `stream`, allocates nothing, never
+ *     synchronises and is CUDA-graph capturable; outputs and workspaces are
+ *     caller-allocated;
+ *   - return value: 0 = launched, <0 = B200TRL_E_* (nothing launched);
+ *     b200trl_last_error() gives a thread-local message;
+ *   - "rows" are logit-tokens: one (batch, position) pair = `vocab` logits.
+ */
+#ifndef B200TRL_H_
+#define B200TRL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b200trl_stream_t; /* == cudaStream_t */
+
+enum b200trl_status {
+    B200TRL_OK = 0,
+    B200TRL_E_INVALID = -1,     /* bad argument (null pointer, size, enum)          */
+    B200TRL_E_UNSUPPORTED = -2, /* dtype / alignment combination has no kernel      */
+    B200TRL_E_LAUNCH = -3       /* cudaGetLastError() != cudaSuccess after launch   */
+};
+
+enum b200trl_dtype { B200TRL_BF16 = 0, B200TRL_F16 = 1, B200TRL_F32 = 2, B200TRL_F64 = 3 };
+
+/* grpo_trainer.py:2130-2137 */
+enum b200trl_loss_type { B200TRL_LOSS_GRPO = 0, B200TRL_LOSS_BNPO = 1, B200TRL_LOSS_DR_GRPO = 2 };
+/* grpo_trainer.py:2100-2109 */
+enum b200trl_is_level { B200TRL_IS_TOKEN = 0, B200TRL_IS_SEQUENCE = 1 };
+/* ppo_trainer.py:511 */
+enum b200trl_kl_estimator { B200TRL_KL_K1 = 0, B200TRL_KL_K3 = 1 };
+
+/* which K1 implementation serves a call (b200trl_set_k1_path) */
+enum b200trl_k1_path {
+    B200TRL_K1_AUTO = 0,     /* smem-resident TMA kernel when bf16 + 16-byte aligned rows, else row kernel */
+    B200TRL_K1_ROW = 1,      /* one CTA per row, plain vector loads, second pass served by L2            */
+    B200TRL_K1_RESIDENT = 2  /* force the TMA-bulk, shared-memory-resident cluster kernel (error if n/a)  */
+};
+
+/* GRPO hyper-parameters as the loss body uses them (grpo_config.py:437-503). */
+typedef struct b200trl_grpo_cfg {
+    float beta;                  /* 0 disables the KL term (grpo_trainer.py:2085)                   */
+    float clip_low;              /* (float)(1 - epsilon_low)  (grpo_trainer.py:2114)                */
+    float clip_high;             /* (float)(1 + epsilon_high)                                       */
+    float delta;                 /* upper clamp of coef_1, used iff has_delta (grpo_trainer.py:2117)*/
+    int32_t has_delta;
+    int32_t loss_type;           /* enum b200trl_loss_type                                          */
+    int32_t is_level;            /* enum b200trl_is_level                                           */
+    float max_completion_length; /* dr_grpo denominator (grpo_trainer.py:2135)                      */
+    float grad_scale;            /* upstream d(loss) known a priori (1/grad_accum, AMP scale)       */
+} b200trl_grpo_cfg;
+
+/* metrics[] layout written by b200trl_grpo_loss (grpo_trainer.py:2150-2172, local means) */
+enum b200trl_grpo_metric {
+    B200TRL_M_LOSS = 0,
+    B200TRL_M_KL = 1,          /* masked batch mean of the k3 KL (0 if beta == 0)        */
+    B200TRL_M_ENTROPY = 2,     /* masked batch mean entropy (0 if no entropy given)      */
+    B200TRL_M_CLIP_LOW = 3,
+    B200TRL_M_CLIP_HIGH = 4,
+    B200TRL_M_CLIP_REGION = 5,
+    B200TRL_M_TOKENS = 6,      /* completion_mask.sum() (before clamp)                   */
+    B200TRL_M_RESERVED = 7,
+    B200TRL_GRPO_NUM_METRICS = 8
+};
+
+/* stats[] layout written by b200trl_ppo_loss (ppo_trainer.py:573-605) */
+enum b200trl_ppo_stat {
+    B200TRL_P_LOSS = 0,
+    B200TRL_P_PG_LOSS = 1,
+    B200TRL_P_VF_LOSS = 2,
+    B200TRL_P_PG_CLIPFRAC = 3,
+    B200TRL_P_VF_CLIPFRAC = 4,
+    B200TRL_P_APPROXKL = 5,
+    B200TRL_P_ENTROPY = 6,
+    B200TRL_P_RATIO = 7,
+    B200TRL_PPO_NUM_STATS = 8
+};
+
+int b200trl_version(void);
+const char* b200trl_last_error(void);
+int b200trl_set_k1_path(int path); /* returns the previous setting */
+
+/* ---- K1: selective_log_softmax + entropy_from_logits, one pass ------------------------------
+ * Replaces trl/trainer/utils.py:1430-1462 and :1465-1490 (and the division by the temperature,
+ * grpo_trainer.py:1258 / ppo_trainer.py:450,559, folded in as `inv_temperature`).
+ * logits: [n_rows, vocab] with `row_stride` elements between rows (strided views of the model
+ * output are accepted, so the slice copy at grpo_trainer.py:1252-1254 is not needed).
+ * logp/entropy/lse: fp32 [n_rows]; entropy and lse may be NULL. */
+int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                                const int64_t* ids, float inv_temperature, float* logp, float* entropy, float* lse,
+                                b200trl_stream_t stream);
+
+/* Backward of the gather-log-softmax: dlogits[r,v] = g[r]*inv_T*(1[v==ids[r]] - exp(x[r,v]*inv_T - lse[r])),
+ * written in the logits dtype.  What autograd produces for utils.py:1449-1461 + grpo_trainer.py:1258. */
+int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                        const int64_t* ids, float inv_temperature, const float* lse, const float* g,
+                        void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream);
+
+/* completion_mask row sums and total (grpo_trainer.py:2131,2133,2142); row_count fp32 [B], total fp32 [1]. */
+int b200trl_mask_stats(const int32_t* mask, int64_t B, int64_t T, float* row_count, float* total_count,
+                       b200trl_stream_t stream);
+
+/* ---- K1+K2 fused: log-prob, entropy AND dlogits of the GRPO loss in one pass over the logits ---
+ * Replaces grpo_trainer.py:2067 (+ :1252-1268) and the autograd backward of :2084-2137 down to the
+ * logits.  Valid when d(loss)/d(logp) of a token is known from that token alone: token-level
+ * importance sampling, or old_logp == NULL (ratio == 1 for either level), and no entropy mask.
+ * old_logp / ref_logp may be NULL (ref must be given iff cfg->beta != 0).  row_count/total_count
+ * come from b200trl_mask_stats.  dlogits == NULL gives the forward only. */
+int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab, int64_t row_stride,
+                               const int64_t* ids, const int32_t* mask, const float* advantages,
+                               const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
+                               float inv_temperature, const float* row_count, const float* total_count,
+                               float* logp, float* entropy, float* lse, void* dlogits, int64_t dl_row_stride,
+                               b200trl_stream_t stream);
+
+/* ---- K2: GRPO loss body + metrics (+ per-token d(loss)/d(logp)) --------------------------------
+ * Replaces grpo_trainer.py:2084-2137 (loss) and :2139-2173 (local metric means).  All [B,T]
+ * inputs fp32 row-major; ent_mask (uint8, from b200trl_entropy_quantile_mask) and entropy may be
+ * NULL.  workspace: >= b200trl_grpo_loss_workspace_bytes(B) bytes, zero-initialised once (the
+ * kernel leaves it zeroed).  loss: fp32 [1]; metrics: fp32 [B200TRL_GRPO_NUM_METRICS];
+ * g: fp32 [B,T] or NULL. */
+int64_t b200trl_grpo_loss_workspace_bytes(int64_t B);
+int b200trl_grpo_loss(const float* logp, const float* old_logp, const float* ref_logp, const float* advantages,
+                      const int32_t* mask, const uint8_t* ent_mask, const float* entropy, int64_t B, int64_t T,
+                      const b200trl_grpo_cfg* cfg, const float* row_count, const float* total_count, void* workspace,
+                      float* loss, float* metrics, float* g, b200trl_stream_t stream);
+
+/* ---- a-4: get_high_entropy_mask (grpo_trainer.py:341-364) ------------------------------------
+ * out_mask[i] = mask[i] && entropies[i]*mask[i] >= quantile(entropies[mask], threshold) with torch's
+ * linear interpolation; all zero if the mask is empty.  workspace >= ..._workspace_bytes(n), any
+ * contents.  out_threshold (fp32 [1]) may be NULL. */
+int64_t b200trl_entropy_quantile_workspace_bytes(int64_t n);
+int b200trl_entropy_quantile_mask(const float* entropies, const int32_t* mask, int64_t n, float threshold,
+                                  void* workspace, uint8_t* out_mask, float* out_threshold, b200trl_stream_t stream);
+
+/* ---- K3: group-relative advantages (grpo_trainer.py:1917-1938) -------------------------------
+ * rewards_per_func: gathered, rank-major fp32 [B_global, n_funcs] (NaN = not applicable).
+ * Outputs: rewards [B_global], adv_all [B_global], adv_local [local_count] =
+ * adv_all[local_offset : local_offset+local_count], mean/std fp32 [B_global/G], is_std_zero uint8. */
+int b200trl_group_advantages(const float* rewards_per_func, const float* weights, int64_t B_global, int64_t n_funcs,
+                             int64_t G, int scale_rewards, int64_t local_offset, int64_t local_count, float* rewards,
+                             float* adv_all, float* adv_local, float* mean, float* std, uint8_t* is_std_zero,
+                             b200trl_stream_t stream);
+
+/* ---- K4: PPO KL reward + score + whitening + reverse GAE (ppo_trainer.py:500-535) ------------
+ * logprobs/ref_logprobs/values: raw fp32 [B,T] (pads filled here as :500-506 does); scores [B];
+ * sequence_lengths int64 [B].  Outputs fp32 [B,T]: rewards, advantages (whitened, pads 0), returns;
+ * optional filled copies logprobs_f/ref_logprobs_f/values_f (NULL to skip).
+ * workspace >= b200trl_ppo_gae_workspace_bytes(B,T), any contents.  One cooperative launch. */
+int64_t b200trl_ppo_gae_workspace_bytes(int64_t B, int64_t T);
+int b200trl_ppo_rewards_gae(const float* logprobs, const float* ref_logprobs, const float* values, const float* scores,
+                            const int64_t* sequence_lengths, int64_t B, int64_t T, float kl_coef, int kl_estimator,
+                            float gamma, float lam, int whiten_rewards, void* workspace, float* rewards,
+                            float* advantages, float* returns, float* logprobs_f, float* ref_logprobs_f,
+                            float* values_f, b200trl_stream_t stream);
+
+/* ---- PPO policy/value loss (ppo_trainer.py:557-605) --------------------------------------------
+ * fused pass: new_logprobs (pads = 1.0), entropy and dlogits of pg_loss for a micro-batch [mb,T,V];
+ * the token weight is (1 - pad)/count(~pad) * grad_scale.  dlogits may be NULL. */
+int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab, int64_t row_stride,
+                              const int64_t* responses, const int64_t* sequence_lengths, const float* old_logprobs,
+                              const float* advantages, float inv_temperature, float cliprange, float grad_scale,
+                              float* new_logprobs, float* entropy, float* lse, void* dlogits, int64_t dl_row_stride,
+                              b200trl_stream_t stream);
+/* loss + stats from new_logprobs (as written above) and the value head; dvpred [mb,T] may be NULL.
+ * workspace as for b200trl_grpo_loss with B = mb. */
+int b200trl_ppo_loss(const float* new_logprobs, const float* old_logprobs, const float* advantages,
+                     const float* returns, const float* values, const float* vpred, const float* entropy,
+                     const int64_t* sequence_lengths, int64_t mb, int64_t T, float cliprange, float cliprange_value,
+                     float vf_coef, float grad_scale, void* workspace, float* stats, float* dvpred,
+                     b200trl_stream_t stream);
+
+/* ---- a-12: masked_mean / masked_var / masked_whiten (trl/core.py:43-76) ------------------------
+ * stats fp32 [3] = {mean, unbiased var, count}; out (whitened, fp32 [n]) may be NULL.
+ * workspace >= b200trl_masked_workspace_bytes(n), any contents. */
+int64_t b200trl_masked_workspace_bytes(int64_t n);
+int b200trl_masked_whiten(const float* values, const uint8_t* mask, int64_t n, int shift_mean, void* workspace,
+                          float* out, float* stats, b200trl_stream_t stream);
+
+/* buf *= (*actual / expected) unless they are equal; used when autograd's grad_output differs from
+ * the grad_scale assumed in the fused forward.  No host sync. */
+int b200trl_rescale_if_needed(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                              const float* actual, float expected, b200trl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TRL_H_ */

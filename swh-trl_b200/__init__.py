@@ -1,0 +1,24 @@
+"""swh-trl_b200 — the TRL per-token policy-loss hot path on B200 (sm_100a).
+
+Host-side mirror of the reference's call surface over ``libb200trl.so`` (C-ABI in ``include/b200trl.h``).
+Import as ``swh_trl_b200``.  No CPU fallback, no Triton, no backend dispatch: importing without the built CUDA
+library raises.
+"""
+
+from . import _lib  # noqa: F401  (raises ImportError if libb200trl.so is missing)
+from ._lib import K1_AUTO, K1_RESIDENT, K1_ROW, B200TRLError, set_k1_path  # noqa: F401
+from .advantages import group_advantages  # noqa: F401
+from .functional import (  # noqa: F401
+    entropy_from_logits,
+    get_high_entropy_mask,
+    logprobs_and_entropy,
+    masked_mean,
+    masked_var,
+    masked_whiten,
+    selective_log_softmax,
+)
+from .grpo import GRPOLoss, GRPOLossOutput, compute_loss, get_per_token_logps_and_entropies  # noqa: F401
+from .patch import patch_trl  # noqa: F401
+from .ppo import INVALID_LOGPROB, PPOLossOutput, ppo_loss, ppo_rewards_gae  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,146 @@
+// C-ABI entry points of K1 (log-prob / entropy / dlogits) — argument checks and path selection.
+#include <atomic>
+
+#include "k1_args.cuh"
+
+using namespace b200trl;
+
+namespace {
+
+std::atomic<int> g_k1_path{B200TRL_K1_AUTO};
+
+int dispatch(const K1Args& a, int dtype, cudaStream_t stream) {
+    const int path = g_k1_path.load();
+    const bool resident_ok = k1_resident_supported(a, dtype);
+    if (path == B200TRL_K1_RESIDENT) {
+        B200TRL_REQUIRE(resident_ok, B200TRL_E_UNSUPPORTED,
+                        "k1: resident path needs bf16 logits, vocab %% 8 == 0, 16-byte aligned rows and vocab >= 16384");
+        return launch_k1_resident(a, stream);
+    }
+    if (path == B200TRL_K1_AUTO && resident_ok) return launch_k1_resident(a, stream);
+    return launch_k1_row(a, dtype, stream);
+}
+
+int fill_common(K1Args& a, const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                const int64_t* ids, float inv_temperature, const char* who) {
+    B200TRL_REQUIRE(logits && ids, B200TRL_E_INVALID, "%s: null pointer", who);
+    B200TRL_REQUIRE(dtype_size(dtype) != 0, B200TRL_E_UNSUPPORTED, "%s: unknown dtype %d", who, dtype);
+    B200TRL_REQUIRE(n_rows >= 0 && vocab > 0 && row_stride >= vocab, B200TRL_E_INVALID,
+                    "%s: bad shape rows=%lld vocab=%lld stride=%lld", who, (long long)n_rows, (long long)vocab,
+                    (long long)row_stride);
+    B200TRL_REQUIRE(inv_temperature > 0.f && std::isfinite(inv_temperature), B200TRL_E_INVALID,
+                    "%s: inv_temperature must be positive and finite", who);
+    a = K1Args{};
+    a.logits = logits;
+    a.n_rows = n_rows;
+    a.vocab = vocab;
+    a.row_stride = row_stride;
+    a.ids = ids;
+    a.inv_temp = inv_temperature;
+    a.c = static_cast<float>(static_cast<double>(inv_temperature) * 1.4426950408889634);
+    a.gmode = G_NONE;
+    a.cfg.grad_scale = 1.f;
+    a.grad_scale = 1.f;
+    return B200TRL_OK;
+}
+
+}  // namespace
+
+extern "C" int b200trl_set_k1_path(int path) {
+    if (path < B200TRL_K1_AUTO || path > B200TRL_K1_RESIDENT) return B200TRL_E_INVALID;
+    return g_k1_path.exchange(path);
+}
+
+extern "C" int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab,
+                                           int64_t row_stride, const int64_t* ids, float inv_temperature, float* logp,
+                                           float* entropy, float* lse, b200trl_stream_t stream) {
+    K1Args a;
+    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, ids, inv_temperature, "logprob_entropy_fwd");
+    if (rc) return rc;
+    B200TRL_REQUIRE(logp, B200TRL_E_INVALID, "logprob_entropy_fwd: logp is null");
+    a.logp = logp;
+    a.entropy = entropy;
+    a.lse = lse;
+    return dispatch(a, dtype, as_stream(stream));
+}
+
+extern "C" int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                                   const int64_t* ids, float inv_temperature, const float* lse, const float* g,
+                                   void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream) {
+    K1Args a;
+    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, ids, inv_temperature, "logprob_bwd");
+    if (rc) return rc;
+    B200TRL_REQUIRE(lse && g && dlogits && dl_row_stride >= vocab, B200TRL_E_INVALID, "logprob_bwd: bad arguments");
+    a.lse_in = lse;
+    a.g = g;
+    a.gmode = G_GIVEN;
+    a.dlogits = dlogits;
+    a.dl_row_stride = dl_row_stride;
+    return dispatch(a, dtype, as_stream(stream));
+}
+
+extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab,
+                                          int64_t row_stride, const int64_t* ids, const int32_t* mask,
+                                          const float* advantages, const float* old_logp, const float* ref_logp,
+                                          const b200trl_grpo_cfg* cfg, float inv_temperature, const float* row_count,
+                                          const float* total_count, float* logp, float* entropy, float* lse,
+                                          void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream) {
+    K1Args a;
+    B200TRL_REQUIRE(B > 0 && T > 0, B200TRL_E_INVALID, "grpo_fused: bad shape");
+    const int rc = fill_common(a, logits, dtype, B * T, vocab, row_stride, ids, inv_temperature, "grpo_fused");
+    if (rc) return rc;
+    B200TRL_REQUIRE(mask && advantages && cfg && row_count && total_count && logp, B200TRL_E_INVALID,
+                    "grpo_fused: null pointer");
+    B200TRL_REQUIRE(cfg->loss_type >= 0 && cfg->loss_type <= 2, B200TRL_E_INVALID, "grpo_fused: unknown loss type %d",
+                    cfg->loss_type);
+    B200TRL_REQUIRE(cfg->is_level == B200TRL_IS_TOKEN || (cfg->is_level == B200TRL_IS_SEQUENCE && old_logp == nullptr),
+                    B200TRL_E_UNSUPPORTED,
+                    "grpo_fused: sequence-level importance sampling with old_logp needs the two-phase path");
+    B200TRL_REQUIRE(cfg->beta == 0.f || ref_logp, B200TRL_E_INVALID, "grpo_fused: beta != 0 needs ref_logp");
+    B200TRL_REQUIRE(!dlogits || dl_row_stride >= vocab, B200TRL_E_INVALID, "grpo_fused: bad dlogits stride");
+    a.logp = logp;
+    a.entropy = entropy;
+    a.lse = lse;
+    a.B = B;
+    a.T = T;
+    a.mask = mask;
+    a.adv = advantages;
+    a.old_lp = old_logp;
+    a.ref_lp = (cfg->beta != 0.f) ? ref_logp : nullptr;
+    a.row_count = row_count;
+    a.total_count = total_count;
+    a.cfg = *cfg;
+    a.gmode = dlogits ? G_GRPO : G_NONE;
+    a.dlogits = dlogits;
+    a.dl_row_stride = dl_row_stride;
+    return dispatch(a, dtype, as_stream(stream));
+}
+
+extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab,
+                                         int64_t row_stride, const int64_t* responses, const int64_t* sequence_lengths,
+                                         const float* old_logprobs, const float* advantages, float inv_temperature,
+                                         float cliprange, float grad_scale, float* new_logprobs, float* entropy,
+                                         float* lse, void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream) {
+    K1Args a;
+    B200TRL_REQUIRE(mb > 0 && T > 0, B200TRL_E_INVALID, "ppo_fused: bad shape");
+    const int rc = fill_common(a, logits, dtype, mb * T, vocab, row_stride, responses, inv_temperature, "ppo_fused");
+    if (rc) return rc;
+    B200TRL_REQUIRE(sequence_lengths && old_logprobs && advantages && new_logprobs, B200TRL_E_INVALID,
+                    "ppo_fused: null pointer");
+    B200TRL_REQUIRE(!dlogits || dl_row_stride >= vocab, B200TRL_E_INVALID, "ppo_fused: bad dlogits stride");
+    a.logp = new_logprobs;
+    a.entropy = entropy;
+    a.lse = lse;
+    a.B = mb;
+    a.T = T;
+    a.seq_len = sequence_lengths;
+    a.old_lp = old_logprobs;
+    a.adv = advantages;
+    a.clip_lo = static_cast<float>(1.0 - static_cast<double>(cliprange));
+    a.clip_hi = static_cast<float>(1.0 + static_cast<double>(cliprange));
+    a.grad_scale = grad_scale;
+    a.gmode = G_PPO;  // also marks pad rows so that new_logprobs gets INVALID_LOGPROB there
+    a.dlogits = dlogits;
+    a.dl_row_stride = dl_row_stride;
+    return dispatch(a, dtype, as_stream(stream));
+}

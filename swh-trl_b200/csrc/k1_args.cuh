@@ -1,0 +1,114 @@
+// Argument block shared by the two K1 implementations (row kernel, resident kernel) and the
+// per-row epilogue that turns a finished log-prob into the scalar d(loss)/d(logp) of that token.
+#pragma once
+
+#include "token_math.cuh"
+
+namespace b200trl {
+
+enum GMode : int {
+    G_NONE = 0,   // forward only (no dlogits)
+    G_GIVEN = 1,  // g[row] supplied (two-phase path / plain autograd backward)
+    G_GRPO = 2,   // GRPO loss gradient computed inline from per-token scalars
+    G_PPO = 3     // PPO policy-loss gradient computed inline
+};
+
+struct K1Args {
+    const void* logits;
+    int64_t n_rows, vocab, row_stride;
+    const int64_t* ids;
+    float c;         // inv_temperature * log2(e)
+    float inv_temp;
+    // forward outputs (nullable)
+    float* logp;
+    float* entropy;
+    float* lse;
+    // backward
+    int gmode;
+    void* dlogits;  // nullable
+    int64_t dl_row_stride;
+    const float* lse_in;  // non-null => skip the forward pass (backward-only)
+    const float* g;       // G_GIVEN
+    // G_GRPO
+    int64_t B, T;
+    const int32_t* mask;
+    const float* adv;
+    const float* old_lp;
+    const float* ref_lp;
+    const float* row_count;
+    const float* total_count;
+    b200trl_grpo_cfg cfg;
+    // G_PPO
+    const int64_t* seq_len;
+    float clip_lo, clip_hi, grad_scale;
+};
+
+// Number of non-pad positions sum_b min(len_b + 1, T) (ppo_trainer.py:501: pad = idx > len); warp-cooperative.
+__device__ __forceinline__ float ppo_unpadded_count(const K1Args& a, int lane) {
+    float n = 0.f;
+    for (int64_t b = lane; b < a.B; b += 32) {
+        const int64_t len = a.seq_len[b];
+        n += static_cast<float>(min(max(len + 1, (int64_t)0), a.T));
+    }
+    return warp_sum(n);
+}
+
+// Row scalars fetched early (latency hidden behind the streaming pass).
+struct RowScalars {
+    float x_sel;   // raw selected logit
+    int64_t id;
+    float aux0;    // G_GIVEN: g; G_GRPO: old; G_PPO: old
+    float aux1;    // G_GRPO: ref
+    float adv;
+    float weight;  // mask * normalisation * grad_scale (0 => dlogits row is zero)
+    float pad;     // G_PPO: 1 if the position is padding
+};
+
+template <typename T>
+__device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t row, float ppo_count) {
+    RowScalars s;
+    s.id = a.ids[row];
+    const T* base = reinterpret_cast<const T*>(a.logits) + row * a.row_stride;
+    s.x_sel = (s.id >= 0 && s.id < a.vocab) ? ElemTraits<T>::load(base + s.id) : __int_as_float(0x7fc00000);
+    s.aux0 = s.aux1 = s.adv = s.weight = s.pad = 0.f;
+    if (a.gmode == G_GIVEN) {
+        s.aux0 = a.g[row];
+        s.weight = 1.f;
+    } else if (a.gmode == G_GRPO) {
+        const int64_t b = row / a.T;
+        const float m = static_cast<float>(a.mask[row]);
+        s.adv = a.adv[b];
+        if (a.old_lp) s.aux0 = a.old_lp[row];
+        if (a.ref_lp) s.aux1 = a.ref_lp[row];
+        s.weight = m * grpo_norm(a.cfg, a.row_count[b], a.total_count[0], static_cast<float>(a.B)) * a.cfg.grad_scale;
+    } else if (a.gmode == G_PPO) {
+        const int64_t b = row / a.T, t = row % a.T;
+        s.pad = (t > a.seq_len[b]) ? 1.f : 0.f;
+        s.adv = a.adv[row];
+        s.aux0 = a.old_lp[row];
+        s.weight = (1.f - s.pad) / ppo_count * a.grad_scale;
+    }
+    return s;
+}
+
+// d(loss)/d(logp) of this token, including mask, normalisation and the upstream scale
+__device__ __forceinline__ float token_grad(const K1Args& a, const RowScalars& s, float logp) {
+    if (a.gmode == G_GIVEN) return s.aux0;
+    if (s.weight == 0.f) return 0.f;
+    if (a.gmode == G_GRPO) {
+        const GrpoTok t = grpo_token(logp, a.old_lp != nullptr, s.aux0, a.ref_lp != nullptr, s.aux1, s.adv, 1.f, a.cfg);
+        return s.weight * (t.dl + t.dkl);
+    }
+    if (a.gmode == G_PPO) {
+        float pg, dpg, clipped, ratio, diff;
+        ppo_policy(logp, s.aux0, s.adv, a.clip_lo, a.clip_hi, pg, dpg, clipped, ratio, diff);
+        return s.weight * dpg;
+    }
+    return 0.f;
+}
+
+int launch_k1_row(const K1Args& a, int dtype, cudaStream_t stream);
+int launch_k1_resident(const K1Args& a, cudaStream_t stream);
+bool k1_resident_supported(const K1Args& a, int dtype);
+
+}  // namespace b200trl

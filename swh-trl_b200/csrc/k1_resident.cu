@@ -1,0 +1,504 @@
+// K1 "resident" implementation (the product path for bf16 logits): every logit row is read from HBM
+// exactly once and dlogits written exactly once.
+//
+//   * a row is split over a thread-block cluster (1/2/4/8 CTAs, picked so a slice fits one CTA's
+//     shared memory); each CTA pulls its slice with 16 KB TMA bulk copies (cp.async.bulk ->
+//     UBLKCP) into a ring of shared-memory slots, signalled through mbarriers;
+//   * 16 consumer warps fold the chunks into an online (reference, sum, sum*delta) partial as they
+//     land (packed bf16 max, f32x2 FMA/ADD, MUFU ex2), the CTAs of the cluster swap partials
+//     through distributed shared memory, and the row's log-prob / entropy / lse come out;
+//   * the per-token d(loss)/d(logp) is evaluated inline (GRPO or PPO surrogate, see k1_args.cuh),
+//     the still-resident slice is rewritten in place as dlogits (bf16) and leaves through TMA
+//     bulk stores; a slot is refilled with the next row's chunk as soon as its store has drained,
+//     so loads of row r+1 overlap the stores of row r.
+//
+// One DMA warp (one elected lane) issues every bulk copy; consumers never touch global memory
+// except for a handful of per-row scalars.  Persistent grid: floor(SMs / cluster) clusters loop over
+// rows.  Replaces trl/trainer/utils.py:1430-1490 + grpo_trainer.py:1258 + the autograd backward
+// down to the logits (see include/b200trl.h).
+#include <algorithm>
+
+#include "k1_args.cuh"
+
+namespace b200trl {
+namespace {
+
+constexpr int kConsumers = 512;
+constexpr int kThreads = kConsumers + 32;
+constexpr int kChunkBytes = 16384;
+constexpr int kChunkElems = kChunkBytes / 2;
+constexpr int kChunkVecs = kChunkBytes / 16;
+constexpr int kMaxSlots = 13;
+constexpr int kMaxCluster = 8;
+constexpr int kStoreLag = 2;     // bulk stores allowed to be still reading shared memory
+constexpr float kSlack = 6.0f;   // reference point may trail the running max by 2^6
+
+struct __align__(16) Part4 {
+    float m, s, u, pad;
+};
+
+struct Smem {
+    // slots first (16 KB each, 128-byte aligned)
+    uint64_t full_bar[kMaxSlots];
+    uint64_t done_bar[kMaxSlots];
+    uint64_t xchg_bar;
+    Part4 xchg[2][kMaxCluster];
+    Part4 warp_part[2][kConsumers / 32];
+    RowScalars row[2];
+    float ppo_count;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+// packed 2 x fp32 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// ------------------------------------------------------------------ consumer state
+struct Acc {
+    float m;      // reference point (log2 units)
+    uint64_t s2;  // two running sums of 2^(y-m)
+    uint64_t u2;  // two running sums of 2^(y-m)*(y-m)
+};
+
+__device__ __forceinline__ void acc_vec(Acc& a, const uint4& v, float c, uint64_t c2) {
+    const uint32_t mx = bf16x2_max(bf16x2_max(v.x, v.y), bf16x2_max(v.z, v.w));
+    const float cm = fmaxf(__uint_as_float(mx << 16), __uint_as_float(mx & 0xffff0000u)) * c;
+    if (cm > a.m + kSlack) {  // rare after the first vector: move the reference point
+        const float d = a.m - cm;
+        const float f = ex2(d);
+        const uint64_t f2 = pack2(f, f);
+        a.u2 = fmul2(f2, ffma2(pack2(d, d), a.s2, a.u2));
+        a.s2 = fmul2(a.s2, f2);
+        a.m = cm;
+    }
+    const uint64_t nm2 = pack2(-a.m, -a.m);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+        const uint64_t d2 = ffma2(x2, c2, nm2);
+        float d0, d1;
+        unpack2(d2, d0, d1);
+        const uint64_t e2 = pack2(ex2(d0), ex2(d1));
+        a.s2 = fadd2(a.s2, e2);
+        a.u2 = ffma2(e2, d2, a.u2);
+    }
+}
+
+__device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t nl2, uint64_t ng2) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+        float d0, d1;
+        unpack2(ffma2(x2, c2, nl2), d0, d1);
+        float o0, o1;
+        unpack2(fmul2(pack2(ex2(d0), ex2(d1)), ng2), o0, o1);
+        o[i] = cvt_bf16x2(o0, o1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ Partial acc_to_partial(const Acc& a) {
+    float s0, s1, u0, u1;
+    unpack2(a.s2, s0, s1);
+    unpack2(a.u2, u0, u1);
+    return Partial{a.m, s0 + s1, u0 + u1};
+}
+
+// ------------------------------------------------------------------ the kernel
+template <bool HAS_FWD, bool HAS_BWD>
+__global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a, const int num_slots) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* slots = smem_raw;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + static_cast<size_t>(num_slots) * kChunkBytes);
+
+    const int tid = threadIdx.x;
+    const uint32_t crank = cluster_rank();
+    const uint32_t csize = cluster_size();
+    const int64_t first_row = cluster_id_x();
+    const int64_t row_step = num_clusters_x();
+
+    // this CTA's slice of every row
+    const int64_t slice_elems = ((a.vocab + csize - 1) / csize + 7) & ~int64_t(7);
+    const int64_t e_begin = static_cast<int64_t>(crank) * slice_elems;
+    const int64_t e_end = min(a.vocab, e_begin + slice_elems);
+    const int64_t my_elems = max(e_end - e_begin, (int64_t)0);
+    const int my_bytes = static_cast<int>(my_elems * 2);
+    const int C = (my_bytes + kChunkBytes - 1) / kChunkBytes;  // chunks per row in this CTA
+    const int64_t n_my_rows = (a.n_rows > first_row) ? (a.n_rows - first_row + row_step - 1) / row_step : 0;
+    const int64_t J = n_my_rows * C;  // chunks this CTA will process
+
+    if (tid == 0) {
+        for (int s = 0; s < num_slots; ++s) {
+            mbar_init(&sm.full_bar[s], 1);
+            mbar_init(&sm.done_bar[s], kConsumers);
+        }
+        mbar_init(&sm.xchg_bar, csize);
+        fence_barrier_init();
+    }
+    if (a.gmode == G_PPO && tid >= kConsumers) {
+        const float n = ppo_unpadded_count(a, tid - kConsumers);
+        if (tid == kConsumers) sm.ppo_count = n;
+    }
+    __syncthreads();
+    if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
+
+    const __nv_bfloat16* logits = reinterpret_cast<const __nv_bfloat16*>(a.logits);
+    __nv_bfloat16* dlogits = reinterpret_cast<__nv_bfloat16*>(a.dlogits);
+
+    if (tid >= kConsumers) {
+        // =========================== DMA warp: one lane drives every bulk copy ===========================
+        if (tid == kConsumers && J > 0) {
+            const uint64_t policy = policy_evict_first();
+            auto issue_load = [&](int64_t j) {
+                const int64_t i = j / C;
+                const int c = static_cast<int>(j - i * C);
+                const int s = static_cast<int>(j % num_slots);
+                const int64_t row = first_row + i * row_step;
+                const uint32_t bytes = static_cast<uint32_t>(min(kChunkBytes, my_bytes - c * kChunkBytes));
+                mbar_expect_tx(&sm.full_bar[s], bytes);
+                bulk_load(slots + static_cast<size_t>(s) * kChunkBytes,
+                          logits + row * a.row_stride + e_begin + static_cast<int64_t>(c) * kChunkElems, bytes,
+                          &sm.full_bar[s], policy);
+            };
+            const int64_t pre = (J < num_slots) ? J : static_cast<int64_t>(num_slots);
+            for (int64_t j = 0; j < pre; ++j) issue_load(j);
+            for (int64_t j = 0; j < J; ++j) {
+                const int s = static_cast<int>(j % num_slots);
+                mbar_wait(&sm.done_bar[s], static_cast<uint32_t>((j / num_slots) & 1));
+                if (HAS_BWD) {
+                    const int64_t i = j / C;
+                    const int c = static_cast<int>(j - i * C);
+                    const int64_t row = first_row + i * row_step;
+                    const uint32_t bytes = static_cast<uint32_t>(min(kChunkBytes, my_bytes - c * kChunkBytes));
+                    bulk_store(dlogits + row * a.dl_row_stride + e_begin + static_cast<int64_t>(c) * kChunkElems,
+                               slots + static_cast<size_t>(s) * kChunkBytes, bytes);
+                    bulk_commit();
+                    if (j >= kStoreLag) {
+                        bulk_wait_read<kStoreLag>();  // store j - kStoreLag has finished reading its slot
+                        const int64_t k = j - kStoreLag + num_slots;
+                        if (k < J) issue_load(k);
+                    }
+                } else {
+                    const int64_t k = j + num_slots;
+                    if (k < J) issue_load(k);
+                }
+            }
+            if (HAS_BWD) bulk_wait_all();
+        }
+    } else {
+        // =========================== consumers ===========================
+        const float c = a.c;
+        const uint64_t c2 = pack2(c, c);
+        const int lane = tid & 31, warp = tid >> 5;
+        int64_t j = 0;  // running chunk counter, identical to the DMA lane's
+        for (int64_t i = 0; i < n_my_rows; ++i) {
+            const int64_t row = first_row + i * row_step;
+            const int par = static_cast<int>(i & 1);
+            RowScalars rs_early;
+            if (tid == 0) rs_early = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+
+            float lse2, logp;
+            if (HAS_FWD) {
+                Acc acc{kNegBig, pack2(0.f, 0.f), pack2(0.f, 0.f)};
+                for (int cidx = 0; cidx < C; ++cidx) {
+                    const int64_t jj = j + cidx;
+                    const int s = static_cast<int>(jj % num_slots);
+                    mbar_wait(&sm.full_bar[s], static_cast<uint32_t>((jj / num_slots) & 1));
+                    const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(s) * kChunkBytes);
+                    const int nvec = min(kChunkVecs, (my_bytes - cidx * kChunkBytes) >> 4);
+                    if (nvec == kChunkVecs) {
+                        const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
+                        acc_vec(acc, v0, c, c2);
+                        acc_vec(acc, v1, c, c2);
+                    } else {
+                        for (int v = tid; v < nvec; v += kConsumers) acc_vec(acc, sv[v], c, c2);
+                    }
+                    if (!HAS_BWD) mbar_arrive(&sm.done_bar[s]);  // forward only: the slot can be refilled
+                }
+                // ---- CTA reduce
+                Partial p = partial_warp_reduce(acc_to_partial(acc));
+                if (lane == 0) sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};
+                if (tid == 0) sm.row[par] = rs_early;
+                consumer_bar();
+                Partial q = partial_empty();
+                if (lane < kConsumers / 32) {
+                    const Part4 w = sm.warp_part[par][lane];
+                    q = Partial{w.m, w.s, w.u};
+                }
+                q = partial_warp_reduce(q);
+                // ---- cluster exchange through distributed shared memory
+                if (csize > 1) {
+                    if (tid == 0) {
+                        const uint32_t slot_addr = smem_u32(&sm.xchg[par][crank]);
+                        const uint32_t bar_addr = smem_u32(&sm.xchg_bar);
+                        for (uint32_t r = 0; r < csize; ++r) {
+                            st_cluster_v4(map_to_rank(slot_addr, r), q.m, q.s, q.u, 0.f);
+                            mbar_arrive_remote(map_to_rank(bar_addr, r));
+                        }
+                    }
+                    mbar_wait_cluster(&sm.xchg_bar, static_cast<uint32_t>(par));
+                    Partial tot = partial_empty();
+                    for (uint32_t r = 0; r < csize; ++r) {
+                        const Part4 w = sm.xchg[par][r];
+                        tot = partial_merge(tot, Partial{w.m, w.s, w.u});
+                    }
+                    q = tot;
+                }
+                const RowStats st = finish_row(q, sm.row[par].x_sel, c);
+                lse2 = st.lse2;
+                logp = st.logp;
+                if (tid == 0 && crank == 0) {
+                    const bool pad = (a.gmode == G_PPO) && sm.row[par].pad != 0.f;
+                    if (a.logp) a.logp[row] = pad ? 1.0f : st.logp;
+                    if (a.entropy) a.entropy[row] = st.entropy;
+                    if (a.lse) a.lse[row] = st.lse;
+                }
+            } else {
+                if (tid == 0) sm.row[par] = rs_early;
+                consumer_bar();
+                lse2 = a.lse_in[row] * kLog2e;
+                logp = (sm.row[par].x_sel * c - lse2) * kLn2;
+            }
+
+            if (HAS_BWD) {
+                const RowScalars rs = sm.row[par];
+                const float gp = token_grad(a, rs, logp) * a.inv_temp;
+                const uint64_t nl2 = pack2(-lse2, -lse2);
+                const uint64_t ng2 = pack2(-gp, -gp);
+                // where the selected id lives inside this CTA's slice (or -1)
+                const int64_t e_id = rs.id - e_begin;
+                const bool mine = (e_id >= 0 && e_id < my_elems);
+                const int id_chunk = mine ? static_cast<int>(e_id / kChunkElems) : -1;
+                const int id_vec = mine ? static_cast<int>((e_id % kChunkElems) >> 3) : -1;
+                const float patch = fmaf(-expf(logp), gp, gp);  // g' * (1 - p_id)
+                for (int cidx = 0; cidx < C; ++cidx) {
+                    const int64_t jj = j + cidx;
+                    const int s = static_cast<int>(jj % num_slots);
+                    if (!HAS_FWD) mbar_wait(&sm.full_bar[s], static_cast<uint32_t>((jj / num_slots) & 1));
+                    uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(s) * kChunkBytes);
+                    const int nvec = min(kChunkVecs, (my_bytes - cidx * kChunkBytes) >> 4);
+                    if (gp == 0.f) {
+                        for (int v = tid; v < nvec; v += kConsumers) sv[v] = make_uint4(0u, 0u, 0u, 0u);
+                    } else {
+                        if (nvec == kChunkVecs) {
+                            const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
+                            sv[tid] = grad_vec(v0, c2, nl2, ng2);
+                            sv[tid + kConsumers] = grad_vec(v1, c2, nl2, ng2);
+                        } else {
+                            for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec(sv[v], c2, nl2, ng2);
+                        }
+                        if (cidx == id_chunk && (id_vec % kConsumers) == tid) {
+                            reinterpret_cast<__nv_bfloat16*>(sv)[e_id % kChunkElems] = __float2bfloat16_rn(patch);
+                        }
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
+                    mbar_arrive(&sm.done_bar[s]);
+                }
+            }
+            j += C;
+        }
+    }
+    // no CTA may leave while a peer can still address its shared memory
+    __syncwarp();
+    if (csize > 1) cluster_sync_all();
+}
+
+int pick_cluster(int64_t vocab, int num_slots) {
+    for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
+        const int64_t slice = ((vocab + cs - 1) / cs + 7) & ~int64_t(7);
+        const int64_t chunks = (slice * 2 + kChunkBytes - 1) / kChunkBytes;
+        if (chunks <= num_slots - 1 || (chunks <= num_slots && cs == kMaxCluster)) return cs;
+    }
+    return 0;
+}
+
+template <bool F, bool Bk>
+int launch_mode(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    auto kern = k1_resident_kernel<F, Bk>;
+    const size_t smem = static_cast<size_t>(num_slots) * kChunkBytes + sizeof(Smem);
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) {
+            set_error("k1_resident: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+            return B200TRL_E_LAUNCH;
+        }
+    }
+    const int sms = num_sms();
+    int64_t clusters = std::min<int64_t>(sms / cs, a.n_rows);
+    if (clusters < 1) clusters = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(clusters * cs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots);
+    if (e != cudaSuccess) {
+        set_error("k1_resident launch failed: %s", cudaGetErrorString(e));
+        return B200TRL_E_LAUNCH;
+    }
+    return check_launch("k1_resident_kernel");
+}
+
+}  // namespace
+
+bool k1_resident_supported(const K1Args& a, int dtype) {
+    if (dtype != B200TRL_BF16) return false;
+    if (a.vocab % 8 != 0 || a.row_stride % 8 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.logits) & 15) != 0) return false;
+    if (a.dlogits && ((reinterpret_cast<uintptr_t>(a.dlogits) & 15) != 0 || a.dl_row_stride % 8 != 0)) return false;
+    if (a.vocab * 2 < 2 * kChunkBytes) return false;  // tiny rows: per-row overheads dominate, use the row kernel
+    return pick_cluster(a.vocab, kMaxSlots) != 0;
+}
+
+int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
+    if (a.n_rows == 0) return B200TRL_OK;
+    const int num_slots = kMaxSlots;
+    const int cs = pick_cluster(a.vocab, num_slots);
+    B200TRL_REQUIRE(cs != 0, B200TRL_E_UNSUPPORTED, "k1_resident: vocab %lld too large for an 8-CTA cluster",
+                    (long long)a.vocab);
+    const bool fwd = (a.lse_in == nullptr), bwd = (a.dlogits != nullptr);
+    if (fwd && bwd) return launch_mode<true, true>(a, cs, num_slots, stream);
+    if (fwd) return launch_mode<true, false>(a, cs, num_slots, stream);
+    B200TRL_REQUIRE(bwd, B200TRL_E_INVALID, "k1_resident: nothing to do");
+    return launch_mode<false, true>(a, cs, num_slots, stream);
+}
+
+}  // namespace b200trl

@@ -1,0 +1,106 @@
+"""The reference's leaf functions, served by the CUDA library.
+
+Same names, argument meaning and error behaviour as ``trl/trainer/utils.py`` (``selective_log_softmax`` :1430,
+``entropy_from_logits`` :1465), ``trl/core.py`` (``masked_mean/var/whiten`` :43-76) and
+``trl/trainer/grpo_trainer.py`` (``get_high_entropy_mask`` :341).  Differences, all deliberate:
+
+* results are computed in fp32 from the logits' own dtype in ONE pass over the logits; for half inputs the
+  returned log-probs are fp32 (the reference's bf16 branch returns bf16 rounded values that differ from its
+  own fp32 path by up to 4.7e-2).  Pass ``out_dtype=logits.dtype`` for the reference's dtype behaviour.
+* there is no CPU path: CPU tensors raise.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class _SelectiveLogSoftmax(torch.autograd.Function):
+    """log_softmax(logits * inv_T)[index]; backward writes dlogits in the logits dtype in one more pass."""
+
+    @staticmethod
+    def forward(ctx, logits, index, inv_temperature, want_entropy):
+        logp, ent, lse = ops.logprob_entropy_fwd(logits, index, inv_temperature, want_entropy=want_entropy)
+        ctx.save_for_backward(logits, index, lse)
+        ctx.inv_temperature = inv_temperature
+        if ent is None:
+            ent = logp.new_empty(0)
+        ctx.mark_non_differentiable(ent)
+        return logp, ent
+
+    @staticmethod
+    def backward(ctx, g_logp, _g_ent):
+        logits, index, lse = ctx.saved_tensors
+        dlogits = ops.logprob_bwd(logits, index, lse, g_logp.contiguous(), ctx.inv_temperature)
+        return dlogits, None, None, None
+
+
+def logprobs_and_entropy(logits: torch.Tensor, index: torch.Tensor, temperature: float = 1.0,
+                         compute_entropy: bool = True):
+    """``(log_softmax(logits / temperature)[index], entropy)`` in a single pass (entropy carries no grad).
+
+    Fuses grpo_trainer.py:1258 (temperature), :1261 (log-probs) and :1265-1267 (entropies).
+    """
+    logp, ent = _SelectiveLogSoftmax.apply(logits, index, 1.0 / float(temperature), bool(compute_entropy))
+    return logp, (ent if compute_entropy else None)
+
+
+def selective_log_softmax(logits: torch.Tensor, index: torch.Tensor, out_dtype: Optional[torch.dtype] = None):
+    """Drop-in for ``trl.trainer.utils.selective_log_softmax`` (utils.py:1430-1462)."""
+    logp, _ = _SelectiveLogSoftmax.apply(logits, index, 1.0, False)
+    if out_dtype is None:
+        out_dtype = logits.dtype if logits.dtype in (torch.float32, torch.float64) else torch.float32
+    return logp if out_dtype == torch.float32 else logp.to(out_dtype)
+
+
+def entropy_from_logits(logits: torch.Tensor, chunk_size: int = 1, out_dtype: Optional[torch.dtype] = None):
+    """Drop-in for ``trl.trainer.utils.entropy_from_logits`` (utils.py:1465-1490).
+
+    ``chunk_size`` only bounded the reference's peak memory; the streaming kernel needs no chunking.  The result
+    is not differentiable (the reference only ever calls it under ``torch.no_grad``, grpo_trainer.py:1266).
+    """
+    del chunk_size
+    ids = torch.zeros(logits.shape[:-1], dtype=torch.int64, device=logits.device)
+    with torch.no_grad():
+        _, ent, _ = ops.logprob_entropy_fwd(logits, ids, 1.0, want_entropy=True, want_lse=False)
+    if out_dtype is None:
+        out_dtype = logits.dtype if logits.dtype in (torch.float32, torch.float64) else torch.float32
+    return ent if out_dtype == torch.float32 else ent.to(out_dtype)
+
+
+def get_high_entropy_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold: float) -> torch.Tensor:
+    """Drop-in for ``get_high_entropy_mask`` (grpo_trainer.py:341-364): exact quantile by radix select."""
+    out, _ = ops.entropy_quantile_mask(entropies, mask, threshold)
+    return out
+
+
+# ---------------------------------------------------------------------------------------- trl/core.py
+def masked_mean(values: torch.Tensor, mask: torch.Tensor, axis: Optional[int] = None) -> torch.Tensor:
+    """trl/core.py:43-48.  The global form runs on the library; the per-axis form is a tiny torch reduction."""
+    if axis is not None:
+        return (values * mask).sum(axis=axis) / mask.sum(axis=axis)
+    _, stats = ops.masked_whiten(values, mask != 0, want_out=False)
+    return stats[0]
+
+
+def masked_var(values: torch.Tensor, mask: torch.Tensor, unbiased: bool = True) -> torch.Tensor:
+    """trl/core.py:51-67; raises the reference's ValueError on an empty mask (this is the reference's host sync)."""
+    _, stats = ops.masked_whiten(values, mask != 0, want_out=False)
+    if unbiased:
+        if float(stats[2]) == 0:
+            raise ValueError(
+                "The sum of the mask is zero, which can happen when `mini_batch_size=1`;"
+                "try increase the `mini_batch_size` or `gradient_accumulation_steps`")
+        return stats[1]
+    n = stats[2]
+    return stats[1] * ((n - 1) / n)
+
+
+def masked_whiten(values: torch.Tensor, mask: torch.Tensor, shift_mean: bool = True) -> torch.Tensor:
+    """trl/core.py:70-76."""
+    out, _ = ops.masked_whiten(values, mask != 0, shift_mean=shift_mean)
+    return out.view_as(values)

@@ -1,0 +1,241 @@
+"""GRPO loss on the B200 library, behind the reference's call surface.
+
+Mirrors ``GRPOTrainer._compute_loss`` (grpo_trainer.py:2058-2175) and
+``GRPOTrainer._get_per_token_logps_and_entropies`` (:1206-1272).
+
+Schedules:
+
+* **fused** — one pass over the logits producing log-probs, entropies and ``dlogits`` (K1 resident kernel with
+  the GRPO surrogate evaluated inline), plus one tiny K2 launch for the loss value and metrics.  Valid when a
+  token's d(loss)/d(logp) depends on that token alone: token-level importance sampling, or
+  ``old_per_token_logps is None`` (ratio == 1), and no entropy-quantile mask.
+* **two-phase** — K1 forward, (entropy-quantile mask,) K2 loss with per-token gradient, K1 backward.  Needed for
+  sequence-level importance sampling with ``old_per_token_logps`` and for ``top_entropy_quantile < 1``.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+
+METRIC_INDEX = {"loss": 0, "kl": 1, "entropy": 2, "clip_ratio/low": 3, "clip_ratio/high": 4, "clip_ratio/region": 5,
+                "num_tokens": 6}
+
+
+@dataclass
+class GRPOLossOutput:
+    loss: torch.Tensor             # 0-d, differentiable wrt the logits
+    metrics: torch.Tensor          # fp32 [8] on device, layout METRIC_INDEX (local means, no host sync)
+    per_token_logps: torch.Tensor  # fp32 [B,T]
+    entropies: torch.Tensor        # fp32 [B,T]
+    schedule: str                  # "fused" | "two-phase"
+
+
+class _FusedGRPO(torch.autograd.Function):
+    """loss = f(logits); dlogits is produced in the forward pass (the upstream scale is known a priori as
+    ``grad_scale``; if autograd hands back something else the buffer is rescaled on the device)."""
+
+    @staticmethod
+    def forward(ctx, logits, ids, mask_i32, row_count, total_count, advantages, old_lp, ref_lp, cfg, inv_temp,
+                grad_scale):
+        want_grad = bool(ctx.needs_input_grad[0])
+        cfg.grad_scale = grad_scale
+        logp, ent, lse, dl = ops.grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages, old_lp,
+                                                    ref_lp, cfg, inv_temp, want_grad=want_grad)
+        cfg.grad_scale = 1.0
+        loss, metrics, _ = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total_count, cfg,
+                                         ent_mask=None, entropy=ent, want_g=False)
+        ctx.grad_scale = grad_scale
+        ctx.dl = dl
+        ctx.logits_shape = logits.shape
+        ctx.mark_non_differentiable(metrics, logp, ent)
+        return loss.reshape(()), metrics, logp, ent
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        dl = ctx.dl
+        ctx.dl = None
+        if dl is None:
+            raise RuntimeError("GRPO fused loss: backward called but logits did not require grad in forward")
+        ops.rescale_if_needed(dl, g_loss, ctx.grad_scale)
+        return (dl.view(ctx.logits_shape),) + (None,) * 10
+
+
+class _TwoPhaseGRPO(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, ids, mask_i32, row_count, total_count, advantages, old_lp, ref_lp, cfg, inv_temp,
+                top_entropy_quantile):
+        logp, ent, lse = ops.logprob_entropy_fwd(logits, ids, inv_temp)
+        B, T = mask_i32.shape
+        logp, ent, lse = logp.view(B, T), ent.view(B, T), lse.view(B, T)
+        ent_mask = None
+        if top_entropy_quantile < 1.0:  # grpo_trainer.py:2079-2082
+            ent_mask, _ = ops.entropy_quantile_mask(ent, mask_i32, 1 - top_entropy_quantile)
+        loss, metrics, g = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total_count, cfg,
+                                         ent_mask=ent_mask, entropy=ent, want_g=bool(ctx.needs_input_grad[0]))
+        ctx.save_for_backward(logits, ids, lse, g if g is not None else lse)
+        ctx.inv_temp = inv_temp
+        ctx.mark_non_differentiable(metrics, logp, ent)
+        return loss.reshape(()), metrics, logp, ent
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        logits, ids, lse, g = ctx.saved_tensors
+        dl = ops.logprob_bwd(logits, ids, lse, g * g_loss, ctx.inv_temp)
+        return (dl,) + (None,) * 10
+
+
+class GRPOLoss:
+    """Callable with the hot-path knobs of ``GRPOConfig`` (grpo_config.py:316, 437-539)."""
+
+    def __init__(self, beta: float = 0.0, epsilon_low: float = 0.2, epsilon_high: float = 0.2,
+                 delta: Optional[float] = None, loss_type: str = "bnpo", importance_sampling_level: str = "token",
+                 max_completion_length: int = 256, temperature: float = 1.0, top_entropy_quantile: float = 1.0):
+        if loss_type not in _lib.LOSS_TYPES:
+            raise ValueError(f"Unknown loss type: {loss_type}")
+        if importance_sampling_level not in _lib.IS_LEVELS:
+            raise ValueError(
+                f"Unknown importance sampling level: {importance_sampling_level}. Possible values are 'token' "
+                "and 'sequence'.")
+        self.beta, self.epsilon_low, self.epsilon_high, self.delta = beta, epsilon_low, epsilon_high, delta
+        self.loss_type, self.importance_sampling_level = loss_type, importance_sampling_level
+        self.max_completion_length, self.temperature = max_completion_length, temperature
+        self.top_entropy_quantile = top_entropy_quantile
+
+    def schedule(self, has_old: bool) -> str:
+        if self.top_entropy_quantile < 1.0:
+            return "two-phase"
+        if self.importance_sampling_level == "sequence" and has_old:
+            return "two-phase"
+        return "fused"
+
+    def __call__(self, logits: torch.Tensor, completion_ids: torch.Tensor, completion_mask: torch.Tensor,
+                 advantages: torch.Tensor, old_per_token_logps: Optional[torch.Tensor] = None,
+                 ref_per_token_logps: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                 schedule: Optional[str] = None) -> GRPOLossOutput:
+        """``logits``: ``[B,T,V]`` *un-tempered* completion logits (the temperature is folded into the kernel)."""
+        if self.beta != 0.0 and ref_per_token_logps is None:
+            raise KeyError("ref_per_token_logps")  # the reference indexes inputs[...] (grpo_trainer.py:2086)
+        cfg = ops.make_cfg(self.beta, self.epsilon_low, self.epsilon_high, self.delta, self.loss_type,
+                           self.importance_sampling_level, self.max_completion_length)
+        mask_i32, row_count, total = ops.mask_stats(completion_mask)
+        inv_temp = 1.0 / float(self.temperature)
+        ref = ref_per_token_logps if self.beta != 0.0 else None
+        sched = schedule or self.schedule(old_per_token_logps is not None)
+        if sched == "fused":
+            if self.schedule(old_per_token_logps is not None) != "fused":
+                raise NotImplementedError("the fused schedule needs a per-token gradient (see GRPOLoss.schedule)")
+            loss, metrics, logp, ent = _FusedGRPO.apply(logits, completion_ids, mask_i32, row_count, total, advantages,
+                                                        old_per_token_logps, ref, cfg, inv_temp, float(grad_scale))
+        else:
+            loss, metrics, logp, ent = _TwoPhaseGRPO.apply(logits, completion_ids, mask_i32, row_count, total,
+                                                           advantages, old_per_token_logps, ref, cfg, inv_temp,
+                                                           float(self.top_entropy_quantile))
+        return GRPOLossOutput(loss, metrics, logp, ent, sched)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Trainer-shaped entry points: bind these onto a GRPOTrainer (see patch.patch_trl) or call them with any object
+# that has the same attributes.
+# ------------------------------------------------------------------------------------------------------------------
+def _model_logits(self, model, input_ids, attention_mask, logits_to_keep, extra):
+    """Model forward exactly as grpo_trainer.py:1230-1254 sets it up; returns the [B, T, V] completion logits view."""
+    model_inputs = {"input_ids": input_ids, "attention_mask": attention_mask, **extra}
+    if "logits_to_keep" in getattr(self, "model_kwarg_keys", ()):
+        model_inputs["logits_to_keep"] = logits_to_keep + 1  # :1247
+    logits = model(**model_inputs).logits
+    return logits[:, :-1, :][:, -logits_to_keep:, :]  # :1252-1254 (a view; the kernel takes the stride)
+
+
+def get_per_token_logps_and_entropies(self, model, input_ids, attention_mask, logits_to_keep, batch_size=None,
+                                      compute_entropy=False, pixel_values=None, image_grid_thw=None,
+                                      pixel_attention_mask=None, image_sizes=None):
+    """Drop-in for ``GRPOTrainer._get_per_token_logps_and_entropies`` (grpo_trainer.py:1206-1272).
+
+    Returns the ``(logps, entropies)`` tuple the fork returns (:1272).  The temperature division (:1258), the
+    log-probs (:1261) and the entropies (:1267) are one kernel pass per micro-chunk.
+    """
+    from .functional import logprobs_and_entropy
+
+    batch_size = batch_size or input_ids.size(0)
+    all_logps, all_ent = [], []
+    for start in range(0, input_ids.size(0), batch_size):
+        sl = slice(start, start + batch_size)
+        extra = {}
+        if image_grid_thw is not None and pixel_values is not None:  # :1234-1238
+            extra["image_grid_thw"] = image_grid_thw[sl]
+            lo = image_grid_thw[:start].prod(-1).sum().item()
+            hi = image_grid_thw[: start + batch_size].prod(-1).sum().item()
+            extra["pixel_values"] = pixel_values[lo:hi]
+        elif pixel_values is not None:
+            extra["pixel_values"] = pixel_values[sl]
+        if pixel_attention_mask is not None:
+            extra["pixel_attention_mask"] = pixel_attention_mask[sl]
+        if image_sizes is not None:
+            extra["image_sizes"] = image_sizes[sl]
+        logits = _model_logits(self, model, input_ids[sl], attention_mask[sl], logits_to_keep, extra)
+        ids = input_ids[sl][:, -logits_to_keep:]
+        logps, ent = logprobs_and_entropy(logits, ids, self.temperature, compute_entropy)
+        all_logps.append(logps)
+        if compute_entropy:
+            all_ent.append(ent)
+    return torch.cat(all_logps, dim=0), (torch.cat(all_ent, dim=0) if compute_entropy else None)
+
+
+def compute_loss(self, model, inputs):
+    """Drop-in for ``GRPOTrainer._compute_loss`` (grpo_trainer.py:2058-2175).
+
+    Metric logging keeps the reference's semantics (mean over ranks of each rank's local mean, nan-aware min/max,
+    :2150-2172) but costs ONE all-gather of an 8-float vector and ONE host read instead of five scalar gathers
+    and seven ``.item()`` calls.
+    """
+    from .distributed import gather_metrics
+
+    prompt_ids, prompt_mask = inputs["prompt_ids"], inputs["prompt_mask"]
+    completion_ids, completion_mask = inputs["completion_ids"], inputs["completion_mask"]
+    input_ids = torch.cat([prompt_ids, completion_ids], dim=1)
+    attention_mask = torch.cat([prompt_mask, completion_mask], dim=1)
+    T = completion_ids.size(1)
+    extra = {k: inputs[k] for k in ("pixel_values", "image_grid_thw", "pixel_attention_mask", "image_sizes")
+             if inputs.get(k) is not None}
+    logits = _model_logits(self, model, input_ids, attention_mask, T, extra)
+
+    loss_fn = GRPOLoss(self.beta, self.epsilon_low, self.epsilon_high, getattr(self.args, "delta", None),
+                       self.loss_type, self.importance_sampling_level, self.max_completion_length, self.temperature,
+                       self.top_entropy_quantile)
+    grad_scale = 1.0 / float(getattr(self, "current_gradient_accumulation_steps", 1) or 1) \
+        if getattr(self, "_b200_prescale", False) else 1.0
+    out = loss_fn(logits, completion_ids, completion_mask, inputs["advantages"], inputs.get("old_per_token_logps"),
+                  inputs.get("ref_per_token_logps") if self.beta != 0.0 else None, grad_scale=grad_scale)
+
+    mode = "train" if self.model.training else "eval"
+    g = gather_metrics(out.metrics, getattr(self, "accelerator", None))  # [world, 8] on host, one sync
+    mi = METRIC_INDEX
+    if self.beta != 0.0:
+        self._metrics[mode]["kl"].append(_nanmean(g[:, mi["kl"]]))
+    self._metrics[mode]["entropy"].append(_nanmean(g[:, mi["entropy"]]))
+    low, high, region = g[:, mi["clip_ratio/low"]], g[:, mi["clip_ratio/high"]], g[:, mi["clip_ratio/region"]]
+    self._metrics[mode]["clip_ratio/low_mean"].append(_nanmean(low))
+    self._metrics[mode]["clip_ratio/low_min"].append(_nanmin(low))
+    self._metrics[mode]["clip_ratio/high_mean"].append(_nanmean(high))
+    self._metrics[mode]["clip_ratio/high_max"].append(_nanmax(high))
+    self._metrics[mode]["clip_ratio/region_mean"].append(_nanmean(region))
+    return out.loss
+
+
+def _nanmean(x: torch.Tensor) -> float:
+    return x.nanmean().item()
+
+
+def _nanmin(x: torch.Tensor) -> float:  # grpo_trainer.py:274-286
+    keep = ~torch.isnan(x)
+    return x[keep].min().item() if bool(keep.any()) else float("nan")
+
+
+def _nanmax(x: torch.Tensor) -> float:  # grpo_trainer.py:289-301
+    keep = ~torch.isnan(x)
+    return x[keep].max().item() if bool(keep.any()) else float("nan")

@@ -1,0 +1,338 @@
+"""Tensor-level wrappers over the C-ABI: argument marshalling only (pointers, sizes, the current stream).
+
+PyTorch is plumbing here — it owns device memory and the stream; every numeric result below is produced by a
+kernel in ``libb200trl.so``.  All wrappers are asynchronous and never synchronise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GrpoCfg, check, lib
+
+_DTYPES = {torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16, torch.float32: _lib.DTYPE_F32,
+           torch.float64: _lib.DTYPE_F64}
+
+launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: swh_trl_b200 has no CPU path (got device {t.device})")
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    _need_cuda(t, name)
+    return t.detach().to(torch.float32).contiguous()
+
+
+def collapse_rows(shape, strides) -> Optional[int]:
+    """Row stride (in elements) if a ``(..., V)`` layout is addressable as ``base + r * row_stride``, else None.
+
+    Pure shape arithmetic (unit-tested on CPU): the last dim must be dense and the leading dims (size-1 dims
+    ignored) must form one arithmetic progression.
+    """
+    V = shape[-1]
+    if V != 1 and strides[-1] != 1:
+        return None
+    dims = [(s, st) for s, st in zip(shape[:-1], strides[:-1]) if s != 1]
+    if any(dims[i][1] != dims[i + 1][0] * dims[i + 1][1] for i in range(len(dims) - 1)):
+        return None
+    row_stride = dims[-1][1] if dims else V
+    return row_stride if row_stride >= V else None
+
+
+def rows_view(logits: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
+    """``(tensor, n_rows, vocab, row_stride)`` with rows addressable as ``base + r * row_stride``.
+
+    A view is used whenever the leading dims collapse to one uniform stride; otherwise one contiguous copy is
+    made (the copy the reference always makes at grpo_trainer.py:1252-1258).
+    """
+    _need_cuda(logits, "logits")
+    if logits.dtype not in _DTYPES:
+        raise TypeError(f"unsupported logits dtype {logits.dtype}")
+    if logits.dim() < 1:
+        raise ValueError("logits must have a vocabulary dimension")
+    V = logits.shape[-1]
+    n = logits.numel() // V if V else 0
+    row_stride = collapse_rows(tuple(logits.shape), tuple(logits.stride()))
+    if row_stride is not None:
+        return logits, n, V, row_stride
+    return logits.contiguous(), n, V, V
+
+
+def make_cfg(beta: float, epsilon_low: float, epsilon_high: float, delta: Optional[float], loss_type: str,
+             importance_sampling_level: str, max_completion_length: int, grad_scale: float = 1.0) -> GrpoCfg:
+    """Pack GRPO hyper-parameters; unknown enums raise the reference's ValueErrors (grpo_trainer.py:2106-2109, 2137)."""
+    if loss_type not in _lib.LOSS_TYPES:
+        raise ValueError(f"Unknown loss type: {loss_type}")
+    if importance_sampling_level not in _lib.IS_LEVELS:
+        raise ValueError(
+            f"Unknown importance sampling level: {importance_sampling_level}. Possible values are 'token' "
+            "and 'sequence'.")
+    cfg = GrpoCfg()
+    cfg.beta = float(beta)
+    cfg.clip_low = 1.0 - float(epsilon_low)  # double arithmetic, rounded once to fp32 like torch's scalar clamp
+    cfg.clip_high = 1.0 + float(epsilon_high)
+    cfg.delta = float(delta) if delta is not None else 0.0
+    cfg.has_delta = 0 if delta is None else 1
+    cfg.loss_type = _lib.LOSS_TYPES[loss_type]
+    cfg.is_level = _lib.IS_LEVELS[importance_sampling_level]
+    cfg.max_completion_length = float(max_completion_length)
+    cfg.grad_scale = float(grad_scale)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def logprob_entropy_fwd(logits: torch.Tensor, ids: torch.Tensor, inv_temperature: float = 1.0,
+                        want_entropy: bool = True, want_lse: bool = True):
+    """fp32 ``(logp, entropy|None, lse|None)`` shaped like ``ids`` — one pass over the logits."""
+    x, n, V, stride = rows_view(logits)
+    _need_cuda(ids, "index")
+    idx = ids.to(torch.int64).contiguous()
+    if idx.numel() != n:
+        raise ValueError(f"index has {idx.numel()} elements, logits has {n} rows")
+    shape = tuple(logits.shape[:-1])
+    logp = torch.empty(shape, dtype=torch.float32, device=x.device)
+    ent = torch.empty(shape, dtype=torch.float32, device=x.device) if want_entropy else None
+    lse = torch.empty(shape, dtype=torch.float32, device=x.device) if want_lse else None
+    if n:
+        check(lib.b200trl_logprob_entropy_fwd(_ptr(x), _DTYPES[x.dtype], n, V, stride, _ptr(idx),
+                                              float(inv_temperature), _ptr(logp), _ptr(ent), _ptr(lse), _stream(x)),
+              "logprob_entropy_fwd")
+        _count()
+    return logp, ent, lse
+
+
+def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: torch.Tensor,
+                inv_temperature: float = 1.0) -> torch.Tensor:
+    """``dlogits`` (logits dtype, contiguous) for per-token upstream gradient ``g``."""
+    x, n, V, stride = rows_view(logits)
+    idx = ids.to(torch.int64).contiguous()
+    out = torch.empty(logits.shape, dtype=x.dtype, device=x.device)
+    if n:
+        check(lib.b200trl_logprob_bwd(_ptr(x), _DTYPES[x.dtype], n, V, stride, _ptr(idx), float(inv_temperature),
+                                      _ptr(_f32(lse, "lse")), _ptr(_f32(g, "g")), _ptr(out), V, _stream(x)),
+              "logprob_bwd")
+        _count()
+    return out
+
+
+def mask_stats(mask: torch.Tensor):
+    """``(mask_i32, row_count[B], total[1])`` for a ``[B,T]`` completion mask."""
+    _need_cuda(mask, "completion_mask")
+    m = mask.to(torch.int32).contiguous()
+    B, T = m.shape
+    row = torch.empty(B, dtype=torch.float32, device=m.device)
+    tot = torch.empty(1, dtype=torch.float32, device=m.device)
+    check(lib.b200trl_mask_stats(_ptr(m), B, T, _ptr(row), _ptr(tot), _stream(m)), "mask_stats")
+    _count(2)  # memset node + kernel
+    return m, row, tot
+
+
+def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages, old_logp, ref_logp, cfg: GrpoCfg,
+                       inv_temperature: float, want_grad: bool = True, dlogits_out: Optional[torch.Tensor] = None):
+    """One pass: ``(logp, entropy, lse, dlogits|None)``; see ``b200trl_grpo_fused_fwd_bwd``."""
+    x, n, V, stride = rows_view(logits)
+    B, T = mask_i32.shape
+    if n != B * T:
+        raise ValueError(f"logits rows {n} != B*T {B * T}")
+    idx = ids.to(torch.int64).contiguous()
+    logp = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    ent = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    lse = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    dl = None
+    if want_grad:
+        dl = dlogits_out if dlogits_out is not None else torch.empty((B, T, V), dtype=x.dtype, device=x.device)
+    check(lib.b200trl_grpo_fused_fwd_bwd(
+        _ptr(x), _DTYPES[x.dtype], B, T, V, stride, _ptr(idx), _ptr(mask_i32), _ptr(_f32(advantages, "advantages")),
+        _ptr(_f32(old_logp, "old_per_token_logps")), _ptr(_f32(ref_logp, "ref_per_token_logps")), C.byref(cfg),
+        float(inv_temperature), _ptr(row_count), _ptr(total_count), _ptr(logp), _ptr(ent), _ptr(lse), _ptr(dl), V,
+        _stream(x)), "grpo_fused_fwd_bwd")
+    _count()
+    return logp, ent, lse, dl
+
+
+# ------------------------------------------------------------------------------------------------ K2
+_ws_cache = {}
+
+
+def _workspace(device, nbytes: int, key: str, zero: bool) -> torch.Tensor:
+    k = (device, key)
+    ws = _ws_cache.get(k)
+    if ws is None or ws.numel() < nbytes:
+        ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _ws_cache[k] = ws
+    return ws
+
+
+def grpo_loss(logp, old_logp, ref_logp, advantages, mask_i32, row_count, total_count, cfg: GrpoCfg,
+              ent_mask: Optional[torch.Tensor] = None, entropy: Optional[torch.Tensor] = None, want_g: bool = False):
+    """``(loss[1], metrics[8], g[B,T]|None)`` — ``b200trl_grpo_loss``."""
+    B, T = mask_i32.shape
+    dev = mask_i32.device
+    ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(B), "grpo_loss", zero=True)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    metrics = torch.empty(_lib.NUM_GRPO_METRICS, dtype=torch.float32, device=dev)
+    g = torch.empty(B, T, dtype=torch.float32, device=dev) if want_g else None
+    em = None if ent_mask is None else ent_mask.to(torch.uint8).contiguous()
+    check(lib.b200trl_grpo_loss(
+        _ptr(_f32(logp, "per_token_logps")), _ptr(_f32(old_logp, "old_per_token_logps")),
+        _ptr(_f32(ref_logp, "ref_per_token_logps")), _ptr(_f32(advantages, "advantages")), _ptr(mask_i32), _ptr(em),
+        _ptr(_f32(entropy, "entropies")), B, T, C.byref(cfg), _ptr(row_count), _ptr(total_count), _ptr(ws), _ptr(loss),
+        _ptr(metrics), _ptr(g), _stream(mask_i32)), "grpo_loss")
+    _count()
+    return loss, metrics, g
+
+
+def entropy_quantile_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold: float):
+    """``(bool mask, threshold[1])`` — ``b200trl_entropy_quantile_mask``."""
+    _need_cuda(entropies, "entropies")
+    e = _f32(entropies, "entropies")
+    m = mask.to(torch.int32).contiguous()
+    out = torch.empty(e.shape, dtype=torch.uint8, device=e.device)
+    thr = torch.empty(1, dtype=torch.float32, device=e.device)
+    if e.numel():
+        check(lib.b200trl_entropy_quantile_mask(_ptr(e), _ptr(m), e.numel(), float(threshold), None, _ptr(out),
+                                                _ptr(thr), _stream(e)), "entropy_quantile_mask")
+        _count()
+    return out.bool(), thr
+
+
+# ------------------------------------------------------------------------------------------------ K3
+def group_advantages(rewards_per_func: torch.Tensor, weights: torch.Tensor, num_generations: int,
+                     scale_rewards: bool, local_offset: int, local_count: int):
+    """``dict(advantages, all, rewards, mean, std, is_std_zero)`` — ``b200trl_group_advantages``."""
+    r = _f32(rewards_per_func, "rewards_per_func")
+    if r.dim() == 1:
+        r = r.unsqueeze(1)
+    w = _f32(weights, "reward_weights")
+    Bg, F = r.shape
+    if Bg % num_generations:
+        raise ValueError(f"global batch {Bg} is not divisible by num_generations {num_generations}")
+    dev = r.device
+    rewards = torch.empty(Bg, dtype=torch.float32, device=dev)
+    adv_all = torch.empty(Bg, dtype=torch.float32, device=dev)
+    adv_loc = torch.empty(local_count, dtype=torch.float32, device=dev)
+    ng = Bg // num_generations
+    mean = torch.empty(ng, dtype=torch.float32, device=dev)
+    std = torch.empty(ng, dtype=torch.float32, device=dev)
+    zero = torch.empty(ng, dtype=torch.uint8, device=dev)
+    check(lib.b200trl_group_advantages(_ptr(r), _ptr(w), Bg, F, num_generations, int(bool(scale_rewards)),
+                                       int(local_offset), int(local_count), _ptr(rewards), _ptr(adv_all),
+                                       _ptr(adv_loc), _ptr(mean), _ptr(std), _ptr(zero), _stream(r)),
+          "group_advantages")
+    _count()
+    return dict(advantages=adv_loc, all=adv_all, rewards=rewards, mean=mean, std=std, is_std_zero=zero.bool())
+
+
+# ------------------------------------------------------------------------------------------------ K4 / PPO
+def ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl_coef, kl_estimator, gamma, lam,
+                    whiten_rewards, want_filled: bool = True):
+    """``dict(rewards, advantages, returns[, logprobs, ref_logprobs, values])`` — ``b200trl_ppo_rewards_gae``."""
+    if kl_estimator not in _lib.KL_ESTIMATORS:
+        raise ValueError(f"Unknown kl_estimator: {kl_estimator}")
+    lp, rlp, val = _f32(logprobs, "logprobs"), _f32(ref_logprobs, "ref_logprobs"), _f32(values, "values")
+    sc = _f32(scores, "scores")
+    sl = sequence_lengths.to(torch.int64).contiguous()
+    B, T = lp.shape
+    dev = lp.device
+    ws = _workspace(dev, lib.b200trl_ppo_gae_workspace_bytes(B, T), "ppo_gae", zero=False)
+    mk = lambda: torch.empty(B, T, dtype=torch.float32, device=dev)  # noqa: E731
+    rewards, adv, ret = mk(), mk(), mk()
+    lpf, rlpf, vf = (mk(), mk(), mk()) if want_filled else (None, None, None)
+    check(lib.b200trl_ppo_rewards_gae(_ptr(lp), _ptr(rlp), _ptr(val), _ptr(sc), _ptr(sl), B, T, float(kl_coef),
+                                      _lib.KL_ESTIMATORS[kl_estimator], float(gamma), float(lam),
+                                      int(bool(whiten_rewards)), _ptr(ws), _ptr(rewards), _ptr(adv), _ptr(ret),
+                                      _ptr(lpf), _ptr(rlpf), _ptr(vf), _stream(lp)), "ppo_rewards_gae")
+    _count()
+    out = dict(rewards=rewards, advantages=adv, returns=ret)
+    if want_filled:
+        out.update(logprobs=lpf, ref_logprobs=rlpf, values=vf)
+    return out
+
+
+def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advantages, inv_temperature, cliprange,
+                      grad_scale: float = 1.0, want_grad: bool = True):
+    """``(new_logprobs, entropy, lse, dlogits|None)`` — ``b200trl_ppo_fused_fwd_bwd``."""
+    x, n, V, stride = rows_view(logits)
+    mb, T = responses.shape
+    if n != mb * T:
+        raise ValueError(f"logits rows {n} != mb*T {mb * T}")
+    idx = responses.to(torch.int64).contiguous()
+    sl = sequence_lengths.to(torch.int64).contiguous()
+    dev = x.device
+    nlp = torch.empty(mb, T, dtype=torch.float32, device=dev)
+    ent = torch.empty(mb, T, dtype=torch.float32, device=dev)
+    lse = torch.empty(mb, T, dtype=torch.float32, device=dev)
+    dl = torch.empty((mb, T, V), dtype=x.dtype, device=dev) if want_grad else None
+    check(lib.b200trl_ppo_fused_fwd_bwd(_ptr(x), _DTYPES[x.dtype], mb, T, V, stride, _ptr(idx), _ptr(sl),
+                                        _ptr(_f32(old_logprobs, "old_logprobs")), _ptr(_f32(advantages, "advantages")),
+                                        float(inv_temperature), float(cliprange), float(grad_scale), _ptr(nlp),
+                                        _ptr(ent), _ptr(lse), _ptr(dl), V, _stream(x)), "ppo_fused_fwd_bwd")
+    _count()
+    return nlp, ent, lse, dl
+
+
+def ppo_loss(new_logprobs, old_logprobs, advantages, returns, values, vpred, entropy, sequence_lengths, cliprange,
+             cliprange_value, vf_coef, grad_scale: float = 1.0, want_dvpred: bool = True):
+    """``(stats[8], dvpred|None)`` — ``b200trl_ppo_loss``."""
+    nlp = _f32(new_logprobs, "new_logprobs")
+    mb, T = nlp.shape
+    dev = nlp.device
+    sl = sequence_lengths.to(torch.int64).contiguous()
+    ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(mb), "ppo_loss", zero=True)
+    stats = torch.empty(_lib.NUM_PPO_STATS, dtype=torch.float32, device=dev)
+    dvp = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_dvpred else None
+    check(lib.b200trl_ppo_loss(_ptr(nlp), _ptr(_f32(old_logprobs, "old_logprobs")), _ptr(_f32(advantages, "advantages")),
+                               _ptr(_f32(returns, "returns")), _ptr(_f32(values, "values")), _ptr(_f32(vpred, "vpred")),
+                               _ptr(_f32(entropy, "entropy")), _ptr(sl), mb, T, float(cliprange),
+                               float(cliprange_value), float(vf_coef), float(grad_scale), _ptr(ws), _ptr(stats),
+                               _ptr(dvp), _stream(nlp)), "ppo_loss")
+    _count()
+    return stats, dvp
+
+
+# ------------------------------------------------------------------------------------------------ a-12
+def masked_whiten(values: torch.Tensor, mask: torch.Tensor, shift_mean: bool = True, want_out: bool = True):
+    """``(whitened|None, stats[3]={mean, unbiased var, count})`` — ``b200trl_masked_whiten``."""
+    v = _f32(values, "values")
+    m = mask.expand_as(values).to(torch.uint8).contiguous()
+    dev = v.device
+    ws = _workspace(dev, lib.b200trl_masked_workspace_bytes(v.numel()), "masked", zero=False)
+    out = torch.empty_like(v) if want_out else None
+    stats = torch.empty(3, dtype=torch.float32, device=dev)
+    check(lib.b200trl_masked_whiten(_ptr(v), _ptr(m), v.numel(), int(bool(shift_mean)), _ptr(ws), _ptr(out),
+                                    _ptr(stats), _stream(v)), "masked_whiten")
+    _count()
+    return out, stats
+
+
+def rescale_if_needed(buf: torch.Tensor, actual: torch.Tensor, expected: float) -> None:
+    """``buf *= actual / expected`` on the device, skipped when equal (no host sync)."""
+    x, n, V, stride = rows_view(buf)
+    if x.data_ptr() != buf.data_ptr():
+        raise ValueError("rescale_if_needed needs a row-addressable buffer")
+    a = actual.detach().to(torch.float32).reshape(1)
+    check(lib.b200trl_rescale_if_needed(_ptr(x), _DTYPES[x.dtype], n, V, stride, _ptr(a), float(expected), _stream(x)),
+          "rescale_if_needed")
+    _count()

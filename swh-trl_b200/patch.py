@@ -1,0 +1,53 @@
+"""``patch_trl()`` — rebind the reference's hot-path names to the B200 implementations.
+
+``selective_log_softmax`` is bound at import time by ten reference modules (``from .utils import …``:
+grpo_trainer.py:68-76, ppo_trainer.py:54-71, rloo_trainer.py:60, dpo_trainer.py:75, bco_trainer.py:68,
+cpo_trainer.py:62, kto_trainer.py:65, orpo_trainer.py:65, nash_md_trainer.py:49, xpo_trainer.py:48), so the
+global has to be replaced in every module that imported it, not only in ``trl.trainer.utils``.
+"""
+
+from __future__ import annotations
+
+import sys
+import types
+
+from . import functional, grpo
+
+_FUNCTIONS = {
+    "selective_log_softmax": functional.selective_log_softmax,
+    "entropy_from_logits": functional.entropy_from_logits,
+    "get_high_entropy_mask": functional.get_high_entropy_mask,
+    "masked_mean": functional.masked_mean,
+    "masked_var": functional.masked_var,
+    "masked_whiten": functional.masked_whiten,
+}
+
+
+def patch_module(mod: types.ModuleType) -> list:
+    """Replace every hot-path global that ``mod`` holds; returns the names replaced."""
+    done = []
+    for name, fn in _FUNCTIONS.items():
+        cur = getattr(mod, name, None)
+        if cur is not None and callable(cur) and cur is not fn:
+            setattr(mod, "_trl_original_" + name, cur)
+            setattr(mod, name, fn)
+            done.append(name)
+    trainer = getattr(mod, "GRPOTrainer", None)
+    if isinstance(trainer, type) and "_compute_loss" in trainer.__dict__:
+        trainer._trl_original_compute_loss = trainer._compute_loss
+        trainer._compute_loss = grpo.compute_loss
+        trainer._get_per_token_logps_and_entropies = grpo.get_per_token_logps_and_entropies
+        done.append("GRPOTrainer._compute_loss")
+    return done
+
+
+def patch_trl(prefix: str = "trl") -> dict:
+    """Patch every already-imported ``trl`` module; returns ``{module name: [patched names]}``."""
+    report = {}
+    for name, mod in list(sys.modules.items()):
+        if mod is None or not (name == prefix or name.startswith(prefix + ".")):
+            continue
+        done = patch_module(mod)
+        if done:
+            report[name] = done
+    return report

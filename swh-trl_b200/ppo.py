@@ -1,0 +1,78 @@
+"""PPO reward shaping, GAE and clipped losses on the B200 library.
+
+The reference has no seam here — the math is inline in ``PPOTrainer.train`` (ppo_trainer.py:500-605) — so these
+functions take the same-named locals of that loop.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, ops
+
+INVALID_LOGPROB = 1.0  # ppo_trainer.py:81
+STAT_INDEX = {"loss": 0, "pg_loss": 1, "vf_loss": 2, "pg_clipfrac": 3, "vf_clipfrac": 4, "approxkl": 5, "entropy": 6,
+              "ratio": 7}
+
+
+def ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl_coef: float = 0.05,
+                    kl_estimator: str = "k1", gamma: float = 1.0, lam: float = 0.95, whiten_rewards: bool = False):
+    """ppo_trainer.py:500-535 in one cooperative launch.
+
+    Inputs are the raw rollout tensors; the pad fills of :500-506 happen inside.  Returns a dict with ``rewards``,
+    ``advantages`` (whitened, pads zero), ``returns`` and the filled ``logprobs`` / ``ref_logprobs`` / ``values``.
+    """
+    return ops.ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl_coef, kl_estimator, gamma,
+                               lam, whiten_rewards)
+
+
+@dataclass
+class PPOLossOutput:
+    loss: torch.Tensor          # 0-d, differentiable wrt logits and vpred
+    stats: torch.Tensor         # fp32 [8] on device, layout STAT_INDEX
+    new_logprobs: torch.Tensor  # fp32 [mb,T], pads = INVALID_LOGPROB
+
+
+class _PPOLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, vpred, responses, old_logprobs, advantages, returns, values, sequence_lengths,
+                inv_temp, cliprange, cliprange_value, vf_coef, grad_scale):
+        need_dl, need_dv = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
+        nlp, ent, _lse, dl = ops.ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advantages,
+                                                   inv_temp, cliprange, grad_scale, want_grad=need_dl)
+        stats, dvp = ops.ppo_loss(nlp, old_logprobs, advantages, returns, values, vpred, ent, sequence_lengths,
+                                  cliprange, cliprange_value, vf_coef, grad_scale, want_dvpred=need_dv)
+        ctx.dl, ctx.dvp, ctx.grad_scale = dl, dvp, grad_scale
+        ctx.shapes = (logits.shape, vpred.shape)
+        ctx.mark_non_differentiable(stats, nlp)
+        return stats[0].clone(), stats, nlp
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        dl, dvp = ctx.dl, ctx.dvp
+        ctx.dl = ctx.dvp = None
+        if dl is not None:
+            ops.rescale_if_needed(dl, g_loss, ctx.grad_scale)
+            dl = dl.view(ctx.shapes[0])
+        if dvp is not None:
+            dvp = (dvp * (g_loss / ctx.grad_scale)).view(ctx.shapes[1])
+        return (dl, dvp) + (None,) * 11
+
+
+def ppo_loss(logits, mb_responses, mb_logprobs, mb_advantage, mb_return, mb_values, vpred, sequence_lengths,
+             temperature: float = 0.7, cliprange: float = 0.2, cliprange_value: float = 0.2, vf_coef: float = 0.1,
+             grad_scale: float = 1.0) -> PPOLossOutput:
+    """Micro-batch loss of ppo_trainer.py:557-605.
+
+    ``logits``: ``[mb,T,V]`` response logits *before* the temperature division of :559 (folded into the kernel as
+    ``1 / (temperature + 1e-7)``); ``vpred``: ``[mb,T]`` raw value predictions; ``sequence_lengths``: ``[mb]``
+    (``padding_mask = idx > len``, :501).  One V-sized pass yields new log-probs, the entropy stat (:592-593,
+    which costs the reference an extra full softmax) and dlogits.
+    """
+    inv_temp = 1.0 / (float(temperature) + 1e-7)
+    loss, stats, nlp = _PPOLoss.apply(logits, vpred, mb_responses, mb_logprobs, mb_advantage, mb_return, mb_values,
+                                      sequence_lengths, inv_temp, float(cliprange), float(cliprange_value),
+                                      float(vf_coef), float(grad_scale))
+    return PPOLossOutput(loss, stats, nlp)

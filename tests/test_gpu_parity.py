@@ -1,0 +1,387 @@
+"""GPU parity: the CUDA library (through the Python mirror and the C-ABI) against
+(a) golden vectors produced by the reference's own source, (b) the CPU oracle on the same seeded inputs,
+(c) size-independent properties at BASELINE config sizes.
+
+Tolerances (north_star): log-probs <= 1e-5 abs vs the reference fp32 path; loss and fp32 gradients <= 1e-4 rel;
+bf16 dlogits are compared with the fp32 oracle gradient rounded to bf16, allowing one bf16 ulp (2^-8 relative);
+mask / group / index results bit-exact.
+"""
+import pytest
+import torch
+
+from oracle import trl_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+BF16_ULP = 2.0 ** -7  # rtol that admits a one-ulp difference of a bf16 value
+
+
+@pytest.fixture(scope="module")
+def S():
+    import swh_trl_b200 as s
+    return s
+
+
+def _regen(case):
+    g = torch.Generator().manual_seed(case["seed"])
+    B, T, V = case["shape"]
+    return torch.randn(B, T, V, generator=g, dtype=torch.float32).to(case["dtype"])
+
+
+def _paths(S, logits):
+    """K1 implementations applicable to this tensor."""
+    out = [S.K1_ROW]
+    V = logits.shape[-1]
+    if logits.dtype == torch.bfloat16 and V % 8 == 0 and V * 2 >= 32768:
+        out.append(S.K1_RESIDENT)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K1 forward
+@pytest.mark.parametrize("i", range(8))
+def test_logprob_entropy_golden(S, i):
+    case = load_golden("logprob_entropy.pt")[i]
+    logits = _regen(case).to(DEV)
+    ids = case["ids"].to(DEV)
+    lp = S.selective_log_softmax(logits, ids)
+    ent = S.entropy_from_logits(logits)
+    torch.testing.assert_close(lp.float().cpu(), case["logp_fp32"].float(), rtol=0, atol=1e-5)
+    torch.testing.assert_close(ent.float().cpu(), case["entropy_fp32"].float(), rtol=0, atol=1e-5)
+    # the reference's own unit-test oracle (tests/test_utils.py:551): gather(log_softmax)
+    want = torch.gather(logits.float().log_softmax(-1), -1, ids.unsqueeze(-1)).squeeze(-1)
+    torch.testing.assert_close(lp.float(), want, rtol=1e-5, atol=1e-5)
+
+
+def test_entropy_reference_shape(S):
+    case = load_golden("logprob_entropy.pt")[8]  # 64 x 384 x 768, tests/test_utils.py:631
+    ent = S.entropy_from_logits(_regen(case).to(DEV), chunk_size=16)
+    torch.testing.assert_close(ent.cpu(), case["entropy_fp32"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("V,temp", [(32000, 1.0), (151936, 1.0), (151936, 0.7), (152064, 1.0), (40960, 0.5),
+                                    (65544, 1.3), (262144, 1.0)])
+@pytest.mark.parametrize("peaked", [False, True])
+def test_k1_forward_vs_oracle(S, V, temp, peaked):
+    B, T = 2, 5
+    logits, ids, _ = O.synth_batch(B, T, V, seed=3, sigma=4.0 if peaked else 1.0, peaked=peaked)
+    want_lp = O.selective_log_softmax(logits.float() / temp, ids)
+    want_ent = O.entropy_from_logits(logits.float() / temp)
+    x, idx = logits.to(DEV), ids.to(DEV)
+    for path in _paths(S, x):
+        prev = S.set_k1_path(path)
+        try:
+            lp, ent = S.logprobs_and_entropy(x, idx, temperature=temp)
+        finally:
+            S.set_k1_path(prev)
+        torch.testing.assert_close(lp.cpu(), want_lp, rtol=0, atol=1e-5, msg=lambda m: f"path {path}: {m}")
+        torch.testing.assert_close(ent.cpu(), want_ent, rtol=1e-5, atol=1e-5, msg=lambda m: f"path {path}: {m}")
+
+
+def test_k1_extreme_values(S):
+    """+-60 logits (online-softmax stability) and a strided row view."""
+    V = 32768
+    g = torch.Generator().manual_seed(1)
+    logits = ((torch.rand(6, V, generator=g) - 0.5) * 120).to(torch.bfloat16)
+    ids = torch.randint(0, V, (6,), generator=g)
+    want = O.selective_log_softmax(logits.float(), ids)
+    big = torch.zeros(6, V + 64, dtype=torch.bfloat16, device=DEV)
+    big[:, :V] = logits.to(DEV)
+    view = big[:, :V]  # row stride V + 64
+    for path in _paths(S, view):
+        prev = S.set_k1_path(path)
+        try:
+            lp = S.selective_log_softmax(view, ids.to(DEV))
+        finally:
+            S.set_k1_path(prev)
+        torch.testing.assert_close(lp.cpu(), want, rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ K1 backward
+@pytest.mark.parametrize("V,dtype", [(1024, torch.float32), (1001, torch.float32), (4104, torch.bfloat16),
+                                     (32000, torch.bfloat16), (151936, torch.bfloat16), (50257, torch.float16)])
+def test_selective_log_softmax_backward(S, V, dtype):
+    g = torch.Generator().manual_seed(V)
+    B, T = 2, 3
+    logits = (torch.randn(B, T, V, generator=g) * 2).to(dtype)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    up = torch.randn(B, T, generator=g)
+    xr = logits.float().requires_grad_(True)
+    (O.selective_log_softmax(xr, ids) * up).sum().backward()
+    for path in _paths(S, logits.to(DEV)):
+        prev = S.set_k1_path(path)
+        try:
+            x = logits.to(DEV).requires_grad_(True)
+            lp = S.selective_log_softmax(x, ids.to(DEV))
+            (lp * up.to(DEV)).sum().backward()
+        finally:
+            S.set_k1_path(prev)
+        assert x.grad.dtype == dtype and x.grad.shape == x.shape
+        if dtype == torch.float32:
+            torch.testing.assert_close(x.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-7)
+        else:
+            torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(dtype).float(), rtol=BF16_ULP, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ GRPO loss
+def _metrics_close(got, ref, beta):
+    from swh_trl_b200.grpo import METRIC_INDEX as mi
+    g = got.cpu()
+    assert g[mi["clip_ratio/low"]].item() == pytest.approx(ref["clip_ratio/low_mean"], abs=1e-6)
+    assert g[mi["clip_ratio/high"]].item() == pytest.approx(ref["clip_ratio/high_mean"], abs=1e-6)
+    assert g[mi["clip_ratio/region"]].item() == pytest.approx(ref["clip_ratio/region_mean"], abs=1e-6)
+    assert g[mi["entropy"]].item() == pytest.approx(ref["entropy"], rel=1e-4)
+    if beta != 0.0:
+        assert g[mi["kl"]].item() == pytest.approx(ref["kl"], rel=1e-4, abs=1e-7)
+
+
+@pytest.mark.parametrize("i", range(36))
+def test_grpo_loss_small_golden(S, i):
+    """36 configurations (loss_type x IS level x old given x beta/delta/eps/temperature/entropy-quantile) whose
+    loss, gradient and metrics were produced by the reference's own _compute_loss."""
+    case = load_golden("grpo_loss_small.pt")[i]
+    B, T, V, P = case["shape"]
+    cfg = dict(case["cfg"])
+    ml, pid, cid, mask, adv, n_old, n_ref = O.synth_loss_case(B, T, V, P, case["seed"])
+    old = (case["logp"] + n_old).to(DEV) if case["with_old"] else None
+    ref = (case["logp"] + n_ref).to(DEV) if cfg["beta"] != 0.0 else None
+    x = ml.to(DEV).requires_grad_(True)
+    kept = x[:, :-1][:, -T:]
+    loss_fn = S.GRPOLoss(**cfg)
+    out = loss_fn(kept, cid.to(DEV), mask.to(DEV), adv.to(DEV), old, ref)
+    out.loss.backward()
+    torch.testing.assert_close(out.loss.detach().cpu(), case["loss"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out.per_token_logps.cpu(), case["logp"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(x.grad.cpu(), case["grad"], rtol=1e-4, atol=2e-8)
+    _metrics_close(out.metrics, case["metrics"], cfg["beta"])
+
+
+@pytest.mark.parametrize("i", range(3))
+@pytest.mark.parametrize("path", ["row", "resident"])
+def test_grpo_c1_golden(S, i, path):
+    """BASELINE config 1 (B=4, T=256, V=32000, G=4), bf16 logits, against the reference fp32 path."""
+    c = load_golden("grpo_c1.pt")[i]
+    B, T, V = c["shape"]
+    logits, ids, mask = O.synth_batch(B, T, V, seed=c["seed"])
+    adv = S.group_advantages(c["rewards"].to(DEV), torch.ones(1, device=DEV), c["G"])["advantages"]
+    torch.testing.assert_close(adv.cpu(), c["advantages"], rtol=1e-5, atol=1e-6)
+    x = logits.to(DEV).requires_grad_(True)
+    loss_fn = S.GRPOLoss(**c["cfg"])
+    prev = S.set_k1_path(S.K1_ROW if path == "row" else S.K1_RESIDENT)
+    try:
+        out = loss_fn(x, ids.to(DEV), mask.to(DEV), adv, None if c["old"] is None else c["old"].to(DEV),
+                      None if c["ref"] is None else c["ref"].to(DEV))
+        out.loss.backward()
+    finally:
+        S.set_k1_path(prev)
+    torch.testing.assert_close(out.per_token_logps.cpu(), c["logp"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(out.entropies.cpu(), c["entropy"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out.loss.detach().cpu(), c["loss"], rtol=1e-4, atol=1e-7)
+    _metrics_close(out.metrics, c["metrics"], c["cfg"]["beta"])
+    got = x.grad.gather(-1, c["grad_cols"].to(DEV)).float().cpu()
+    want = c["grad_at_cols"].to(torch.bfloat16).float()
+    torch.testing.assert_close(got, want, rtol=BF16_ULP, atol=1e-12)
+    torch.testing.assert_close(x.grad.float().abs().sum(-1).cpu(), c["grad_abs_sum"], rtol=2e-3, atol=1e-9)
+
+
+def test_grpo_errors(S):
+    with pytest.raises(ValueError):
+        S.GRPOLoss(loss_type="nope")
+    with pytest.raises(ValueError):
+        S.GRPOLoss(importance_sampling_level="nope")
+    with pytest.raises(RuntimeError):
+        S.selective_log_softmax(torch.randn(2, 8), torch.zeros(2, dtype=torch.long))  # CPU tensors: no fallback
+
+
+def test_grpo_grad_scale_and_rescale(S):
+    """dlogits is written in the forward for an assumed upstream scale; a different grad_output is fixed up."""
+    B, T, V = 2, 6, 32768
+    logits, ids, mask = O.synth_batch(B, T, V, seed=9, edge_rows=False)
+    adv = torch.tensor([0.7, -1.1], device=DEV)
+    loss_fn = S.GRPOLoss(beta=0.0)
+    grads = []
+    for scale, mult in [(1.0, 1.0), (0.25, 0.25), (1.0, 0.25)]:
+        x = logits.to(DEV).requires_grad_(True)
+        out = loss_fn(x, ids.to(DEV), mask.to(DEV), adv, grad_scale=scale)
+        (out.loss * mult).backward()
+        grads.append(x.grad.float())
+    torch.testing.assert_close(grads[1], grads[0] * 0.25, rtol=BF16_ULP, atol=1e-12)
+    torch.testing.assert_close(grads[2], grads[0] * 0.25, rtol=2 * BF16_ULP, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ advantages
+@pytest.mark.parametrize("i", range(7))
+def test_group_advantages_golden(S, i):
+    c = load_golden("advantages.pt")[i]
+    n_local = c["B_global"] // c["world"]
+    for r, want in enumerate(c["per_rank"]):
+        out = S.group_advantages(c["rewards_per_func"].to(DEV), c["weights"].to(DEV), c["G"], c["scale_rewards"],
+                                 process_index=r, local_batch=n_local, gathered=True)
+        torch.testing.assert_close(out["all"].cpu(), want["all_process_advantages"], rtol=2e-5, atol=1e-6,
+                                   equal_nan=True)
+        # ordering / indexing is exact: the local slice is element-for-element the global one
+        assert torch.equal(out["advantages"], out["all"][r * n_local:(r + 1) * n_local])
+        torch.testing.assert_close(out["advantages"].cpu(), want["advantages"], rtol=2e-5, atol=1e-6, equal_nan=True)
+        assert torch.equal(out["is_std_zero"].cpu(), want["is_std_zero"])
+        torch.testing.assert_close(out["rewards"].cpu(), want["rewards"], rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ entropy mask
+def test_entropy_mask_literals(S):
+    from tests.test_oracle_golden import ENTROPY_MASK_LITERALS
+    for ent, mask, thr, want in ENTROPY_MASK_LITERALS:
+        got = S.get_high_entropy_mask(ent.to(DEV), mask.to(DEV), thr)
+        assert torch.equal(got.cpu(), torch.tensor(want, dtype=torch.bool)), (thr, got)
+
+
+def test_entropy_mask_golden_and_random(S):
+    for c in load_golden("misc.pt")["entropy_mask"]:
+        got = S.get_high_entropy_mask(c["entropies"].to(DEV), c["mask"].to(DEV), c["threshold"])
+        assert torch.equal(got.cpu(), c["expected"])
+    g = torch.Generator().manual_seed(4)
+    ent = torch.rand(16, 1024, generator=g) * 3
+    ent[3, :100] = 0.5  # ties
+    mask = (torch.arange(1024).unsqueeze(0) < torch.randint(0, 1025, (16, 1), generator=g)).int()
+    for thr in (0.0, 0.2, 0.37, 0.8, 1.0):
+        got = S.get_high_entropy_mask(ent.to(DEV), mask.to(DEV), thr)
+        assert torch.equal(got.cpu(), O.get_high_entropy_mask(ent, mask, thr)), thr
+
+
+# ------------------------------------------------------------------------------------------------ masked stats
+def test_masked_stats(S):
+    x, m = torch.Tensor([1, 2, 3, 4]).to(DEV), torch.Tensor([0, 1, 1, 0]).to(DEV)  # tests/test_core.py:21-46
+    assert S.masked_mean(x, m).item() == pytest.approx(2.5)
+    assert S.masked_var(x, m).item() == pytest.approx(0.5)
+    w = S.masked_whiten(x, m)[1:3].cpu()
+    ref = torch.tensor([2.0, 3.0])
+    ref = (ref - ref.mean()) * torch.rsqrt(ref.var() + 1e-8)
+    assert abs((w - ref).sum().item()) < 1e-5
+    with pytest.raises(ValueError):
+        S.masked_var(x, torch.zeros(4, device=DEV))
+    c = load_golden("misc.pt")["masked"]
+    torch.testing.assert_close(S.masked_mean(c["x"].to(DEV), c["mask"].to(DEV)).cpu(), c["mean"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(S.masked_var(c["x"].to(DEV), c["mask"].to(DEV)).cpu(), c["var"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(S.masked_whiten(c["x"].to(DEV), c["mask"].to(DEV)).cpu(), c["whiten"], rtol=1e-4,
+                               atol=1e-5)
+    torch.testing.assert_close(S.masked_whiten(c["x"].to(DEV), c["mask"].to(DEV), False).cpu(), c["whiten_noshift"],
+                               rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ PPO
+@pytest.mark.parametrize("i", range(18))
+def test_ppo_gae_golden(S, i):
+    """Includes BASELINE config 3 (B=64, T=512) at indices 16-17.  The warp scan reassociates the recurrence, so
+    values agree to fp32 round-off, not bit-exactly; positions are exact."""
+    c = load_golden("ppo_gae.pt")[i]
+    lp, rlp, values, scores, lens = O.synth_ppo_case(c["B"], c["T"], c["seed"])
+    out = S.ppo_rewards_gae(lp.to(DEV), rlp.to(DEV), values.to(DEV), scores.to(DEV), lens.to(DEV), c["kl_coef"],
+                            c["kl_estimator"], c["gamma"], c["lam"], c["whiten_rewards"])
+    torch.testing.assert_close(out["rewards"].cpu(), c["rewards"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["returns"].cpu(), c["returns"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out["advantages"].cpu(), c["advantages"], rtol=1e-4, atol=1e-4)
+    pad = torch.arange(c["T"]).unsqueeze(0) > lens.unsqueeze(1)
+    assert torch.equal(out["advantages"].cpu()[pad], torch.zeros(int(pad.sum())))  # :535 exact zeros at pads
+    assert torch.equal((out["advantages"].cpu() == 0), (c["advantages"] == 0))
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_ppo_loss_golden(S, i):
+    from swh_trl_b200.ppo import STAT_INDEX as si
+    c = load_golden("ppo_loss.pt")[i]
+    x = c["logits"].to(DEV).requires_grad_(True)
+    vp = c["vpred"].to(DEV).requires_grad_(True)
+    out = S.ppo_loss(x, c["responses"].to(DEV), c["old_logprobs"].to(DEV), c["advantages"].to(DEV),
+                     c["returns"].to(DEV), c["values"].to(DEV), vp, c["sequence_lengths"].to(DEV), c["temperature"],
+                     c["cliprange"], c["cliprange_value"], c["vf_coef"])
+    out.loss.backward()
+    ref = c["out"]
+    torch.testing.assert_close(out.loss.detach().cpu(), ref["loss"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out.new_logprobs.cpu(), ref["new_logprobs"], rtol=0, atol=1e-5)
+    torch.testing.assert_close(x.grad.cpu(), c["grad_logits"], rtol=1e-4, atol=2e-8)
+    torch.testing.assert_close(vp.grad.cpu(), c["grad_vpred"], rtol=1e-4, atol=1e-8)
+    st = out.stats.cpu()
+    for k in ("pg_loss", "vf_loss", "pg_clipfrac", "vf_clipfrac", "approxkl"):
+        assert st[si[k]].item() == pytest.approx(ref[k].item(), rel=1e-4, abs=1e-6), k
+    assert st[si["entropy"]].item() == pytest.approx(ref["entropy"].mean().item(), rel=1e-4)
+    assert st[si["ratio"]].item() == pytest.approx(ref["ratio"].mean().item(), rel=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_config2_properties(S):
+    """A quarter of BASELINE config 2 (V=151936, 4 x 1024 rows; full width, fewer sequences): the fused pass must
+    (a) agree bit-for-bit with the forward-only pass, (b) give dlogits rows that sum to ~0 (softmax gradient),
+    zero where masked, (c) match the row kernel, (d) match the oracle on sampled rows, (e) be linear in the
+    advantages when nothing clips."""
+    B, T, V = 4, 1024, 151936
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(B, T, V, generator=g, device=DEV, dtype=torch.float32).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g, device=DEV)
+    lens = torch.tensor([1024, 0, 700, 512], device=DEV)
+    mask = (torch.arange(T, device=DEV).unsqueeze(0) < lens.unsqueeze(1)).int()
+    adv = torch.tensor([1.0, -0.5, 0.3, -2.0], device=DEV)
+    loss_fn = S.GRPOLoss(beta=0.0, loss_type="bnpo")
+
+    def run(path, a):
+        prev = S.set_k1_path(path)
+        try:
+            xx = x.clone().requires_grad_(True)
+            out = loss_fn(xx, ids, mask, a)
+            out.loss.backward()
+            return out, xx.grad
+        finally:
+            S.set_k1_path(prev)
+
+    out_res, g_res = run(S.K1_RESIDENT, adv)
+    out_row, g_row = run(S.K1_ROW, adv)
+    prev = S.set_k1_path(S.K1_RESIDENT)
+    lp_fwd, ent_fwd = S.logprobs_and_entropy(x, ids)
+    S.set_k1_path(prev)
+    assert torch.equal(lp_fwd, out_res.per_token_logps) and torch.equal(ent_fwd, out_res.entropies)
+    torch.testing.assert_close(out_res.per_token_logps, out_row.per_token_logps, rtol=0, atol=2e-6)
+    torch.testing.assert_close(g_res.float(), g_row.float(), rtol=BF16_ULP, atol=1e-12)
+    # (b)
+    assert torch.count_nonzero(g_res[mask == 0]) == 0
+    row_sum = g_res.float().sum(-1)
+    scale = g_res.float().abs().sum(-1).clamp(min=1e-20)
+    assert float((row_sum.abs() / scale).max()) < 2e-2  # bf16 rounding noise of 152k terms
+    assert bool((out_res.per_token_logps <= 0).all()) and bool((out_res.entropies >= 0).all())
+    assert float(out_res.entropies.max()) <= torch.log(torch.tensor(float(V))) + 1e-4
+    # (d) oracle on a few rows
+    rows = [(0, 0), (0, 1023), (2, 699), (3, 17)]
+    for b, t in rows:
+        xr = x[b, t].float().cpu().requires_grad_(True)
+        lp = O.selective_log_softmax(xr.unsqueeze(0), ids[b, t].cpu().reshape(1))
+        assert lp.item() == pytest.approx(out_res.per_token_logps[b, t].item(), abs=1e-5)
+        ntok = float(mask.sum())
+        (-(lp * adv[b].cpu()) / ntok).sum().backward()  # ratio == 1: loss_t = -A * exp(lp - lp.detach())
+        torch.testing.assert_close(g_res[b, t].float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP,
+                                   atol=1e-14)
+    # (e)
+    _, g2 = run(S.K1_RESIDENT, adv * 2)
+    torch.testing.assert_close(g2.float(), g_res.float() * 2, rtol=0, atol=0)
+
+
+def test_ppo_fused_large_vocab(S):
+    """PPO fused pass on the resident kernel (V=32768 bf16) vs the oracle."""
+    mb, T, V = 3, 9, 32768
+    g = torch.Generator().manual_seed(12)
+    logits = (torch.randn(mb, T, V, generator=g) * 2).to(torch.bfloat16)
+    responses = torch.randint(0, V, (mb, T), generator=g)
+    lens = torch.tensor([8, 4, 6])
+    adv = torch.randn(mb, T, generator=g)
+    ret = torch.randn(mb, T, generator=g)
+    val = torch.randn(mb, T, generator=g)
+    vpred = val + torch.randn(mb, T, generator=g) * 0.3
+    base = O.selective_log_softmax(logits.float() / (0.7 + 1e-7), responses)
+    pad = torch.arange(T).unsqueeze(0) > lens.unsqueeze(1)
+    old = (base + torch.randn(mb, T, generator=g) * 0.3).masked_fill(pad, 1.0)
+    xr = logits.float().requires_grad_(True)
+    loss_r, stats_r, _ = O.ppo_loss(xr, responses, old, adv, ret, val, vpred, lens)
+    loss_r.backward()
+    x = logits.to(DEV).requires_grad_(True)
+    out = S.ppo_loss(x, responses.to(DEV), old.to(DEV), adv.to(DEV), ret.to(DEV), val.to(DEV), vpred.to(DEV),
+                     lens.to(DEV))
+    out.loss.backward()
+    assert out.loss.item() == pytest.approx(loss_r.item(), rel=1e-4)
+    torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)

@@ -1,0 +1,80 @@
+"""Host-side logic that needs no GPU: layout arithmetic, config packing, schedule choice, trl patching."""
+import sys
+import types
+
+import pytest
+import torch
+
+import swh_trl_b200 as S
+from swh_trl_b200 import ops
+
+
+def test_collapse_rows():
+    x = torch.empty(4, 7, 32)
+    assert ops.collapse_rows(tuple(x.shape), tuple(x.stride())) == 32
+    big = torch.empty(4, 9, 32)
+    sl = big[:, :-1][:, -7:]  # the slice of grpo_trainer.py:1252-1254: not one arithmetic progression
+    assert ops.collapse_rows(tuple(sl.shape), tuple(sl.stride())) is None
+    wide = torch.empty(6, 40)[:, :32]  # padded rows
+    assert ops.collapse_rows(tuple(wide.shape), tuple(wide.stride())) == 40
+    one = torch.empty(1, 5, 32)[:, 1:]
+    assert ops.collapse_rows(tuple(one.shape), tuple(one.stride())) == 32
+    tr = torch.empty(32, 4).t()  # vocab dim not dense
+    assert ops.collapse_rows(tuple(tr.shape), tuple(tr.stride())) is None
+    assert ops.collapse_rows((32,), (1,)) == 32
+
+
+def test_make_cfg():
+    cfg = ops.make_cfg(0.04, 0.2, 0.28, 2.0, "dr_grpo", "sequence", 256, 0.5)
+    assert cfg.clip_low == torch.tensor(1 - 0.2, dtype=torch.float32).item()
+    assert cfg.clip_high == torch.tensor(1 + 0.28, dtype=torch.float32).item()
+    assert (cfg.has_delta, cfg.loss_type, cfg.is_level) == (1, 2, 1)
+    assert ops.make_cfg(0, 0.2, 0.2, None, "bnpo", "token", 8).has_delta == 0
+    with pytest.raises(ValueError, match="Unknown loss type"):  # grpo_trainer.py:2137
+        ops.make_cfg(0, 0.2, 0.2, None, "x", "token", 8)
+    with pytest.raises(ValueError, match="Unknown importance sampling level"):  # :2106-2109
+        ops.make_cfg(0, 0.2, 0.2, None, "bnpo", "x", 8)
+
+
+def test_schedule_choice():
+    assert S.GRPOLoss().schedule(has_old=True) == "fused"
+    assert S.GRPOLoss(importance_sampling_level="sequence").schedule(has_old=False) == "fused"
+    assert S.GRPOLoss(importance_sampling_level="sequence").schedule(has_old=True) == "two-phase"
+    assert S.GRPOLoss(top_entropy_quantile=0.2).schedule(has_old=False) == "two-phase"
+
+
+def test_patch_trl_rebinds_every_importer():
+    """Ten reference modules bind selective_log_softmax at import time."""
+    def orig(logits, index):
+        return None
+    pkg = types.ModuleType("faketrl")
+    utils = types.ModuleType("faketrl.trainer.utils")
+    utils.selective_log_softmax = orig
+    utils.entropy_from_logits = orig
+    grpo_mod = types.ModuleType("faketrl.trainer.grpo_trainer")
+    grpo_mod.selective_log_softmax = orig  # `from .utils import selective_log_softmax`
+    grpo_mod.get_high_entropy_mask = orig
+
+    class GRPOTrainer:
+        def _compute_loss(self, model, inputs):
+            return "reference"
+    grpo_mod.GRPOTrainer = GRPOTrainer
+    core = types.ModuleType("faketrl.core")
+    core.masked_whiten = orig
+    other = types.ModuleType("faketrl.other")
+    mods = {"faketrl": pkg, "faketrl.trainer.utils": utils, "faketrl.trainer.grpo_trainer": grpo_mod,
+            "faketrl.core": core, "faketrl.other": other}
+    sys.modules.update(mods)
+    try:
+        report = S.patch_trl("faketrl")
+    finally:
+        for k in mods:
+            sys.modules.pop(k)
+    assert utils.selective_log_softmax is S.selective_log_softmax
+    assert grpo_mod.selective_log_softmax is S.selective_log_softmax
+    assert grpo_mod.get_high_entropy_mask is S.get_high_entropy_mask
+    assert core.masked_whiten is S.masked_whiten
+    assert GRPOTrainer._compute_loss is S.compute_loss
+    assert GRPOTrainer._trl_original_compute_loss(None, None, None) == "reference"
+    assert "faketrl.other" not in report and set(report) == {"faketrl.trainer.utils", "faketrl.trainer.grpo_trainer",
+                                                              "faketrl.core"}

@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol
+that include/b200trl.h declares; argument validation that needs no launch returns the documented codes."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "b200trl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200trl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from swh_trl_b200 import _lib
+    names = _declared()
+    assert len(names) >= 19
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/b200trl.h but not exported"
+    assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
+
+
+def test_version_and_error_text():
+    from swh_trl_b200 import _lib
+    assert _lib.lib.b200trl_version() >= 100
+    assert _lib.lib.b200trl_grpo_loss_workspace_bytes(16) >= 16 * 8 * 4
+    assert _lib.lib.b200trl_ppo_gae_workspace_bytes(64, 512) > 0
+
+
+def test_argument_validation_without_gpu():
+    """Null pointers / bad enums are rejected before any CUDA call (status -1 / -2 + message)."""
+    from swh_trl_b200 import _lib
+    lib = _lib.lib
+    rc = lib.b200trl_logprob_entropy_fwd(None, 0, 4, 1024, 1024, None, 1.0, None, None, None, None)
+    assert rc == -1 and b"null" in lib.b200trl_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.b200trl_logprob_entropy_fwd(p, 9, 4, 1024, 1024, p, 1.0, p, None, None, None)
+    assert rc == -2
+    rc = lib.b200trl_logprob_entropy_fwd(p, 0, 4, 1024, 8, p, 1.0, p, None, None, None)  # stride < vocab
+    assert rc == -1
+    rc = lib.b200trl_group_advantages(p, p, 10, 1, 4, 1, 0, 10, p, p, p, p, p, p, None)  # 10 % 4 != 0
+    assert rc == -1 and b"multiple" in lib.b200trl_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "group_advantages")
+    with pytest.raises(NotImplementedError):
+        _lib.check(-2, "x")
+    assert lib.b200trl_set_k1_path(7) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    import swh_trl_b200 as S
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        S.selective_log_softmax(torch.randn(2, 3, 16), torch.zeros(2, 3, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        S.GRPOLoss()(torch.randn(1, 2, 16), torch.zeros(1, 2, dtype=torch.long), torch.ones(1, 2), torch.ones(1))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under swh-trl_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "swh-trl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("test oracle", ""), os.path.join(dirpath, f)
