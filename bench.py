@@ -95,7 +95,7 @@ class ClockSampler:
         self.proc, self.gpu = None, gpu_index
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -256,7 +256,7 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
-    loss_val = float(out.loss)
+    loss_val = float(out.loss.detach())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ops.launch_count
@@ -291,15 +291,17 @@ def run_b200(args):
         host_small.copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller needs the loss on the host
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    e2e_s = float("nan")
+    if e2e_steps:
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
     del host_logits, dev_logits
 
     # ---- max over ranks
@@ -326,8 +328,8 @@ def run_b200(args):
                        "metric_readback": "packed metrics all-gathered on device every step; host read deferred",
                        "loss": loss_val},
             "clocks": clocks,
-            "e2e": {"value": tokens_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": ({"value": tokens_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "steps": e2e_steps} if e2e_steps else None),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k1_resident_kernel<fwd,bwd>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
@@ -352,10 +354,11 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

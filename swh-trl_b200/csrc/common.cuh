@@ -114,11 +114,11 @@ struct RowStats {
 };
 __device__ __forceinline__ RowStats finish_row(const Partial& p, float x_sel, float c) {
     RowStats r;
-    const float l2s = lg2(p.s);
+    const float l2s = log2f(p.s);  // full-precision log2: once per row
     r.lse2 = p.m + l2s;
     r.lse = r.lse2 * kLn2;
     r.entropy = kLn2 * (l2s - p.u / p.s);
-    r.logp = (x_sel * c - r.lse2) * kLn2;
+    r.logp = fmaf(x_sel, c, -r.lse2) * kLn2;
     return r;
 }
 

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                 if (tid == 0) sm.row[par] = rs_early;
                 consumer_bar();
                 lse2 = a.lse_in[row] * kLog2e;
-                logp = (sm.row[par].x_sel * c - lse2) * kLn2;
+                logp = fmaf(sm.row[par].x_sel, c, -lse2) * kLn2;
             }
 
             if (HAS_BWD) {

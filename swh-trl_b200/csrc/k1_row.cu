@@ -85,12 +85,15 @@ __device__ __forceinline__ uint4 pack16<double>(const float* in) {
     return v;
 }
 
-// fold n values (already in log2 units, y = x*c) into a partial with one rescale
+// fold N raw logits into a partial with at most one rescale.  The exponent argument is a single FMA
+// x*c - m (one rounding of a small number) — rounding x*c first would cost ~|y| * 2^-24 in the exponent,
+// which peaked rows turn into a 1e-5-level entropy error.
 template <int N>
-__device__ __forceinline__ void partial_add(Partial& p, const float* y) {
-    float mx = y[0];
+__device__ __forceinline__ void partial_add(Partial& p, const float* x, float c) {
+    float mx = x[0];
 #pragma unroll
-    for (int i = 1; i < N; ++i) mx = fmaxf(mx, y[i]);
+    for (int i = 1; i < N; ++i) mx = fmaxf(mx, x[i]);
+    mx *= c;
     if (mx > p.m) {  // move the reference point (also the first touch: p.m == kNegBig)
         const float d = p.m - mx;
         const float f = ex2(d);
@@ -100,7 +103,7 @@ __device__ __forceinline__ void partial_add(Partial& p, const float* y) {
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const float d = y[i] - p.m;
+        const float d = fmaf(x[i], c, -p.m);
         const float e = ex2(d);
         p.s += e;
         p.u = fmaf(e, d, p.u);
@@ -153,14 +156,12 @@ __global__ void __launch_bounds__(BLOCK) k1_row_kernel(const K1Args a) {
         for (int64_t i = tid; i < nvec; i += BLOCK) {
             float f[VN];
             unpack16<T>(__ldg(xv + i), f);
-#pragma unroll
-            for (int k = 0; k < VN; ++k) f[k] *= a.c;
-            partial_add<VN>(p, f);
+            partial_add<VN>(p, f, a.c);
         }
         for (int64_t i = tid; i < head + (V - tail0); i += BLOCK) {
             const int64_t j = (i < head) ? i : tail0 + (i - head);
-            float y = ElemTraits<T>::load(x + j) * a.c;
-            partial_add<1>(p, &y);
+            const float y = ElemTraits<T>::load(x + j);
+            partial_add<1>(p, &y, a.c);
         }
         p = block_reduce_partial<BLOCK>(p, s_part);  // contains a __syncthreads: s_row is visible after it
         const RowStats rs = finish_row(p, s_row.x_sel, a.c);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK) k1_row_kernel(const K1Args a) {
     } else {
         __syncthreads();
         lse2 = a.lse_in[row] * kLog2e;
-        logp = (s_row.x_sel * a.c - lse2) * kLn2;
+        logp = fmaf(s_row.x_sel, a.c, -lse2) * kLn2;
     }
     if (a.dlogits == nullptr) return;
 
