@@ -24,7 +24,8 @@ namespace b200trl {
 namespace {
 
 constexpr int kConsumers = 512;
-constexpr int kThreads = kConsumers + 32;
+constexpr int kWarps = kConsumers / 32;
+constexpr int kThreads = kConsumers + 64;  // + DMA warp + reducer warp
 constexpr int kChunkBytes = 16384;
 constexpr int kChunkElems = kChunkBytes / 2;
 constexpr int kChunkVecs = kChunkBytes / 16;
@@ -37,14 +38,27 @@ struct __align__(16) Part4 {
     float m, s, u, pad;
 };
 
+// What the consumers need to turn a resident slice into dlogits (written by the reducer warp).
+struct __align__(16) RowResult {
+    float lse2;    // log2-domain logsumexp of the scaled row
+    float ng;      // -g' = -(d loss / d logp) * inv_T   (0 => the row's dlogits are zero)
+    float patch;   // value at the selected id: g' * (1 - p_id)
+    int id_chunk;  // chunk of this CTA's slice holding the selected id, or -1
+    int id_vec;    // 16-byte vector inside that chunk
+    int id_elem;   // element inside that chunk
+    int pad0, pad1;
+};
+
 struct Smem {
     // slots first (16 KB each, 128-byte aligned)
-    uint64_t full_bar[kMaxSlots];
-    uint64_t done_bar[kMaxSlots];
-    uint64_t xchg_bar;
+    uint64_t full_bar[kMaxSlots];  // DMA -> consumers: chunk landed (tx-count)
+    uint64_t done_bar[kMaxSlots];  // consumers -> DMA: slot may be stored / refilled (one arrive per warp)
+    uint64_t part_bar[2];          // consumers -> reducer: 16 warp partials of a row are in warp_part
+    uint64_t res_bar[2];           // reducer -> consumers: RowResult of a row is ready
+    uint64_t xchg_bar[2];          // peers -> reducer: every CTA of the cluster delivered its partial
     Part4 xchg[2][kMaxCluster];
     Part4 warp_part[2][kConsumers / 32];
-    RowScalars row[2];
+    RowResult result[2];
     float ppo_count;
 };
 
@@ -236,6 +250,26 @@ __device__ __forceinline__ Partial acc_to_partial(const Acc& a) {
 }
 
 // ------------------------------------------------------------------ the kernel
+// Warp roles: 0..15 consumers, 16 DMA (one lane), 17 reducer (row statistics + cluster exchange).
+//
+// Consumer schedule for row i (fused mode), software-pipelined so that the reduce / DSMEM exchange latency of
+// row i hides behind useful work:
+//     forward chunks [k_pre, C) of row i          (chunks [0, k_pre) were folded one step earlier)
+//     publish the warp partial of row i            -> reducer
+//     forward chunks [0, k_pre) of row i+1         (already prefetched into the spare slots)
+//     wait for RowResult(i)                        <- reducer
+//     backward chunks [0, C) of row i              -> DMA stores, slots refilled with row i+1 / i+2
+struct Cursor {
+    int slot;
+    uint32_t par;
+    __device__ __forceinline__ void advance(int num_slots) {
+        if (++slot == num_slots) {
+            slot = 0;
+            par ^= 1u;
+        }
+    }
+};
+
 template <bool HAS_FWD, bool HAS_BWD>
 __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a, const int num_slots) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -243,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw + static_cast<size_t>(num_slots) * kChunkBytes);
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_rank();
     const uint32_t csize = cluster_size();
     const int64_t first_row = cluster_id_x();
@@ -255,20 +290,27 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
     const int64_t my_elems = max(e_end - e_begin, (int64_t)0);
     const int my_bytes = static_cast<int>(my_elems * 2);
     const int C = (my_bytes + kChunkBytes - 1) / kChunkBytes;  // chunks per row in this CTA
-    const int64_t n_my_rows = (a.n_rows > first_row) ? (a.n_rows - first_row + row_step - 1) / row_step : 0;
-    const int64_t J = n_my_rows * C;  // chunks this CTA will process
+    const int n_my_rows =
+        (a.n_rows > first_row) ? static_cast<int>((a.n_rows - first_row + row_step - 1) / row_step) : 0;
+    const int spare = max(num_slots - C, 0);
+    const int k_pre = (HAS_FWD && HAS_BWD) ? min(spare, C) : 0;  // chunks of the next row folded early
+    const int last_bytes = my_bytes - (C - 1) * kChunkBytes;      // bytes of the last chunk of a slice
 
     if (tid == 0) {
         for (int s = 0; s < num_slots; ++s) {
             mbar_init(&sm.full_bar[s], 1);
-            mbar_init(&sm.done_bar[s], kConsumers);
+            mbar_init(&sm.done_bar[s], kWarps);
         }
-        mbar_init(&sm.xchg_bar, csize);
+        for (int p = 0; p < 2; ++p) {
+            mbar_init(&sm.part_bar[p], kWarps);
+            mbar_init(&sm.res_bar[p], 1);
+            mbar_init(&sm.xchg_bar[p], csize);
+        }
         fence_barrier_init();
     }
-    if (a.gmode == G_PPO && tid >= kConsumers) {
-        const float n = ppo_unpadded_count(a, tid - kConsumers);
-        if (tid == kConsumers) sm.ppo_count = n;
+    if (a.gmode == G_PPO && warp == kWarps) {
+        const float n = ppo_unpadded_count(a, lane);
+        if (lane == 0) sm.ppo_count = n;
     }
     __syncthreads();
     if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -276,157 +318,224 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
     const __nv_bfloat16* logits = reinterpret_cast<const __nv_bfloat16*>(a.logits);
     __nv_bfloat16* dlogits = reinterpret_cast<__nv_bfloat16*>(a.dlogits);
 
-    if (tid >= kConsumers) {
+    if (warp == kWarps) {
         // =========================== DMA warp: one lane drives every bulk copy ===========================
-        if (tid == kConsumers && J > 0) {
+        if (lane == 0 && n_my_rows > 0 && C > 0) {
             const uint64_t policy = policy_evict_first();
-            auto issue_load = [&](int64_t j) {
-                const int64_t i = j / C;
-                const int c = static_cast<int>(j - i * C);
-                const int s = static_cast<int>(j % num_slots);
-                const int64_t row = first_row + i * row_step;
-                const uint32_t bytes = static_cast<uint32_t>(min(kChunkBytes, my_bytes - c * kChunkBytes));
-                mbar_expect_tx(&sm.full_bar[s], bytes);
-                bulk_load(slots + static_cast<size_t>(s) * kChunkBytes,
-                          logits + row * a.row_stride + e_begin + static_cast<int64_t>(c) * kChunkElems, bytes,
-                          &sm.full_bar[s], policy);
+            const int64_t J = static_cast<int64_t>(n_my_rows) * C;
+            // load cursor
+            int64_t k_next = 0;
+            int l_row = 0, l_c = 0, l_slot = 0;
+            auto issue_load = [&]() {
+                const int64_t row = first_row + static_cast<int64_t>(l_row) * row_step;
+                const uint32_t bytes = static_cast<uint32_t>(l_c == C - 1 ? last_bytes : kChunkBytes);
+                mbar_expect_tx(&sm.full_bar[l_slot], bytes);
+                bulk_load(slots + static_cast<size_t>(l_slot) * kChunkBytes,
+                          logits + row * a.row_stride + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
+                          &sm.full_bar[l_slot], policy);
+                ++k_next;
+                if (++l_c == C) {
+                    l_c = 0;
+                    ++l_row;
+                }
+                if (++l_slot == num_slots) l_slot = 0;
             };
-            const int64_t pre = (J < num_slots) ? J : static_cast<int64_t>(num_slots);
-            for (int64_t j = 0; j < pre; ++j) issue_load(j);
+            while (k_next < J && k_next < num_slots) issue_load();
+            const int lag = HAS_BWD ? min(2, spare) : 0;  // stores allowed to be still reading their slot
+            Cursor cur{0, 0u};
+            int s_row = 0, s_c = 0;
+            int64_t drained = 0;  // slots [0, drained) of the chunk stream are free again
             for (int64_t j = 0; j < J; ++j) {
-                const int s = static_cast<int>(j % num_slots);
-                mbar_wait(&sm.done_bar[s], static_cast<uint32_t>((j / num_slots) & 1));
+                mbar_wait(&sm.done_bar[cur.slot], cur.par);
                 if (HAS_BWD) {
-                    const int64_t i = j / C;
-                    const int c = static_cast<int>(j - i * C);
-                    const int64_t row = first_row + i * row_step;
-                    const uint32_t bytes = static_cast<uint32_t>(min(kChunkBytes, my_bytes - c * kChunkBytes));
-                    bulk_store(dlogits + row * a.dl_row_stride + e_begin + static_cast<int64_t>(c) * kChunkElems,
-                               slots + static_cast<size_t>(s) * kChunkBytes, bytes);
+                    const int64_t row = first_row + static_cast<int64_t>(s_row) * row_step;
+                    const uint32_t bytes = static_cast<uint32_t>(s_c == C - 1 ? last_bytes : kChunkBytes);
+                    bulk_store(dlogits + row * a.dl_row_stride + e_begin + static_cast<int64_t>(s_c) * kChunkElems,
+                               slots + static_cast<size_t>(cur.slot) * kChunkBytes, bytes);
                     bulk_commit();
-                    if (j >= kStoreLag) {
-                        bulk_wait_read<kStoreLag>();  // store j - kStoreLag has finished reading its slot
-                        const int64_t k = j - kStoreLag + num_slots;
-                        if (k < J) issue_load(k);
+                    const bool row_end = (s_c == C - 1);
+                    if (row_end || lag == 0) {
+                        bulk_wait_read<0>();
+                        drained = j + 1;
+                    } else if (lag == 1) {
+                        bulk_wait_read<1>();
+                        drained = j;
+                    } else {
+                        bulk_wait_read<2>();
+                        drained = j - 1;
+                    }
+                    if (++s_c == C) {
+                        s_c = 0;
+                        ++s_row;
                     }
                 } else {
-                    const int64_t k = j + num_slots;
-                    if (k < J) issue_load(k);
+                    drained = j + 1;
                 }
+                while (k_next < J && k_next - num_slots < drained) issue_load();
+                cur.advance(num_slots);
             }
             if (HAS_BWD) bulk_wait_all();
+        }
+    } else if (warp == kWarps + 1) {
+        // =========================== reducer warp: row statistics, cluster exchange, token gradient ===========
+        if (HAS_FWD) {
+            const float c = a.c;
+            for (int i = 0; i < n_my_rows; ++i) {
+                const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
+                const int par = i & 1;
+                const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
+                RowScalars rs;
+                if (lane == 0) rs = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+                mbar_wait(&sm.part_bar[par], rpar);
+                Partial q = partial_empty();
+                if (lane < kWarps) {
+                    const Part4 w = sm.warp_part[par][lane];
+                    q = Partial{w.m, w.s, w.u};
+                }
+                q = partial_warp_reduce(q);
+                if (lane == 0) {
+                    if (csize > 1) {
+                        const uint32_t slot_addr = smem_u32(&sm.xchg[par][crank]);
+                        const uint32_t bar_addr = smem_u32(&sm.xchg_bar[par]);
+                        for (uint32_t r = 0; r < csize; ++r) {
+                            st_cluster_v4(map_to_rank(slot_addr, r), q.m, q.s, q.u, 0.f);
+                            mbar_arrive_remote(map_to_rank(bar_addr, r));
+                        }
+                        mbar_wait_cluster(&sm.xchg_bar[par], rpar);
+                        Partial tot = partial_empty();
+                        for (uint32_t r = 0; r < csize; ++r) {  // rank order: identical result in every CTA
+                            const Part4 w = sm.xchg[par][r];
+                            tot = partial_merge(tot, Partial{w.m, w.s, w.u});
+                        }
+                        q = tot;
+                    }
+                    const RowStats st = finish_row(q, rs.x_sel, c);
+                    if (crank == 0) {
+                        const bool pad = (a.gmode == G_PPO) && rs.pad != 0.f;
+                        if (a.logp) a.logp[row] = pad ? 1.0f : st.logp;
+                        if (a.entropy) a.entropy[row] = st.entropy;
+                        if (a.lse) a.lse[row] = st.lse;
+                    }
+                    if (HAS_BWD) {
+                        const float gp = token_grad(a, rs, st.logp) * a.inv_temp;
+                        const int64_t e_id = rs.id - e_begin;
+                        const bool mine = (e_id >= 0 && e_id < my_elems);
+                        RowResult rr;
+                        rr.lse2 = st.lse2;
+                        rr.ng = -gp;
+                        rr.patch = fmaf(-expf(st.logp), gp, gp);  // g' * (1 - p_id)
+                        rr.id_chunk = mine ? static_cast<int>(e_id / kChunkElems) : -1;
+                        rr.id_elem = mine ? static_cast<int>(e_id % kChunkElems) : -1;
+                        rr.id_vec = mine ? (rr.id_elem >> 3) : -1;
+                        rr.pad0 = rr.pad1 = 0;
+                        sm.result[par] = rr;
+                    }
+                    mbar_arrive(&sm.res_bar[par]);
+                }
+                __syncwarp();
+            }
         }
     } else {
         // =========================== consumers ===========================
         const float c = a.c;
         const uint64_t c2 = pack2(c, c);
-        const int lane = tid & 31, warp = tid >> 5;
-        int64_t j = 0;  // running chunk counter, identical to the DMA lane's
-        for (int64_t i = 0; i < n_my_rows; ++i) {
-            const int64_t row = first_row + i * row_step;
-            const int par = static_cast<int>(i & 1);
-            RowScalars rs_early;
-            if (tid == 0) rs_early = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+        Cursor fcur{0, 0u}, bcur{0, 0u};
 
-            float lse2, logp;
-            if (HAS_FWD) {
-                Acc acc{kNegBig, pack2(0.f, 0.f), pack2(0.f, 0.f)};
-                for (int cidx = 0; cidx < C; ++cidx) {
-                    const int64_t jj = j + cidx;
-                    const int s = static_cast<int>(jj % num_slots);
-                    mbar_wait(&sm.full_bar[s], static_cast<uint32_t>((jj / num_slots) & 1));
-                    const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(s) * kChunkBytes);
-                    const int nvec = min(kChunkVecs, (my_bytes - cidx * kChunkBytes) >> 4);
-                    if (nvec == kChunkVecs) {
-                        const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
-                        acc_vec(acc, v0, c, c2);
-                        acc_vec(acc, v1, c, c2);
-                    } else {
-                        for (int v = tid; v < nvec; v += kConsumers) acc_vec(acc, sv[v], c, c2);
-                    }
-                    if (!HAS_BWD) mbar_arrive(&sm.done_bar[s]);  // forward only: the slot can be refilled
-                }
-                // ---- CTA reduce
-                Partial p = partial_warp_reduce(acc_to_partial(acc));
-                if (lane == 0) sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};
-                if (tid == 0) sm.row[par] = rs_early;
-                consumer_bar();
-                Partial q = partial_empty();
-                if (lane < kConsumers / 32) {
-                    const Part4 w = sm.warp_part[par][lane];
-                    q = Partial{w.m, w.s, w.u};
-                }
-                q = partial_warp_reduce(q);
-                // ---- cluster exchange through distributed shared memory
-                if (csize > 1) {
-                    if (tid == 0) {
-                        const uint32_t slot_addr = smem_u32(&sm.xchg[par][crank]);
-                        const uint32_t bar_addr = smem_u32(&sm.xchg_bar);
-                        for (uint32_t r = 0; r < csize; ++r) {
-                            st_cluster_v4(map_to_rank(slot_addr, r), q.m, q.s, q.u, 0.f);
-                            mbar_arrive_remote(map_to_rank(bar_addr, r));
-                        }
-                    }
-                    mbar_wait_cluster(&sm.xchg_bar, static_cast<uint32_t>(par));
-                    Partial tot = partial_empty();
-                    for (uint32_t r = 0; r < csize; ++r) {
-                        const Part4 w = sm.xchg[par][r];
-                        tot = partial_merge(tot, Partial{w.m, w.s, w.u});
-                    }
-                    q = tot;
-                }
-                const RowStats st = finish_row(q, sm.row[par].x_sel, c);
-                lse2 = st.lse2;
-                logp = st.logp;
-                if (tid == 0 && crank == 0) {
-                    const bool pad = (a.gmode == G_PPO) && sm.row[par].pad != 0.f;
-                    if (a.logp) a.logp[row] = pad ? 1.0f : st.logp;
-                    if (a.entropy) a.entropy[row] = st.entropy;
-                    if (a.lse) a.lse[row] = st.lse;
-                }
+        auto fwd_chunk = [&](Acc& acc, int cidx) {
+            mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
+            const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
+            if (cidx != C - 1 || last_bytes == kChunkBytes) {
+                const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
+                acc_vec(acc, v0, c, c2);
+                acc_vec(acc, v1, c, c2);
             } else {
-                if (tid == 0) sm.row[par] = rs_early;
-                consumer_bar();
-                lse2 = a.lse_in[row] * kLog2e;
-                logp = fmaf(sm.row[par].x_sel, c, -lse2) * kLn2;
+                const int nvec = last_bytes >> 4;
+                for (int v = tid; v < nvec; v += kConsumers) acc_vec(acc, sv[v], c, c2);
+            }
+            if (!HAS_BWD) {  // forward only: the slot can be refilled as soon as every warp has read it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.done_bar[fcur.slot]);
+            }
+            fcur.advance(num_slots);
+        };
+
+        Acc acc{kNegBig, pack2(0.f, 0.f), pack2(0.f, 0.f)};
+        if (HAS_FWD && n_my_rows > 0) {
+            for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx);
+        }
+        for (int i = 0; i < n_my_rows; ++i) {
+            const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
+            const int par = i & 1;
+            const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
+
+            if (HAS_FWD) {
+                for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx);
+                const Partial p = partial_warp_reduce(acc_to_partial(acc));
+                if (!HAS_BWD && i >= 2) mbar_wait(&sm.res_bar[par], static_cast<uint32_t>(((i - 2) >> 1) & 1));
+                if (lane == 0) {
+                    sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};
+                    mbar_arrive(&sm.part_bar[par]);
+                }
+                acc = Acc{kNegBig, pack2(0.f, 0.f), pack2(0.f, 0.f)};
+                if (i + 1 < n_my_rows) {
+                    for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx);
+                }
             }
 
             if (HAS_BWD) {
-                const RowScalars rs = sm.row[par];
-                const float gp = token_grad(a, rs, logp) * a.inv_temp;
-                const uint64_t nl2 = pack2(-lse2, -lse2);
-                const uint64_t ng2 = pack2(-gp, -gp);
-                // where the selected id lives inside this CTA's slice (or -1)
-                const int64_t e_id = rs.id - e_begin;
-                const bool mine = (e_id >= 0 && e_id < my_elems);
-                const int id_chunk = mine ? static_cast<int>(e_id / kChunkElems) : -1;
-                const int id_vec = mine ? static_cast<int>((e_id % kChunkElems) >> 3) : -1;
-                const float patch = fmaf(-expf(logp), gp, gp);  // g' * (1 - p_id)
+                RowResult rr;
+                if (HAS_FWD) {
+                    mbar_wait(&sm.res_bar[par], rpar);
+                    rr = sm.result[par];
+                } else {
+                    if (tid == 0) {
+                        const RowScalars rs = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+                        const float lse2 = a.lse_in[row] * kLog2e;
+                        const float logp = fmaf(rs.x_sel, c, -lse2) * kLn2;
+                        const float gp = token_grad(a, rs, logp) * a.inv_temp;
+                        const int64_t e_id = rs.id - e_begin;
+                        const bool mine = (e_id >= 0 && e_id < my_elems);
+                        RowResult w;
+                        w.lse2 = lse2;
+                        w.ng = -gp;
+                        w.patch = fmaf(-expf(logp), gp, gp);
+                        w.id_chunk = mine ? static_cast<int>(e_id / kChunkElems) : -1;
+                        w.id_elem = mine ? static_cast<int>(e_id % kChunkElems) : -1;
+                        w.id_vec = mine ? (w.id_elem >> 3) : -1;
+                        w.pad0 = w.pad1 = 0;
+                        sm.result[par] = w;
+                    }
+                    consumer_bar();
+                    rr = sm.result[par];
+                }
+                const uint64_t nl2 = pack2(-rr.lse2, -rr.lse2);
+                const uint64_t ng2 = pack2(rr.ng, rr.ng);
+                const bool zero_row = (rr.ng == 0.f);
+                const bool patch_mine = (rr.id_vec >= 0) && ((rr.id_vec & (kConsumers - 1)) == tid);
                 for (int cidx = 0; cidx < C; ++cidx) {
-                    const int64_t jj = j + cidx;
-                    const int s = static_cast<int>(jj % num_slots);
-                    if (!HAS_FWD) mbar_wait(&sm.full_bar[s], static_cast<uint32_t>((jj / num_slots) & 1));
-                    uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(s) * kChunkBytes);
-                    const int nvec = min(kChunkVecs, (my_bytes - cidx * kChunkBytes) >> 4);
-                    if (gp == 0.f) {
+                    if (!HAS_FWD) mbar_wait(&sm.full_bar[bcur.slot], bcur.par);
+                    uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(bcur.slot) * kChunkBytes);
+                    const bool full = (cidx != C - 1 || last_bytes == kChunkBytes);
+                    const int nvec = full ? kChunkVecs : (last_bytes >> 4);
+                    if (zero_row) {
                         for (int v = tid; v < nvec; v += kConsumers) sv[v] = make_uint4(0u, 0u, 0u, 0u);
                     } else {
-                        if (nvec == kChunkVecs) {
+                        if (full) {
                             const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
                             sv[tid] = grad_vec(v0, c2, nl2, ng2);
                             sv[tid + kConsumers] = grad_vec(v1, c2, nl2, ng2);
                         } else {
                             for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec(sv[v], c2, nl2, ng2);
                         }
-                        if (cidx == id_chunk && (id_vec % kConsumers) == tid) {
-                            reinterpret_cast<__nv_bfloat16*>(sv)[e_id % kChunkElems] = __float2bfloat16_rn(patch);
-                        }
+                        if (patch_mine && cidx == rr.id_chunk)
+                            reinterpret_cast<__nv_bfloat16*>(sv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
                     }
                     fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
-                    mbar_arrive(&sm.done_bar[s]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
+                    bcur.advance(num_slots);
                 }
             }
-            j += C;
         }
     }
     // no CTA may leave while a peer can still address its shared memory
