@@ -262,11 +262,15 @@ def run_b200(args):
     launches0 = ops.launch_count
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profiler_range:  # ncu --profile-from-start off: only the timed region is captured
+        torch.cuda.profiler.start()
     t_start.record()
     for _ in range(args.steps):
         step(record=True)
     t_end.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     launches = ops.launch_count - launches0
     clocks = sampler.stop() if sampler else None
@@ -359,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
