@@ -97,18 +97,22 @@ int b200trl_set_k1_path(int path); /* returns the previous setting */
 /* ---- K1: selective_log_softmax + entropy_from_logits, one pass ------------------------------
  * Replaces trl/trainer/utils.py:1430-1462 and :1465-1490 (and the division by the temperature,
  * grpo_trainer.py:1258 / ppo_trainer.py:450,559, folded in as `inv_temperature`).
- * logits: [n_rows, vocab] with `row_stride` elements between rows (strided views of the model
- * output are accepted, so the slice copy at grpo_trainer.py:1252-1254 is not needed).
+ * logits: [n_rows, vocab] with `row_stride` elements between rows.  With rows_per_batch = T > 0 the
+ * rows are addressed as (b, t) = (r / T, r % T) at b * batch_stride + t * row_stride, i.e. the
+ * `logits[:, :-1][:, -T:]` view of the model output is read in place and the slice copy at
+ * grpo_trainer.py:1252-1254 is not needed (rows_per_batch = 0: flat; batch_stride = 0: dense).
  * logp/entropy/lse: fp32 [n_rows]; entropy and lse may be NULL. */
 int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
-                                const int64_t* ids, float inv_temperature, float* logp, float* entropy, float* lse,
+                                int64_t rows_per_batch, int64_t batch_stride, const int64_t* ids,
+                                float inv_temperature, float* logp, float* entropy, float* lse,
                                 b200trl_stream_t stream);
 
 /* Backward of the gather-log-softmax: dlogits[r,v] = g[r]*inv_T*(1[v==ids[r]] - exp(x[r,v]*inv_T - lse[r])),
  * written in the logits dtype.  What autograd produces for utils.py:1449-1461 + grpo_trainer.py:1258. */
 int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
-                        const int64_t* ids, float inv_temperature, const float* lse, const float* g,
-                        void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream);
+                        int64_t rows_per_batch, int64_t batch_stride, const int64_t* ids, float inv_temperature,
+                        const float* lse, const float* g, void* dlogits, int64_t dl_row_stride,
+                        int64_t dl_batch_stride, b200trl_stream_t stream);
 
 /* completion_mask row sums and total (grpo_trainer.py:2131,2133,2142); row_count fp32 [B], total fp32 [1]. */
 int b200trl_mask_stats(const int32_t* mask, int64_t B, int64_t T, float* row_count, float* total_count,
@@ -119,13 +123,14 @@ int b200trl_mask_stats(const int32_t* mask, int64_t B, int64_t T, float* row_cou
  * logits.  Valid when d(loss)/d(logp) of a token is known from that token alone: token-level
  * importance sampling, or old_logp == NULL (ratio == 1 for either level), and no entropy mask.
  * old_logp / ref_logp may be NULL (ref must be given iff cfg->beta != 0).  row_count/total_count
- * come from b200trl_mask_stats.  dlogits == NULL gives the forward only. */
+ * come from b200trl_mask_stats.  dlogits == NULL gives the forward only.  batch_stride /
+ * dl_batch_stride (0 = dense) let logits and dlogits live inside the model's [B, L, V] tensors. */
 int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab, int64_t row_stride,
-                               const int64_t* ids, const int32_t* mask, const float* advantages,
-                               const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
-                               float inv_temperature, const float* row_count, const float* total_count,
-                               float* logp, float* entropy, float* lse, void* dlogits, int64_t dl_row_stride,
-                               b200trl_stream_t stream);
+                               int64_t batch_stride, const int64_t* ids, const int32_t* mask,
+                               const float* advantages, const float* old_logp, const float* ref_logp,
+                               const b200trl_grpo_cfg* cfg, float inv_temperature, const float* row_count,
+                               const float* total_count, float* logp, float* entropy, float* lse, void* dlogits,
+                               int64_t dl_row_stride, int64_t dl_batch_stride, b200trl_stream_t stream);
 
 /* ---- K2: GRPO loss body + metrics (+ per-token d(loss)/d(logp)) --------------------------------
  * Replaces grpo_trainer.py:2084-2137 (loss) and :2139-2173 (local metric means).  All [B,T]
@@ -172,9 +177,10 @@ int b200trl_ppo_rewards_gae(const float* logprobs, const float* ref_logprobs, co
  * fused pass: new_logprobs (pads = 1.0), entropy and dlogits of pg_loss for a micro-batch [mb,T,V];
  * the token weight is (1 - pad)/count(~pad) * grad_scale.  dlogits may be NULL. */
 int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab, int64_t row_stride,
-                              const int64_t* responses, const int64_t* sequence_lengths, const float* old_logprobs,
-                              const float* advantages, float inv_temperature, float cliprange, float grad_scale,
-                              float* new_logprobs, float* entropy, float* lse, void* dlogits, int64_t dl_row_stride,
+                              int64_t batch_stride, const int64_t* responses, const int64_t* sequence_lengths,
+                              const float* old_logprobs, const float* advantages, float inv_temperature,
+                              float cliprange, float grad_scale, float* new_logprobs, float* entropy, float* lse,
+                              void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
                               b200trl_stream_t stream);
 /* loss + stats from new_logprobs (as written above) and the value head; dvpred [mb,T] may be NULL.
  * workspace as for b200trl_grpo_loss with B = mb. */

@@ -50,11 +50,11 @@ PROTOTYPES = {
     "b200trl_version": (C.c_int, []),
     "b200trl_last_error": (C.c_char_p, []),
     "b200trl_set_k1_path": (C.c_int, [_i32]),
-    "b200trl_logprob_entropy_fwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p]),
-    "b200trl_logprob_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _p, _f, _p, _p, _p, _i64, _p]),
+    "b200trl_logprob_entropy_fwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p]),
+    "b200trl_logprob_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _i64, _i64, _p]),
     "b200trl_mask_stats": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
-    "b200trl_grpo_fused_fwd_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p,
-                                             C.POINTER(GrpoCfg), _f, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "b200trl_grpo_fused_fwd_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p,
+                                             C.POINTER(GrpoCfg), _f, _p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "b200trl_grpo_loss_workspace_bytes": (_i64, [_i64]),
     "b200trl_grpo_loss": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, C.POINTER(GrpoCfg), _p, _p, _p, _p, _p,
                                     _p, _p]),
@@ -64,8 +64,8 @@ PROTOTYPES = {
     "b200trl_ppo_gae_workspace_bytes": (_i64, [_i64, _i64]),
     "b200trl_ppo_rewards_gae": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _f, _i32, _f, _f, _i32, _p, _p, _p, _p, _p,
                                           _p, _p, _p]),
-    "b200trl_ppo_fused_fwd_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _f, _f, _f, _p, _p, _p,
-                                            _p, _i64, _p]),
+    "b200trl_ppo_fused_fwd_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _f, _f, _f, _p,
+                                            _p, _p, _p, _i64, _i64, _p]),
     "b200trl_ppo_loss": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _f, _f, _f, _p, _p, _p, _p]),
     "b200trl_masked_workspace_bytes": (_i64, [_i64]),
     "b200trl_masked_whiten": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p]),

@@ -22,7 +22,8 @@ int dispatch(const K1Args& a, int dtype, cudaStream_t stream) {
 }
 
 int fill_common(K1Args& a, const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
-                const int64_t* ids, float inv_temperature, const char* who) {
+                int64_t rows_per_batch, int64_t batch_stride, const int64_t* ids, float inv_temperature,
+                const char* who) {
     B200TRL_REQUIRE(logits && ids, B200TRL_E_INVALID, "%s: null pointer", who);
     B200TRL_REQUIRE(dtype_size(dtype) != 0, B200TRL_E_UNSUPPORTED, "%s: unknown dtype %d", who, dtype);
     B200TRL_REQUIRE(n_rows >= 0 && vocab > 0 && row_stride >= vocab, B200TRL_E_INVALID,
@@ -35,6 +36,15 @@ int fill_common(K1Args& a, const void* logits, int dtype, int64_t n_rows, int64_
     a.n_rows = n_rows;
     a.vocab = vocab;
     a.row_stride = row_stride;
+    B200TRL_REQUIRE(rows_per_batch >= 0 && (rows_per_batch == 0 || n_rows % rows_per_batch == 0), B200TRL_E_INVALID,
+                    "%s: rows_per_batch %lld does not divide n_rows %lld", who, (long long)rows_per_batch,
+                    (long long)n_rows);
+    if (rows_per_batch > 0 && batch_stride == 0) batch_stride = rows_per_batch * row_stride;
+    B200TRL_REQUIRE(rows_per_batch == 0 || batch_stride >= (rows_per_batch - 1) * row_stride + vocab, B200TRL_E_INVALID,
+                    "%s: batch_stride %lld too small", who, (long long)batch_stride);
+    if (rows_per_batch > 0 && batch_stride == rows_per_batch * row_stride) rows_per_batch = 0;  // flat after all
+    a.rows_per_batch = rows_per_batch;
+    a.batch_stride = rows_per_batch ? batch_stride : 0;
     a.ids = ids;
     a.inv_temp = inv_temperature;
     a.c = static_cast<float>(static_cast<double>(inv_temperature) * 1.4426950408889634);
@@ -42,6 +52,31 @@ int fill_common(K1Args& a, const void* logits, int dtype, int64_t n_rows, int64_
     a.cfg.grad_scale = 1.f;
     a.grad_scale = 1.f;
     return B200TRL_OK;
+}
+
+// dlogits uses the same (batch, row) decomposition as the logits; a batched dlogits layout forces the logits to
+// be addressed batched too (a flat logits tensor is a batched one with batch_stride = T * row_stride).
+int set_dl_layout(K1Args& a, int64_t rows_per_batch, int64_t dl_batch_stride, const char* who) {
+    if (rows_per_batch <= 0) {
+        a.dl_batch_stride = 0;
+        return 0;
+    }
+    if (dl_batch_stride == 0) dl_batch_stride = rows_per_batch * a.dl_row_stride;
+    if (dl_batch_stride < (rows_per_batch - 1) * a.dl_row_stride + a.vocab) {
+        set_error("%s: dl_batch_stride %lld too small", who, (long long)dl_batch_stride);
+        return 1;
+    }
+    const bool dl_flat = (dl_batch_stride == rows_per_batch * a.dl_row_stride);
+    if (a.rows_per_batch == 0 && dl_flat) {
+        a.dl_batch_stride = 0;
+        return 0;
+    }
+    if (a.rows_per_batch == 0) {  // logits flat, dlogits batched: address both batched
+        a.rows_per_batch = rows_per_batch;
+        a.batch_stride = rows_per_batch * a.row_stride;
+    }
+    a.dl_batch_stride = dl_batch_stride;
+    return 0;
 }
 
 }  // namespace
@@ -52,10 +87,12 @@ extern "C" int b200trl_set_k1_path(int path) {
 }
 
 extern "C" int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab,
-                                           int64_t row_stride, const int64_t* ids, float inv_temperature, float* logp,
-                                           float* entropy, float* lse, b200trl_stream_t stream) {
+                                           int64_t row_stride, int64_t rows_per_batch, int64_t batch_stride,
+                                           const int64_t* ids, float inv_temperature, float* logp, float* entropy,
+                                           float* lse, b200trl_stream_t stream) {
     K1Args a;
-    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, ids, inv_temperature, "logprob_entropy_fwd");
+    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, rows_per_batch, batch_stride, ids,
+                               inv_temperature, "logprob_entropy_fwd");
     if (rc) return rc;
     B200TRL_REQUIRE(logp, B200TRL_E_INVALID, "logprob_entropy_fwd: logp is null");
     a.logp = logp;
@@ -65,10 +102,12 @@ extern "C" int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_
 }
 
 extern "C" int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
-                                   const int64_t* ids, float inv_temperature, const float* lse, const float* g,
-                                   void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream) {
+                                   int64_t rows_per_batch, int64_t batch_stride, const int64_t* ids,
+                                   float inv_temperature, const float* lse, const float* g, void* dlogits,
+                                   int64_t dl_row_stride, int64_t dl_batch_stride, b200trl_stream_t stream) {
     K1Args a;
-    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, ids, inv_temperature, "logprob_bwd");
+    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, rows_per_batch, batch_stride, ids,
+                               inv_temperature, "logprob_bwd");
     if (rc) return rc;
     B200TRL_REQUIRE(lse && g && dlogits && dl_row_stride >= vocab, B200TRL_E_INVALID, "logprob_bwd: bad arguments");
     a.lse_in = lse;
@@ -76,18 +115,21 @@ extern "C" int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows
     a.gmode = G_GIVEN;
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
+    if (set_dl_layout(a, rows_per_batch, dl_batch_stride, "logprob_bwd")) return B200TRL_E_INVALID;
     return dispatch(a, dtype, as_stream(stream));
 }
 
 extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab,
-                                          int64_t row_stride, const int64_t* ids, const int32_t* mask,
-                                          const float* advantages, const float* old_logp, const float* ref_logp,
-                                          const b200trl_grpo_cfg* cfg, float inv_temperature, const float* row_count,
-                                          const float* total_count, float* logp, float* entropy, float* lse,
-                                          void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream) {
+                                          int64_t row_stride, int64_t batch_stride, const int64_t* ids,
+                                          const int32_t* mask, const float* advantages, const float* old_logp,
+                                          const float* ref_logp, const b200trl_grpo_cfg* cfg, float inv_temperature,
+                                          const float* row_count, const float* total_count, float* logp,
+                                          float* entropy, float* lse, void* dlogits, int64_t dl_row_stride,
+                                          int64_t dl_batch_stride, b200trl_stream_t stream) {
     K1Args a;
     B200TRL_REQUIRE(B > 0 && T > 0, B200TRL_E_INVALID, "grpo_fused: bad shape");
-    const int rc = fill_common(a, logits, dtype, B * T, vocab, row_stride, ids, inv_temperature, "grpo_fused");
+    const int rc = fill_common(a, logits, dtype, B * T, vocab, row_stride, T, batch_stride, ids, inv_temperature,
+                               "grpo_fused");
     if (rc) return rc;
     B200TRL_REQUIRE(mask && advantages && cfg && row_count && total_count && logp, B200TRL_E_INVALID,
                     "grpo_fused: null pointer");
@@ -113,17 +155,21 @@ extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t
     a.gmode = dlogits ? G_GRPO : G_NONE;
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
+    if (dlogits && set_dl_layout(a, T, dl_batch_stride, "grpo_fused")) return B200TRL_E_INVALID;
     return dispatch(a, dtype, as_stream(stream));
 }
 
 extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab,
-                                         int64_t row_stride, const int64_t* responses, const int64_t* sequence_lengths,
-                                         const float* old_logprobs, const float* advantages, float inv_temperature,
-                                         float cliprange, float grad_scale, float* new_logprobs, float* entropy,
-                                         float* lse, void* dlogits, int64_t dl_row_stride, b200trl_stream_t stream) {
+                                         int64_t row_stride, int64_t batch_stride, const int64_t* responses,
+                                         const int64_t* sequence_lengths, const float* old_logprobs,
+                                         const float* advantages, float inv_temperature, float cliprange,
+                                         float grad_scale, float* new_logprobs, float* entropy, float* lse,
+                                         void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
+                                         b200trl_stream_t stream) {
     K1Args a;
     B200TRL_REQUIRE(mb > 0 && T > 0, B200TRL_E_INVALID, "ppo_fused: bad shape");
-    const int rc = fill_common(a, logits, dtype, mb * T, vocab, row_stride, responses, inv_temperature, "ppo_fused");
+    const int rc = fill_common(a, logits, dtype, mb * T, vocab, row_stride, T, batch_stride, responses,
+                               inv_temperature, "ppo_fused");
     if (rc) return rc;
     B200TRL_REQUIRE(sequence_lengths && old_logprobs && advantages && new_logprobs, B200TRL_E_INVALID,
                     "ppo_fused: null pointer");
@@ -142,5 +188,6 @@ extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t 
     a.gmode = G_PPO;  // also marks pad rows so that new_logprobs gets INVALID_LOGPROB there
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
+    if (dlogits && set_dl_layout(a, T, dl_batch_stride, "ppo_fused")) return B200TRL_E_INVALID;
     return dispatch(a, dtype, as_stream(stream));
 }

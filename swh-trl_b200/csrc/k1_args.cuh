@@ -16,6 +16,8 @@ enum GMode : int {
 struct K1Args {
     const void* logits;
     int64_t n_rows, vocab, row_stride;
+    int64_t rows_per_batch;  // 0: flat (row r at r * row_stride); else row r = (b, t) at b * batch_stride + t * row_stride
+    int64_t batch_stride;
     const int64_t* ids;
     float c;         // inv_temperature * log2(e)
     float inv_temp;
@@ -27,6 +29,7 @@ struct K1Args {
     int gmode;
     void* dlogits;  // nullable
     int64_t dl_row_stride;
+    int64_t dl_batch_stride;
     const float* lse_in;  // non-null => skip the forward pass (backward-only)
     const float* g;       // G_GIVEN
     // G_GRPO
@@ -42,6 +45,18 @@ struct K1Args {
     const int64_t* seq_len;
     float clip_lo, clip_hi, grad_scale;
 };
+
+// element offset of a row in the logits / dlogits tensors
+__device__ __forceinline__ int64_t logits_offset(const K1Args& a, int64_t row) {
+    if (a.rows_per_batch == 0) return row * a.row_stride;
+    const int64_t b = row / a.rows_per_batch;
+    return b * a.batch_stride + (row - b * a.rows_per_batch) * a.row_stride;
+}
+__device__ __forceinline__ int64_t dlogits_offset(const K1Args& a, int64_t row) {
+    if (a.rows_per_batch == 0) return row * a.dl_row_stride;
+    const int64_t b = row / a.rows_per_batch;
+    return b * a.dl_batch_stride + (row - b * a.rows_per_batch) * a.dl_row_stride;
+}
 
 // Number of non-pad positions sum_b min(len_b + 1, T) (ppo_trainer.py:501: pad = idx > len); warp-cooperative.
 __device__ __forceinline__ float ppo_unpadded_count(const K1Args& a, int lane) {
@@ -68,7 +83,7 @@ template <typename T>
 __device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t row, float ppo_count) {
     RowScalars s;
     s.id = a.ids[row];
-    const T* base = reinterpret_cast<const T*>(a.logits) + row * a.row_stride;
+    const T* base = reinterpret_cast<const T*>(a.logits) + logits_offset(a, row);
     s.x_sel = (s.id >= 0 && s.id < a.vocab) ? ElemTraits<T>::load(base + s.id) : __int_as_float(0x7fc00000);
     s.aux0 = s.aux1 = s.adv = s.weight = s.pad = 0.f;
     if (a.gmode == G_GIVEN) {

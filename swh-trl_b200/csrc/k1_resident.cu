@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                 const uint32_t bytes = static_cast<uint32_t>(l_c == C - 1 ? last_bytes : kChunkBytes);
                 mbar_expect_tx(&sm.full_bar[l_slot], bytes);
                 bulk_load(slots + static_cast<size_t>(l_slot) * kChunkBytes,
-                          logits + row * a.row_stride + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
+                          logits + logits_offset(a, row) + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
                           &sm.full_bar[l_slot], policy);
                 ++k_next;
                 if (++l_c == C) {
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                 if (HAS_BWD) {
                     const int64_t row = first_row + static_cast<int64_t>(s_row) * row_step;
                     const uint32_t bytes = static_cast<uint32_t>(s_c == C - 1 ? last_bytes : kChunkBytes);
-                    bulk_store(dlogits + row * a.dl_row_stride + e_begin + static_cast<int64_t>(s_c) * kChunkElems,
+                    bulk_store(dlogits + dlogits_offset(a, row) + e_begin + static_cast<int64_t>(s_c) * kChunkElems,
                                slots + static_cast<size_t>(cur.slot) * kChunkBytes, bytes);
                     bulk_commit();
                     const bool row_end = (s_c == C - 1);
@@ -590,9 +590,11 @@ int launch_mode(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
 
 bool k1_resident_supported(const K1Args& a, int dtype) {
     if (dtype != B200TRL_BF16) return false;
-    if (a.vocab % 8 != 0 || a.row_stride % 8 != 0) return false;
+    if (a.vocab % 8 != 0 || a.row_stride % 8 != 0 || a.batch_stride % 8 != 0) return false;
     if ((reinterpret_cast<uintptr_t>(a.logits) & 15) != 0) return false;
-    if (a.dlogits && ((reinterpret_cast<uintptr_t>(a.dlogits) & 15) != 0 || a.dl_row_stride % 8 != 0)) return false;
+    if (a.dlogits && ((reinterpret_cast<uintptr_t>(a.dlogits) & 15) != 0 || a.dl_row_stride % 8 != 0 ||
+                      a.dl_batch_stride % 8 != 0))
+        return false;
     if (a.vocab * 2 < 2 * kChunkBytes) return false;  // tiny rows: per-row overheads dominate, use the row kernel
     return pick_cluster(a.vocab, kMaxSlots) != 0;
 }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(BLOCK) k1_row_kernel(const K1Args a) {
 
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x;
-    const T* x = reinterpret_cast<const T*>(a.logits) + row * a.row_stride;
+    const T* x = reinterpret_cast<const T*>(a.logits) + logits_offset(a, row);
     const int64_t V = a.vocab;
 
     if (a.gmode == G_PPO && tid < 32) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(BLOCK) k1_row_kernel(const K1Args a) {
 
     // ---- backward: dlogits = g' * (onehot - softmax), g' = g * inv_T
     const float gp = token_grad(a, s_row, logp) * a.inv_temp;
-    T* dx = reinterpret_cast<T*>(a.dlogits) + row * a.dl_row_stride;
+    T* dx = reinterpret_cast<T*>(a.dlogits) + dlogits_offset(a, row);
     const int64_t id = s_row.id;
     const bool same_align = ((reinterpret_cast<uintptr_t>(dx) & 15) == (addr & 15));
     if (same_align) {

@@ -41,11 +41,28 @@ class _FusedGRPO(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, ids, mask_i32, row_count, total_count, advantages, old_lp, ref_lp, cfg, inv_temp,
-                grad_scale):
+                grad_scale, keep):
         want_grad = bool(ctx.needs_input_grad[0])
         cfg.grad_scale = grad_scale
-        logp, ent, lse, dl = ops.grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages, old_lp,
-                                                    ref_lp, cfg, inv_temp, want_grad=want_grad)
+        dl = dl_view = None
+        x = logits
+        if keep is not None:
+            # `logits` is the model output [B, L, V]; the loss sees rows [L-1-T, L-1) (grpo_trainer.py:1252-1254).
+            # They are read in place through the batch stride and dlogits is written straight into a [B, L, V]
+            # buffer, so neither the slice copy nor autograd's zero-pad-and-copy of the slice backward happens.
+            T = keep
+            lo = logits.shape[1] - 1 - T
+            x = logits[:, lo:lo + T]
+            if want_grad:
+                dl = torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
+                dl[:, :lo].zero_()
+                dl[:, lo + T:].zero_()
+                dl_view = dl[:, lo:lo + T]
+        logp, ent, lse, dl_out = ops.grpo_fused_fwd_bwd(x, ids, mask_i32, row_count, total_count, advantages, old_lp,
+                                                        ref_lp, cfg, inv_temp, want_grad=want_grad,
+                                                        dlogits_out=dl_view)
+        if dl is None:
+            dl = dl_out
         cfg.grad_scale = 1.0
         loss, metrics, _ = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total_count, cfg,
                                          ent_mask=None, entropy=ent, want_g=False)
@@ -62,13 +79,19 @@ class _FusedGRPO(torch.autograd.Function):
         if dl is None:
             raise RuntimeError("GRPO fused loss: backward called but logits did not require grad in forward")
         ops.rescale_if_needed(dl, g_loss, ctx.grad_scale)
-        return (dl.view(ctx.logits_shape),) + (None,) * 10
+        return (dl.view(ctx.logits_shape),) + (None,) * 11
 
 
 class _TwoPhaseGRPO(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, ids, mask_i32, row_count, total_count, advantages, old_lp, ref_lp, cfg, inv_temp,
-                top_entropy_quantile):
+                top_entropy_quantile, keep):
+        if keep is not None:
+            lo = logits.shape[1] - 1 - keep
+            logits_full, logits = logits, logits[:, lo:lo + keep]
+            ctx.full_shape, ctx.lo = logits_full.shape, lo
+        else:
+            ctx.full_shape = None
         logp, ent, lse = ops.logprob_entropy_fwd(logits, ids, inv_temp)
         B, T = mask_i32.shape
         logp, ent, lse = logp.view(B, T), ent.view(B, T), lse.view(B, T)
@@ -86,7 +109,11 @@ class _TwoPhaseGRPO(torch.autograd.Function):
     def backward(ctx, g_loss, *_):
         logits, ids, lse, g = ctx.saved_tensors
         dl = ops.logprob_bwd(logits, ids, lse, g * g_loss, ctx.inv_temp)
-        return (dl,) + (None,) * 10
+        if ctx.full_shape is not None:
+            full = torch.zeros(ctx.full_shape, dtype=dl.dtype, device=dl.device)
+            full[:, ctx.lo:ctx.lo + dl.shape[1]] = dl
+            dl = full
+        return (dl,) + (None,) * 11
 
 
 class GRPOLoss:
@@ -116,8 +143,18 @@ class GRPOLoss:
     def __call__(self, logits: torch.Tensor, completion_ids: torch.Tensor, completion_mask: torch.Tensor,
                  advantages: torch.Tensor, old_per_token_logps: Optional[torch.Tensor] = None,
                  ref_per_token_logps: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
-                 schedule: Optional[str] = None) -> GRPOLossOutput:
-        """``logits``: ``[B,T,V]`` *un-tempered* completion logits (the temperature is folded into the kernel)."""
+                 schedule: Optional[str] = None, logits_to_keep: Optional[int] = None) -> GRPOLossOutput:
+        """``logits``: ``[B,T,V]`` *un-tempered* completion logits (the temperature is folded into the kernel).
+
+        With ``logits_to_keep=T`` ``logits`` is instead the raw model output ``[B, L, V]`` (``L >= T + 1``): rows
+        ``[L-1-T, L-1)`` of every sequence are used in place (what grpo_trainer.py:1252-1254 slices out) and the
+        gradient comes back with the model output's shape.
+        """
+        if logits_to_keep is not None:
+            if logits.dim() != 3 or logits.shape[1] < logits_to_keep + 1:
+                raise ValueError("logits_to_keep needs model logits of shape [B, L >= T + 1, V]")
+            if not logits.is_contiguous():
+                logits = logits.contiguous()
         if self.beta != 0.0 and ref_per_token_logps is None:
             raise KeyError("ref_per_token_logps")  # the reference indexes inputs[...] (grpo_trainer.py:2086)
         cfg = ops.make_cfg(self.beta, self.epsilon_low, self.epsilon_high, self.delta, self.loss_type,
@@ -130,11 +167,12 @@ class GRPOLoss:
             if self.schedule(old_per_token_logps is not None) != "fused":
                 raise NotImplementedError("the fused schedule needs a per-token gradient (see GRPOLoss.schedule)")
             loss, metrics, logp, ent = _FusedGRPO.apply(logits, completion_ids, mask_i32, row_count, total, advantages,
-                                                        old_per_token_logps, ref, cfg, inv_temp, float(grad_scale))
+                                                        old_per_token_logps, ref, cfg, inv_temp, float(grad_scale),
+                                                        logits_to_keep)
         else:
             loss, metrics, logp, ent = _TwoPhaseGRPO.apply(logits, completion_ids, mask_i32, row_count, total,
                                                            advantages, old_per_token_logps, ref, cfg, inv_temp,
-                                                           float(self.top_entropy_quantile))
+                                                           float(self.top_entropy_quantile), logits_to_keep)
         return GRPOLossOutput(loss, metrics, logp, ent, sched)
 
 
@@ -142,13 +180,18 @@ class GRPOLoss:
 # Trainer-shaped entry points: bind these onto a GRPOTrainer (see patch.patch_trl) or call them with any object
 # that has the same attributes.
 # ------------------------------------------------------------------------------------------------------------------
-def _model_logits(self, model, input_ids, attention_mask, logits_to_keep, extra):
-    """Model forward exactly as grpo_trainer.py:1230-1254 sets it up; returns the [B, T, V] completion logits view."""
+def _model_logits_raw(self, model, input_ids, attention_mask, logits_to_keep, extra):
+    """Model forward exactly as grpo_trainer.py:1230-1249 sets it up; returns the raw [B, L, V] output."""
     model_inputs = {"input_ids": input_ids, "attention_mask": attention_mask, **extra}
     if "logits_to_keep" in getattr(self, "model_kwarg_keys", ()):
         model_inputs["logits_to_keep"] = logits_to_keep + 1  # :1247
-    logits = model(**model_inputs).logits
-    return logits[:, :-1, :][:, -logits_to_keep:, :]  # :1252-1254 (a view; the kernel takes the stride)
+    return model(**model_inputs).logits
+
+
+def _model_logits(self, model, input_ids, attention_mask, logits_to_keep, extra):
+    """The [B, T, V] completion-logits *view* (:1252-1254); the kernels read it in place through its strides."""
+    logits = _model_logits_raw(self, model, input_ids, attention_mask, logits_to_keep, extra)
+    return logits[:, :-1, :][:, -logits_to_keep:, :]
 
 
 def get_per_token_logps_and_entropies(self, model, input_ids, attention_mask, logits_to_keep, batch_size=None,
@@ -202,7 +245,7 @@ def compute_loss(self, model, inputs):
     T = completion_ids.size(1)
     extra = {k: inputs[k] for k in ("pixel_values", "image_grid_thw", "pixel_attention_mask", "image_sizes")
              if inputs.get(k) is not None}
-    logits = _model_logits(self, model, input_ids, attention_mask, T, extra)
+    logits = _model_logits_raw(self, model, input_ids, attention_mask, T, extra)
 
     loss_fn = GRPOLoss(self.beta, self.epsilon_low, self.epsilon_high, getattr(self.args, "delta", None),
                        self.loss_type, self.importance_sampling_level, self.max_completion_length, self.temperature,
@@ -210,7 +253,8 @@ def compute_loss(self, model, inputs):
     grad_scale = 1.0 / float(getattr(self, "current_gradient_accumulation_steps", 1) or 1) \
         if getattr(self, "_b200_prescale", False) else 1.0
     out = loss_fn(logits, completion_ids, completion_mask, inputs["advantages"], inputs.get("old_per_token_logps"),
-                  inputs.get("ref_per_token_logps") if self.beta != 0.0 else None, grad_scale=grad_scale)
+                  inputs.get("ref_per_token_logps") if self.beta != 0.0 else None, grad_scale=grad_scale,
+                  logits_to_keep=T)
 
     mode = "train" if self.model.training else "eval"
     g = gather_metrics(out.metrics, getattr(self, "accelerator", None))  # [world, 8] on host, one sync

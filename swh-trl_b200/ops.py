@@ -61,11 +61,48 @@ def collapse_rows(shape, strides) -> Optional[int]:
     return row_stride if row_stride >= V else None
 
 
-def rows_view(logits: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
-    """``(tensor, n_rows, vocab, row_stride)`` with rows addressable as ``base + r * row_stride``.
+def collapse_rows2(shape, strides):
+    """``(row_stride, rows_per_batch, batch_stride)`` for a ``(..., V)`` layout addressable with at most two
+    levels (batch, row) — e.g. the ``logits[:, :-1][:, -T:]`` view of a ``[B, L, V]`` model output — else None.
+    ``rows_per_batch == 0`` means flat.  Pure shape arithmetic (unit-tested on CPU)."""
+    V = shape[-1]
+    if V != 1 and strides[-1] != 1:
+        return None
+    groups = []
+    for s, st in zip(shape[:-1], strides[:-1]):
+        if s == 1:
+            continue
+        if groups and groups[-1][1] == s * st:
+            groups[-1] = (groups[-1][0] * s, st)
+        else:
+            groups.append((s, st))
+    if not groups:
+        return V, 0, 0
+    if len(groups) == 1:
+        return (groups[0][1], 0, 0) if groups[0][1] >= V else None
+    if len(groups) == 2:
+        (_, bs), (rpb, rs) = groups
+        if rs >= V and bs >= (rpb - 1) * rs + V:
+            return rs, rpb, bs
+    return None
 
-    A view is used whenever the leading dims collapse to one uniform stride; otherwise one contiguous copy is
-    made (the copy the reference always makes at grpo_trainer.py:1252-1258).
+
+class Rows:
+    """A logits-like tensor resolved to the C-ABI's row addressing."""
+
+    __slots__ = ("t", "n", "V", "row_stride", "rows_per_batch", "batch_stride")
+
+    def __init__(self, t, n, V, row_stride, rows_per_batch=0, batch_stride=0):
+        self.t, self.n, self.V = t, n, V
+        self.row_stride, self.rows_per_batch, self.batch_stride = row_stride, rows_per_batch, batch_stride
+
+
+def rows_view(logits: torch.Tensor, rows_per_batch: Optional[int] = None) -> Rows:
+    """Resolve ``logits (..., V)`` to row addressing without copying when its layout has at most two levels.
+
+    ``rows_per_batch``: if given, a two-level layout must split exactly there (the fused kernels index per-sequence
+    data by ``row // T``).  Otherwise one contiguous copy is made — the copy the reference always makes at
+    grpo_trainer.py:1252-1258.
     """
     _need_cuda(logits, "logits")
     if logits.dtype not in _DTYPES:
@@ -74,10 +111,12 @@ def rows_view(logits: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
         raise ValueError("logits must have a vocabulary dimension")
     V = logits.shape[-1]
     n = logits.numel() // V if V else 0
-    row_stride = collapse_rows(tuple(logits.shape), tuple(logits.stride()))
-    if row_stride is not None:
-        return logits, n, V, row_stride
-    return logits.contiguous(), n, V, V
+    lay = collapse_rows2(tuple(logits.shape), tuple(logits.stride())) if n else (V, 0, 0)
+    if lay is not None:
+        rs, rpb, bs = lay
+        if rpb == 0 or rows_per_batch is None or rpb == rows_per_batch:
+            return Rows(logits, n, V, rs, rpb, bs)
+    return Rows(logits.contiguous(), n, V, V)
 
 
 def make_cfg(beta: float, epsilon_low: float, epsilon_high: float, delta: Optional[float], loss_type: str,
@@ -106,7 +145,8 @@ def make_cfg(beta: float, epsilon_low: float, epsilon_high: float, delta: Option
 def logprob_entropy_fwd(logits: torch.Tensor, ids: torch.Tensor, inv_temperature: float = 1.0,
                         want_entropy: bool = True, want_lse: bool = True):
     """fp32 ``(logp, entropy|None, lse|None)`` shaped like ``ids`` — one pass over the logits."""
-    x, n, V, stride = rows_view(logits)
+    r = rows_view(logits)
+    x, n, V = r.t, r.n, r.V
     _need_cuda(ids, "index")
     idx = ids.to(torch.int64).contiguous()
     if idx.numel() != n:
@@ -116,9 +156,9 @@ def logprob_entropy_fwd(logits: torch.Tensor, ids: torch.Tensor, inv_temperature
     ent = torch.empty(shape, dtype=torch.float32, device=x.device) if want_entropy else None
     lse = torch.empty(shape, dtype=torch.float32, device=x.device) if want_lse else None
     if n:
-        check(lib.b200trl_logprob_entropy_fwd(_ptr(x), _DTYPES[x.dtype], n, V, stride, _ptr(idx),
-                                              float(inv_temperature), _ptr(logp), _ptr(ent), _ptr(lse), _stream(x)),
-              "logprob_entropy_fwd")
+        check(lib.b200trl_logprob_entropy_fwd(_ptr(x), _DTYPES[x.dtype], n, V, r.row_stride, r.rows_per_batch,
+                                              r.batch_stride, _ptr(idx), float(inv_temperature), _ptr(logp),
+                                              _ptr(ent), _ptr(lse), _stream(x)), "logprob_entropy_fwd")
         _count()
     return logp, ent, lse
 
@@ -126,13 +166,14 @@ def logprob_entropy_fwd(logits: torch.Tensor, ids: torch.Tensor, inv_temperature
 def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: torch.Tensor,
                 inv_temperature: float = 1.0) -> torch.Tensor:
     """``dlogits`` (logits dtype, contiguous) for per-token upstream gradient ``g``."""
-    x, n, V, stride = rows_view(logits)
+    r = rows_view(logits)
+    x, n, V = r.t, r.n, r.V
     idx = ids.to(torch.int64).contiguous()
     out = torch.empty(logits.shape, dtype=x.dtype, device=x.device)
     if n:
-        check(lib.b200trl_logprob_bwd(_ptr(x), _DTYPES[x.dtype], n, V, stride, _ptr(idx), float(inv_temperature),
-                                      _ptr(_f32(lse, "lse")), _ptr(_f32(g, "g")), _ptr(out), V, _stream(x)),
-              "logprob_bwd")
+        check(lib.b200trl_logprob_bwd(_ptr(x), _DTYPES[x.dtype], n, V, r.row_stride, r.rows_per_batch, r.batch_stride,
+                                      _ptr(idx), float(inv_temperature), _ptr(_f32(lse, "lse")), _ptr(_f32(g, "g")),
+                                      _ptr(out), V, 0, _stream(x)), "logprob_bwd")
         _count()
     return out
 
@@ -152,22 +193,28 @@ def mask_stats(mask: torch.Tensor):
 def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages, old_logp, ref_logp, cfg: GrpoCfg,
                        inv_temperature: float, want_grad: bool = True, dlogits_out: Optional[torch.Tensor] = None):
     """One pass: ``(logp, entropy, lse, dlogits|None)``; see ``b200trl_grpo_fused_fwd_bwd``."""
-    x, n, V, stride = rows_view(logits)
     B, T = mask_i32.shape
+    r = rows_view(logits, rows_per_batch=T)
+    x, n, V = r.t, r.n, r.V
     if n != B * T:
         raise ValueError(f"logits rows {n} != B*T {B * T}")
     idx = ids.to(torch.int64).contiguous()
     logp = torch.empty(B, T, dtype=torch.float32, device=x.device)
     ent = torch.empty(B, T, dtype=torch.float32, device=x.device)
     lse = torch.empty(B, T, dtype=torch.float32, device=x.device)
-    dl = None
+    dl, dl_rs, dl_bs = None, V, 0
     if want_grad:
         dl = dlogits_out if dlogits_out is not None else torch.empty((B, T, V), dtype=x.dtype, device=x.device)
+        d = collapse_rows2(tuple(dl.shape), tuple(dl.stride()))
+        if d is None or (d[1] not in (0, T)) or dl.dtype != x.dtype:
+            raise ValueError("dlogits_out must be a [B,T,V] view with at most (batch, row) strides and the logits dtype")
+        dl_rs, dl_bs = d[0], d[2]
     check(lib.b200trl_grpo_fused_fwd_bwd(
-        _ptr(x), _DTYPES[x.dtype], B, T, V, stride, _ptr(idx), _ptr(mask_i32), _ptr(_f32(advantages, "advantages")),
-        _ptr(_f32(old_logp, "old_per_token_logps")), _ptr(_f32(ref_logp, "ref_per_token_logps")), C.byref(cfg),
-        float(inv_temperature), _ptr(row_count), _ptr(total_count), _ptr(logp), _ptr(ent), _ptr(lse), _ptr(dl), V,
-        _stream(x)), "grpo_fused_fwd_bwd")
+        _ptr(x), _DTYPES[x.dtype], B, T, V, r.row_stride, r.batch_stride, _ptr(idx), _ptr(mask_i32),
+        _ptr(_f32(advantages, "advantages")), _ptr(_f32(old_logp, "old_per_token_logps")),
+        _ptr(_f32(ref_logp, "ref_per_token_logps")), C.byref(cfg), float(inv_temperature), _ptr(row_count),
+        _ptr(total_count), _ptr(logp), _ptr(ent), _ptr(lse), _ptr(dl), dl_rs, dl_bs, _stream(x)),
+        "grpo_fused_fwd_bwd")
     _count()
     return logp, ent, lse, dl
 
@@ -274,8 +321,9 @@ def ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl
 def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advantages, inv_temperature, cliprange,
                       grad_scale: float = 1.0, want_grad: bool = True):
     """``(new_logprobs, entropy, lse, dlogits|None)`` — ``b200trl_ppo_fused_fwd_bwd``."""
-    x, n, V, stride = rows_view(logits)
     mb, T = responses.shape
+    r = rows_view(logits, rows_per_batch=T)
+    x, n, V = r.t, r.n, r.V
     if n != mb * T:
         raise ValueError(f"logits rows {n} != mb*T {mb * T}")
     idx = responses.to(torch.int64).contiguous()
@@ -285,10 +333,11 @@ def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advanta
     ent = torch.empty(mb, T, dtype=torch.float32, device=dev)
     lse = torch.empty(mb, T, dtype=torch.float32, device=dev)
     dl = torch.empty((mb, T, V), dtype=x.dtype, device=dev) if want_grad else None
-    check(lib.b200trl_ppo_fused_fwd_bwd(_ptr(x), _DTYPES[x.dtype], mb, T, V, stride, _ptr(idx), _ptr(sl),
-                                        _ptr(_f32(old_logprobs, "old_logprobs")), _ptr(_f32(advantages, "advantages")),
-                                        float(inv_temperature), float(cliprange), float(grad_scale), _ptr(nlp),
-                                        _ptr(ent), _ptr(lse), _ptr(dl), V, _stream(x)), "ppo_fused_fwd_bwd")
+    check(lib.b200trl_ppo_fused_fwd_bwd(_ptr(x), _DTYPES[x.dtype], mb, T, V, r.row_stride, r.batch_stride, _ptr(idx),
+                                        _ptr(sl), _ptr(_f32(old_logprobs, "old_logprobs")),
+                                        _ptr(_f32(advantages, "advantages")), float(inv_temperature), float(cliprange),
+                                        float(grad_scale), _ptr(nlp), _ptr(ent), _ptr(lse), _ptr(dl), V, 0,
+                                        _stream(x)), "ppo_fused_fwd_bwd")
     _count()
     return nlp, ent, lse, dl
 
@@ -329,10 +378,11 @@ def masked_whiten(values: torch.Tensor, mask: torch.Tensor, shift_mean: bool = T
 
 def rescale_if_needed(buf: torch.Tensor, actual: torch.Tensor, expected: float) -> None:
     """``buf *= actual / expected`` on the device, skipped when equal (no host sync)."""
-    x, n, V, stride = rows_view(buf)
-    if x.data_ptr() != buf.data_ptr():
-        raise ValueError("rescale_if_needed needs a row-addressable buffer")
+    row_stride = collapse_rows(tuple(buf.shape), tuple(buf.stride()))
+    if row_stride is None:
+        raise ValueError("rescale_if_needed needs a buffer with one uniform row stride")
+    V = buf.shape[-1]
     a = actual.detach().to(torch.float32).reshape(1)
-    check(lib.b200trl_rescale_if_needed(_ptr(x), _DTYPES[x.dtype], n, V, stride, _ptr(a), float(expected), _stream(x)),
-          "rescale_if_needed")
+    check(lib.b200trl_rescale_if_needed(_ptr(buf), _DTYPES[buf.dtype], buf.numel() // V, V, row_stride, _ptr(a),
+                                        float(expected), _stream(buf)), "rescale_if_needed")
     _count()

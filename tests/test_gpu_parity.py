@@ -395,3 +395,95 @@ def test_ppo_fused_large_vocab(S):
     out.loss.backward()
     assert out.loss.item() == pytest.approx(loss_r.item(), rel=1e-4)
     torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ layouts / trainer surface
+@pytest.mark.parametrize("path", ["row", "resident"])
+def test_logits_to_keep_in_place(S, path):
+    """Model output [B, L, V] used in place (rows [L-1-T, L-1), grpo_trainer.py:1252-1254): no slice copy, and the
+    gradient comes back in the model output's shape with zeros outside the completion rows."""
+    B, T, V, L = 3, 6, 32768, 10
+    g = torch.Generator().manual_seed(21)
+    ml = (torch.randn(B, L, V, generator=g) * 2).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    mask = (torch.arange(T).unsqueeze(0) < torch.tensor([[6], [3], [5]])).int()
+    adv = torch.tensor([0.5, -1.0, 2.0])
+    kept = ml[:, :-1][:, -T:].float()
+    lp0 = O.selective_log_softmax(kept, ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.3
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1
+    cfg = O.GRPOConfigLite(beta=0.04, loss_type="grpo", max_completion_length=T, temperature=0.9)
+    xr = ml.float().requires_grad_(True)
+    loss_r, _, _, _ = O.grpo_compute_loss(xr[:, :-1][:, -T:], ids, mask, adv, cfg, old, ref)
+    loss_r.backward()
+    prev = S.set_k1_path(S.K1_ROW if path == "row" else S.K1_RESIDENT)
+    try:
+        x = ml.to(DEV).requires_grad_(True)
+        fn = S.GRPOLoss(beta=0.04, loss_type="grpo", max_completion_length=T, temperature=0.9)
+        out = fn(x, ids.to(DEV), mask.to(DEV), adv.to(DEV), old.to(DEV), ref.to(DEV), logits_to_keep=T)
+        out.loss.backward()
+        # the same through the strided [B,T,V] view (two-level layout, dense gradient scattered by autograd)
+        x2 = ml.to(DEV).requires_grad_(True)
+        out2 = fn(x2[:, :-1][:, -T:], ids.to(DEV), mask.to(DEV), adv.to(DEV), old.to(DEV), ref.to(DEV))
+        out2.loss.backward()
+        lp_view, ent_view = S.logprobs_and_entropy(x2.detach()[:, :-1][:, -T:], ids.to(DEV), temperature=0.9)
+    finally:
+        S.set_k1_path(prev)
+    assert x.grad.shape == (B, L, V)
+    assert out.loss.item() == pytest.approx(loss_r.item(), rel=1e-4)
+    torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)
+    assert torch.count_nonzero(x.grad[:, :L - 1 - T]) == 0 and torch.count_nonzero(x.grad[:, L - 1:]) == 0
+    assert torch.equal(x.grad, x2.grad) and torch.equal(out.loss, out2.loss)
+    assert torch.equal(lp_view, out.per_token_logps)
+
+
+def test_trainer_surface_compute_loss(S):
+    """compute_loss / get_per_token_logps_and_entropies bound onto a GRPOTrainer-shaped object, against the
+    reference's own _compute_loss outputs (golden) including the logged metrics."""
+    import types
+    from collections import defaultdict
+
+    for i in (1, 13, 22, 34):  # bnpo/token, grpo/token+old+kl, grpo/seq+old, dr_grpo/seq+old+entropy-quantile
+        case = load_golden("grpo_loss_small.pt")[i]
+        B, T, V, P = case["shape"]
+        cfg = case["cfg"]
+        ml, pid, cid, mask, adv, n_old, n_ref = O.synth_loss_case(B, T, V, P, case["seed"])
+        x = ml.to(DEV).requires_grad_(True)
+        calls = {}
+
+        state = {"pos": 0}
+
+        def model(**kw):
+            calls.update(kw)
+            n = kw["input_ids"].shape[0]
+            lo = state["pos"] % B  # micro-chunks arrive in order
+            state["pos"] += n
+            return types.SimpleNamespace(logits=x[lo:lo + n])
+        stub = types.SimpleNamespace(
+            beta=cfg["beta"], epsilon_low=cfg["epsilon_low"], epsilon_high=cfg["epsilon_high"],
+            loss_type=cfg["loss_type"], importance_sampling_level=cfg["importance_sampling_level"],
+            top_entropy_quantile=cfg["top_entropy_quantile"], max_completion_length=cfg["max_completion_length"],
+            temperature=cfg["temperature"], args=types.SimpleNamespace(delta=cfg["delta"]), accelerator=None,
+            _metrics={"train": defaultdict(list), "eval": defaultdict(list)}, model_kwarg_keys=set(),
+            model=types.SimpleNamespace(training=True))
+        inputs = {"prompt_ids": pid.to(DEV), "prompt_mask": torch.ones_like(pid).to(DEV),
+                  "completion_ids": cid.to(DEV), "completion_mask": mask.to(DEV), "advantages": adv.to(DEV)}
+        if case["with_old"]:
+            inputs["old_per_token_logps"] = (case["logp"] + n_old).to(DEV)
+        if cfg["beta"] != 0.0:
+            inputs["ref_per_token_logps"] = (case["logp"] + n_ref).to(DEV)
+        loss = S.compute_loss(stub, model, inputs)
+        loss.backward()
+        assert calls["input_ids"].shape == (B, P + T) and "logits_to_keep" not in calls
+        torch.testing.assert_close(loss.detach().cpu(), case["loss"], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(x.grad.cpu(), case["grad"], rtol=1e-4, atol=2e-8)
+        logged = {k: v[-1] for k, v in stub._metrics["train"].items()}
+        for k, want in case["metrics"].items():
+            assert logged[k] == pytest.approx(want, rel=1e-4, abs=1e-6), (i, k)
+        # the no-grad helper returns the (logps, entropies) tuple of the fork (grpo_trainer.py:1272)
+        with torch.no_grad():
+            lp, ent = S.get_per_token_logps_and_entropies(stub, model, torch.cat([pid, cid], 1).to(DEV),
+                                                          torch.ones(B, P + T, dtype=torch.long, device=DEV), T,
+                                                          batch_size=4, compute_entropy=True)
+        torch.testing.assert_close(lp.cpu(), case["logp"], rtol=0, atol=1e-5)
+        assert ent.shape == (B, T)

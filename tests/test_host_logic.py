@@ -22,6 +22,17 @@ def test_collapse_rows():
     tr = torch.empty(32, 4).t()  # vocab dim not dense
     assert ops.collapse_rows(tuple(tr.shape), tuple(tr.stride())) is None
     assert ops.collapse_rows((32,), (1,)) == 32
+    # two-level (batch, row) layouts: the slice the trainer takes from the model output is read in place
+    assert ops.collapse_rows2(tuple(sl.shape), tuple(sl.stride())) == (32, 7, 9 * 32)
+    assert ops.collapse_rows2(tuple(x.shape), tuple(x.stride())) == (32, 0, 0)
+    assert ops.collapse_rows2(tuple(wide.shape), tuple(wide.stride())) == (40, 0, 0)
+    four = torch.empty(2, 3, 9, 32)[:, :, 1:8]  # leading dims merge: still (batch, row)
+    assert ops.collapse_rows2(tuple(four.shape), tuple(four.stride())) == (32, 7, 288)
+    three = torch.empty(2, 5, 9, 32)[:, 1:4, 1:8]  # three levels: needs a copy
+    assert ops.collapse_rows2(tuple(three.shape), tuple(three.stride())) is None
+    merged = torch.empty(2, 3, 7, 32)  # dense: merges to flat
+    assert ops.collapse_rows2(tuple(merged.shape), tuple(merged.stride())) == (32, 0, 0)
+    assert ops.collapse_rows2(tuple(tr.shape), tuple(tr.stride())) is None
 
 
 def test_make_cfg():

@@ -36,14 +36,16 @@ def test_argument_validation_without_gpu():
     """Null pointers / bad enums are rejected before any CUDA call (status -1 / -2 + message)."""
     from swh_trl_b200 import _lib
     lib = _lib.lib
-    rc = lib.b200trl_logprob_entropy_fwd(None, 0, 4, 1024, 1024, None, 1.0, None, None, None, None)
+    rc = lib.b200trl_logprob_entropy_fwd(None, 0, 4, 1024, 1024, 0, 0, None, 1.0, None, None, None, None)
     assert rc == -1 and b"null" in lib.b200trl_last_error()
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
-    rc = lib.b200trl_logprob_entropy_fwd(p, 9, 4, 1024, 1024, p, 1.0, p, None, None, None)
+    rc = lib.b200trl_logprob_entropy_fwd(p, 9, 4, 1024, 1024, 0, 0, p, 1.0, p, None, None, None)
     assert rc == -2
-    rc = lib.b200trl_logprob_entropy_fwd(p, 0, 4, 1024, 8, p, 1.0, p, None, None, None)  # stride < vocab
+    rc = lib.b200trl_logprob_entropy_fwd(p, 0, 4, 1024, 8, 0, 0, p, 1.0, p, None, None, None)  # stride < vocab
     assert rc == -1
+    rc = lib.b200trl_logprob_entropy_fwd(p, 0, 4, 1024, 1024, 3, 0, p, 1.0, p, None, None, None)  # 4 % 3 != 0
+    assert rc == -1 and b"rows_per_batch" in lib.b200trl_last_error()
     rc = lib.b200trl_group_advantages(p, p, 10, 1, 4, 1, 0, 10, p, p, p, p, p, p, None)  # 10 % 4 != 0
     assert rc == -1 and b"multiple" in lib.b200trl_last_error()
     with pytest.raises(ValueError):
