@@ -18,6 +18,7 @@ from .functional import (  # noqa: F401
     selective_log_softmax,
 )
 from .grpo import GRPOLoss, GRPOLossOutput, compute_loss, get_per_token_logps_and_entropies  # noqa: F401
+from .liger_seam import B200FusedLinearGRPOLoss  # noqa: F401
 from .patch import patch_trl  # noqa: F401
 from .ppo import INVALID_LOGPROB, PPOLossOutput, ppo_loss, ppo_rewards_gae  # noqa: F401
 

@@ -1,0 +1,124 @@
+"""Drop-in for the reference's one real operator seam: ``self.liger_grpo_loss``.
+
+The reference builds ``LigerFusedLinearGRPOLoss(beta, epsilon_low, epsilon_high, temperature, use_ref_model,
+loss_type, max_completion_length)`` (grpo_trainer.py:878-886) and calls it with ``_input, lin_weight,
+selected_token_ids, attention_mask, advantages, bias, old_per_token_logps, ref_per_token_logps`` returning
+``(loss, metrics)`` with ``metrics[0]`` = mean KL iff ``beta != 0`` and ``metrics[-1]`` = clip ratio
+(grpo_trainer.py:2026-2039).  Any object with that shape drops in when ``use_liger_loss=True``.
+
+``liger-kernel`` is a third-party dependency that is not vendored in the reference; its arithmetic is defined here
+as what ``use_liger_loss=False`` computes — the reference's own loss applied to ``hidden @ W.T (+ bias)`` — which
+is what the parity tests check.
+
+Schedule (grads-in-forward, the full ``[B,T,V]`` logits tensor is never materialised):
+for each chunk of whole sequences: ``logits_c = hidden_c @ W.T`` (library GEMM) → K1 resident kernel turns the chunk
+*in place* into ``dlogits_c`` while emitting log-probs / entropies (one pass) → ``dH_c = dlogits_c @ W`` and
+``dW += dlogits_c.T @ hidden_c`` (library GEMMs).  The three GEMMs are plain cuBLAS calls; everything that is not a
+plain GEMM runs in ``libb200trl``.  Unlike Liger, the entropy mask is the only unsupported option: sequence-level
+importance sampling without old log-probs and ``delta`` work (Liger rejects them, grpo_trainer.py:794-802,
+grpo_config.py:615-616).
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class _FusedLinearGRPO(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, bias, ids, mask, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs):
+        B, T, H = hidden.shape
+        V = weight.shape[0]
+        need_dh, need_dw = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
+        need_db = bias is not None and bool(ctx.needs_input_grad[2])
+        want_grad = need_dh or need_dw or need_db
+        mask_i32, row_count, total = ops.mask_stats(mask)
+        logp = torch.empty(B, T, dtype=torch.float32, device=hidden.device)
+        ent = torch.empty(B, T, dtype=torch.float32, device=hidden.device)
+        dh = torch.empty_like(hidden) if need_dh else None
+        dw = torch.zeros(V, H, dtype=torch.float32, device=hidden.device) if need_dw else None
+        db = torch.zeros(V, dtype=torch.float32, device=hidden.device) if need_db else None
+        h2 = hidden.reshape(B * T, H)
+        for b0 in range(0, B, chunk_seqs):
+            b1 = min(B, b0 + chunk_seqs)
+            nb = b1 - b0
+            rows = slice(b0 * T, b1 * T)
+            logits = torch.matmul(h2[rows], weight.t())  # [rows, V] in the hidden dtype; fp32 accumulate inside cuBLAS
+            if bias is not None:
+                logits += bias
+            logits = logits.view(nb, T, V)
+            # loss normalisation is over the WHOLE batch: grpo / dr_grpo divide by B (grpo_trainer.py:2131, 2135)
+            cfg.grad_scale = 1.0 if cfg.loss_type == 1 else float(nb) / float(B)  # bnpo divides by the token total
+            lp, en, _, dl = ops.grpo_fused_fwd_bwd(
+                logits, ids[b0:b1], mask_i32[b0:b1], row_count[b0:b1], total, advantages[b0:b1],
+                None if old_lp is None else old_lp[b0:b1], None if ref_lp is None else ref_lp[b0:b1], cfg, inv_temp,
+                want_grad=want_grad, dlogits_out=logits if want_grad else None)  # in place: dlogits overwrite logits
+            logp[b0:b1], ent[b0:b1] = lp, en
+            if want_grad:
+                dl2 = dl.view(nb * T, V)
+                if need_dh:
+                    torch.matmul(dl2, weight, out=dh.view(B * T, H)[rows])
+                if need_dw:
+                    dw += torch.matmul(dl2.t(), h2[rows])
+                if need_db:
+                    db += dl2.float().sum(0)
+            del logits
+        cfg.grad_scale = 1.0
+        loss, metrics, _ = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total, cfg,
+                                         entropy=ent, want_g=False)
+        ctx.grads = (dh, None if dw is None else dw.to(weight.dtype), None if db is None else db.to(bias.dtype))
+        ctx.mark_non_differentiable(metrics, logp, ent)
+        return loss.reshape(()), metrics, logp, ent
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        dh, dw, db = ctx.grads
+        ctx.grads = None
+        scale = g_loss  # tiny tensors scaled lazily; H- and W-sized grads only if the upstream grad is not 1
+        outs = []
+        for g in (dh, dw, db):
+            outs.append(None if g is None else g * scale.to(g.dtype))
+        return (outs[0], outs[1], outs[2]) + (None,) * 8
+
+
+class B200FusedLinearGRPOLoss:
+    """Same constructor / call shape as ``liger_kernel.chunked_loss.LigerFusedLinearGRPOLoss`` as the reference uses
+    it (grpo_trainer.py:878-886, 2026-2035)."""
+
+    def __init__(self, beta: float = 0.04, epsilon_low: float = 0.2, epsilon_high: float = 0.2,
+                 temperature: float = 1.0, use_ref_model: bool = True, loss_type: str = "bnpo",
+                 max_completion_length: Optional[int] = None, importance_sampling_level: str = "token",
+                 delta: Optional[float] = None, chunk_size: int = 1):
+        self.beta, self.epsilon_low, self.epsilon_high = beta, epsilon_low, epsilon_high
+        self.temperature, self.use_ref_model, self.loss_type = temperature, use_ref_model, loss_type
+        self.max_completion_length = max_completion_length
+        self.importance_sampling_level, self.delta = importance_sampling_level, delta
+        self.chunk_size = max(1, int(chunk_size))  # sequences per logits chunk
+        ops.make_cfg(beta, epsilon_low, epsilon_high, delta, loss_type, importance_sampling_level,
+                     max_completion_length or 1)  # validates enums like the reference (ValueError)
+
+    def __call__(self, _input, lin_weight, selected_token_ids, attention_mask, advantages, bias=None,
+                 old_per_token_logps=None, ref_per_token_logps=None):
+        if self.beta != 0.0 and ref_per_token_logps is None:
+            raise ValueError("beta != 0 needs ref_per_token_logps (the reference passes them, grpo_trainer.py:2034)")
+        if self.importance_sampling_level == "sequence" and old_per_token_logps is not None:
+            raise NotImplementedError(
+                "sequence-level importance sampling with old_per_token_logps needs the per-sequence ratio before the "
+                "gradient: use the two-phase GRPOLoss on materialised logits")
+        T = selected_token_ids.shape[1]
+        cfg = ops.make_cfg(self.beta, self.epsilon_low, self.epsilon_high, self.delta, self.loss_type,
+                           self.importance_sampling_level, self.max_completion_length or T)
+        ref = ref_per_token_logps if self.beta != 0.0 else None
+        loss, m, logp, ent = _FusedLinearGRPO.apply(_input, lin_weight, bias, selected_token_ids, attention_mask,
+                                                    advantages, old_per_token_logps, ref, cfg,
+                                                    1.0 / float(self.temperature), self.chunk_size)
+        self.last_per_token_logps, self.last_entropies, self.last_metrics = logp, ent, m
+        metrics = []
+        if self.beta != 0.0:
+            metrics.append(m[1])  # mean KL (grpo_trainer.py:2038)
+        metrics.append(m[5])      # clip ratio = region mean (:2039)
+        return loss, metrics

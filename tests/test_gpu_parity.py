@@ -487,3 +487,136 @@ def test_trainer_surface_compute_loss(S):
                                                           batch_size=4, compute_entropy=True)
         torch.testing.assert_close(lp.cpu(), case["logp"], rtol=0, atol=1e-5)
         assert ent.shape == (B, T)
+
+
+# ------------------------------------------------------------------------------------------------ Liger seam (a-13)
+@pytest.mark.parametrize("dtype,V,H,loss_type,beta,with_old,level", [
+    (torch.float32, 64, 32, "bnpo", 0.04, True, "token"),
+    (torch.float32, 96, 16, "grpo", 0.0, False, "sequence"),
+    (torch.float32, 64, 32, "dr_grpo", 0.1, True, "token"),
+    (torch.bfloat16, 32768, 64, "bnpo", 0.04, True, "token"),
+    (torch.bfloat16, 32768, 64, "grpo", 0.04, False, "token"),
+])
+def test_fused_linear_grpo_seam(S, dtype, V, H, loss_type, beta, with_old, level):
+    """The Liger-shaped operator (grpo_trainer.py:878-886, 2026-2039) against the reference's non-Liger path applied
+    to hidden @ W.T — the definition SURVEY §8c gives for this boundary."""
+    B, T = 4, 8
+    g = torch.Generator().manual_seed(V + H)
+    hidden = torch.randn(B, T, H, generator=g).to(dtype)
+    W = (torch.randn(V, H, generator=g) * (0.5 if dtype == torch.float32 else 0.2)).to(dtype)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    mask = (torch.arange(T).unsqueeze(0) < torch.tensor([[8], [5], [0], [7]])).int()
+    adv = torch.randn(B, generator=g)
+    temp = 0.8
+    hr, Wr = hidden.float().clone().requires_grad_(True), W.float().clone().requires_grad_(True)
+    logits_r = hr @ Wr.t()
+    if dtype != torch.float32:
+        # the GEMM output is rounded to bf16 (straight-through for the gradient)
+        logits_r = logits_r.detach().to(dtype).float() + (logits_r - logits_r.detach())
+    lp0 = O.selective_log_softmax(logits_r.detach() / temp, ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.3 if with_old else None
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1 if beta else None
+    cfg = O.GRPOConfigLite(beta=beta, loss_type=loss_type, importance_sampling_level=level, max_completion_length=T,
+                           temperature=temp, delta=3.0)
+    loss_r, met_r, _, _ = O.grpo_compute_loss(logits_r, ids, mask, adv, cfg, old, ref)
+    loss_r.backward()
+
+    fn = S.B200FusedLinearGRPOLoss(beta=beta, epsilon_low=0.2, epsilon_high=0.2, temperature=temp, use_ref_model=True,
+                                   loss_type=loss_type, max_completion_length=T, importance_sampling_level=level,
+                                   delta=3.0, chunk_size=3)
+    h = hidden.to(DEV).requires_grad_(True)
+    w = W.to(DEV).requires_grad_(True)
+    loss, metrics = fn(_input=h, lin_weight=w, selected_token_ids=ids.to(DEV), attention_mask=mask.to(DEV),
+                       advantages=adv.to(DEV), bias=None, old_per_token_logps=None if old is None else old.to(DEV),
+                       ref_per_token_logps=None if ref is None else ref.to(DEV))
+    loss.backward()
+    assert len(metrics) == (2 if beta else 1)
+    assert metrics[-1].item() == pytest.approx(met_r["clip_ratio/region"].item(), abs=1e-6)
+    if beta:
+        assert metrics[0].item() == pytest.approx(met_r["kl"].item(), rel=2e-3 if dtype != torch.float32 else 1e-4)
+    if dtype == torch.float32:
+        assert loss.item() == pytest.approx(loss_r.item(), rel=1e-4, abs=1e-7)
+        torch.testing.assert_close(h.grad.cpu(), hr.grad, rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(w.grad.cpu(), Wr.grad, rtol=1e-3, atol=1e-6)
+    else:
+        assert loss.item() == pytest.approx(loss_r.item(), rel=2e-3, abs=1e-6)
+        # bf16 GEMM operands (dlogits rounded to bf16): compare in aggregate, 2% of the gradient norm
+        for got, want in ((h.grad, hr.grad), (w.grad, Wr.grad)):
+            err = (got.float().cpu() - want).norm() / want.norm().clamp(min=1e-12)
+            assert float(err) < 2e-2, float(err)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("V", [8, 24, 1000])
+def test_tiny_and_boundary_vocab(S, V):
+    """Smallest vocabularies, ids at 0 and V-1, single row, single token."""
+    for shape in ((1, 1), (1, 5), (3, 1)):
+        g = torch.Generator().manual_seed(V + shape[1])
+        logits = torch.randn(*shape, V, generator=g) * 3
+        ids = torch.randint(0, V, shape, generator=g)
+        ids.view(-1)[0] = 0
+        ids.view(-1)[-1] = V - 1
+        for dt in (torch.float32, torch.bfloat16):
+            x = logits.to(dt)
+            want = O.selective_log_softmax(x.float(), ids)
+            got = S.selective_log_softmax(x.to(DEV), ids.to(DEV))
+            torch.testing.assert_close(got.cpu(), want, rtol=0, atol=1e-5)
+            ent = S.entropy_from_logits(x.to(DEV))
+            torch.testing.assert_close(ent.cpu(), O.entropy_from_logits(x.double()).float(), rtol=1e-5, atol=1e-5)
+
+
+def test_empty_inputs(S):
+    """Zero rows: nothing is launched, shapes are preserved (the reference returns empty tensors too)."""
+    x = torch.empty(0, 7, 128, device=DEV, dtype=torch.bfloat16)
+    ids = torch.empty(0, 7, dtype=torch.long, device=DEV)
+    assert S.selective_log_softmax(x, ids).shape == (0, 7)
+    assert S.entropy_from_logits(x).shape == (0, 7)
+    m = S.get_high_entropy_mask(torch.empty(0, 4, device=DEV), torch.empty(0, 4, dtype=torch.int32, device=DEV), 0.5)
+    assert m.shape == (0, 4)
+
+
+@pytest.mark.parametrize("V", [262144 + 8, 524288, 786432])
+def test_large_vocab_clusters(S, V):
+    """Vocabularies that need 4- and 8-CTA clusters (slice > one CTA's shared memory), fused fwd+bwd, ids at both
+    ends of the row and on a cluster-slice boundary."""
+    B, T = 1, 6
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn(B, T, V, generator=g) * 1.5).to(torch.bfloat16)
+    ids = torch.tensor([[0, V - 1, V // 2, V // 4, V // 4 - 1, 12345]])
+    mask = torch.ones(B, T, dtype=torch.int32)
+    adv = torch.tensor([1.3])
+    xr = logits.float().requires_grad_(True)
+    cfg = O.GRPOConfigLite(beta=0.0, loss_type="bnpo", max_completion_length=T)
+    loss_r, _, lp_r, ent_r = O.grpo_compute_loss(xr, ids, mask, adv, cfg)
+    loss_r.backward()
+    prev = S.set_k1_path(S.K1_RESIDENT)
+    try:
+        x = logits.to(DEV).requires_grad_(True)
+        out = S.GRPOLoss(beta=0.0, max_completion_length=T)(x, ids.to(DEV), mask.to(DEV), adv.to(DEV))
+        out.loss.backward()
+    finally:
+        S.set_k1_path(prev)
+    torch.testing.assert_close(out.per_token_logps.cpu(), lp_r.detach(), rtol=0, atol=1e-5)
+    torch.testing.assert_close(out.entropies.cpu(), O.entropy_from_logits(logits.double()).float(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-14)
+
+
+def test_two_phase_equals_fused_where_both_apply(S):
+    """Token-level IS can run on either schedule: same loss, same dlogits."""
+    B, T, V = 2, 16, 32768
+    logits, ids, mask = O.synth_batch(B, T, V, seed=5, edge_rows=False)
+    adv = torch.tensor([0.9, -0.4], device=DEV)
+    lp0 = O.selective_log_softmax(logits.float(), ids)
+    g = torch.Generator().manual_seed(3)
+    old = (lp0 + torch.randn(B, T, generator=g) * 0.3).to(DEV)
+    ref = (lp0 + torch.randn(B, T, generator=g) * 0.1).to(DEV)
+    fn = S.GRPOLoss(beta=0.04, loss_type="grpo", max_completion_length=T)
+    outs = []
+    for sched in ("fused", "two-phase"):
+        x = logits.to(DEV).requires_grad_(True)
+        o = fn(x, ids.to(DEV), mask.to(DEV), adv, old, ref, schedule=sched)
+        o.loss.backward()
+        outs.append((o, x.grad))
+        assert o.schedule == sched
+    assert torch.equal(outs[0][0].loss, outs[1][0].loss)
+    torch.testing.assert_close(outs[0][1].float(), outs[1][1].float(), rtol=BF16_ULP, atol=1e-14)
