@@ -17,6 +17,7 @@
 // rows.  Replaces trl/trainer/utils.py:1430-1490 + grpo_trainer.py:1258 + the autograd backward
 // down to the logits (see include/b200trl.h).
 #include <algorithm>
+#include <cstdlib>
 
 #include "k1_args.cuh"
 
@@ -197,23 +198,34 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
 
 // ------------------------------------------------------------------ consumer state
 struct Acc {
-    float m;      // reference point (log2 units)
-    uint64_t s2;  // two running sums of 2^(y-m)
-    uint64_t u2;  // two running sums of 2^(y-m)*(y-m)
+    float m;       // reference point (log2 units)
+    uint64_t s2;   // running sums of 2^(y-m)        (two independent chains: s2/u2 and t2/v2)
+    uint64_t u2;   // running sums of 2^(y-m)*(y-m)
+    uint64_t t2;
+    uint64_t v2;
 };
 
-__device__ __forceinline__ void acc_vec(Acc& a, const uint4& v, float c, uint64_t c2) {
-    const uint32_t mx = bf16x2_max(bf16x2_max(v.x, v.y), bf16x2_max(v.z, v.w));
-    const float cm = fmaxf(__uint_as_float(mx << 16), __uint_as_float(mx & 0xffff0000u)) * c;
-    if (cm > a.m + kSlack) {  // rare after the first vector: move the reference point
-        const float d = a.m - cm;
-        const float f = ex2(d);
-        const uint64_t f2 = pack2(f, f);
-        a.u2 = fmul2(f2, ffma2(pack2(d, d), a.s2, a.u2));
-        a.s2 = fmul2(a.s2, f2);
-        a.m = cm;
-    }
-    const uint64_t nm2 = pack2(-a.m, -a.m);
+__device__ __forceinline__ Acc acc_empty() {
+    return Acc{kNegBig, 0ull, 0ull, 0ull, 0ull};  // bit pattern 0 == (0.f, 0.f)
+}
+
+__device__ __forceinline__ uint32_t vec_max(const uint4& v) {
+    return bf16x2_max(bf16x2_max(v.x, v.y), bf16x2_max(v.z, v.w));
+}
+
+// move the reference point to cm (rare after the first chunk)
+__device__ __forceinline__ void acc_rescale(Acc& a, float cm) {
+    const float d = a.m - cm;
+    const float f = ex2(d);
+    const uint64_t f2 = pack2(f, f), d2 = pack2(d, d);
+    a.u2 = fmul2(f2, ffma2(d2, a.s2, a.u2));
+    a.s2 = fmul2(a.s2, f2);
+    a.v2 = fmul2(f2, ffma2(d2, a.t2, a.v2));
+    a.t2 = fmul2(a.t2, f2);
+    a.m = cm;
+}
+
+__device__ __forceinline__ void acc_words(uint64_t& s2, uint64_t& u2, const uint4& v, uint64_t c2, uint64_t nm2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -222,9 +234,27 @@ __device__ __forceinline__ void acc_vec(Acc& a, const uint4& v, float c, uint64_
         float d0, d1;
         unpack2(d2, d0, d1);
         const uint64_t e2 = pack2(ex2(d0), ex2(d1));
-        a.s2 = fadd2(a.s2, e2);
-        a.u2 = ffma2(e2, d2, a.u2);
+        s2 = fadd2(s2, e2);
+        u2 = ffma2(e2, d2, u2);
     }
+}
+
+// fold one 16-byte vector
+__device__ __forceinline__ void acc_vec(Acc& a, const uint4& v, float c, uint64_t c2) {
+    const uint32_t mx = vec_max(v);
+    const float cm = fmaxf(__uint_as_float(mx << 16), __uint_as_float(mx & 0xffff0000u)) * c;
+    if (cm > a.m + kSlack) acc_rescale(a, cm);
+    acc_words(a.s2, a.u2, v, c2, pack2(-a.m, -a.m));
+}
+
+// fold two vectors with ONE reference-point check and two independent accumulation chains
+__device__ __forceinline__ void acc_vec2(Acc& a, const uint4& v0, const uint4& v1, float c, uint64_t c2) {
+    const uint32_t mx = bf16x2_max(vec_max(v0), vec_max(v1));
+    const float cm = fmaxf(__uint_as_float(mx << 16), __uint_as_float(mx & 0xffff0000u)) * c;
+    if (cm > a.m + kSlack) acc_rescale(a, cm);
+    const uint64_t nm2 = pack2(-a.m, -a.m);
+    acc_words(a.s2, a.u2, v0, c2, nm2);
+    acc_words(a.t2, a.v2, v1, c2, nm2);
 }
 
 __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t nl2, uint64_t ng2) {
@@ -244,8 +274,8 @@ __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t 
 
 __device__ __forceinline__ Partial acc_to_partial(const Acc& a) {
     float s0, s1, u0, u1;
-    unpack2(a.s2, s0, s1);
-    unpack2(a.u2, u0, u1);
+    unpack2(fadd2(a.s2, a.t2), s0, s1);
+    unpack2(fadd2(a.u2, a.v2), u0, u1);
     return Partial{a.m, s0 + s1, u0 + u1};
 }
 
@@ -270,8 +300,8 @@ struct Cursor {
     }
 };
 
-template <bool HAS_FWD, bool HAS_BWD>
-__global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a, const int num_slots) {
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL>
+__global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* slots = smem_raw;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw + static_cast<size_t>(num_slots) * kChunkBytes);
@@ -341,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                 if (++l_slot == num_slots) l_slot = 0;
             };
             while (k_next < J && k_next < num_slots) issue_load();
-            const int lag = HAS_BWD ? min(2, spare) : 0;  // stores allowed to be still reading their slot
+            const int lag = HAS_BWD ? min(max_lag, spare) : 0;  // stores allowed to be still reading their slot
             Cursor cur{0, 0u};
             int s_row = 0, s_c = 0;
             int64_t drained = 0;  // slots [0, drained) of the chunk stream are free again
@@ -446,8 +476,12 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
             const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
             if (cidx != C - 1 || last_bytes == kChunkBytes) {
                 const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
-                acc_vec(acc, v0, c, c2);
-                acc_vec(acc, v1, c, c2);
+                if (DUAL) {
+                    acc_vec2(acc, v0, v1, c, c2);
+                } else {
+                    acc_vec(acc, v0, c, c2);
+                    acc_vec(acc, v1, c, c2);
+                }
             } else {
                 const int nvec = last_bytes >> 4;
                 for (int v = tid; v < nvec; v += kConsumers) acc_vec(acc, sv[v], c, c2);
@@ -459,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
             fcur.advance(num_slots);
         };
 
-        Acc acc{kNegBig, pack2(0.f, 0.f), pack2(0.f, 0.f)};
+        Acc acc = acc_empty();
         if (HAS_FWD && n_my_rows > 0) {
             for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx);
         }
@@ -476,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                     sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};
                     mbar_arrive(&sm.part_bar[par]);
                 }
-                acc = Acc{kNegBig, pack2(0.f, 0.f), pack2(0.f, 0.f)};
+                acc = acc_empty();
                 if (i + 1 < n_my_rows) {
                     for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx);
                 }
@@ -543,8 +577,15 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
     if (csize > 1) cluster_sync_all();
 }
 
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 int pick_cluster(int64_t vocab, int num_slots) {
+    static const int forced = env_int("B200TRL_K1_CLUSTER", 0);  // tuning knob: force a (larger) cluster size
     for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
+        if (cs < forced) continue;
         const int64_t slice = ((vocab + cs - 1) / cs + 7) & ~int64_t(7);
         const int64_t chunks = (slice * 2 + kChunkBytes - 1) / kChunkBytes;
         if (chunks <= num_slots - 1 || (chunks <= num_slots && cs == kMaxCluster)) return cs;
@@ -552,9 +593,9 @@ int pick_cluster(int64_t vocab, int num_slots) {
     return 0;
 }
 
-template <bool F, bool Bk>
-int launch_mode(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk>;
+template <bool F, bool Bk, bool DUAL>
+int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    auto kern = k1_resident_kernel<F, Bk, DUAL>;
     const size_t smem = static_cast<size_t>(num_slots) * kChunkBytes + sizeof(Smem);
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -578,12 +619,22 @@ int launch_mode(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots);
+    static const int max_lag = std::min(2, std::max(0, env_int("B200TRL_K1_LAG", 1)));  // 1 measured best (0: -10 %, 2: -3 %)
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots, max_lag);
     if (e != cudaSuccess) {
         set_error("k1_resident launch failed: %s", cudaGetErrorString(e));
         return B200TRL_E_LAUNCH;
     }
     return check_launch("k1_resident_kernel");
+}
+
+template <bool F, bool Bk>
+int launch_mode(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    // measured on B200 (tools/k1_variants.py): two accumulation chains help the forward-only kernel (+5 %) and
+    // cost the fused kernel 2 % (it is bound by the row hand-off, not by the fold), so the default follows the mode
+    static const int dual_env = env_int("B200TRL_K1_DUAL", -1);
+    const bool dual = dual_env < 0 ? !Bk : dual_env != 0;
+    return dual ? launch_mode_t<F, Bk, true>(a, cs, num_slots, stream) : launch_mode_t<F, Bk, false>(a, cs, num_slots, stream);
 }
 
 }  // namespace
