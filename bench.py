@@ -85,14 +85,17 @@ def synth_device(rank, B, T, V, dev, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    The sampler is started before the warm-up (nvidia-smi takes a while to come up on an 8-GPU box) and every
+    sample carries a timestamp; only samples inside [mark_start, mark_end] are summarised."""
+
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.proc, self.gpu = None, gpu_index
+        self.proc, self.t0, self.t1 = None, None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE,
@@ -100,35 +103,46 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons, power = [], [], set(), []
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]),
+                             [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        where = "timed region"
+        if not inside:  # region shorter than the sampling period: take the sample closest to it
+            mid = 0.5 * ((self.t0 or rows[-1][0]) + (self.t1 or rows[-1][0]))
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+            where = "nearest sample to the timed region"
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                "reasons": reasons, "power_w_max": max(r[3] for r in inside), "samples": len(inside), "window": where}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -254,22 +268,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
     loss_val = float(out.loss.detach())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ops.launch_count
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if args.profiler_range:  # ncu --profile-from-start off: only the timed region is captured
         torch.cuda.profiler.start()
+    if sampler:
+        sampler.mark_start()
     t_start.record()
     for _ in range(args.steps):
         step(record=True)
     t_end.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     if args.profiler_range:
         torch.cuda.profiler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)

@@ -620,3 +620,39 @@ def test_two_phase_equals_fused_where_both_apply(S):
         assert o.schedule == sched
     assert torch.equal(outs[0][0].loss, outs[1][0].loss)
     torch.testing.assert_close(outs[0][1].float(), outs[1][1].float(), rtol=BF16_ULP, atol=1e-14)
+
+
+@pytest.mark.parametrize("path", ["row", "resident"])
+def test_no_out_of_bounds_writes(S, path):
+    """compute-sanitizer is closed on this pool, so bounds are checked by hand: logits and dlogits live inside larger
+    buffers whose margins (and row padding) hold a sentinel that must survive the fused pass bit-for-bit."""
+    B, T, V, PADV = 2, 5, 40968, 40968 + 72  # V % 8 == 0; padded row stride
+    g = torch.Generator().manual_seed(2)
+    margin = 4096
+    sent = torch.tensor(-1.2345e30, dtype=torch.bfloat16)
+    n = B * T * PADV
+    src = torch.full((n + 2 * margin,), sent.item(), dtype=torch.bfloat16, device=DEV)
+    dst = torch.full((n + 2 * margin,), sent.item(), dtype=torch.bfloat16, device=DEV)
+    x = src[margin:margin + n].view(B, T, PADV)[:, :, :V]
+    x.copy_((torch.randn(B, T, V, generator=g) * 2).to(torch.bfloat16))
+    dl = dst[margin:margin + n].view(B, T, PADV)[:, :, :V]
+    ids = torch.randint(0, V, (B, T), generator=g).to(DEV)
+    mask = torch.tensor([[1, 1, 1, 1, 0], [1, 1, 0, 0, 0]], dtype=torch.int32, device=DEV)
+    adv = torch.tensor([1.0, -2.0], device=DEV)
+    from swh_trl_b200 import ops
+    m32, rc, tot = ops.mask_stats(mask)
+    cfg = ops.make_cfg(0.0, 0.2, 0.2, None, "bnpo", "token", T)
+    prev = S.set_k1_path(S.K1_ROW if path == "row" else S.K1_RESIDENT)
+    try:
+        lp, ent, lse, out = ops.grpo_fused_fwd_bwd(x, ids, m32, rc, tot, adv, None, None, cfg, 1.0, dlogits_out=dl)
+    finally:
+        S.set_k1_path(prev)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == dl.data_ptr()
+    for buf in (src, dst):
+        assert bool((buf[:margin] == sent.to(DEV)).all()) and bool((buf[margin + n:] == sent.to(DEV)).all())
+        pad = buf[margin:margin + n].view(B, T, PADV)[:, :, V:]
+        assert bool((pad == sent.to(DEV)).all())
+    want = O.selective_log_softmax(x.float().cpu(), ids.cpu())
+    torch.testing.assert_close(lp.cpu(), want, rtol=0, atol=1e-5)
+    assert torch.count_nonzero(dl[mask == 0]) == 0 and torch.count_nonzero(dl[mask == 1]) > 0
