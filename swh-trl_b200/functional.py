@@ -24,6 +24,7 @@ class _SelectiveLogSoftmax(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, index, inv_temperature, want_entropy):
+        ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         logp, ent, lse = ops.logprob_entropy_fwd(logits, index, inv_temperature, want_entropy=want_entropy)
         ctx.save_for_backward(logits, index, lse)
         ctx.inv_temperature = inv_temperature
@@ -34,6 +35,8 @@ class _SelectiveLogSoftmax(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_logp, _g_ent):
+        if g_logp is None:
+            return None, None, None, None
         logits, index, lse = ctx.saved_tensors
         dlogits = ops.logprob_bwd(logits, index, lse, g_logp.contiguous(), ctx.inv_temperature)
         return dlogits, None, None, None

@@ -42,6 +42,7 @@ class _FusedGRPO(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, ids, mask_i32, row_count, total_count, advantages, old_lp, ref_lp, cfg, inv_temp,
                 grad_scale, keep):
+        ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         want_grad = bool(ctx.needs_input_grad[0])
         cfg.grad_scale = grad_scale
         dl = dl_view = None
@@ -74,6 +75,8 @@ class _FusedGRPO(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, *_):
+        if g_loss is None:
+            return (None,) * 12
         dl = ctx.dl
         ctx.dl = None
         if dl is None:
@@ -86,6 +89,7 @@ class _TwoPhaseGRPO(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, ids, mask_i32, row_count, total_count, advantages, old_lp, ref_lp, cfg, inv_temp,
                 top_entropy_quantile, keep):
+        ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         if keep is not None:
             lo = logits.shape[1] - 1 - keep
             logits_full, logits = logits, logits[:, lo:lo + keep]
@@ -107,6 +111,8 @@ class _TwoPhaseGRPO(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, *_):
+        if g_loss is None:
+            return (None,) * 12
         logits, ids, lse, g = ctx.saved_tensors
         dl = ops.logprob_bwd(logits, ids, lse, g * g_loss, ctx.inv_temp)
         if ctx.full_shape is not None:

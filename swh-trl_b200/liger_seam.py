@@ -31,6 +31,7 @@ from . import ops
 class _FusedLinearGRPO(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hidden, weight, bias, ids, mask, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs):
+        ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         B, T, H = hidden.shape
         V = weight.shape[0]
         need_dh, need_dw = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
@@ -76,6 +77,8 @@ class _FusedLinearGRPO(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, *_):
+        if g_loss is None:
+            return (None,) * 11
         dh, dw, db = ctx.grads
         ctx.grads = None
         scale = g_loss  # tiny tensors scaled lazily; H- and W-sized grads only if the upstream grad is not 1

@@ -39,6 +39,7 @@ class _PPOLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, vpred, responses, old_logprobs, advantages, returns, values, sequence_lengths,
                 inv_temp, cliprange, cliprange_value, vf_coef, grad_scale):
+        ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         need_dl, need_dv = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
         nlp, ent, _lse, dl = ops.ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advantages,
                                                    inv_temp, cliprange, grad_scale, want_grad=need_dl)
@@ -51,6 +52,8 @@ class _PPOLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, *_):
+        if g_loss is None:
+            return (None,) * 13
         dl, dvp = ctx.dl, ctx.dvp
         ctx.dl = ctx.dvp = None
         if dl is not None:

@@ -320,7 +320,7 @@ def test_ppo_loss_golden(S, i):
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_config2_properties(S):
     """A quarter of BASELINE config 2 (V=151936, 4 x 1024 rows; full width, fewer sequences): the fused pass must
-    (a) agree bit-for-bit with the forward-only pass, (b) give dlogits rows that sum to ~0 (softmax gradient),
+    (a) agree with the forward-only pass to fp32 round-off, (b) give dlogits rows that sum to ~0 (softmax gradient),
     zero where masked, (c) match the row kernel, (d) match the oracle on sampled rows, (e) be linear in the
     advantages when nothing clips."""
     B, T, V = 4, 1024, 151936
@@ -347,7 +347,9 @@ def test_config2_properties(S):
     prev = S.set_k1_path(S.K1_RESIDENT)
     lp_fwd, ent_fwd = S.logprobs_and_entropy(x, ids)
     S.set_k1_path(prev)
-    assert torch.equal(lp_fwd, out_res.per_token_logps) and torch.equal(ent_fwd, out_res.entropies)
+    # (a) forward-only and fused instantiations fold in a different order (two vs one accumulation chain)
+    torch.testing.assert_close(lp_fwd, out_res.per_token_logps, rtol=0, atol=2e-6)
+    torch.testing.assert_close(ent_fwd, out_res.entropies, rtol=0, atol=2e-6)
     torch.testing.assert_close(out_res.per_token_logps, out_row.per_token_logps, rtol=0, atol=2e-6)
     torch.testing.assert_close(g_res.float(), g_row.float(), rtol=BF16_ULP, atol=1e-12)
     # (b)
@@ -434,7 +436,7 @@ def test_logits_to_keep_in_place(S, path):
     torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)
     assert torch.count_nonzero(x.grad[:, :L - 1 - T]) == 0 and torch.count_nonzero(x.grad[:, L - 1:]) == 0
     assert torch.equal(x.grad, x2.grad) and torch.equal(out.loss, out2.loss)
-    assert torch.equal(lp_view, out.per_token_logps)
+    torch.testing.assert_close(lp_view, out.per_token_logps, rtol=0, atol=2e-6)
 
 
 def test_trainer_surface_compute_loss(S):
@@ -618,7 +620,7 @@ def test_two_phase_equals_fused_where_both_apply(S):
         o.loss.backward()
         outs.append((o, x.grad))
         assert o.schedule == sched
-    assert torch.equal(outs[0][0].loss, outs[1][0].loss)
+    torch.testing.assert_close(outs[0][0].loss, outs[1][0].loss, rtol=1e-6, atol=1e-8)
     torch.testing.assert_close(outs[0][1].float(), outs[1][1].float(), rtol=BF16_ULP, atol=1e-14)
 
 
@@ -656,3 +658,50 @@ def test_no_out_of_bounds_writes(S, path):
     want = O.selective_log_softmax(x.float().cpu(), ids.cpu())
     torch.testing.assert_close(lp.cpu(), want, rtol=0, atol=1e-5)
     assert torch.count_nonzero(dl[mask == 0]) == 0 and torch.count_nonzero(dl[mask == 1]) > 0
+
+
+def test_cuda_graph_capture(S):
+    """The C-ABI never allocates or synchronises, so a whole step (mask stats, fused K1, K2, K3, K4) can be captured
+    in a CUDA graph and replayed on new data."""
+    from swh_trl_b200 import ops
+    B, T, V = 2, 8, 32768
+    logits, ids, mask = O.synth_batch(B, T, V, seed=11, edge_rows=False)
+    x = logits.to(DEV)
+    idx, m = ids.to(DEV), mask.to(DEV)
+    rewards = torch.tensor([[0.3], [-0.7]], device=DEV)
+    w = torch.ones(1, device=DEV)
+    cfg = ops.make_cfg(0.0, 0.2, 0.2, None, "bnpo", "token", T)
+    dl = torch.empty_like(x)
+    lp_in = -torch.rand(4, 16, device=DEV)
+    val = torch.randn(4, 16, device=DEV)
+    sc = torch.randn(4, device=DEV)
+    ln = torch.tensor([15, 7, 3, 10], device=DEV)
+
+    def step():
+        adv = ops.group_advantages(rewards, w, 2, True, 0, B)["advantages"]
+        m32, rc, tot = ops.mask_stats(m)
+        lp, ent, lse, _ = ops.grpo_fused_fwd_bwd(x, idx, m32, rc, tot, adv, None, None, cfg, 1.0, dlogits_out=dl)
+        loss, metrics, _ = ops.grpo_loss(lp, None, None, adv, m32, rc, tot, cfg, entropy=ent)
+        gae = ops.ppo_rewards_gae(lp_in, lp_in * 0.9, val, sc, ln, 0.05, "k1", 1.0, 0.95, True, want_filled=False)
+        return loss, lp, gae["advantages"]
+
+    step()  # warm-up outside capture (workspace allocation, kernel attributes)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            loss, lp, adv_ppo = step()
+    torch.cuda.current_stream().wait_stream(side)
+    # new data in the same buffers, then replay
+    logits2, ids2, _ = O.synth_batch(B, T, V, seed=12, edge_rows=False)
+    x.copy_(logits2.to(DEV))
+    idx.copy_(ids2.to(DEV))
+    graph.replay()
+    torch.cuda.synchronize()
+    want_lp = O.selective_log_softmax(logits2.float(), ids2)
+    torch.testing.assert_close(lp.cpu(), want_lp, rtol=0, atol=1e-5)
+    eager_loss, _, eager_adv = step()
+    torch.testing.assert_close(loss, eager_loss, rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(adv_ppo, eager_adv, rtol=1e-6, atol=1e-7)
