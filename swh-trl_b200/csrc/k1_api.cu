@@ -17,7 +17,7 @@ int dispatch(const K1Args& a, int dtype, cudaStream_t stream) {
                         "k1: resident path needs bf16 logits, vocab %% 8 == 0, 16-byte aligned rows and vocab >= 16384");
         return launch_k1_resident(a, stream);
     }
-    if (path == B200TRL_K1_AUTO && resident_ok) return launch_k1_resident(a, stream);
+    if (path == B200TRL_K1_AUTO && k1_resident_preferred(a, dtype)) return launch_k1_resident(a, stream);
     return launch_k1_row(a, dtype, stream);
 }
 

@@ -125,5 +125,6 @@ __device__ __forceinline__ float token_grad(const K1Args& a, const RowScalars& s
 int launch_k1_row(const K1Args& a, int dtype, cudaStream_t stream);
 int launch_k1_resident(const K1Args& a, cudaStream_t stream);
 bool k1_resident_supported(const K1Args& a, int dtype);
+bool k1_resident_preferred(const K1Args& a, int dtype);
 
 }  // namespace b200trl

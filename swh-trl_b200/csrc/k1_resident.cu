@@ -24,9 +24,7 @@
 namespace b200trl {
 namespace {
 
-constexpr int kConsumers = 512;
-constexpr int kWarps = kConsumers / 32;
-constexpr int kThreads = kConsumers + 64;  // + DMA warp + reducer warp
+constexpr int kMaxConsumers = 512;  // consumer threads per CTA: 512 (1 CTA / SM) or 256 (2 CTAs / SM)
 constexpr int kChunkBytes = 16384;
 constexpr int kChunkElems = kChunkBytes / 2;
 constexpr int kChunkVecs = kChunkBytes / 16;
@@ -58,7 +56,7 @@ struct Smem {
     uint64_t res_bar[2];           // reducer -> consumers: RowResult of a row is ready
     uint64_t xchg_bar[2];          // peers -> reducer: every CTA of the cluster delivered its partial
     Part4 xchg[2][kMaxCluster];
-    Part4 warp_part[2][kConsumers / 32];
+    Part4 warp_part[2][kMaxConsumers / 32];
     RowResult result[2];
     float ppo_count;
 };
@@ -159,7 +157,10 @@ __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+template <int NC>
+__device__ __forceinline__ void consumer_bar() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+}
 
 // packed 2 x fp32 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2)
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -300,8 +301,12 @@ struct Cursor {
     }
 };
 
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL>
-__global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag) {
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC>
+__global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)
+    k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag) {
+    constexpr int kConsumers = NC;
+    constexpr int kWarps = NC / 32;
+    constexpr int kVpt = kChunkVecs / NC;  // 16-byte vectors per thread per full chunk (2 or 4)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* slots = smem_raw;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw + static_cast<size_t>(num_slots) * kChunkBytes);
@@ -475,12 +480,17 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
             mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
             const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
             if (cidx != C - 1 || last_bytes == kChunkBytes) {
-                const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
-                if (DUAL) {
-                    acc_vec2(acc, v0, v1, c, c2);
-                } else {
-                    acc_vec(acc, v0, c, c2);
-                    acc_vec(acc, v1, c, c2);
+                uint4 v[kVpt];
+#pragma unroll
+                for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+#pragma unroll
+                for (int k = 0; k < kVpt; k += 2) {
+                    if (DUAL) {
+                        acc_vec2(acc, v[k], v[k + 1], c, c2);
+                    } else {
+                        acc_vec(acc, v[k], c, c2);
+                        acc_vec(acc, v[k + 1], c, c2);
+                    }
                 }
             } else {
                 const int nvec = last_bytes >> 4;
@@ -539,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                         w.pad0 = w.pad1 = 0;
                         sm.result[par] = w;
                     }
-                    consumer_bar();
+                    consumer_bar<NC>();
                     rr = sm.result[par];
                 }
                 const uint64_t nl2 = pack2(-rr.lse2, -rr.lse2);
@@ -555,9 +565,11 @@ __global__ void __launch_bounds__(kThreads, 1) k1_resident_kernel(const K1Args a
                         for (int v = tid; v < nvec; v += kConsumers) sv[v] = make_uint4(0u, 0u, 0u, 0u);
                     } else {
                         if (full) {
-                            const uint4 v0 = sv[tid], v1 = sv[tid + kConsumers];
-                            sv[tid] = grad_vec(v0, c2, nl2, ng2);
-                            sv[tid + kConsumers] = grad_vec(v1, c2, nl2, ng2);
+                            uint4 v[kVpt];
+#pragma unroll
+                            for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+#pragma unroll
+                            for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec(v[k], c2, nl2, ng2);
                         } else {
                             for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec(sv[v], c2, nl2, ng2);
                         }
@@ -593,9 +605,11 @@ int pick_cluster(int64_t vocab, int num_slots) {
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL>
+template <bool F, bool Bk, bool DUAL, int NC>
 int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL>;
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC>;
+    constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
+    constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
     const size_t smem = static_cast<size_t>(num_slots) * kChunkBytes + sizeof(Smem);
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -605,7 +619,7 @@ int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
         }
     }
     const int sms = num_sms();
-    int64_t clusters = std::min<int64_t>(sms / cs, a.n_rows);
+    int64_t clusters = std::min<int64_t>(static_cast<int64_t>(sms) * kCtasPerSm / cs, a.n_rows);
     if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(clusters * cs));
@@ -619,6 +633,18 @@ int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // persistent kernel with a static row stride: every cluster of the grid must be co-resident, otherwise the
+    // late ones form a second wave.  Ask the driver how many clusters of this shape fit (GPC geometry limits it).
+    {
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0 &&
+            max_clusters < clusters) {
+            clusters = max_clusters;
+            cfg.gridDim = dim3(static_cast<unsigned>(clusters * cs));
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     static const int max_lag = std::min(2, std::max(0, env_int("B200TRL_K1_LAG", 1)));  // 1 measured best (0: -10 %, 2: -3 %)
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots, max_lag);
     if (e != cudaSuccess) {
@@ -628,13 +654,37 @@ int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     return check_launch("k1_resident_kernel");
 }
 
+// Two CTA geometries:
+//   wide : 512 consumers, 13 slots (208 KB), 1 CTA / SM   — a row slice of up to 12 chunks per CTA
+//   twin : 256 consumers,  6 slots ( 96 KB), 2 CTAs / SM  — slices of up to 5 chunks; the two CTAs of an SM drift
+//          apart, so one computes while the other waits on its row hand-off or on HBM
+struct Geom {
+    int cs, slots, nc;
+};
+constexpr int kTwinSlots = 6;
+
+Geom pick_geom(int64_t vocab) {
+    static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin
+    const Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
+    const Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
+    if (mode == 2 && twin.cs) return twin;
+    if (mode == 1 || !twin.cs) return wide;
+    // measured (tools/k1_variants.py, B200): rows that fit one twin CTA (<= 80 KB, e.g. V = 32000) gain 2 % fused /
+    // 20 % forward-only from two drifting CTAs per SM; anything that would need a cluster in twin form is faster wide
+    return twin.cs == 1 ? twin : wide;
+}
+
 template <bool F, bool Bk>
-int launch_mode(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
     // measured on B200 (tools/k1_variants.py): two accumulation chains help the forward-only kernel (+5 %) and
     // cost the fused kernel 2 % (it is bound by the row hand-off, not by the fold), so the default follows the mode
     static const int dual_env = env_int("B200TRL_K1_DUAL", -1);
     const bool dual = dual_env < 0 ? !Bk : dual_env != 0;
-    return dual ? launch_mode_t<F, Bk, true>(a, cs, num_slots, stream) : launch_mode_t<F, Bk, false>(a, cs, num_slots, stream);
+    if (g.nc == 256)
+        return dual ? launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream)
+                    : launch_mode_t<F, Bk, false, 256>(a, g.cs, g.slots, stream);
+    return dual ? launch_mode_t<F, Bk, true, 512>(a, g.cs, g.slots, stream)
+                : launch_mode_t<F, Bk, false, 512>(a, g.cs, g.slots, stream);
 }
 
 }  // namespace
@@ -650,17 +700,23 @@ bool k1_resident_supported(const K1Args& a, int dtype) {
     return pick_cluster(a.vocab, kMaxSlots) != 0;
 }
 
+// AUTO policy: clusters of 4 and 8 CTAs are limited by GPC geometry to far fewer co-resident clusters than SMs
+// (measured: V = 262144 forward-only 0.62 ms resident vs 0.41 ms row kernel), so rows that need them go to the row
+// kernel unless the resident path is forced.
+bool k1_resident_preferred(const K1Args& a, int dtype) {
+    return k1_resident_supported(a, dtype) && pick_cluster(a.vocab, kMaxSlots) <= 2;
+}
+
 int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
     if (a.n_rows == 0) return B200TRL_OK;
-    const int num_slots = kMaxSlots;
-    const int cs = pick_cluster(a.vocab, num_slots);
-    B200TRL_REQUIRE(cs != 0, B200TRL_E_UNSUPPORTED, "k1_resident: vocab %lld too large for an 8-CTA cluster",
+    const Geom g = pick_geom(a.vocab);
+    B200TRL_REQUIRE(g.cs != 0, B200TRL_E_UNSUPPORTED, "k1_resident: vocab %lld too large for an 8-CTA cluster",
                     (long long)a.vocab);
     const bool fwd = (a.lse_in == nullptr), bwd = (a.dlogits != nullptr);
-    if (fwd && bwd) return launch_mode<true, true>(a, cs, num_slots, stream);
-    if (fwd) return launch_mode<true, false>(a, cs, num_slots, stream);
+    if (fwd && bwd) return launch_mode<true, true>(a, g, stream);
+    if (fwd) return launch_mode<true, false>(a, g, stream);
     B200TRL_REQUIRE(bwd, B200TRL_E_INVALID, "k1_resident: nothing to do");
-    return launch_mode<false, true>(a, cs, num_slots, stream);
+    return launch_mode<false, true>(a, g, stream);
 }
 
 }  // namespace b200trl

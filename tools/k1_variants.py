@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import swh_trl_b200 as S
 from swh_trl_b200 import ops
 DEV = torch.device("cuda", 0)
-B, T, V = 16, 1024, 151936
+B, T, V = int(os.environ.get('KV_B', 16)), int(os.environ.get('KV_T', 1024)), int(os.environ.get('KV_V', 151936))
 g = torch.Generator(device=DEV).manual_seed(0)
 logits = torch.empty(B, T, V, dtype=torch.bfloat16, device=DEV)
 for b in range(B):
@@ -16,7 +16,7 @@ ids = torch.randint(0, V, (B, T), generator=g, device=DEV)
 lens = torch.randint(T // 2, T + 1, (B,), generator=g, device=DEV)
 mask = (torch.arange(T, device=DEV).unsqueeze(0) < lens.unsqueeze(1)).int()
 adv = torch.randn(B, generator=g, device=DEV)
-S.set_k1_path(S.K1_RESIDENT)
+S.set_k1_path(S.K1_ROW if os.environ.get('KV_ROW') else S.K1_RESIDENT)
 lp0, _, lse0 = ops.logprob_entropy_fwd(logits, ids, 1.0)
 old = lp0 + torch.randn(B, T, generator=g, device=DEV) * 0.3
 ref = lp0 + torch.randn(B, T, generator=g, device=DEV) * 0.1
@@ -32,5 +32,5 @@ def t(fn, n=20):
     return statistics.median(ts), min(ts)
 fused = t(lambda: ops.grpo_fused_fwd_bwd(logits, ids, m32, rc, tot, adv, old, ref, cfg, 1.0, dlogits_out=dl))
 fwd = t(lambda: ops.logprob_entropy_fwd(logits, ids, 1.0))
-print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("B200TRL")}, "fused_ms": fused, "fwd_ms": fwd,
+print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("B200TRL") or k.startswith("KV_")}, "fused_ms": fused, "fwd_ms": fwd,
                   "fused_frac": 4 * V * B * T / fused[0] / 1e6 / 6546.6, "fwd_frac": 2 * V * B * T / fwd[0] / 1e6 / 6546.6}))
