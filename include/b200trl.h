@@ -90,6 +90,16 @@ enum b200trl_ppo_stat {
     B200TRL_PPO_NUM_STATS = 8
 };
 
+/* stats[] layout written by b200trl_rloo_loss (rloo_trainer.py:486-507) */
+enum b200trl_rloo_stat {
+    B200TRL_R_LOSS = 0,        /* pg_loss = mean_b max(-A r, -A clamp(r)), r = exp(sum_t new - sum_t old) */
+    B200TRL_R_PG_CLIPFRAC = 1,
+    B200TRL_R_APPROXKL = 2,
+    B200TRL_R_ENTROPY = 3,
+    B200TRL_R_RATIO = 4,       /* mean token-level ratio (new_ratio, :476) */
+    B200TRL_RLOO_NUM_STATS = 8
+};
+
 int b200trl_version(void);
 const char* b200trl_last_error(void);
 int b200trl_set_k1_path(int path); /* returns the previous setting */
@@ -189,6 +199,22 @@ int b200trl_ppo_loss(const float* new_logprobs, const float* old_logprobs, const
                      const int64_t* sequence_lengths, int64_t mb, int64_t T, float cliprange, float cliprange_value,
                      float vf_coef, float grad_scale, void* workspace, float* stats, float* dvpred,
                      b200trl_stream_t stream);
+
+/* ---- RLOO ---------------------------------------------------------------------
+ * rewards + leave-one-out advantages, trl/trainer/rloo_trainer.py:397-441.  logprobs/ref_logprobs raw fp32 [B,T]
+ * (pads filled here), scores [B], sequence_lengths int64 [B]; sample i of prompt p is row i * (B / rloo_k) + p.
+ * Outputs fp32 [B]: advantages, rlhf_reward, non_score_reward; optional filled log-probs. */
+int b200trl_rloo_rewards_advantages(const float* logprobs, const float* ref_logprobs, const float* scores,
+                                    const int64_t* sequence_lengths, int64_t B, int64_t T, float kl_coef,
+                                    int64_t rloo_k, int normalize_reward, float reward_clip_range,
+                                    int normalize_advantage, int token_level_kl, float* advantages,
+                                    float* rlhf_reward, float* non_score_reward, float* logprobs_f,
+                                    float* ref_logprobs_f, b200trl_stream_t stream);
+/* sequence-ratio clipped loss + stats (rloo_trainer.py:476-507) from new log-probs; g fp32 [mb,T] (nullable) is
+ * d(loss)/d(new_logprob) for b200trl_logprob_bwd.  workspace as for b200trl_grpo_loss with B = mb. */
+int b200trl_rloo_loss(const float* new_logprobs, const float* old_logprobs, const float* advantages,
+                      const float* entropy, const int64_t* sequence_lengths, int64_t mb, int64_t T, float cliprange,
+                      float grad_scale, void* workspace, float* stats, float* g, b200trl_stream_t stream);
 
 /* ---- a-12: masked_mean / masked_var / masked_whiten (trl/core.py:43-76) ------------------------
  * stats fp32 [3] = {mean, unbiased var, count}; out (whitened, fp32 [n]) may be NULL.

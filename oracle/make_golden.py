@@ -245,6 +245,38 @@ def gold_misc():
     save("misc.pt", out)
 
 
+def gold_rloo():
+    cases = []
+    for i, (B, T, k, nr, na, tl) in enumerate([(8, 16, 2, False, False, True), (12, 20, 4, True, True, True),
+                                               (12, 20, 3, True, False, False), (64, 53, 2, False, True, True)]):
+        lp, rlp, _, scores, lens = O.synth_ppo_case(B, T, 500 + i)
+        out = R.ref_rloo_rewards_advantages(lp, rlp, scores, lens, kl_coef=0.05, rloo_k=k, normalize_reward=nr,
+                                            reward_clip_range=1.5, normalize_advantage=na, token_level_kl=tl)
+        cases.append(dict(B=B, T=T, seed=500 + i, rloo_k=k, normalize_reward=nr, normalize_advantage=na,
+                          token_level_kl=tl, kl_coef=0.05, reward_clip_range=1.5,
+                          advantages=out["advantages"], rlhf_reward=out["rlhf_reward"],
+                          non_score_reward=out["non_score_reward"]))
+    loss_cases = []
+    for i, (mb, T, V) in enumerate([(4, 16, 64), (6, 12, 136)]):
+        g = torch.Generator().manual_seed(600 + i)
+        logits = torch.randn(mb, T, V, generator=g) * 2
+        responses = torch.randint(0, V, (mb, T), generator=g)
+        lens = torch.randint(T // 2, T, (mb,), generator=g)
+        lens[0] = T - 1
+        pad = torch.arange(T).unsqueeze(0) > lens.unsqueeze(1)
+        with torch.no_grad():
+            base = O.selective_log_softmax(logits / (0.7 + 1e-7), responses)
+        old = (base + torch.randn(mb, T, generator=g) * 0.05).masked_fill(pad, 1.0)
+        adv = torch.randn(mb, generator=g)
+        x = logits.clone().requires_grad_(True)
+        out = R.ref_rloo_loss(x, responses, old, adv, pad, temperature=0.7, cliprange=0.2)
+        out["loss"].backward()
+        loss_cases.append(dict(logits=logits, responses=responses, old_logprobs=old, advantages=adv,
+                               sequence_lengths=lens, temperature=0.7, cliprange=0.2,
+                               out={k: v.detach().clone() for k, v in out.items()}, grad_logits=x.grad.clone()))
+    save("rloo.pt", dict(adv=cases, loss=loss_cases))
+
+
 if __name__ == "__main__":
     assert R.available(), "needs /root/reference"
     torch.set_num_threads(os.cpu_count() or 1)
@@ -254,3 +286,4 @@ if __name__ == "__main__":
     gold_advantages()
     gold_ppo()
     gold_misc()
+    gold_rloo()

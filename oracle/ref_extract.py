@@ -269,3 +269,40 @@ def ref_ppo_loss(logits, responses, old_logprobs, advantages, returns, values, v
     out = {k: ns[k] for k in ("loss", "pg_loss", "vf_loss", "vf_clipfrac", "pg_clipfrac", "approxkl", "entropy",
                               "ratio", "new_logprobs")}
     return out
+
+
+# ---------------------------------------------------------------- RLOO (§8f-3)
+def ref_rloo_rewards_advantages(logprobs, ref_logprobs, scores, sequence_lengths, *, kl_coef, rloo_k, normalize_reward,
+                                reward_clip_range, normalize_advantage, token_level_kl):
+    """Exec rloo_trainer.py:397-441."""
+    ns = dict(_BASE_NS)
+    ns.update(
+        INVALID_LOGPROB=1.0,
+        responses=torch.zeros_like(logprobs, dtype=torch.long),
+        logprobs=logprobs.clone(), ref_logprobs=ref_logprobs.clone(), scores=scores.clone(),
+        sequence_lengths=sequence_lengths.clone(),
+        args=types.SimpleNamespace(kl_coef=kl_coef, rloo_k=rloo_k, normalize_reward=normalize_reward,
+                                   reward_clip_range=reward_clip_range, normalize_advantage=normalize_advantage,
+                                   token_level_kl=token_level_kl),
+    )
+    run_lines("trl/trainer/rloo_trainer.py", 397, 441, ns, anchor_first="response_idxs = torch.arange",
+              anchor_last="advantages = (advantages - advantages.mean()")
+    return {k: ns[k] for k in ("advantages", "rlhf_reward", "non_score_reward", "logprobs", "ref_logprobs",
+                               "padding_mask")}
+
+
+def ref_rloo_loss(logits, responses, old_logprobs, advantages, padding_mask, *, temperature, cliprange):
+    """Exec rloo_trainer.py:470-489 and :497-500 (skipping backward/optimizer)."""
+    utils = ref_utils()
+    ns = dict(_BASE_NS)
+    ns.update(utils)
+    mb = responses.shape[0]
+    ns.update(INVALID_LOGPROB=1.0, logits=logits / (temperature + 1e-7), mb_responses=responses,
+              mb_logprobs=old_logprobs, mb_advantage=advantages, padding_mask=padding_mask,
+              micro_batch_inds=torch.arange(mb), args=types.SimpleNamespace(cliprange=cliprange))
+    run_lines("trl/trainer/rloo_trainer.py", 470, 489, ns, anchor_first="new_logprobs = selective_log_softmax",
+              anchor_last="loss = pg_loss")
+    with torch.no_grad():
+        run_lines("trl/trainer/rloo_trainer.py", 497, 500, ns, anchor_first="pg_clipfrac = (pg_losses2",
+                  anchor_last="approxkl = 0.5")
+    return {k: ns[k] for k in ("loss", "pg_clipfrac", "approxkl", "entropy", "new_ratio", "ratio")}

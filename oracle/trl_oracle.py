@@ -474,3 +474,55 @@ def synth_ppo_case(B, T, seed):
     lens[0] = T - 1  # response fills the window: actual_end falls back to sequence_length (:515)
     lens[1] = T - 2
     return lp, rlp, values, scores, lens
+
+
+# --------------------------------------------------------------------------
+# §8f-3 (next): RLOO rewards / leave-one-out advantages / sequence-ratio loss
+# --------------------------------------------------------------------------
+def rloo_rewards_advantages(logprobs, ref_logprobs, scores, sequence_lengths, kl_coef=0.05, rloo_k=2,
+                            normalize_reward=False, reward_clip_range=10.0, normalize_advantage=False,
+                            token_level_kl=True):
+    """rloo_trainer.py:397-441.  Returns ``(advantages [B], rlhf_reward [B], non_score_reward [B], logprobs_f,
+    ref_logprobs_f)``; sample ``i`` of prompt ``p`` sits at ``i * (B / rloo_k) + p`` (``reshape(rloo_k, -1)``)."""
+    B, T = logprobs.shape
+    pad = torch.arange(T).unsqueeze(0).expand(B, T) > sequence_lengths.unsqueeze(1)  # :398
+    lp = logprobs.masked_fill(pad, INVALID_LOGPROB)  # :399
+    rlp = ref_logprobs.masked_fill(pad, INVALID_LOGPROB)  # :400
+    kl = lp - rlp  # :404
+    if normalize_reward:  # :407-409
+        scores = (scores - scores.mean()) / (scores.std() + 1e-8)
+        scores = scores.clamp(-reward_clip_range, reward_clip_range)
+    if token_level_kl:  # :412-426
+        kl_reward = -kl_coef * kl
+        eos = T - 1 - pad.long().fliplr().argmax(dim=1, keepdim=True)
+        last = torch.zeros_like(kl).scatter_(1, eos, scores.reshape(-1, 1).to(kl.dtype))
+        non_score = kl_reward.sum(1)
+        rlhf = (last + kl_reward).sum(1)
+    else:  # :427-431
+        non_score = -kl_coef * kl.sum(1)
+        rlhf = non_score + scores
+    r = rlhf.reshape(rloo_k, -1)  # :434
+    adv = (r - (r.sum(0) - r) / (rloo_k - 1)).flatten()  # :435-437
+    if normalize_advantage:  # :440-441
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    return adv, rlhf, non_score, lp, rlp
+
+
+def rloo_loss(logits, responses, old_logprobs, advantages, sequence_lengths, temperature=0.7, cliprange=0.2):
+    """rloo_trainer.py:466-507: sequence-level ratio from summed log-probs, clipped surrogate, stats."""
+    mb, T = responses.shape
+    pad = torch.arange(T).unsqueeze(0).expand(mb, T) > sequence_lengths.unsqueeze(1)
+    scaled = logits / (temperature + 1e-7)  # :467
+    new_lp = selective_log_softmax(scaled, responses).masked_fill(pad, INVALID_LOGPROB)  # :470-473
+    new_ratio = (new_lp - old_logprobs).exp()  # :476
+    diff = new_lp.sum(1) - old_logprobs.sum(1)  # :477-479
+    ratio = diff.exp()  # :480
+    pg1 = -advantages * ratio  # :483
+    pg2 = -advantages * ratio.clamp(1.0 - cliprange, 1.0 + cliprange)  # :484
+    loss = torch.max(pg1, pg2).mean()  # :485-489
+    with torch.no_grad():  # :496-507
+        prob = scaled.softmax(-1)
+        entropy = torch.logsumexp(scaled, dim=-1) - (prob * scaled).sum(-1)
+        stats = {"pg_clipfrac": (pg2 > pg1).float().mean(), "approxkl": 0.5 * (diff ** 2).mean(),
+                 "pg_loss": loss.detach(), "entropy": entropy.mean(), "ratio": new_ratio.mean()}
+    return loss, stats, new_lp

@@ -21,5 +21,6 @@ from .grpo import GRPOLoss, GRPOLossOutput, compute_loss, get_per_token_logps_an
 from .liger_seam import B200FusedLinearGRPOLoss  # noqa: F401
 from .patch import patch_trl  # noqa: F401
 from .ppo import INVALID_LOGPROB, PPOLossOutput, ppo_loss, ppo_rewards_gae  # noqa: F401
+from .rloo import RLOOLossOutput, rloo_loss, rloo_rewards_advantages  # noqa: F401
 
 __version__ = "0.1.0"

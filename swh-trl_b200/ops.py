@@ -386,3 +386,47 @@ def rescale_if_needed(buf: torch.Tensor, actual: torch.Tensor, expected: float) 
     check(lib.b200trl_rescale_if_needed(_ptr(buf), _DTYPES[buf.dtype], buf.numel() // V, V, row_stride, _ptr(a),
                                         float(expected), _stream(buf)), "rescale_if_needed")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------ RLOO
+def rloo_rewards_advantages(logprobs, ref_logprobs, scores, sequence_lengths, kl_coef, rloo_k, normalize_reward,
+                            reward_clip_range, normalize_advantage, token_level_kl, want_filled: bool = True):
+    """``dict(advantages, rlhf_reward, non_score_reward[, logprobs, ref_logprobs])`` — rloo_trainer.py:397-441."""
+    lp, rlp = _f32(logprobs, "logprobs"), _f32(ref_logprobs, "ref_logprobs")
+    sc = _f32(scores, "scores")
+    sl = sequence_lengths.to(torch.int64).contiguous()
+    B, T = lp.shape
+    dev = lp.device
+    adv = torch.empty(B, dtype=torch.float32, device=dev)
+    rlhf = torch.empty(B, dtype=torch.float32, device=dev)
+    ns = torch.empty(B, dtype=torch.float32, device=dev)
+    lpf = torch.empty_like(lp) if want_filled else None
+    rlpf = torch.empty_like(rlp) if want_filled else None
+    check(lib.b200trl_rloo_rewards_advantages(_ptr(lp), _ptr(rlp), _ptr(sc), _ptr(sl), B, T, float(kl_coef),
+                                              int(rloo_k), int(bool(normalize_reward)), float(reward_clip_range),
+                                              int(bool(normalize_advantage)), int(bool(token_level_kl)), _ptr(adv),
+                                              _ptr(rlhf), _ptr(ns), _ptr(lpf), _ptr(rlpf), _stream(lp)),
+          "rloo_rewards_advantages")
+    _count()
+    out = dict(advantages=adv, rlhf_reward=rlhf, non_score_reward=ns)
+    if want_filled:
+        out.update(logprobs=lpf, ref_logprobs=rlpf)
+    return out
+
+
+def rloo_loss(new_logprobs, old_logprobs, advantages, entropy, sequence_lengths, cliprange, grad_scale: float = 1.0,
+              want_g: bool = True):
+    """``(stats[8], g[mb,T]|None)`` — ``b200trl_rloo_loss``."""
+    nlp = _f32(new_logprobs, "new_logprobs")
+    mb, T = nlp.shape
+    dev = nlp.device
+    sl = sequence_lengths.to(torch.int64).contiguous()
+    ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(mb), "rloo_loss", zero=True)
+    stats = torch.empty(8, dtype=torch.float32, device=dev)
+    g = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_g else None
+    check(lib.b200trl_rloo_loss(_ptr(nlp), _ptr(_f32(old_logprobs, "old_logprobs")),
+                                _ptr(_f32(advantages, "advantages")), _ptr(_f32(entropy, "entropy")), _ptr(sl), mb, T,
+                                float(cliprange), float(grad_scale), _ptr(ws), _ptr(stats), _ptr(g), _stream(nlp)),
+          "rloo_loss")
+    _count()
+    return stats, g

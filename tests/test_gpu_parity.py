@@ -705,3 +705,37 @@ def test_cuda_graph_capture(S):
     eager_loss, _, eager_adv = step()
     torch.testing.assert_close(loss, eager_loss, rtol=1e-6, atol=1e-8)
     torch.testing.assert_close(adv_ppo, eager_adv, rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ RLOO (§8f-3)
+@pytest.mark.parametrize("i", range(4))
+def test_rloo_advantages_golden(S, i):
+    c = load_golden("rloo.pt")["adv"][i]
+    lp, rlp, _, scores, lens = O.synth_ppo_case(c["B"], c["T"], c["seed"])
+    out = S.rloo_rewards_advantages(lp.to(DEV), rlp.to(DEV), scores.to(DEV), lens.to(DEV), c["kl_coef"], c["rloo_k"],
+                                    c["normalize_reward"], c["reward_clip_range"], c["normalize_advantage"],
+                                    c["token_level_kl"])
+    torch.testing.assert_close(out["rlhf_reward"].cpu(), c["rlhf_reward"].flatten(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["non_score_reward"].cpu(), c["non_score_reward"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["advantages"].cpu(), c["advantages"], rtol=1e-4, atol=2e-5)
+    # leave-one-out structure is exact: the advantages of the rloo_k samples of one prompt sum to ~0 before normalising
+    if not c["normalize_advantage"]:
+        assert float(out["advantages"].reshape(c["rloo_k"], -1).sum(0).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_rloo_loss_golden(S, i):
+    from swh_trl_b200.rloo import STAT_INDEX as si
+    c = load_golden("rloo.pt")["loss"][i]
+    x = c["logits"].to(DEV).requires_grad_(True)
+    out = S.rloo_loss(x, c["responses"].to(DEV), c["old_logprobs"].to(DEV), c["advantages"].to(DEV),
+                      c["sequence_lengths"].to(DEV), c["temperature"], c["cliprange"])
+    out.loss.backward()
+    ref = c["out"]
+    assert out.loss.item() == pytest.approx(ref["loss"].item(), rel=1e-4, abs=1e-6)
+    torch.testing.assert_close(x.grad.cpu(), c["grad_logits"], rtol=1e-4, atol=2e-8)
+    st = out.stats.cpu()
+    assert st[si["pg_clipfrac"]].item() == pytest.approx(ref["pg_clipfrac"].item(), abs=1e-6)
+    assert st[si["approxkl"]].item() == pytest.approx(ref["approxkl"].item(), rel=1e-4, abs=1e-7)
+    assert st[si["entropy"]].item() == pytest.approx(ref["entropy"].mean().item(), rel=1e-4)
+    assert st[si["ratio"]].item() == pytest.approx(ref["new_ratio"].mean().item(), rel=1e-4)

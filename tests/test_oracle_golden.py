@@ -178,3 +178,30 @@ def test_grpo_c1_logp_entropy_vs_reference():
         assert float(logits.double().abs().sum()) == pytest.approx(c["input_checksum"], rel=1e-12)
         torch.testing.assert_close(O.selective_log_softmax(logits.float(), ids), c["logp"], rtol=0, atol=1e-6)
         torch.testing.assert_close(O.entropy_from_logits(logits.float()), c["entropy"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_rloo_advantages_vs_reference(i):
+    c = load_golden("rloo.pt")["adv"][i]
+    lp, rlp, _, scores, lens = O.synth_ppo_case(c["B"], c["T"], c["seed"])
+    adv, rlhf, non_score, _, _ = O.rloo_rewards_advantages(lp, rlp, scores, lens, c["kl_coef"], c["rloo_k"],
+                                                           c["normalize_reward"], c["reward_clip_range"],
+                                                           c["normalize_advantage"], c["token_level_kl"])
+    torch.testing.assert_close(adv, c["advantages"], rtol=0, atol=0)
+    torch.testing.assert_close(rlhf.reshape(c["rloo_k"], -1), c["rlhf_reward"], rtol=0, atol=0)  # reshaped at :434
+    torch.testing.assert_close(non_score, c["non_score_reward"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("i", range(2))
+def test_rloo_loss_vs_reference(i):
+    c = load_golden("rloo.pt")["loss"][i]
+    x = c["logits"].clone().requires_grad_(True)
+    loss, stats, _ = O.rloo_loss(x, c["responses"], c["old_logprobs"], c["advantages"], c["sequence_lengths"],
+                                 c["temperature"], c["cliprange"])
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), c["out"]["loss"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(x.grad, c["grad_logits"], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(stats["pg_clipfrac"], c["out"]["pg_clipfrac"])
+    torch.testing.assert_close(stats["approxkl"], c["out"]["approxkl"], rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(stats["entropy"], c["out"]["entropy"].mean(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(stats["ratio"], c["out"]["new_ratio"].mean(), rtol=1e-5, atol=1e-6)
