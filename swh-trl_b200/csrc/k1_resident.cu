@@ -24,11 +24,10 @@
 namespace b200trl {
 namespace {
 
-constexpr int kMaxConsumers = 512;  // consumer threads per CTA: 512 (1 CTA / SM) or 256 (2 CTAs / SM)
-constexpr int kChunkBytes = 16384;
-constexpr int kChunkElems = kChunkBytes / 2;
-constexpr int kChunkVecs = kChunkBytes / 16;
+constexpr int kMaxConsumers = 768;  // consumer threads per CTA: 768 or 512 (1 CTA / SM), 256 (2 CTAs / SM)
+constexpr int kChunkBytes = 16384;  // default chunk; per-geometry value: chunk_bytes_for()
 constexpr int kMaxSlots = 13;
+__host__ __device__ constexpr int chunk_bytes_for(int consumers) { return consumers == 768 ? 24576 : 16384; }
 constexpr int kMaxCluster = 8;
 constexpr int kStoreLag = 2;     // bulk stores allowed to be still reading shared memory
 constexpr float kSlack = 6.0f;   // reference point may trail the running max by 2^6
@@ -258,16 +257,47 @@ __device__ __forceinline__ void acc_vec2(Acc& a, const uint4& v0, const uint4& v
     acc_words(a.t2, a.v2, v1, c2, nm2);
 }
 
+// 2^d for a packed pair on the FMA pipe (no MUFU): Cody-Waite split d = j + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial (max relative error 7.5e-5 = 2^-13.7, far below the bf16 rounding of the dlogits it feeds), exponent
+// inserted with an integer add.  Used for a fraction of the backward exponentials to unload the 16-lane SFU,
+// which is what bounds the compute phases of the fused kernel.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t d2) {
+    float d0, d1;
+    unpack2(d2, d0, d1);
+    d2 = pack2(fmaxf(d0, -125.f), fmaxf(d1, -125.f));  // below that the result is < 2^-125: flush region
+    const uint64_t magic = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23: the add rounds d to an integer
+    const uint64_t t2 = fadd2(d2, magic);
+    const uint64_t j2 = fadd2(t2, pack2(-12582912.f, -12582912.f));
+    const uint64_t f2 = ffma2(j2, pack2(-1.f, -1.f), d2);
+    uint64_t p2 = ffma2(f2, pack2(0.055171408f, 0.055171408f), pack2(0.24261075f, 0.24261075f));
+    p2 = ffma2(p2, f2, pack2(0.69326097f, 0.69326097f));
+    p2 = ffma2(p2, f2, pack2(0.99992812f, 0.99992812f));
+    float p0, p1, t0, t1;
+    unpack2(p2, p0, p1);
+    unpack2(t2, t0, t1);
+    const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+    return pack2(r0, r1);
+}
+
+template <int POLY_WORDS>
 __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t nl2, uint64_t ng2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
-        float d0, d1;
-        unpack2(ffma2(x2, c2, nl2), d0, d1);
+        const uint64_t d2 = ffma2(x2, c2, nl2);
+        uint64_t e2;
+        if (i < POLY_WORDS) {
+            e2 = exp2_poly2(d2);
+        } else {
+            float d0, d1;
+            unpack2(d2, d0, d1);
+            e2 = pack2(ex2(d0), ex2(d1));
+        }
         float o0, o1;
-        unpack2(fmul2(pack2(ex2(d0), ex2(d1)), ng2), o0, o1);
+        unpack2(fmul2(e2, ng2), o0, o1);
         o[i] = cvt_bf16x2(o0, o1);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
@@ -301,12 +331,17 @@ struct Cursor {
     }
 };
 
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC>
-__global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, int POLY>
+__global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
     k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag) {
     constexpr int kConsumers = NC;
     constexpr int kWarps = NC / 32;
-    constexpr int kVpt = kChunkVecs / NC;  // 16-byte vectors per thread per full chunk (2 or 4)
+    // chunk geometry of this instantiation: 512 and 256 consumers use 16 KB chunks (2 / 4 vectors per thread),
+    // 768 consumers use 24 KB chunks (2 vectors per thread)
+    constexpr int kChunkBytes = chunk_bytes_for(NC);
+    constexpr int kChunkElems = kChunkBytes / 2;
+    constexpr int kChunkVecs = kChunkBytes / 16;
+    constexpr int kVpt = kChunkVecs / NC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* slots = smem_raw;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw + static_cast<size_t>(num_slots) * kChunkBytes);
@@ -555,7 +590,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)
                 const uint64_t nl2 = pack2(-rr.lse2, -rr.lse2);
                 const uint64_t ng2 = pack2(rr.ng, rr.ng);
                 const bool zero_row = (rr.ng == 0.f);
-                const bool patch_mine = (rr.id_vec >= 0) && ((rr.id_vec & (kConsumers - 1)) == tid);
+                const bool patch_mine = (rr.id_vec >= 0) && ((rr.id_vec % kConsumers) == tid);
                 for (int cidx = 0; cidx < C; ++cidx) {
                     if (!HAS_FWD) mbar_wait(&sm.full_bar[bcur.slot], bcur.par);
                     uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(bcur.slot) * kChunkBytes);
@@ -569,9 +604,9 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)
 #pragma unroll
                             for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
 #pragma unroll
-                            for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec(v[k], c2, nl2, ng2);
+                            for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec<POLY>(v[k], c2, nl2, ng2);
                         } else {
-                            for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec(sv[v], c2, nl2, ng2);
+                            for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec<POLY>(sv[v], c2, nl2, ng2);
                         }
                         if (patch_mine && cidx == rr.id_chunk)
                             reinterpret_cast<__nv_bfloat16*>(sv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
@@ -594,23 +629,24 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-int pick_cluster(int64_t vocab, int num_slots) {
+int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     static const int forced = env_int("B200TRL_K1_CLUSTER", 0);  // tuning knob: force a (larger) cluster size
     for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
         if (cs < forced) continue;
         const int64_t slice = ((vocab + cs - 1) / cs + 7) & ~int64_t(7);
-        const int64_t chunks = (slice * 2 + kChunkBytes - 1) / kChunkBytes;
+        const int64_t chunks = (slice * 2 + chunk_bytes - 1) / chunk_bytes;
         if (chunks <= num_slots - 1 || (chunks <= num_slots && cs == kMaxCluster)) return cs;
     }
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC>
-int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL, NC>;
+template <bool F, bool Bk, bool DUAL, int NC, int POLY>
+int launch_mode_p(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, POLY>;
     constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
+    static_assert(chunk_bytes_for(NC) % (NC * 16) == 0, "a full chunk must give every consumer the same vector count");
     constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
-    const size_t smem = static_cast<size_t>(num_slots) * kChunkBytes + sizeof(Smem);
+    const size_t smem = static_cast<size_t>(num_slots) * chunk_bytes_for(NC) + sizeof(Smem);
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) {
@@ -655,23 +691,42 @@ int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
 }
 
 // Two CTA geometries:
-//   wide : 512 consumers, 13 slots (208 KB), 1 CTA / SM   — a row slice of up to 12 chunks per CTA
-//   twin : 256 consumers,  6 slots ( 96 KB), 2 CTAs / SM  — slices of up to 5 chunks; the two CTAs of an SM drift
-//          apart, so one computes while the other waits on its row hand-off or on HBM
+//   wide  : 512 consumers, 13 x 16 KB slots (208 KB), 1 CTA / SM  — a row slice of up to 12 chunks per CTA
+//   dense : 768 consumers,  9 x 24 KB slots (216 KB), 1 CTA / SM  — more warps to hide the fold's latencies
+//   twin  : 256 consumers,  6 x 16 KB slots ( 96 KB), 2 CTAs / SM — slices of up to 5 chunks; the two CTAs of an SM
+//           drift apart, so one computes while the other waits on its row hand-off or on HBM
 struct Geom {
     int cs, slots, nc;
 };
 constexpr int kTwinSlots = 6;
+constexpr int kDenseSlots = 9;  // 9 x 24 KB = 216 KB
 
 Geom pick_geom(int64_t vocab) {
-    static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin
+    static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense
     const Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
     const Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
+    const Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768)), kDenseSlots, 768};
+    if (mode == 3 && dense.cs && dense.cs <= wide.cs) return dense;
     if (mode == 2 && twin.cs) return twin;
     if (mode == 1 || !twin.cs) return wide;
     // measured (tools/k1_variants.py, B200): rows that fit one twin CTA (<= 80 KB, e.g. V = 32000) gain 2 % fused /
     // 20 % forward-only from two drifting CTAs per SM; anything that would need a cluster in twin form is faster wide
-    return twin.cs == 1 ? twin : wide;
+    if (twin.cs == 1) return twin;
+    // 24 consumer warps hide the fold's latencies better than 16 (forward-only +9 %, fused +2..11 % over V = 65 k .. 152 k)
+    // whenever the coarser 24 KB chunks do not force a larger cluster
+    if (dense.cs && dense.cs <= wide.cs) return dense;
+    return wide;
+}
+
+// POLY = words (of 4) per 16-byte vector whose backward exponentials run on the FMA pipe instead of the SFU
+template <bool F, bool Bk, bool DUAL, int NC>
+int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    if (!Bk) return launch_mode_p<F, Bk, DUAL, NC, 0>(a, cs, num_slots, stream);
+    // measured (tools/k1_variants.py): 1 word in 4 on the polynomial is 3 % SLOWER, 2 in 4 is 6 % slower — the
+    // compute phases are issue/latency-bound, not SFU-bound — so the default is 0; kept as a knob for other parts
+    static const int poly = std::min(1, std::max(0, env_int("B200TRL_K1_POLY", 0)));
+    if (poly == 1 && NC == 512) return launch_mode_p<F, Bk, DUAL, NC, (Bk && NC == 512) ? 1 : 0>(a, cs, num_slots, stream);
+    return launch_mode_p<F, Bk, DUAL, NC, 0>(a, cs, num_slots, stream);
 }
 
 template <bool F, bool Bk>
@@ -683,6 +738,9 @@ int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
     if (g.nc == 256)
         return dual ? launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream)
                     : launch_mode_t<F, Bk, false, 256>(a, g.cs, g.slots, stream);
+    if (g.nc == 768)
+        return dual ? launch_mode_t<F, Bk, true, 768>(a, g.cs, g.slots, stream)
+                    : launch_mode_t<F, Bk, false, 768>(a, g.cs, g.slots, stream);
     return dual ? launch_mode_t<F, Bk, true, 512>(a, g.cs, g.slots, stream)
                 : launch_mode_t<F, Bk, false, 512>(a, g.cs, g.slots, stream);
 }
