@@ -224,6 +224,8 @@ def run_b200(args):
     from swh_trl_b200 import ops
 
     B, T, V, G = CFG["B"], CFG["T"], CFG["V"], CFG["G"]
+    if args.skip_masked:
+        S.set_skip_masked(True)
     logits, ids, mask = synth_device(rank, B, T, V, dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     rewards_local = torch.randn(B, 1, generator=gen, device=dev)
@@ -349,6 +351,8 @@ def run_b200(args):
                        "parallelism": f"sequence-sharded x{world}, no V-sized collective",
                        "l2": "inputs 4.98 GB per GPU per step >> 126 MB L2, no flush needed",
                        "metric_readback": "packed metrics all-gathered on device every step; host read deferred",
+                       "skip_masked_rows": bool(args.skip_masked),
+                       "masked_token_fraction": float(1.0 - mask.float().mean()),
                        "loss": loss_val},
             "clocks": clocks,
             "e2e": ({"value": tokens_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -383,6 +387,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region")
+    ap.add_argument("--skip-masked", action="store_true",
+                    help="opt-in: do not read rows with completion_mask == 0 (reported in config; NOT the default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

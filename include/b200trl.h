@@ -103,6 +103,11 @@ enum b200trl_rloo_stat {
 int b200trl_version(void);
 const char* b200trl_last_error(void);
 int b200trl_set_k1_path(int path); /* returns the previous setting */
+/* Opt-in: in the fused GRPO / PPO passes, rows the loss ignores (completion_mask == 0, PPO padding) are not read
+ * from HBM; their dlogits are zeros and their logp / entropy / lse outputs are 0 (PPO: 1.0).  Loss, metrics and
+ * gradients are unchanged; only the per-token outputs at masked positions differ from the reference (which
+ * computes and then discards them).  Returns the previous setting. */
+int b200trl_set_skip_masked(int on);
 
 /* ---- K1: selective_log_softmax + entropy_from_logits, one pass ------------------------------
  * Replaces trl/trainer/utils.py:1430-1462 and :1465-1490 (and the division by the temperature,

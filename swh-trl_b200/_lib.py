@@ -50,6 +50,7 @@ PROTOTYPES = {
     "b200trl_version": (C.c_int, []),
     "b200trl_last_error": (C.c_char_p, []),
     "b200trl_set_k1_path": (C.c_int, [_i32]),
+    "b200trl_set_skip_masked": (C.c_int, [_i32]),
     "b200trl_logprob_entropy_fwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p]),
     "b200trl_logprob_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _i64, _i64, _p]),
     "b200trl_mask_stats": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
@@ -103,6 +104,11 @@ def check(status: int, what: str) -> None:
     if status == -2:
         raise NotImplementedError(f"{what}: {msg}")
     raise B200TRLError(f"{what}: {msg}")
+
+
+def set_skip_masked(on: bool) -> bool:
+    """Opt-in: do not read rows the loss ignores in the fused passes (see ``b200trl_set_skip_masked``)."""
+    return bool(lib.b200trl_set_skip_masked(int(bool(on))))
 
 
 def set_k1_path(path: int) -> int:

@@ -8,6 +8,7 @@ using namespace b200trl;
 namespace {
 
 std::atomic<int> g_k1_path{B200TRL_K1_AUTO};
+std::atomic<int> g_skip_masked{0};
 
 int dispatch(const K1Args& a, int dtype, cudaStream_t stream) {
     const int path = g_k1_path.load();
@@ -86,6 +87,8 @@ extern "C" int b200trl_set_k1_path(int path) {
     return g_k1_path.exchange(path);
 }
 
+extern "C" int b200trl_set_skip_masked(int on) { return g_skip_masked.exchange(on ? 1 : 0); }
+
 extern "C" int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab,
                                            int64_t row_stride, int64_t rows_per_batch, int64_t batch_stride,
                                            const int64_t* ids, float inv_temperature, float* logp, float* entropy,
@@ -153,6 +156,7 @@ extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t
     a.total_count = total_count;
     a.cfg = *cfg;
     a.gmode = dlogits ? G_GRPO : G_NONE;
+    a.skip_masked = g_skip_masked.load();
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
     if (dlogits && set_dl_layout(a, T, dl_batch_stride, "grpo_fused")) return B200TRL_E_INVALID;
@@ -186,6 +190,7 @@ extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t 
     a.clip_hi = static_cast<float>(1.0 + static_cast<double>(cliprange));
     a.grad_scale = grad_scale;
     a.gmode = G_PPO;  // also marks pad rows so that new_logprobs gets INVALID_LOGPROB there
+    a.skip_masked = dlogits ? g_skip_masked.load() : 0;
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
     if (dlogits && set_dl_layout(a, T, dl_batch_stride, "ppo_fused")) return B200TRL_E_INVALID;

@@ -44,6 +44,9 @@ struct K1Args {
     // G_PPO
     const int64_t* seq_len;
     float clip_lo, clip_hi, grad_scale;
+    // fused modes only: rows whose loss weight is zero (completion_mask == 0 / PPO padding) are not read from HBM;
+    // their dlogits are zeros and their logp / entropy / lse outputs are 0.  Opt-in (b200trl_set_skip_masked).
+    int skip_masked;
 };
 
 // element offset of a row in the logits / dlogits tensors
@@ -56,6 +59,13 @@ __device__ __forceinline__ int64_t dlogits_offset(const K1Args& a, int64_t row) 
     if (a.rows_per_batch == 0) return row * a.dl_row_stride;
     const int64_t b = row / a.rows_per_batch;
     return b * a.dl_batch_stride + (row - b * a.rows_per_batch) * a.dl_row_stride;
+}
+
+// true when the loss ignores this row (only meaningful in the fused GRPO / PPO modes)
+__device__ __forceinline__ bool row_is_masked(const K1Args& a, int64_t row) {
+    if (a.gmode == G_GRPO) return a.mask[row] == 0;
+    if (a.gmode == G_PPO) return (row % a.T) > a.seq_len[row / a.T];
+    return false;
 }
 
 // Number of non-pad positions sum_b min(len_b + 1, T) (ppo_trainer.py:501: pad = idx > len); warp-cooperative.

@@ -331,7 +331,7 @@ struct Cursor {
     }
 };
 
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, int POLY>
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, int POLY, bool SKIP>
 __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
     k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag) {
     constexpr int kConsumers = NC;
@@ -396,17 +396,28 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             // load cursor
             int64_t k_next = 0;
             int l_row = 0, l_c = 0, l_slot = 0;
+            // masked-row skipping: the flag of the row being loaded and (prefetched) of the one after it
+            auto masked_at = [&](int r) {
+                return SKIP && r < n_my_rows && row_is_masked(a, first_row + static_cast<int64_t>(r) * row_step);
+            };
+            bool l_masked = masked_at(0), l_masked_next = masked_at(1);
             auto issue_load = [&]() {
                 const int64_t row = first_row + static_cast<int64_t>(l_row) * row_step;
                 const uint32_t bytes = static_cast<uint32_t>(l_c == C - 1 ? last_bytes : kChunkBytes);
-                mbar_expect_tx(&sm.full_bar[l_slot], bytes);
-                bulk_load(slots + static_cast<size_t>(l_slot) * kChunkBytes,
-                          logits + logits_offset(a, row) + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
-                          &sm.full_bar[l_slot], policy);
+                if (SKIP && l_masked) {
+                    mbar_arrive(&sm.full_bar[l_slot]);  // nothing to fetch: the slot is "full" right away
+                } else {
+                    mbar_expect_tx(&sm.full_bar[l_slot], bytes);
+                    bulk_load(slots + static_cast<size_t>(l_slot) * kChunkBytes,
+                              logits + logits_offset(a, row) + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
+                              &sm.full_bar[l_slot], policy);
+                }
                 ++k_next;
                 if (++l_c == C) {
                     l_c = 0;
                     ++l_row;
+                    l_masked = l_masked_next;
+                    l_masked_next = masked_at(l_row + 1);
                 }
                 if (++l_slot == num_slots) l_slot = 0;
             };
@@ -450,13 +461,34 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         // =========================== reducer warp: row statistics, cluster exchange, token gradient ===========
         if (HAS_FWD) {
             const float c = a.c;
+            uint32_t xphase[2] = {0u, 0u};  // phase parity of the two exchange barriers (one flip per use)
             for (int i = 0; i < n_my_rows; ++i) {
                 const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
                 const int par = i & 1;
                 const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
                 RowScalars rs;
-                if (lane == 0) rs = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+                const bool skip_row = SKIP && row_is_masked(a, row);
+                if (lane == 0 && !skip_row) rs = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
                 mbar_wait(&sm.part_bar[par], rpar);
+                if (skip_row) {  // nothing was read: outputs are zero, the row's dlogits are zero
+                    if (lane == 0) {
+                        if (crank == 0) {
+                            if (a.logp) a.logp[row] = (a.gmode == G_PPO) ? 1.0f : 0.f;
+                            if (a.entropy) a.entropy[row] = 0.f;
+                            if (a.lse) a.lse[row] = 0.f;
+                        }
+                        RowResult rr;
+                        rr.lse2 = 0.f;
+                        rr.ng = 0.f;
+                        rr.patch = 0.f;
+                        rr.id_chunk = rr.id_vec = rr.id_elem = -1;
+                        rr.pad0 = rr.pad1 = 0;
+                        sm.result[par] = rr;
+                        mbar_arrive(&sm.res_bar[par]);
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 Partial q = partial_empty();
                 if (lane < kWarps) {
                     const Part4 w = sm.warp_part[par][lane];
@@ -471,7 +503,8 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                             st_cluster_v4(map_to_rank(slot_addr, r), q.m, q.s, q.u, 0.f);
                             mbar_arrive_remote(map_to_rank(bar_addr, r));
                         }
-                        mbar_wait_cluster(&sm.xchg_bar[par], rpar);
+                        mbar_wait_cluster(&sm.xchg_bar[par], xphase[par]);
+                        xphase[par] ^= 1u;
                         Partial tot = partial_empty();
                         for (uint32_t r = 0; r < csize; ++r) {  // rank order: identical result in every CTA
                             const Part4 w = sm.xchg[par][r];
@@ -511,10 +544,12 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         const uint64_t c2 = pack2(c, c);
         Cursor fcur{0, 0u}, bcur{0, 0u};
 
-        auto fwd_chunk = [&](Acc& acc, int cidx) {
+        auto fwd_chunk = [&](Acc& acc, int cidx, bool skip) {
             mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
             const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
-            if (cidx != C - 1 || last_bytes == kChunkBytes) {
+            if (SKIP && skip) {
+                // masked row: nothing was loaded into this slot
+            } else if (cidx != C - 1 || last_bytes == kChunkBytes) {
                 uint4 v[kVpt];
 #pragma unroll
                 for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
@@ -539,16 +574,21 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         };
 
         Acc acc = acc_empty();
+        auto masked_at = [&](int r) {
+            return SKIP && r < n_my_rows && row_is_masked(a, first_row + static_cast<int64_t>(r) * row_step);
+        };
+        bool cur_masked = masked_at(0), nxt_masked = masked_at(1);
         if (HAS_FWD && n_my_rows > 0) {
-            for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx);
+            for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, cur_masked);
         }
         for (int i = 0; i < n_my_rows; ++i) {
             const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
             const int par = i & 1;
             const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
+            const bool nn_masked = masked_at(i + 2);  // prefetched: consumed two iterations later
 
             if (HAS_FWD) {
-                for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx);
+                for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx, cur_masked);
                 const Partial p = partial_warp_reduce(acc_to_partial(acc));
                 if (!HAS_BWD && i >= 2) mbar_wait(&sm.res_bar[par], static_cast<uint32_t>(((i - 2) >> 1) & 1));
                 if (lane == 0) {
@@ -557,9 +597,11 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 }
                 acc = acc_empty();
                 if (i + 1 < n_my_rows) {
-                    for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx);
+                    for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, nxt_masked);
                 }
             }
+            cur_masked = nxt_masked;
+            nxt_masked = nn_masked;
 
             if (HAS_BWD) {
                 RowResult rr;
@@ -640,9 +682,9 @@ int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC, int POLY>
-int launch_mode_p(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, POLY>;
+template <bool F, bool Bk, bool DUAL, int NC, int POLY, bool SKIP>
+int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, POLY, SKIP>;
     constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
     static_assert(chunk_bytes_for(NC) % (NC * 16) == 0, "a full chunk must give every consumer the same vector count");
     constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
@@ -716,6 +758,14 @@ Geom pick_geom(int64_t vocab) {
     // whenever the coarser 24 KB chunks do not force a larger cluster
     if (dense.cs && dense.cs <= wide.cs) return dense;
     return wide;
+}
+
+template <bool F, bool Bk, bool DUAL, int NC, int POLY>
+int launch_mode_p(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    constexpr bool kFused = F && Bk;
+    if (kFused && a.skip_masked && (a.gmode == G_GRPO || a.gmode == G_PPO))
+        return launch_mode_s<F, Bk, DUAL, NC, POLY, kFused>(a, cs, num_slots, stream);
+    return launch_mode_s<F, Bk, DUAL, NC, POLY, false>(a, cs, num_slots, stream);
 }
 
 // POLY = words (of 4) per 16-byte vector whose backward exponentials run on the FMA pipe instead of the SFU

@@ -134,6 +134,17 @@ __global__ void __launch_bounds__(BLOCK) k1_row_kernel(const K1Args a) {
     const T* x = reinterpret_cast<const T*>(a.logits) + logits_offset(a, row);
     const int64_t V = a.vocab;
 
+    if (a.skip_masked && a.dlogits && a.lse_in == nullptr && row_is_masked(a, row)) {
+        // opt-in: a row the loss ignores is not read; outputs are zero (PPO: INVALID_LOGPROB), dlogits are zero
+        T* dz = reinterpret_cast<T*>(a.dlogits) + dlogits_offset(a, row);
+        for (int64_t j = tid; j < V; j += BLOCK) ElemTraits<T>::store(dz + j, 0.f);
+        if (tid == 0) {
+            if (a.logp) a.logp[row] = (a.gmode == G_PPO) ? 1.0f : 0.f;
+            if (a.entropy) a.entropy[row] = 0.f;
+            if (a.lse) a.lse[row] = 0.f;
+        }
+        return;
+    }
     if (a.gmode == G_PPO && tid < 32) {
         const float n = ppo_unpadded_count(a, tid);
         if (tid == 0) s_ppo_count = n;

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kBlock) grpo_loss_kernel(const GrpoLossArgs a)
         float s[1] = {0.f};
         if (has_old) {
             for (int64_t t = tid; t < a.T; t += kBlock)
-                s[0] += (a.logp[base + t] - a.old_lp[base + t]) * static_cast<float>(a.mask[base + t]);
+                if (a.mask[base + t] != 0) s[0] += a.logp[base + t] - a.old_lp[base + t];
         }
         block_sum<1, kBlock>(s, red);
         grpo_surrogate(s[0] / fmaxf(len, 1.f), adv, a.cfg, seq_loss, seq_d, seq_low, seq_high);
@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(kBlock) grpo_loss_kernel(const GrpoLossArgs a)
     for (int64_t t = tid; t < a.T; t += kBlock) {
         const int64_t i = base + t;
         const float m = static_cast<float>(a.mask[i]);
+        if (m == 0.f) {  // the loss ignores this token: never let its (possibly skipped / garbage) log-prob in
+            if (!seq && a.g) a.g[i] = 0.f;
+            continue;
+        }
         const float keep = a.ent_mask ? static_cast<float>(a.ent_mask[i] != 0) : 1.f;
         const float lp = a.logp[i];
         float loss, kl = 0.f, dkl = 0.f, low, high, dl;
@@ -134,6 +138,10 @@ __global__ void __launch_bounds__(kBlock) grpo_loss_kernel(const GrpoLossArgs a)
         for (int64_t t = tid; t < a.T; t += kBlock) {
             const int64_t i = base + t;
             const float m = static_cast<float>(a.mask[i]);
+            if (m == 0.f) {
+                a.g[i] = 0.f;
+                continue;
+            }
             float kl, dkl = 0.f;
             if (a.cfg.beta != 0.f && has_ref) grpo_kl(a.logp[i], a.ref_lp[i], a.cfg.beta, kl, dkl);
             a.g[i] = m * norm * a.cfg.grad_scale * (coef + dkl);

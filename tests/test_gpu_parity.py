@@ -739,3 +739,42 @@ def test_rloo_loss_golden(S, i):
     assert st[si["approxkl"]].item() == pytest.approx(ref["approxkl"].item(), rel=1e-4, abs=1e-7)
     assert st[si["entropy"]].item() == pytest.approx(ref["entropy"].mean().item(), rel=1e-4)
     assert st[si["ratio"]].item() == pytest.approx(ref["new_ratio"].mean().item(), rel=1e-4)
+
+
+@pytest.mark.parametrize("path", ["row", "resident"])
+def test_skip_masked_rows(S, path):
+    """Opt-in: rows the loss ignores are not read.  Loss, metrics and gradients are unchanged; per-token outputs at
+    masked positions are zero instead of the (discarded) reference values."""
+    B, T, V = 4, 12, 32768
+    logits, ids, _ = O.synth_batch(B, T, V, seed=8, edge_rows=False)
+    lens = torch.tensor([12, 0, 7, 1])
+    mask = (torch.arange(T).unsqueeze(0) < lens.unsqueeze(1)).int()
+    adv = torch.tensor([0.4, 1.0, -0.8, 2.0])
+    lp0 = O.selective_log_softmax(logits.float(), ids)
+    g = torch.Generator().manual_seed(1)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.3
+    old[mask == 0] = -200.0  # would overflow exp(lp - old) if masked tokens leaked into the loss
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1
+    fn = S.GRPOLoss(beta=0.04, loss_type="grpo", max_completion_length=T)
+    res = {}
+    prev = S.set_k1_path(S.K1_ROW if path == "row" else S.K1_RESIDENT)
+    try:
+        for skip in (False, True):
+            was = S.set_skip_masked(skip)
+            try:
+                x = logits.to(DEV).requires_grad_(True)
+                o = fn(x, ids.to(DEV), mask.to(DEV), adv.to(DEV), old.to(DEV), ref.to(DEV))
+                o.loss.backward()
+                res[skip] = (o, x.grad)
+            finally:
+                S.set_skip_masked(was)
+    finally:
+        S.set_k1_path(prev)
+    (o0, g0), (o1, g1) = res[False], res[True]
+    assert torch.isfinite(o1.loss) and torch.equal(o0.loss, o1.loss)
+    assert torch.equal(g0, g1)
+    assert torch.equal(o0.metrics, o1.metrics)
+    m = mask.to(DEV).bool()
+    assert torch.equal(o0.per_token_logps[m], o1.per_token_logps[m])
+    assert torch.count_nonzero(o1.per_token_logps[~m]) == 0 and torch.count_nonzero(o1.entropies[~m]) == 0
+    assert torch.count_nonzero(o0.per_token_logps[~m]) > 0  # the default computes them like the reference
