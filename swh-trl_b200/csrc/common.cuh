@@ -78,6 +78,25 @@ __device__ __forceinline__ Partial partial_warp_reduce(Partial p) {
     return p;
 }
 
+// Same result as the merge tree up to fp32 round-off, but one ex2 per lane instead of two per merge level: find the
+// warp-wide reference first (5 max shuffles), rescale once, then plain shuffle sums.  This sits on the per-row
+// critical path of the resident kernel (consumer warps -> reducer warp -> RowResult).
+__device__ __forceinline__ Partial partial_warp_reduce_fast(Partial p) {
+    float m = p.m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float d = p.m - m;  // <= 0, finite
+    const float f = ex2(d);
+    float s = p.s * f;
+    float u = f * fmaf(d, p.s, p.u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+    }
+    return Partial{m, s, u};
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

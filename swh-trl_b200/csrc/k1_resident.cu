@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                     const Part4 w = sm.warp_part[par][lane];
                     q = Partial{w.m, w.s, w.u};
                 }
-                q = partial_warp_reduce(q);
+                q = partial_warp_reduce_fast(q);
                 if (lane == 0) {
                     if (csize > 1) {
                         const uint32_t slot_addr = smem_u32(&sm.xchg[par][crank]);
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
 
             if (HAS_FWD) {
                 for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx, cur_masked);
-                const Partial p = partial_warp_reduce(acc_to_partial(acc));
+                const Partial p = partial_warp_reduce_fast(acc_to_partial(acc));
                 if (!HAS_BWD && i >= 2) mbar_wait(&sm.res_bar[par], static_cast<uint32_t>(((i - 2) >> 1) & 1));
                 if (lane == 0) {
                     sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};

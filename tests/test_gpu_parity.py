@@ -348,9 +348,9 @@ def test_config2_properties(S):
     lp_fwd, ent_fwd = S.logprobs_and_entropy(x, ids)
     S.set_k1_path(prev)
     # (a) forward-only and fused instantiations fold in a different order (two vs one accumulation chain)
-    torch.testing.assert_close(lp_fwd, out_res.per_token_logps, rtol=0, atol=2e-6)
-    torch.testing.assert_close(ent_fwd, out_res.entropies, rtol=0, atol=2e-6)
-    torch.testing.assert_close(out_res.per_token_logps, out_row.per_token_logps, rtol=0, atol=2e-6)
+    torch.testing.assert_close(lp_fwd, out_res.per_token_logps, rtol=0, atol=5e-6)
+    torch.testing.assert_close(ent_fwd, out_res.entropies, rtol=0, atol=5e-6)
+    torch.testing.assert_close(out_res.per_token_logps, out_row.per_token_logps, rtol=0, atol=5e-6)
     torch.testing.assert_close(g_res.float(), g_row.float(), rtol=BF16_ULP, atol=1e-12)
     # (b)
     assert torch.count_nonzero(g_res[mask == 0]) == 0
@@ -436,7 +436,7 @@ def test_logits_to_keep_in_place(S, path):
     torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)
     assert torch.count_nonzero(x.grad[:, :L - 1 - T]) == 0 and torch.count_nonzero(x.grad[:, L - 1:]) == 0
     assert torch.equal(x.grad, x2.grad) and torch.equal(out.loss, out2.loss)
-    torch.testing.assert_close(lp_view, out.per_token_logps, rtol=0, atol=2e-6)
+    torch.testing.assert_close(lp_view, out.per_token_logps, rtol=0, atol=5e-6)
 
 
 def test_trainer_surface_compute_loss(S):
