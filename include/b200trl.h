@@ -162,7 +162,7 @@ int b200trl_grpo_loss(const float* logp, const float* old_logp, const float* ref
 /* ---- a-4: get_high_entropy_mask (grpo_trainer.py:341-364) ------------------------------------
  * out_mask[i] = mask[i] && entropies[i]*mask[i] >= quantile(entropies[mask], threshold) with torch's
  * linear interpolation; all zero if the mask is empty.  workspace >= ..._workspace_bytes(n), any
- * contents.  out_threshold (fp32 [1]) may be NULL. */
+ * contents.  out_threshold (fp32 [1]) may be NULL.  One cooperative launch (multi-CTA radix select). */
 int64_t b200trl_entropy_quantile_workspace_bytes(int64_t n);
 int b200trl_entropy_quantile_mask(const float* entropies, const int32_t* mask, int64_t n, float threshold,
                                   void* workspace, uint8_t* out_mask, float* out_threshold, b200trl_stream_t stream);

@@ -146,6 +146,9 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint3
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
@@ -333,7 +336,7 @@ struct Cursor {
 
 template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, int POLY, bool SKIP>
 __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
-    k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag) {
+    k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag, const int l2_prefetch) {
     constexpr int kConsumers = NC;
     constexpr int kWarps = NC / 32;
     // chunk geometry of this instantiation: 512 and 256 consumers use 16 KB chunks (2 / 4 vectors per thread),
@@ -404,6 +407,14 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             auto issue_load = [&]() {
                 const int64_t row = first_row + static_cast<int64_t>(l_row) * row_step;
                 const uint32_t bytes = static_cast<uint32_t>(l_c == C - 1 ? last_bytes : kChunkBytes);
+                if (l2_prefetch && l_c == 0 && l_row + 1 < n_my_rows && !(SKIP && l_masked_next)) {
+                    // pull the NEXT row's slice into L2 now: its shared-memory slots only free up while this row is
+                    // being written back, and a bulk load that hits L2 lands in a fraction of the HBM queueing time
+                    const __nv_bfloat16* nxt = logits + logits_offset(a, row + row_step) + e_begin;
+                    for (int cc = 0; cc < C; ++cc)
+                        bulk_prefetch_l2(nxt + static_cast<int64_t>(cc) * kChunkElems,
+                                         static_cast<uint32_t>(cc == C - 1 ? last_bytes : kChunkBytes));
+                }
                 if (SKIP && l_masked) {
                     mbar_arrive(&sm.full_bar[l_slot]);  // nothing to fetch: the slot is "full" right away
                 } else {
@@ -724,7 +735,8 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
         }
     }
     static const int max_lag = std::min(2, std::max(0, env_int("B200TRL_K1_LAG", 1)));  // 1 measured best (0: -10 %, 2: -3 %)
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots, max_lag);
+    static const int l2_prefetch = env_int("B200TRL_K1_L2PREFETCH", 0);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots, max_lag, Bk ? l2_prefetch : 0);
     if (e != cudaSuccess) {
         set_error("k1_resident launch failed: %s", cudaGetErrorString(e));
         return B200TRL_E_LAUNCH;

@@ -1,7 +1,13 @@
 // a-4  b200trl_entropy_quantile_mask : get_high_entropy_mask, trl/trainer/grpo_trainer.py:341-364
 //      exact torch.quantile(linear) of the non-pad entropies by radix select, then the >= compare.
 //      b200trl_rescale_if_needed     : device-side fix-up when autograd's grad_output != assumed grad_scale.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200trl {
 namespace {
@@ -17,40 +23,76 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
     return __uint_as_float(u);
 }
 
-// Single CTA: the data is [B,T] fp32 (<= a few MB, L2 resident); 4 histogram passes pick the k-th smallest key.
+// Cooperative multi-CTA radix select: every CTA histograms its share of the (L2-resident) [B,T] data into shared
+// memory with warp-aggregated atomics (entropies cluster in a few exponent bins, plain atomics would serialise),
+// merges into a global 256-bin histogram, and after a grid.sync every CTA walks the same histogram to the same
+// bin.  4 passes pick the k-th smallest key exactly; one more pass finds the next order statistic.
+struct QuantileWs {
+    unsigned int hist[4][256];
+    unsigned long long count;
+    unsigned long long cnt_le;
+    unsigned int any_nan;
+    unsigned int min_gt;
+};
+
+__device__ __forceinline__ void hist_add(unsigned int* hist, uint32_t bin, bool active) {
+    // warp-aggregated: one atomic per distinct bin per warp
+    const unsigned int act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned int peers = __match_any_sync(act, bin);
+    const int leader = __ffs(peers) - 1;
+    if ((threadIdx.x & 31) == leader) atomicAdd(&hist[bin], __popc(peers));
+}
+
 __global__ void __launch_bounds__(kSelBlock) entropy_quantile_kernel(const float* __restrict__ ent,
                                                                      const int32_t* __restrict__ mask, int64_t n,
-                                                                     float q, uint8_t* __restrict__ out,
+                                                                     float q, QuantileWs* ws,
+                                                                     uint8_t* __restrict__ out,
                                                                      float* __restrict__ thr_out) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int hist[256];
-    __shared__ unsigned long long s_count;
-    __shared__ unsigned int s_prefix, s_rank, s_any_nan, s_min_gt;
-    __shared__ unsigned long long s_cnt_le;
+    __shared__ unsigned int s_prefix, s_rank;
     const int tid = threadIdx.x;
+    const int64_t start = static_cast<int64_t>(blockIdx.x) * kSelBlock + tid;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kSelBlock;
+    const int64_t n_round = ((n + stride - 1) / stride) * stride;  // uniform trip count: warp collectives inside
 
-    // count non-pad entries, detect NaN
-    if (tid == 0) {
-        s_count = 0ull;
-        s_any_nan = 0u;
+    // ---- pass 0: zero the workspace (block 0), count non-pad entries, detect NaN
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < 4 * 256; i += kSelBlock) (&ws->hist[0][0])[i] = 0u;
+        if (tid == 0) {
+            ws->count = 0ull;
+            ws->cnt_le = 0ull;
+            ws->any_nan = 0u;
+            ws->min_gt = 0xffffffffu;
+        }
     }
-    __syncthreads();
+    __threadfence();
+    grid.sync();
     {
         unsigned long long c = 0;
         unsigned int nan = 0;
-        for (int64_t i = tid; i < n; i += kSelBlock) {
+        for (int64_t i = start; i < n; i += stride) {
             if (mask[i] != 0) {
                 ++c;
                 nan |= isnan(ent[i]) ? 1u : 0u;
             }
         }
-        atomicAdd(&s_count, c);
-        if (nan) atomicOr(&s_any_nan, 1u);
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+        }
+        if ((tid & 31) == 0) {
+            if (c) atomicAdd(&ws->count, c);
+            if (nan) atomicOr(&ws->any_nan, 1u);
+        }
     }
-    __syncthreads();
-    const unsigned long long cnt = s_count;
+    __threadfence();
+    grid.sync();
+    const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(&ws->count);
     if (cnt == 0ull) {  // :358-359 — no non-pad token: all False
-        for (int64_t i = tid; i < n; i += kSelBlock) out[i] = 0;
-        if (thr_out && tid == 0) thr_out[0] = __int_as_float(0x7fc00000);
+        for (int64_t i = start; i < n; i += stride) out[i] = 0;
+        if (thr_out && blockIdx.x == 0 && tid == 0) thr_out[0] = __int_as_float(0x7fc00000);
         return;
     }
     // torch.quantile: rank = q * (cnt - 1) evaluated in fp32, lerp between floor and ceil ranks
@@ -60,64 +102,78 @@ __global__ void __launch_bounds__(kSelBlock) entropy_quantile_kernel(const float
     const unsigned long long k_hi = static_cast<unsigned long long>(ceilf(rank));
     const float w = rank - rank_lo_f;
 
-    // radix select of the k_lo-th smallest (0-based)
-    if (tid == 0) {
-        s_prefix = 0u;
-        s_rank = static_cast<unsigned int>(k_lo);  // cnt < 2^32 for any [B,T] that fits here
-    }
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    // ---- radix select of the k_lo-th smallest (0-based), 8 bits per pass
+    uint32_t prefix = 0u;
+    unsigned int r = static_cast<unsigned int>(k_lo);
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
         if (tid < 256) hist[tid] = 0u;
         __syncthreads();
-        const uint32_t prefix = s_prefix;
-        const uint32_t hi_mask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-        for (int64_t i = tid; i < n; i += kSelBlock) {
-            if (mask[i] != 0) {
+        const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
+        for (int64_t i = start; i < n_round; i += stride) {
+            bool active = false;
+            uint32_t bin = 0;
+            if (i < n && mask[i] != 0) {
                 const uint32_t key = ordered_key(ent[i]);
-                if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+                active = ((key & hi_mask) == prefix);
+                bin = (key >> shift) & 0xffu;
             }
+            hist_add(hist, bin, active);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned int r = s_rank, b = 0;
+        if (tid < 256 && hist[tid]) atomicAdd(&ws->hist[pass][tid], hist[tid]);
+        __threadfence();
+        grid.sync();
+        if (tid == 0) {  // every CTA walks the same global histogram to the same bin
+            const volatile unsigned int* gh = ws->hist[pass];
+            unsigned int rr = r, b = 0;
             for (; b < 256; ++b) {
-                if (r < hist[b]) break;
-                r -= hist[b];
+                const unsigned int h = gh[b];
+                if (rr < h) break;
+                rr -= h;
             }
-            s_rank = r;
+            s_rank = rr;
             s_prefix = prefix | (b << shift);
         }
         __syncthreads();
+        r = s_rank;
+        prefix = s_prefix;
+        __syncthreads();
     }
-    const uint32_t key_lo = s_prefix;
-    // the next order statistic: equal to key_lo if duplicated far enough, else the smallest key above it
-    if (tid == 0) {
-        s_cnt_le = 0ull;
-        s_min_gt = 0xffffffffu;
-    }
-    __syncthreads();
+    const uint32_t key_lo = prefix;
+    // ---- the next order statistic: equal to key_lo if duplicated far enough, else the smallest key above it
     {
         unsigned long long le = 0;
         uint32_t mn = 0xffffffffu;
-        for (int64_t i = tid; i < n; i += kSelBlock) {
+        for (int64_t i = start; i < n; i += stride) {
             if (mask[i] != 0) {
                 const uint32_t key = ordered_key(ent[i]);
                 if (key <= key_lo) ++le;
                 else mn = min(mn, key);
             }
         }
-        atomicAdd(&s_cnt_le, le);
-        atomicMin(&s_min_gt, mn);
+        for (int o = 16; o > 0; o >>= 1) {
+            le += __shfl_xor_sync(0xffffffffu, le, o);
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if ((tid & 31) == 0) {
+            if (le) atomicAdd(&ws->cnt_le, le);
+            atomicMin(&ws->min_gt, mn);
+        }
     }
-    __syncthreads();
+    __threadfence();
+    grid.sync();
+    const unsigned long long cnt_le = *reinterpret_cast<volatile unsigned long long*>(&ws->cnt_le);
+    const uint32_t min_gt = *reinterpret_cast<volatile unsigned int*>(&ws->min_gt);
     const float x_lo = key_to_float(key_lo);
-    const float x_hi = (k_hi == k_lo || s_cnt_le > k_hi) ? x_lo : key_to_float(s_min_gt);
+    const float x_hi = (k_hi == k_lo || cnt_le > k_hi) ? x_lo : key_to_float(min_gt);
     // at::lerp: w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
     const float diff = x_hi - x_lo;
     float thr = (w < 0.5f) ? fmaf(w, diff, x_lo) : x_hi - diff * (1.f - w);
-    if (s_any_nan) thr = __int_as_float(0x7fc00000);
-    if (thr_out && tid == 0) thr_out[0] = thr;
+    if (*reinterpret_cast<volatile unsigned int*>(&ws->any_nan)) thr = __int_as_float(0x7fc00000);
+    if (thr_out && blockIdx.x == 0 && tid == 0) thr_out[0] = thr;
     // (entropies * mask) >= threshold, and not padding (:361-364)
-    for (int64_t i = tid; i < n; i += kSelBlock) {
+    for (int64_t i = start; i < n; i += stride) {
         const bool m = mask[i] != 0;
         out[i] = (m && (ent[i] * 1.0f >= thr)) ? 1 : 0;
     }
@@ -143,18 +199,34 @@ __global__ void rescale_kernel(T* buf, int64_t n_rows, int64_t vocab, int64_t ro
 
 using namespace b200trl;
 
-extern "C" int64_t b200trl_entropy_quantile_workspace_bytes(int64_t) { return 64; }
+extern "C" int64_t b200trl_entropy_quantile_workspace_bytes(int64_t) { return static_cast<int64_t>(sizeof(QuantileWs)); }
 
 extern "C" int b200trl_entropy_quantile_mask(const float* entropies, const int32_t* mask, int64_t n, float threshold,
-                                             void* /*workspace*/, uint8_t* out_mask, float* out_threshold,
+                                             void* workspace, uint8_t* out_mask, float* out_threshold,
                                              b200trl_stream_t stream) {
-    B200TRL_REQUIRE(entropies && mask && out_mask, B200TRL_E_INVALID, "entropy_quantile_mask: null pointer");
+    B200TRL_REQUIRE(entropies && mask && out_mask && workspace, B200TRL_E_INVALID,
+                    "entropy_quantile_mask: null pointer");
     B200TRL_REQUIRE(n > 0 && n < (int64_t(1) << 32), B200TRL_E_INVALID, "entropy_quantile_mask: bad size %lld",
                     (long long)n);
     B200TRL_REQUIRE(threshold >= 0.f && threshold <= 1.f, B200TRL_E_INVALID,
                     "entropy_quantile_mask: quantile %f outside [0,1]", threshold);
-    entropy_quantile_kernel<<<1, kSelBlock, 0, as_stream(stream)>>>(entropies, mask, n, threshold, out_mask,
-                                                                    out_threshold);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_quantile_kernel, kSelBlock, 0) != cudaSuccess ||
+        per_sm < 1) {
+        set_error("entropy_quantile_mask: occupancy query failed");
+        return B200TRL_E_LAUNCH;
+    }
+    const int64_t want = (n + kSelBlock * 32 - 1) / (kSelBlock * 32);  // ~4 elements per thread per pass
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(per_sm) * num_sms()));
+    QuantileWs* ws = static_cast<QuantileWs*>(workspace);
+    void* params[] = {&entropies, &mask, &n, &threshold, &ws, &out_mask, &out_threshold};
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(entropy_quantile_kernel),
+                                                     dim3(static_cast<unsigned>(grid)), dim3(kSelBlock), params, 0,
+                                                     as_stream(stream));
+    if (e != cudaSuccess) {
+        set_error("entropy_quantile_mask: cooperative launch failed: %s", cudaGetErrorString(e));
+        return B200TRL_E_LAUNCH;
+    }
     return check_launch("entropy_quantile_kernel");
 }
 

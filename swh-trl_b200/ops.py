@@ -259,7 +259,8 @@ def entropy_quantile_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold
     out = torch.empty(e.shape, dtype=torch.uint8, device=e.device)
     thr = torch.empty(1, dtype=torch.float32, device=e.device)
     if e.numel():
-        check(lib.b200trl_entropy_quantile_mask(_ptr(e), _ptr(m), e.numel(), float(threshold), None, _ptr(out),
+        ws = _workspace(e.device, lib.b200trl_entropy_quantile_workspace_bytes(e.numel()), "quantile", zero=False)
+        check(lib.b200trl_entropy_quantile_mask(_ptr(e), _ptr(m), e.numel(), float(threshold), _ptr(ws), _ptr(out),
                                                 _ptr(thr), _stream(e)), "entropy_quantile_mask")
         _count()
     return out.bool(), thr
