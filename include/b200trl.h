@@ -221,6 +221,18 @@ int b200trl_rloo_loss(const float* new_logprobs, const float* old_logprobs, cons
                       const float* entropy, const int64_t* sequence_lengths, int64_t mb, int64_t T, float cliprange,
                       float grad_scale, void* workspace, float* stats, float* g, b200trl_stream_t stream);
 
+/* ---- K5 (forward): lm_head GEMM fused with the log-softmax statistics on tcgen05 / TMEM ----------------------
+ * logp / entropy / lse of (hidden @ weight^T) * inv_temperature without ever materialising the [n_rows, vocab]
+ * logits (what `_get_per_token_logps_and_entropies` needs for the no-grad old / ref passes when the
+ * Liger path is on, grpo_trainer.py:1163-1203 + :1261-1267).  hidden: bf16 [n_rows, hidden_size]; weight: bf16
+ * [vocab, hidden_size] (lm_head.weight); strides in elements, multiples of 8.  workspace >=
+ * b200trl_fused_linear_workspace_bytes(n_rows, vocab), any contents.  Two launches (GEMM+stats, merge). */
+int64_t b200trl_fused_linear_workspace_bytes(int64_t n_rows, int64_t vocab);
+int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidden_row_stride, const void* weight,
+                                     int64_t weight_row_stride, int64_t n_rows, int64_t hidden_size, int64_t vocab,
+                                     const int64_t* ids, float inv_temperature, void* workspace, float* logp,
+                                     float* entropy, float* lse, b200trl_stream_t stream);
+
 /* ---- a-12: masked_mean / masked_var / masked_whiten (trl/core.py:43-76) ------------------------
  * stats fp32 [3] = {mean, unbiased var, count}; out (whitened, fp32 [n]) may be NULL.
  * workspace >= b200trl_masked_workspace_bytes(n), any contents. */

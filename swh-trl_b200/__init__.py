@@ -10,6 +10,7 @@ from ._lib import K1_AUTO, K1_RESIDENT, K1_ROW, B200TRLError, set_k1_path, set_s
 from .advantages import group_advantages  # noqa: F401
 from .functional import (  # noqa: F401
     entropy_from_logits,
+    fused_linear_logprobs,
     get_high_entropy_mask,
     logprobs_and_entropy,
     masked_mean,

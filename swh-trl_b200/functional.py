@@ -75,6 +75,18 @@ def entropy_from_logits(logits: torch.Tensor, chunk_size: int = 1, out_dtype: Op
     return ent if out_dtype == torch.float32 else ent.to(out_dtype)
 
 
+def fused_linear_logprobs(hidden: torch.Tensor, lin_weight: torch.Tensor, index: torch.Tensor,
+                          temperature: float = 1.0, compute_entropy: bool = True):
+    """``(log_softmax((hidden @ lin_weight.T) / temperature)[index], entropy)`` without materialising the logits:
+    tcgen05 GEMM tiles stay in tensor memory and are folded into per-row statistics (K5).  No gradient — this is
+    the no-grad old / ref log-prob pass of the Liger configuration (grpo_trainer.py:1855-1897 with hidden states
+    from ``_get_last_hidden_state``, :1163-1203)."""
+    with torch.no_grad():
+        logp, ent, _ = ops.fused_linear_logprob_fwd(hidden, lin_weight, index, 1.0 / float(temperature),
+                                                    want_entropy=compute_entropy)
+    return logp, ent
+
+
 def get_high_entropy_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold: float) -> torch.Tensor:
     """Drop-in for ``get_high_entropy_mask`` (grpo_trainer.py:341-364): exact quantile by radix select."""
     out, _ = ops.entropy_quantile_mask(entropies, mask, threshold)

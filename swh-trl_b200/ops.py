@@ -431,3 +431,33 @@ def rloo_loss(new_logprobs, old_logprobs, advantages, entropy, sequence_lengths,
           "rloo_loss")
     _count()
     return stats, g
+
+
+# ------------------------------------------------------------------------------------------------ K5 (forward)
+def fused_linear_logprob_fwd(hidden: torch.Tensor, weight: torch.Tensor, ids: torch.Tensor, inv_temperature: float = 1.0,
+                             want_entropy: bool = True, want_lse: bool = False):
+    """``(logp, entropy|None, lse|None)`` of ``(hidden @ weight.T) * inv_temperature`` — logits never materialised."""
+    _need_cuda(hidden, "hidden")
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError("fused_linear_logprob_fwd needs bf16 hidden states and weights")
+    H = hidden.shape[-1]
+    h2 = hidden.reshape(-1, H)
+    if h2.stride(-1) != 1:
+        h2 = h2.contiguous()
+    w = weight if weight.stride(-1) == 1 else weight.contiguous()
+    n, V = h2.shape[0], w.shape[0]
+    idx = ids.to(torch.int64).contiguous()
+    if idx.numel() != n:
+        raise ValueError(f"index has {idx.numel()} elements, hidden has {n} rows")
+    shape = tuple(hidden.shape[:-1])
+    dev = hidden.device
+    logp = torch.empty(shape, dtype=torch.float32, device=dev)
+    ent = torch.empty(shape, dtype=torch.float32, device=dev) if want_entropy else None
+    lse = torch.empty(shape, dtype=torch.float32, device=dev) if want_lse else None
+    if n:
+        ws = _workspace(dev, lib.b200trl_fused_linear_workspace_bytes(n, V), "fused_linear", zero=False)
+        check(lib.b200trl_fused_linear_logprob_fwd(_ptr(h2), h2.stride(0), _ptr(w), w.stride(0), n, H, V, _ptr(idx),
+                                                   float(inv_temperature), _ptr(ws), _ptr(logp), _ptr(ent), _ptr(lse),
+                                                   _stream(h2)), "fused_linear_logprob_fwd")
+        _count(2)
+    return logp, ent, lse

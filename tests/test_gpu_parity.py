@@ -778,3 +778,30 @@ def test_skip_masked_rows(S, path):
     assert torch.equal(o0.per_token_logps[m], o1.per_token_logps[m])
     assert torch.count_nonzero(o1.per_token_logps[~m]) == 0 and torch.count_nonzero(o1.entropies[~m]) == 0
     assert torch.count_nonzero(o0.per_token_logps[~m]) > 0  # the default computes them like the reference
+
+
+# ------------------------------------------------------------------------------------------------ K5 (tcgen05, §8f-1)
+@pytest.mark.parametrize("N,H,V,temp", [(128, 64, 256, 1.0), (300, 192, 1000, 0.8), (1, 8, 8, 1.0), (129, 200, 257, 1.3),
+                                        (256, 3584, 4096, 1.0), (640, 512, 40000, 0.7)])
+def test_fused_linear_logprobs(S, N, H, V, temp):
+    """lm_head GEMM fused with the log-softmax statistics on tcgen05 / TMEM (no logits in memory) against the oracle
+    applied to the fp32 product of the same bf16 operands — ragged M / N / K tiles included."""
+    g = torch.Generator().manual_seed(N + V)
+    hidden = torch.randn(N, H, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g) / H ** 0.5 * 2).to(torch.bfloat16)
+    ids = torch.randint(0, V, (N,), generator=g)
+    ids[0], ids[-1] = 0, V - 1
+    logits = hidden.double() @ W.double().t()
+    want_lp = O.selective_log_softmax(logits / temp, ids).float()
+    want_ent = O.entropy_from_logits(logits / temp).float()
+    lp, ent = S.fused_linear_logprobs(hidden.to(DEV), W.to(DEV), ids.to(DEV), temperature=temp)
+    # fp32 accumulation over K in tensor memory vs the exact (fp64) product: a few fp32 ulps of the logits
+    torch.testing.assert_close(lp.cpu(), want_lp, rtol=5e-6, atol=3e-5)
+    torch.testing.assert_close(ent.cpu(), want_ent, rtol=2e-5, atol=3e-5)
+    # 3-D hidden states and a strided (padded) weight
+    if N % 4 == 0:
+        wpad = torch.zeros(V, H + 8, dtype=torch.bfloat16, device=DEV)
+        wpad[:, :H] = W.to(DEV)
+        lp3, _ = S.fused_linear_logprobs(hidden.to(DEV).view(4, N // 4, H), wpad[:, :H], ids.to(DEV).view(4, N // 4),
+                                         temperature=temp, compute_entropy=False)
+        assert lp3.shape == (4, N // 4) and torch.equal(lp3.reshape(-1), lp)
