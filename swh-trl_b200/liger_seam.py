@@ -116,6 +116,18 @@ class B200FusedLinearGRPOLoss:
         cfg = ops.make_cfg(self.beta, self.epsilon_low, self.epsilon_high, self.delta, self.loss_type,
                            self.importance_sampling_level, self.max_completion_length or T)
         ref = ref_per_token_logps if self.beta != 0.0 else None
+        needs_grad = torch.is_grad_enabled() and (_input.requires_grad or lin_weight.requires_grad or
+                                                  (bias is not None and bias.requires_grad))
+        if (not needs_grad and bias is None and _input.dtype == torch.bfloat16 and lin_weight.dtype == torch.bfloat16
+                and _input.shape[-1] % 8 == 0):
+            # evaluation / no-grad call: K5 keeps the GEMM tiles in tensor memory, no logits chunk at all
+            logp, ent, _ = ops.fused_linear_logprob_fwd(_input, lin_weight, selected_token_ids,
+                                                        1.0 / float(self.temperature))
+            mask_i32, row_count, total = ops.mask_stats(attention_mask)
+            loss, m, _ = ops.grpo_loss(logp, old_per_token_logps, ref, advantages, mask_i32, row_count, total, cfg,
+                                       entropy=ent, want_g=False)
+            self.last_per_token_logps, self.last_entropies, self.last_metrics = logp, ent, m
+            return loss.reshape(()), ([m[1]] if self.beta != 0.0 else []) + [m[5]]
         loss, m, logp, ent = _FusedLinearGRPO.apply(_input, lin_weight, bias, selected_token_ids, attention_mask,
                                                     advantages, old_per_token_logps, ref, cfg,
                                                     1.0 / float(self.temperature), self.chunk_size)

@@ -805,3 +805,31 @@ def test_fused_linear_logprobs(S, N, H, V, temp):
         lp3, _ = S.fused_linear_logprobs(hidden.to(DEV).view(4, N // 4, H), wpad[:, :H], ids.to(DEV).view(4, N // 4),
                                          temperature=temp, compute_entropy=False)
         assert lp3.shape == (4, N // 4) and torch.equal(lp3.reshape(-1), lp)
+
+
+def test_seam_no_grad_uses_fused_forward(S):
+    """Under no_grad the Liger-shaped operator takes the K5 route (no logits at all) and agrees with its own
+    grads-in-forward route."""
+    B, T, H, V = 2, 64, 128, 32768
+    g = torch.Generator().manual_seed(4)
+    hidden = torch.randn(B, T, H, generator=g).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(V, H, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    ids = torch.randint(0, V, (B, T), generator=g).to(DEV)
+    mask = torch.ones(B, T, dtype=torch.int32, device=DEV)
+    mask[1, 40:] = 0
+    adv = torch.tensor([0.5, -1.5], device=DEV)
+    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T)
+    with torch.no_grad():
+        lp_ref, _ = S.fused_linear_logprobs(hidden, W, ids)
+    old, ref = lp_ref + 0.1, lp_ref - 0.05
+    with torch.no_grad():
+        loss0, m0 = fn(hidden, W, ids, mask, adv, None, old, ref)
+    h = hidden.clone().requires_grad_(True)
+    loss1, m1 = fn(h, W, ids, mask, adv, None, old, ref)
+    assert loss0.item() == pytest.approx(loss1.item(), rel=2e-2, abs=1e-4)  # route 1 rounds the logits to bf16
+    assert m0[-1].item() == pytest.approx(m1[-1].item(), abs=2e-2)
+    # against the oracle on the exact product
+    logits = hidden.float().cpu() @ W.float().cpu().t()
+    cfg = O.GRPOConfigLite(beta=0.04, loss_type="bnpo", max_completion_length=T)
+    want, _, _, _ = O.grpo_compute_loss(logits, ids.cpu(), mask.cpu(), adv.cpu(), cfg, old.cpu(), ref.cpu())
+    assert loss0.item() == pytest.approx(want.item(), rel=1e-4, abs=1e-7)
