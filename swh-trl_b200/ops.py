@@ -224,7 +224,8 @@ _ws_cache = {}
 
 
 def _workspace(device, nbytes: int, key: str, zero: bool) -> torch.Tensor:
-    k = (device, key)
+    # one workspace per (device, stream, kernel family): kernels of different streams never share scratch memory
+    k = (device, torch.cuda.current_stream(device).cuda_stream, key)
     ws = _ws_cache.get(k)
     if ws is None or ws.numel() < nbytes:
         ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
