@@ -108,6 +108,12 @@ int b200trl_set_k1_path(int path); /* returns the previous setting */
  * gradients are unchanged; only the per-token outputs at masked positions differ from the reference (which
  * computes and then discards them).  Returns the previous setting. */
 int b200trl_set_skip_masked(int on);
+/* Diagnostics, trace builds only (`make -C swh-trl_b200/csrc trace` -> lib/libb200trl_trace.so; the production
+ * library returns B200TRL_E_UNSUPPORTED): while `buffer` (device memory, 4 * 3 * 169 uint64, zeroed by the caller) is
+ * set, the resident K1 kernel logs phase timestamps (tag << 56 | row << 40 | chunk << 32 | clock32) of three roles
+ * (consumer warp 0, reducer, DMA) of its first four CTAs for 8 rows per CTA starting at its `first_row`-th row; each
+ * role's block starts with its event count.  NULL switches tracing off.  See tools/k1_trace.py. */
+int b200trl_k1_set_trace(void* buffer, int64_t first_row);
 
 /* ---- K1: selective_log_softmax + entropy_from_logits, one pass ------------------------------
  * Replaces trl/trainer/utils.py:1430-1462 and :1465-1490 (and the division by the temperature,

@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200trl.so")
+# B200TRL_LIB selects another build of the same library (e.g. the trace build, `make -C swh-trl_b200/csrc trace`)
+LIB_PATH = os.environ.get("B200TRL_LIB") or os.path.join(_HERE, "lib", "libb200trl.so")
 
 
 class B200TRLError(RuntimeError):
@@ -51,6 +52,7 @@ PROTOTYPES = {
     "b200trl_last_error": (C.c_char_p, []),
     "b200trl_set_k1_path": (C.c_int, [_i32]),
     "b200trl_set_skip_masked": (C.c_int, [_i32]),
+    "b200trl_k1_set_trace": (C.c_int, [_p, _i64]),
     "b200trl_logprob_entropy_fwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p]),
     "b200trl_logprob_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _i64, _i64, _p]),
     "b200trl_mask_stats": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),

@@ -9,8 +9,12 @@ namespace {
 
 std::atomic<int> g_k1_path{B200TRL_K1_AUTO};
 std::atomic<int> g_skip_masked{0};
+std::atomic<unsigned long long*> g_trace{nullptr};
+std::atomic<int> g_trace_row0{0};
 
-int dispatch(const K1Args& a, int dtype, cudaStream_t stream) {
+int dispatch(K1Args a, int dtype, cudaStream_t stream) {
+    a.trace = g_trace.load();
+    a.trace_row0 = g_trace_row0.load();
     const int path = g_k1_path.load();
     const bool resident_ok = k1_resident_supported(a, dtype);
     if (path == B200TRL_K1_RESIDENT) {
@@ -88,6 +92,20 @@ extern "C" int b200trl_set_k1_path(int path) {
 }
 
 extern "C" int b200trl_set_skip_masked(int on) { return g_skip_masked.exchange(on ? 1 : 0); }
+
+extern "C" int b200trl_k1_set_trace(void* buffer, int64_t first_row) {
+#ifdef B200TRL_K1_TRACE
+    B200TRL_REQUIRE(first_row >= 0, B200TRL_E_INVALID, "k1_set_trace: bad arguments");
+    g_trace_row0.store(static_cast<int>(first_row));
+    g_trace.store(static_cast<unsigned long long*>(buffer));
+    return B200TRL_OK;
+#else
+    (void)buffer;
+    (void)first_row;
+    set_error("k1_set_trace: this build has no trace hooks (make -C swh-trl_b200/csrc trace)");
+    return B200TRL_E_UNSUPPORTED;
+#endif
+}
 
 extern "C" int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab,
                                            int64_t row_stride, int64_t rows_per_batch, int64_t batch_stride,

@@ -47,6 +47,9 @@ struct K1Args {
     // fused modes only: rows whose loss weight is zero (completion_mask == 0 / PPO padding) are not read from HBM;
     // their dlogits are zeros and their logp / entropy / lse outputs are 0.  Opt-in (b200trl_set_skip_masked).
     int skip_masked;
+    // diagnostics (b200trl_k1_set_trace, trace builds only): phase timestamps of the first 4 CTAs of the resident kernel
+    unsigned long long* trace;
+    int trace_row0;  // first traced row (per-CTA row counter)
 };
 
 // element offset of a row in the logits / dlogits tensors
@@ -89,12 +92,12 @@ struct RowScalars {
     float pad;     // G_PPO: 1 if the position is padding
 };
 
-template <typename T>
-__device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t row, float ppo_count) {
+// Split in two so that a caller can software-pipeline the dependent pair (ids[row] -> logits[row, id]):
+// everything addressed by the row alone ...
+__device__ __forceinline__ RowScalars load_row_scalars_direct(const K1Args& a, int64_t row, float ppo_count) {
     RowScalars s;
     s.id = a.ids[row];
-    const T* base = reinterpret_cast<const T*>(a.logits) + logits_offset(a, row);
-    s.x_sel = (s.id >= 0 && s.id < a.vocab) ? ElemTraits<T>::load(base + s.id) : __int_as_float(0x7fc00000);
+    s.x_sel = 0.f;
     s.aux0 = s.aux1 = s.adv = s.weight = s.pad = 0.f;
     if (a.gmode == G_GIVEN) {
         s.aux0 = a.g[row];
@@ -113,6 +116,19 @@ __device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t 
         s.aux0 = a.old_lp[row];
         s.weight = (1.f - s.pad) / ppo_count * a.grad_scale;
     }
+    return s;
+}
+// ... and the selected logit, addressed through the id (NaN for an out-of-range id, as a gather would fault)
+template <typename T>
+__device__ __forceinline__ float load_selected_logit(const K1Args& a, int64_t row, int64_t id) {
+    const T* base = reinterpret_cast<const T*>(a.logits) + logits_offset(a, row);
+    return (id >= 0 && id < a.vocab) ? ElemTraits<T>::load(base + id) : __int_as_float(0x7fc00000);
+}
+
+template <typename T>
+__device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t row, float ppo_count) {
+    RowScalars s = load_row_scalars_direct(a, row, ppo_count);
+    s.x_sel = load_selected_logit<T>(a, row, s.id);
     return s;
 }
 

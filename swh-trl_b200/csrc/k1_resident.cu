@@ -47,6 +47,48 @@ struct __align__(16) RowResult {
     int pad0, pad1;
 };
 
+// ------------------------------------------------------------------ diagnostics
+// Phase timestamps (b200trl_k1_set_trace), compiled in only with -DB200TRL_K1_TRACE (`make trace` ->
+// lib/libb200trl_trace.so; the hooks cost the production kernel ~20 % even when switched off, so it has none).
+// Event = tag << 56 | row << 40 | chunk << 32 | low 32 bits of clock64, kept in a small shared-memory log per role
+// (0 consumer warp 0, 1 reducer, 2 DMA) and copied out when the CTA finishes; first four CTAs, kTraceRows rows
+// starting at trace_row0.
+constexpr int kTraceCtas = 4, kTraceRoles = 3, kTraceRows = 8, kTraceEvents = 168;
+#ifdef B200TRL_K1_TRACE
+struct TraceLog {
+    unsigned long long ev[kTraceRoles][kTraceEvents];
+    int n[kTraceRoles];
+};
+struct Tracer {
+    TraceLog* log;
+    int role, n, row0;
+    __device__ __forceinline__ void init(const K1Args& a, TraceLog* l, int r, bool active) {
+        log = (a.trace && active && blockIdx.x < kTraceCtas) ? l : nullptr;
+        role = r;
+        n = 0;
+        row0 = a.trace_row0;
+    }
+    __device__ __forceinline__ void ev(int tag, int row, int chunk) {
+        if (log && n < kTraceEvents && row >= row0 && row < row0 + kTraceRows) {
+            const unsigned long long t = static_cast<unsigned long long>(clock64()) & 0xffffffffull;
+            log->ev[role][n++] = (static_cast<unsigned long long>(tag) << 56) |
+                                 (static_cast<unsigned long long>(row & 0xffff) << 40) |
+                                 (static_cast<unsigned long long>(chunk & 0xff) << 32) | t;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (log) log->n[role] = n;
+    }
+};
+#else
+struct TraceLog {};
+struct Tracer {
+    __device__ __forceinline__ void init(const K1Args&, TraceLog*, int, bool) {}
+    __device__ __forceinline__ void ev(int, int, int) {}
+    __device__ __forceinline__ void finish() {}
+};
+#endif
+
 struct Smem {
     // slots first (16 KB each, 128-byte aligned)
     uint64_t full_bar[kMaxSlots];  // DMA -> consumers: chunk landed (tx-count)
@@ -58,6 +100,7 @@ struct Smem {
     Part4 warp_part[2][kMaxConsumers / 32];
     RowResult result[2];
     float ppo_count;
+    TraceLog trace;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -81,19 +124,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAITC_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAITC_DONE;\n\t"
-        "bra WAITC_LOOP;\n\t"
-        "WAITC_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
@@ -128,11 +158,13 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t ra
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// One-way DSMEM message: 16 bytes land in a peer's shared memory and complete 16 bytes of its mbarrier's transaction
+// count -- no release/acquire round trip on the sender's side.
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     cluster_addr),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar)
+                 : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
@@ -260,30 +292,6 @@ __device__ __forceinline__ void acc_vec2(Acc& a, const uint4& v0, const uint4& v
     acc_words(a.t2, a.v2, v1, c2, nm2);
 }
 
-// 2^d for a packed pair on the FMA pipe (no MUFU): Cody-Waite split d = j + f, f in [-0.5, 0.5], degree-3 minimax
-// polynomial (max relative error 7.5e-5 = 2^-13.7, far below the bf16 rounding of the dlogits it feeds), exponent
-// inserted with an integer add.  Used for a fraction of the backward exponentials to unload the 16-lane SFU,
-// which is what bounds the compute phases of the fused kernel.
-__device__ __forceinline__ uint64_t exp2_poly2(uint64_t d2) {
-    float d0, d1;
-    unpack2(d2, d0, d1);
-    d2 = pack2(fmaxf(d0, -125.f), fmaxf(d1, -125.f));  // below that the result is < 2^-125: flush region
-    const uint64_t magic = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23: the add rounds d to an integer
-    const uint64_t t2 = fadd2(d2, magic);
-    const uint64_t j2 = fadd2(t2, pack2(-12582912.f, -12582912.f));
-    const uint64_t f2 = ffma2(j2, pack2(-1.f, -1.f), d2);
-    uint64_t p2 = ffma2(f2, pack2(0.055171408f, 0.055171408f), pack2(0.24261075f, 0.24261075f));
-    p2 = ffma2(p2, f2, pack2(0.69326097f, 0.69326097f));
-    p2 = ffma2(p2, f2, pack2(0.99992812f, 0.99992812f));
-    float p0, p1, t0, t1;
-    unpack2(p2, p0, p1);
-    unpack2(t2, t0, t1);
-    const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-    const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-    return pack2(r0, r1);
-}
-
-template <int POLY_WORDS>
 __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t nl2, uint64_t ng2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
@@ -291,19 +299,18 @@ __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t 
     for (int i = 0; i < 4; ++i) {
         const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
         const uint64_t d2 = ffma2(x2, c2, nl2);
-        uint64_t e2;
-        if (i < POLY_WORDS) {
-            e2 = exp2_poly2(d2);
-        } else {
-            float d0, d1;
-            unpack2(d2, d0, d1);
-            e2 = pack2(ex2(d0), ex2(d1));
-        }
+        float d0, d1;
+        unpack2(d2, d0, d1);
+        const uint64_t e2 = pack2(ex2(d0), ex2(d1));
         float o0, o1;
         unpack2(fmul2(e2, ng2), o0, o1);
         o[i] = cvt_bf16x2(o0, o1);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// streaming 16-byte store: dlogits are not read again by this kernel
+__device__ __forceinline__ void st_global_cs(uint4* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ Partial acc_to_partial(const Acc& a) {
@@ -334,7 +341,7 @@ struct Cursor {
     }
 };
 
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, int POLY, bool SKIP>
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP>
 __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
     k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag, const int l2_prefetch) {
     constexpr int kConsumers = NC;
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         for (int p = 0; p < 2; ++p) {
             mbar_init(&sm.part_bar[p], kWarps);
             mbar_init(&sm.res_bar[p], 1);
-            mbar_init(&sm.xchg_bar[p], csize);
+            mbar_init(&sm.xchg_bar[p], 1);  // one local arrive.expect_tx per row; peers complete the bytes
         }
         fence_barrier_init();
     }
@@ -396,6 +403,8 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         if (lane == 0 && n_my_rows > 0 && C > 0) {
             const uint64_t policy = policy_evict_first();
             const int64_t J = static_cast<int64_t>(n_my_rows) * C;
+            Tracer tr;
+            tr.init(a, &sm.trace, 2, true);
             // load cursor
             int64_t k_next = 0;
             int l_row = 0, l_c = 0, l_slot = 0;
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 if (SKIP && l_masked) {
                     mbar_arrive(&sm.full_bar[l_slot]);  // nothing to fetch: the slot is "full" right away
                 } else {
+                    tr.ev(21, l_row, l_c);
                     mbar_expect_tx(&sm.full_bar[l_slot], bytes);
                     bulk_load(slots + static_cast<size_t>(l_slot) * kChunkBytes,
                               logits + logits_offset(a, row) + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
@@ -433,13 +443,15 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 if (++l_slot == num_slots) l_slot = 0;
             };
             while (k_next < J && k_next < num_slots) issue_load();
-            const int lag = HAS_BWD ? min(max_lag, spare) : 0;  // stores allowed to be still reading their slot
+            constexpr bool kBulkStore = HAS_BWD && !DIRECT;  // dlogits leave through TMA bulk stores (else: consumers' STG)
+            const int lag = kBulkStore ? min(max_lag, spare) : 0;  // stores allowed to be still reading their slot
             Cursor cur{0, 0u};
             int s_row = 0, s_c = 0;
             int64_t drained = 0;  // slots [0, drained) of the chunk stream are free again
             for (int64_t j = 0; j < J; ++j) {
                 mbar_wait(&sm.done_bar[cur.slot], cur.par);
-                if (HAS_BWD) {
+                tr.ev(20, static_cast<int>(j / C), static_cast<int>(j % C));
+                if (kBulkStore) {
                     const int64_t row = first_row + static_cast<int64_t>(s_row) * row_step;
                     const uint32_t bytes = static_cast<uint32_t>(s_c == C - 1 ? last_bytes : kChunkBytes);
                     bulk_store(dlogits + dlogits_offset(a, row) + e_begin + static_cast<int64_t>(s_c) * kChunkElems,
@@ -456,6 +468,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         bulk_wait_read<2>();
                         drained = j - 1;
                     }
+                    tr.ev(22, s_row, s_c);  // store issued and the allowed lag drained
                     if (++s_c == C) {
                         s_c = 0;
                         ++s_row;
@@ -466,21 +479,39 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 while (k_next < J && k_next - num_slots < drained) issue_load();
                 cur.advance(num_slots);
             }
-            if (HAS_BWD) bulk_wait_all();
+            if (kBulkStore) bulk_wait_all();
+            tr.finish();
         }
     } else if (warp == kWarps + 1) {
         // =========================== reducer warp: row statistics, cluster exchange, token gradient ===========
         if (HAS_FWD) {
             const float c = a.c;
             uint32_t xphase[2] = {0u, 0u};  // phase parity of the two exchange barriers (one flip per use)
+            // Row scalars are fetched two rows ahead (lane 0): the id-addressed logit of row i+1 and the directly
+            // addressed scalars of row i+2 are issued before row i is processed, so neither of the two dependent
+            // global-load latencies sits on a row's hand-off.
+            const float ppo_count = (a.gmode == G_PPO) ? sm.ppo_count : 1.f;
+            Tracer tr;
+            tr.init(a, &sm.trace, 1, lane == 0);
+            RowScalars rs{}, rs_next{};
+            if (lane == 0 && n_my_rows > 0) {
+                rs = load_row_scalars<__nv_bfloat16>(a, first_row, ppo_count);
+                if (n_my_rows > 1) rs_next = load_row_scalars_direct(a, first_row + row_step, ppo_count);
+            }
             for (int i = 0; i < n_my_rows; ++i) {
                 const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
                 const int par = i & 1;
                 const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
-                RowScalars rs;
                 const bool skip_row = SKIP && row_is_masked(a, row);
-                if (lane == 0 && !skip_row) rs = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+                float x_next = 0.f;
+                RowScalars rs_after{};
+                if (lane == 0) {
+                    if (i + 1 < n_my_rows) x_next = load_selected_logit<__nv_bfloat16>(a, row + row_step, rs_next.id);
+                    if (i + 2 < n_my_rows) rs_after = load_row_scalars_direct(a, row + 2 * row_step, ppo_count);
+                }
+                tr.ev(10, i, 0);
                 mbar_wait(&sm.part_bar[par], rpar);
+                tr.ev(11, i, 0);
                 if (skip_row) {  // nothing was read: outputs are zero, the row's dlogits are zero
                     if (lane == 0) {
                         if (crank == 0) {
@@ -498,6 +529,9 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         mbar_arrive(&sm.res_bar[par]);
                     }
                     __syncwarp();
+                    rs = rs_next;
+                    rs.x_sel = x_next;
+                    rs_next = rs_after;
                     continue;
                 }
                 Partial q = partial_empty();
@@ -505,16 +539,20 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                     const Part4 w = sm.warp_part[par][lane];
                     q = Partial{w.m, w.s, w.u};
                 }
-                q = partial_warp_reduce_fast(q);
+                q = partial_warp_reduce_fast(q);  // every lane holds the CTA's partial
+                if (csize > 1) {
+                    // lane r posts this CTA's partial to CTA r (itself included); the bytes complete the receiver's
+                    // barrier, so the only latency on the row's hand-off is one DSMEM write
+                    if (lane == 0) mbar_expect_tx(&sm.xchg_bar[par], 16u * csize);
+                    if (lane < csize)
+                        st_async_v4(map_to_rank(smem_u32(&sm.xchg[par][crank]), lane), q.m, q.s, q.u, 0.f,
+                                    map_to_rank(smem_u32(&sm.xchg_bar[par]), lane));
+                }
                 if (lane == 0) {
                     if (csize > 1) {
-                        const uint32_t slot_addr = smem_u32(&sm.xchg[par][crank]);
-                        const uint32_t bar_addr = smem_u32(&sm.xchg_bar[par]);
-                        for (uint32_t r = 0; r < csize; ++r) {
-                            st_cluster_v4(map_to_rank(slot_addr, r), q.m, q.s, q.u, 0.f);
-                            mbar_arrive_remote(map_to_rank(bar_addr, r));
-                        }
-                        mbar_wait_cluster(&sm.xchg_bar[par], xphase[par]);
+                        tr.ev(12, i, 0);
+                        mbar_wait(&sm.xchg_bar[par], xphase[par]);
+                        tr.ev(13, i, 0);
                         xphase[par] ^= 1u;
                         Partial tot = partial_empty();
                         for (uint32_t r = 0; r < csize; ++r) {  // rank order: identical result in every CTA
@@ -524,12 +562,6 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         q = tot;
                     }
                     const RowStats st = finish_row(q, rs.x_sel, c);
-                    if (crank == 0) {
-                        const bool pad = (a.gmode == G_PPO) && rs.pad != 0.f;
-                        if (a.logp) a.logp[row] = pad ? 1.0f : st.logp;
-                        if (a.entropy) a.entropy[row] = st.entropy;
-                        if (a.lse) a.lse[row] = st.lse;
-                    }
                     if (HAS_BWD) {
                         const float gp = token_grad(a, rs, st.logp) * a.inv_temp;
                         const int64_t e_id = rs.id - e_begin;
@@ -544,19 +576,35 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         rr.pad0 = rr.pad1 = 0;
                         sm.result[par] = rr;
                     }
-                    mbar_arrive(&sm.res_bar[par]);
+                    mbar_arrive(&sm.res_bar[par]);  // the consumers are waiting for this: publish first, store after
+                    tr.ev(14, i, 0);
+                    if (crank == 0) {
+                        const bool pad = (a.gmode == G_PPO) && rs.pad != 0.f;
+                        if (a.logp) a.logp[row] = pad ? 1.0f : st.logp;
+                        if (a.entropy) a.entropy[row] = st.entropy;
+                        if (a.lse) a.lse[row] = st.lse;
+                    }
                 }
                 __syncwarp();
+                rs = rs_next;
+                rs.x_sel = x_next;
+                rs_next = rs_after;
             }
+            tr.finish();
         }
     } else {
         // =========================== consumers ===========================
         const float c = a.c;
         const uint64_t c2 = pack2(c, c);
         Cursor fcur{0, 0u}, bcur{0, 0u};
+        Tracer tr;
+        tr.init(a, &sm.trace, 0, tid == 0);
+        int t_row = 0;  // row whose chunk the next fwd_chunk call folds (tracing only)
 
         auto fwd_chunk = [&](Acc& acc, int cidx, bool skip) {
+            tr.ev(1, t_row, cidx);
             mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
+            tr.ev(2, t_row, cidx);
             const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
             if (SKIP && skip) {
                 // masked row: nothing was loaded into this slot
@@ -581,6 +629,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.done_bar[fcur.slot]);
             }
+            tr.ev(3, t_row, cidx);
             fcur.advance(num_slots);
         };
 
@@ -599,14 +648,18 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             const bool nn_masked = masked_at(i + 2);  // prefetched: consumed two iterations later
 
             if (HAS_FWD) {
+                t_row = i;
                 for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx, cur_masked);
                 const Partial p = partial_warp_reduce_fast(acc_to_partial(acc));
+                tr.ev(4, i, 0);
                 if (!HAS_BWD && i >= 2) mbar_wait(&sm.res_bar[par], static_cast<uint32_t>(((i - 2) >> 1) & 1));
                 if (lane == 0) {
                     sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};
                     mbar_arrive(&sm.part_bar[par]);
                 }
+                tr.ev(5, i, 0);
                 acc = acc_empty();
+                t_row = i + 1;
                 if (i + 1 < n_my_rows) {
                     for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, nxt_masked);
                 }
@@ -617,7 +670,9 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             if (HAS_BWD) {
                 RowResult rr;
                 if (HAS_FWD) {
+                    tr.ev(6, i, 0);
                     mbar_wait(&sm.res_bar[par], rpar);
+                    tr.ev(7, i, 0);
                     rr = sm.result[par];
                 } else {
                     if (tid == 0) {
@@ -644,34 +699,72 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 const uint64_t ng2 = pack2(rr.ng, rr.ng);
                 const bool zero_row = (rr.ng == 0.f);
                 const bool patch_mine = (rr.id_vec >= 0) && ((rr.id_vec % kConsumers) == tid);
+                __nv_bfloat16* grow = nullptr;  // DIRECT: this CTA's slice of the dlogits row
+                if (DIRECT) grow = dlogits + dlogits_offset(a, row) + e_begin;
                 for (int cidx = 0; cidx < C; ++cidx) {
                     if (!HAS_FWD) mbar_wait(&sm.full_bar[bcur.slot], bcur.par);
                     uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(bcur.slot) * kChunkBytes);
                     const bool full = (cidx != C - 1 || last_bytes == kChunkBytes);
                     const int nvec = full ? kChunkVecs : (last_bytes >> 4);
-                    if (zero_row) {
-                        for (int v = tid; v < nvec; v += kConsumers) sv[v] = make_uint4(0u, 0u, 0u, 0u);
-                    } else {
-                        if (full) {
+                    if (DIRECT) {
+                        // gradients go straight from registers to global memory (coalesced 16-byte stores); the slot is
+                        // released as soon as every warp has READ it, so its refill overlaps this chunk's arithmetic
+                        uint4* gv = reinterpret_cast<uint4*>(grow + static_cast<int64_t>(cidx) * kChunkElems);
+                        if (zero_row) {
+                            if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
+                            for (int v = tid; v < nvec; v += kConsumers) st_global_cs(gv + v, make_uint4(0u, 0u, 0u, 0u));
+                        } else if (full) {
                             uint4 v[kVpt];
 #pragma unroll
                             for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
 #pragma unroll
-                            for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec<POLY>(v[k], c2, nl2, ng2);
+                            for (int k = 0; k < kVpt; ++k) st_global_cs(gv + tid + k * kConsumers, grad_vec(v[k], c2, nl2, ng2));
                         } else {
-                            for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec<POLY>(sv[v], c2, nl2, ng2);
+                            for (int v = tid; v < nvec; v += kConsumers) st_global_cs(gv + v, grad_vec(sv[v], c2, nl2, ng2));
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
                         }
-                        if (patch_mine && cidx == rr.id_chunk)
-                            reinterpret_cast<__nv_bfloat16*>(sv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                        if (!zero_row && patch_mine && cidx == rr.id_chunk)  // same thread wrote the vector holding it
+                            reinterpret_cast<__nv_bfloat16*>(gv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                    } else {
+                        if (zero_row) {
+                            for (int v = tid; v < nvec; v += kConsumers) sv[v] = make_uint4(0u, 0u, 0u, 0u);
+                        } else {
+                            if (full) {
+                                uint4 v[kVpt];
+#pragma unroll
+                                for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+#pragma unroll
+                                for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec(v[k], c2, nl2, ng2);
+                            } else {
+                                for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec(sv[v], c2, nl2, ng2);
+                            }
+                            if (patch_mine && cidx == rr.id_chunk)
+                                reinterpret_cast<__nv_bfloat16*>(sv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                        }
+                        fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
                     }
-                    fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
+                    tr.ev(8, i, cidx);
                     bcur.advance(num_slots);
                 }
             }
         }
+        tr.finish();
     }
+#ifdef B200TRL_K1_TRACE
+    __syncthreads();
+    if (a.trace && blockIdx.x < kTraceCtas) {
+        unsigned long long* out = a.trace + static_cast<size_t>(blockIdx.x) * kTraceRoles * (kTraceEvents + 1);
+        for (int r = 0; r < kTraceRoles; ++r) {
+            if (tid == 0) out[r * (kTraceEvents + 1)] = static_cast<unsigned long long>(sm.trace.n[r]);
+            for (int k = tid; k < kTraceEvents; k += blockDim.x) out[r * (kTraceEvents + 1) + 1 + k] = sm.trace.ev[r][k];
+        }
+    }
+#endif
     // no CTA may leave while a peer can still address its shared memory
     __syncwarp();
     if (csize > 1) cluster_sync_all();
@@ -693,9 +786,9 @@ int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC, int POLY, bool SKIP>
+template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP>
 int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, POLY, SKIP>;
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP>;
     constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
     static_assert(chunk_bytes_for(NC) % (NC * 16) == 0, "a full chunk must give every consumer the same vector count");
     constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
@@ -734,8 +827,17 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
             (void)cudaGetLastError();
         }
     }
+    static const int cap_clusters = env_int("B200TRL_K1_MAXCLUSTERS", 0);  // tuning knob: use fewer clusters
+    if (cap_clusters > 0 && cap_clusters < clusters) {
+        clusters = cap_clusters;
+        cfg.gridDim = dim3(static_cast<unsigned>(clusters * cs));
+    }
     static const int max_lag = std::min(2, std::max(0, env_int("B200TRL_K1_LAG", 1)));  // 1 measured best (0: -10 %, 2: -3 %)
     static const int l2_prefetch = env_int("B200TRL_K1_L2PREFETCH", 0);
+    static const int verbose = env_int("B200TRL_K1_VERBOSE", 0);
+    if (verbose)
+        fprintf(stderr, "k1_resident<fwd=%d,bwd=%d> consumers=%d cluster=%d slots=%d smem=%zu clusters=%lld\n", (int)F, (int)Bk,
+                NC, cs, num_slots, smem, (long long)clusters);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, num_slots, max_lag, Bk ? l2_prefetch : 0);
     if (e != cudaSuccess) {
         set_error("k1_resident launch failed: %s", cudaGetErrorString(e));
@@ -772,23 +874,23 @@ Geom pick_geom(int64_t vocab) {
     return wide;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC, int POLY>
+template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT>
 int launch_mode_p(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     constexpr bool kFused = F && Bk;
     if (kFused && a.skip_masked && (a.gmode == G_GRPO || a.gmode == G_PPO))
-        return launch_mode_s<F, Bk, DUAL, NC, POLY, kFused>(a, cs, num_slots, stream);
-    return launch_mode_s<F, Bk, DUAL, NC, POLY, false>(a, cs, num_slots, stream);
+        return launch_mode_s<F, Bk, DUAL, NC, DIRECT, kFused>(a, cs, num_slots, stream);
+    return launch_mode_s<F, Bk, DUAL, NC, DIRECT, false>(a, cs, num_slots, stream);
 }
 
-// POLY = words (of 4) per 16-byte vector whose backward exponentials run on the FMA pipe instead of the SFU
+// DIRECT: the consumers store dlogits themselves (registers -> global) instead of rewriting the slot for a TMA bulk
+// store; the slot is then free as soon as it has been read.  Env knob B200TRL_K1_DIRECT: -1 auto, 0 bulk stores, 1 direct.
 template <bool F, bool Bk, bool DUAL, int NC>
 int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    if (!Bk) return launch_mode_p<F, Bk, DUAL, NC, 0>(a, cs, num_slots, stream);
-    // measured (tools/k1_variants.py): 1 word in 4 on the polynomial is 3 % SLOWER, 2 in 4 is 6 % slower — the
-    // compute phases are issue/latency-bound, not SFU-bound — so the default is 0; kept as a knob for other parts
-    static const int poly = std::min(1, std::max(0, env_int("B200TRL_K1_POLY", 0)));
-    if (poly == 1 && NC == 512) return launch_mode_p<F, Bk, DUAL, NC, (Bk && NC == 512) ? 1 : 0>(a, cs, num_slots, stream);
-    return launch_mode_p<F, Bk, DUAL, NC, 0>(a, cs, num_slots, stream);
+    if (!Bk) return launch_mode_p<F, Bk, DUAL, NC, false>(a, cs, num_slots, stream);
+    static const int direct_env = env_int("B200TRL_K1_DIRECT", -1);
+    const bool direct = direct_env < 0 ? (F && Bk) : direct_env != 0;
+    return direct ? launch_mode_p<F, Bk, DUAL, NC, Bk>(a, cs, num_slots, stream)
+                  : launch_mode_p<F, Bk, DUAL, NC, false>(a, cs, num_slots, stream);
 }
 
 template <bool F, bool Bk>

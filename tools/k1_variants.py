@@ -32,5 +32,8 @@ def t(fn, n=20):
     return statistics.median(ts), min(ts)
 fused = t(lambda: ops.grpo_fused_fwd_bwd(logits, ids, m32, rc, tot, adv, old, ref, cfg, 1.0, dlogits_out=dl))
 fwd = t(lambda: ops.logprob_entropy_fwd(logits, ids, 1.0))
-print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("B200TRL") or k.startswith("KV_")}, "fused_ms": fused, "fwd_ms": fwd,
+gtok = torch.randn(B, T, generator=g, device=DEV) * 1e-4
+del dl
+bwd = t(lambda: ops.logprob_bwd(logits, ids, lse0, gtok, 1.0))  # includes torch.empty of the result
+print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("B200TRL") or k.startswith("KV_")}, "fused_ms": fused, "fwd_ms": fwd, "bwd_ms": bwd,
                   "fused_frac": 4 * V * B * T / fused[0] / 1e6 / 6546.6, "fwd_frac": 2 * V * B * T / fwd[0] / 1e6 / 6546.6}))
