@@ -27,7 +27,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -85,23 +84,48 @@ def synth_device(rank, B, T, V, dev, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
 
-    The sampler is started before the warm-up (nvidia-smi takes a while to come up on an 8-GPU box) and every
-    sample carries a timestamp; only samples inside [mark_start, mark_end] are summarised."""
+    A thread polls NVML every 2 ms (in process: nvidia-smi needs seconds to come up on an 8-GPU box and its -lms
+    period is coarser than a short timed region); samples carry a timestamp and only those between ``mark_start`` and
+    ``mark_end`` are summarised.  Falls back to one ``nvidia-smi`` query per mark if NVML is not importable."""
 
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+               ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap"),
+               ("hw_power_brake_slowdown", "HwPowerBrakeSlowdown"))
 
-    def __init__(self, gpu_index):
-        self.proc, self.t0, self.t1 = None, None, None
+    def __init__(self, cuda_index):
+        import threading
+        self.rows, self.t0, self.t1, self.err = [], None, None, None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES may renumber: resolve through the UUID
+                uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+                self.h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                self.h = N.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.N = N
+            self.max_sm = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        except Exception as e:  # noqa: BLE001 - any NVML failure just disables the sampler
+            self.err = f"nvml unavailable: {type(e).__name__}"
+
+    def _poll(self):
+        N = self.N
+        while not self._stop.is_set():
+            try:
+                sm = float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                pw = N.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                active = [name for name, sym in self.REASONS if bits & getattr(N, "nvmlClocksEventReason" + sym)]
+                self.rows.append((time.time(), sm, pw, active))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.002)
 
     def mark_start(self):
         self.t0 = time.time()
@@ -110,39 +134,22 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
-        import datetime
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        rows = []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]), float(f[3]),
-                             [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
-            except ValueError:
-                continue
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no sampler"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        rows = list(self.rows)
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
         where = "timed region"
-        if not inside:  # region shorter than the sampling period: take the sample closest to it
+        if not inside:  # region shorter than the polling period: take the sample closest to it
             mid = 0.5 * ((self.t0 or rows[-1][0]) + (self.t1 or rows[-1][0]))
             inside = [min(rows, key=lambda r: abs(r[0] - mid))]
             where = "nearest sample to the timed region"
-        reasons = sorted({n for r in inside for n in r[4]})
-        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
-                "reasons": reasons, "power_w_max": max(r[3] for r in inside), "samples": len(inside), "window": where}
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "power_w_max": max(r[2] for r in inside), "samples": len(inside), "window": where, "source": "nvml"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -358,7 +365,7 @@ def run_b200(args):
             "e2e": ({"value": tokens_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "steps": e2e_steps} if e2e_steps else None),
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k1_resident_kernel<fwd,bwd>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k1_resident_kernel<fwd,bwd> (fused log-prob + entropy + dlogits)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_ms,
                          "frac_of_nominal_8TBps": achieved / 8000.0,
@@ -381,7 +388,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -846,7 +846,7 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     return check_launch("k1_resident_kernel");
 }
 
-// Two CTA geometries:
+// Three CTA geometries:
 //   wide  : 512 consumers, 13 x 16 KB slots (208 KB), 1 CTA / SM  — a row slice of up to 12 chunks per CTA
 //   dense : 768 consumers,  9 x 24 KB slots (216 KB), 1 CTA / SM  — more warps to hide the fold's latencies
 //   twin  : 256 consumers,  6 x 16 KB slots ( 96 KB), 2 CTAs / SM — slices of up to 5 chunks; the two CTAs of an SM
@@ -857,7 +857,7 @@ struct Geom {
 constexpr int kTwinSlots = 6;
 constexpr int kDenseSlots = 9;  // 9 x 24 KB = 216 KB
 
-Geom pick_geom(int64_t vocab) {
+Geom pick_geom(int64_t vocab, bool fused) {
     static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense
     const Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
     const Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
@@ -865,12 +865,16 @@ Geom pick_geom(int64_t vocab) {
     if (mode == 3 && dense.cs && dense.cs <= wide.cs) return dense;
     if (mode == 2 && twin.cs) return twin;
     if (mode == 1 || !twin.cs) return wide;
-    // measured (tools/k1_variants.py, B200): rows that fit one twin CTA (<= 80 KB, e.g. V = 32000) gain 2 % fused /
-    // 20 % forward-only from two drifting CTAs per SM; anything that would need a cluster in twin form is faster wide
+    // measured (tools/k1_sweep.sh, B200): rows that fit one twin CTA (<= 80 KB, e.g. V = 32000) are fastest with two
+    // drifting CTAs per SM (fused 91.7 %, forward-only 87.6 % of the measured HBM peak); anything that would need a
+    // cluster in twin form is faster with 1 CTA / SM
     if (twin.cs == 1) return twin;
-    // 24 consumer warps hide the fold's latencies better than 16 (forward-only +9 %, fused +2..11 % over V = 65 k .. 152 k)
-    // whenever the coarser 24 KB chunks do not force a larger cluster
-    if (dense.cs && dense.cs <= wide.cs) return dense;
+    const bool dense_ok = dense.cs && dense.cs <= wide.cs;
+    // fused pass: finer 16 KB chunks and a deeper ring beat 24 warps (V = 65 k .. 152 k: +1.5 .. 2.5 %); below ~56 k
+    // the two are equal and dense keeps the shorter tail chunk
+    if (fused && vocab >= 57344) return wide;
+    // forward-only / backward-only: 24 consumer warps hide the fold's latencies better than 16 (forward-only +10 %)
+    if (dense_ok) return dense;
     return wide;
 }
 
@@ -895,10 +899,10 @@ int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
 
 template <bool F, bool Bk>
 int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
-    // measured on B200 (tools/k1_variants.py): two accumulation chains help the forward-only kernel (+5 %) and
-    // cost the fused kernel 2 % (it is bound by the row hand-off, not by the fold), so the default follows the mode
+    // measured on B200 (tools/k1_sweep.sh): two accumulation chains with one reference-point check per vector pair
+    // help every mode (forward-only +3 %, fused +2..4 %) now that the row hand-off no longer bounds the fused pass
     static const int dual_env = env_int("B200TRL_K1_DUAL", -1);
-    const bool dual = dual_env < 0 ? !Bk : dual_env != 0;
+    const bool dual = dual_env != 0;
     if (g.nc == 256)
         return dual ? launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream)
                     : launch_mode_t<F, Bk, false, 256>(a, g.cs, g.slots, stream);
@@ -931,10 +935,10 @@ bool k1_resident_preferred(const K1Args& a, int dtype) {
 
 int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
     if (a.n_rows == 0) return B200TRL_OK;
-    const Geom g = pick_geom(a.vocab);
+    const bool fwd = (a.lse_in == nullptr), bwd = (a.dlogits != nullptr);
+    const Geom g = pick_geom(a.vocab, fwd && bwd);
     B200TRL_REQUIRE(g.cs != 0, B200TRL_E_UNSUPPORTED, "k1_resident: vocab %lld too large for an 8-CTA cluster",
                     (long long)a.vocab);
-    const bool fwd = (a.lse_in == nullptr), bwd = (a.dlogits != nullptr);
     if (fwd && bwd) return launch_mode<true, true>(a, g, stream);
     if (fwd) return launch_mode<true, false>(a, g, stream);
     B200TRL_REQUIRE(bwd, B200TRL_E_INVALID, "k1_resident: nothing to do");

@@ -1,13 +1,12 @@
 #!/bin/bash
 run() { env "$@" python tools/k1_variants.py; }
-run KV_TAG=default
-run KV_TAG=bulk_stores B200TRL_K1_DIRECT=0
-run KV_TAG=direct_all B200TRL_K1_DIRECT=1
-run KV_TAG=direct_wide B200TRL_K1_GEOM=1
-run KV_TAG=direct_dual B200TRL_K1_DUAL=1
-run KV_TAG=v32000 KV_V=32000 KV_B=64
-run KV_TAG=v32000_bulk KV_V=32000 KV_B=64 B200TRL_K1_DIRECT=0
-run KV_TAG=v128256 KV_V=128256
-run KV_TAG=v128256_bulk KV_V=128256 B200TRL_K1_DIRECT=0
-run KV_TAG=v50304 KV_V=50304 KV_B=32
-run KV_TAG=v50304_bulk KV_V=50304 KV_B=32 B200TRL_K1_DIRECT=0
+for v in 151936 128256 65536 50304; do
+  b=16; [ $v -lt 70000 ] && b=32
+  run KV_TAG=v${v}_dense_dual0 KV_V=$v KV_B=$b B200TRL_K1_GEOM=3 B200TRL_K1_DUAL=0
+  run KV_TAG=v${v}_dense_dual1 KV_V=$v KV_B=$b B200TRL_K1_GEOM=3 B200TRL_K1_DUAL=1
+  run KV_TAG=v${v}_wide_dual0 KV_V=$v KV_B=$b B200TRL_K1_GEOM=1 B200TRL_K1_DUAL=0
+  run KV_TAG=v${v}_wide_dual1 KV_V=$v KV_B=$b B200TRL_K1_GEOM=1 B200TRL_K1_DUAL=1
+done
+run KV_TAG=v32000_twin_dual0 KV_V=32000 KV_B=64 B200TRL_K1_DUAL=0
+run KV_TAG=v32000_twin_dual1 KV_V=32000 KV_B=64 B200TRL_K1_DUAL=1
+run KV_TAG=v32000_dense_dual1 KV_V=32000 KV_B=64 B200TRL_K1_DUAL=1 B200TRL_K1_GEOM=3
