@@ -246,6 +246,22 @@ int64_t b200trl_masked_workspace_bytes(int64_t n);
 int b200trl_masked_whiten(const float* values, const uint8_t* mask, int64_t n, int shift_mean, void* workspace,
                           float* out, float* stats, b200trl_stream_t stream);
 
+/* ---- f-4: the integer masks either side of the loss (bit-exact index work, one launch each) ------------------
+ * first_true_indices (trl/trainer/utils.py:877-897): out[r] = first t with bools[r, t] != 0, else T.
+ * bools: uint8 [rows, T] (a torch.bool tensor's storage). */
+int b200trl_first_true_indices(const uint8_t* bools, int64_t rows, int64_t T, int64_t* out, b200trl_stream_t stream);
+/* "Mask everything after the first EOS token" (trl/trainer/grpo_trainer.py:1812-1817): eos_idx[b] (nullable) =
+ * first t with completion_ids[b, t] == eos_token_id, else T; completion_mask[b, t] = (t <= eos_idx[b]) as int32. */
+int b200trl_completion_mask(const int64_t* completion_ids, int64_t B, int64_t T, int64_t eos_token_id,
+                            int32_t* completion_mask, int64_t* eos_idx, b200trl_stream_t stream);
+/* truncate_response (utils.py:1036-1056) fused with the sequence length the PPO / RLOO loops derive from it
+ * (ppo_trainer.py:455-464, rloo_trainer.py:347-355): postprocessed (nullable) = responses with everything after
+ * the first stop token replaced by pad (has_stop_token = 0: unchanged, the `stop_token_id is None` branch);
+ * sequence_length[b] (nullable) = first_true_indices(postprocessed[b] == pad) - 1. */
+int b200trl_truncate_response(const int64_t* responses, int64_t B, int64_t T, int has_stop_token,
+                              int64_t stop_token_id, int64_t pad_token_id, int64_t* postprocessed,
+                              int64_t* sequence_length, b200trl_stream_t stream);
+
 /* buf *= (*actual / expected) unless they are equal; used when autograd's grad_output differs from
  * the grad_scale assumed in the fused forward.  No host sync. */
 int b200trl_rescale_if_needed(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,

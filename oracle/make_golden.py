@@ -245,6 +245,29 @@ def gold_misc():
     save("misc.pt", out)
 
 
+def gold_masks():
+    """EOS completion mask, first_true_indices, truncate_response + sequence lengths, from the reference's source."""
+    m = R.ref_masks()
+    g = torch.Generator().manual_seed(77)
+    cases = []
+    for B, T, vocab, eos, pad in [(6, 17, 5, 2, 0), (9, 64, 11, 3, 10), (4, 1, 3, 1, 0), (5, 33, 1000, 7, 999),
+                                  (3, 100, 4, 3, 3)]:
+        ids = torch.randint(0, vocab, (B, T), generator=g)
+        ids[0] = (eos + 1) % vocab if vocab > 1 else ids[0]   # a row without EOS
+        ids[-1, 0] = eos                                       # EOS at position 0
+        if T > 2:
+            ids[1, -1] = eos                                   # EOS at the last position (unless an earlier one exists)
+        mask, eos_idx = R.ref_completion_mask(ids, eos)
+        post = m["truncate_response"](eos, pad, ids)
+        seq_len = m["first_true_indices"](post == pad) - 1
+        seq_len_nostop = m["first_true_indices"](ids == pad) - 1   # stop_token_id is None (ppo_trainer.py:457)
+        bools = torch.rand(B, 3, T, generator=g) > 0.9
+        cases.append(dict(ids=ids, eos=eos, pad=pad, completion_mask=mask, eos_idx=eos_idx, truncated=post,
+                          sequence_length=seq_len, sequence_length_nostop=seq_len_nostop, bools=bools,
+                          first_true=m["first_true_indices"](bools)))
+    save("masks.pt", cases)
+
+
 def gold_rloo():
     cases = []
     for i, (B, T, k, nr, na, tl) in enumerate([(8, 16, 2, False, False, True), (12, 20, 4, True, True, True),
@@ -279,6 +302,10 @@ def gold_rloo():
 
 if __name__ == "__main__":
     assert R.available(), "needs /root/reference"
+    if len(sys.argv) > 1:  # regenerate selected files only: python oracle/make_golden.py masks rloo
+        for name in sys.argv[1:]:
+            globals()["gold_" + name]()
+        sys.exit(0)
     torch.set_num_threads(os.cpu_count() or 1)
     gold_logprob_entropy()
     gold_grpo_loss()
@@ -287,3 +314,4 @@ if __name__ == "__main__":
     gold_ppo()
     gold_misc()
     gold_rloo()
+    gold_masks()

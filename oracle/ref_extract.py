@@ -105,6 +105,21 @@ def ref_utils():
     return load_defs("trl/trainer/utils.py", ["selective_log_softmax", "entropy_from_logits", "first_true_indices"])
 
 
+def ref_masks():
+    """first_true_indices / truncate_response as defined in the reference (utils.py:877-897, 1036-1056)."""
+    return load_defs("trl/trainer/utils.py", ["first_true_indices", "truncate_response"])
+
+
+def ref_completion_mask(completion_ids, eos_token_id):
+    """The inline EOS block of _generate_and_score_completions (grpo_trainer.py:1812-1817), executed verbatim."""
+    ns = dict(_BASE_NS)
+    ns.update(completion_ids=completion_ids, device=completion_ids.device,
+              self=types.SimpleNamespace(eos_token_id=eos_token_id))
+    run_lines("trl/trainer/grpo_trainer.py", 1813, 1817, ns, anchor_first="is_eos = completion_ids ==",
+              anchor_last="completion_mask = (sequence_indices <=")
+    return ns["completion_mask"], ns["eos_idx"]
+
+
 def ref_core():
     return load_defs("trl/core.py", ["masked_mean", "masked_var", "masked_whiten"])
 

@@ -323,6 +323,19 @@ def first_true_indices(bools: torch.Tensor) -> torch.Tensor:
     return torch.where(bools, pos, torch.full_like(pos, n)).min(dim=-1).values
 
 
+def truncate_response(stop_token_id, pad_token_id, responses):
+    """utils.py:1036-1056 — everything after the first stop token becomes pad (the stop token stays)."""
+    trunc = first_true_indices(responses == stop_token_id).unsqueeze(-1)
+    idxs = torch.arange(responses.shape[1]).unsqueeze(0)
+    return torch.where(idxs > trunc, torch.full_like(responses, pad_token_id), responses)
+
+
+def response_lengths(stop_token_id, pad_token_id, responses):
+    """ppo_trainer.py:455-464 / rloo_trainer.py:347-355 — post-processed responses and their last-token index."""
+    post = responses if stop_token_id is None else truncate_response(stop_token_id, pad_token_id, responses)
+    return post, first_true_indices(post == pad_token_id) - 1
+
+
 # --------------------------------------------------------------------------
 # a-9 / a-10: PPO reward shaping + GAE (ppo_trainer.py:500-535)
 # --------------------------------------------------------------------------

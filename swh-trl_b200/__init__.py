@@ -20,6 +20,12 @@ from .functional import (  # noqa: F401
 )
 from .grpo import GRPOLoss, GRPOLossOutput, compute_loss, get_per_token_logps_and_entropies  # noqa: F401
 from .liger_seam import B200FusedLinearGRPOLoss  # noqa: F401
+from .masks import (  # noqa: F401
+    completion_mask_from_eos,
+    first_true_indices,
+    truncate_response,
+    truncate_response_with_lengths,
+)
 from .patch import patch_trl  # noqa: F401
 from .ppo import INVALID_LOGPROB, PPOLossOutput, ppo_loss, ppo_rewards_gae  # noqa: F401
 from .rloo import RLOOLossOutput, rloo_loss, rloo_rewards_advantages  # noqa: F401

@@ -77,6 +77,9 @@ PROTOTYPES = {
     "b200trl_fused_linear_logprob_fwd": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p, _p]),
     "b200trl_masked_workspace_bytes": (_i64, [_i64]),
     "b200trl_masked_whiten": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p]),
+    "b200trl_first_true_indices": (C.c_int, [_p, _i64, _i64, _p, _p]),
+    "b200trl_completion_mask": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
+    "b200trl_truncate_response": (C.c_int, [_p, _i64, _i64, _i32, _i64, _i64, _p, _p, _p]),
     "b200trl_rescale_if_needed": (C.c_int, [_p, _i32, _i64, _i64, _i64, _p, _f, _p]),
 }
 

@@ -64,8 +64,10 @@ __device__ __forceinline__ int64_t dlogits_offset(const K1Args& a, int64_t row) 
     return b * a.dl_batch_stride + (row - b * a.rows_per_batch) * a.dl_row_stride;
 }
 
-// true when the loss ignores this row (only meaningful in the fused GRPO / PPO modes)
+// true when the row's dlogits are known to be zero before reading it: the loss ignores it (fused GRPO / PPO
+// modes) or its upstream gradient is exactly zero (backward of a masked token, e.g. DPO prompt positions)
 __device__ __forceinline__ bool row_is_masked(const K1Args& a, int64_t row) {
+    if (a.gmode == G_GIVEN) return a.g[row] == 0.f;
     if (a.gmode == G_GRPO) return a.mask[row] == 0;
     if (a.gmode == G_PPO) return (row % a.T) > a.seq_len[row / a.T];
     return false;

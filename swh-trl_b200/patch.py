@@ -11,7 +11,7 @@ from __future__ import annotations
 import sys
 import types
 
-from . import functional, grpo
+from . import functional, grpo, masks
 
 _FUNCTIONS = {
     "selective_log_softmax": functional.selective_log_softmax,
@@ -20,6 +20,8 @@ _FUNCTIONS = {
     "masked_mean": functional.masked_mean,
     "masked_var": functional.masked_var,
     "masked_whiten": functional.masked_whiten,
+    "first_true_indices": masks.first_true_indices,   # ppo_trainer.py:60, rloo_trainer.py:55
+    "truncate_response": masks.truncate_response,     # ppo_trainer.py:70, rloo_trainer.py:61
 }
 
 

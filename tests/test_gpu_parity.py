@@ -833,3 +833,71 @@ def test_seam_no_grad_uses_fused_forward(S):
     cfg = O.GRPOConfigLite(beta=0.04, loss_type="bnpo", max_completion_length=T)
     want, _, _, _ = O.grpo_compute_loss(logits, ids.cpu(), mask.cpu(), adv.cpu(), cfg, old.cpu(), ref.cpu())
     assert loss0.item() == pytest.approx(want.item(), rel=1e-4, abs=1e-7)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_masks_golden(S, i):
+    """f-4: the EOS completion mask, first_true_indices, truncate_response and the PPO/RLOO sequence lengths are
+    bit-exact against vectors produced by the reference's own source."""
+    c = load_golden("masks.pt")[i]
+    ids, eos, pad = c["ids"].to(DEV), c["eos"], c["pad"]
+    mask, eos_idx = S.completion_mask_from_eos(ids, eos)
+    assert mask.dtype == torch.int32 and torch.equal(mask.cpu(), c["completion_mask"])
+    assert torch.equal(eos_idx.cpu(), c["eos_idx"])
+    assert torch.equal(S.first_true_indices(ids == eos).cpu(), c["eos_idx"])
+    ft = S.first_true_indices(c["bools"].to(DEV))
+    assert ft.shape == c["first_true"].shape and torch.equal(ft.cpu(), c["first_true"])
+    assert torch.equal(S.truncate_response(eos, pad, ids).cpu(), c["truncated"])
+    post, lens = S.truncate_response_with_lengths(eos, pad, ids)
+    assert torch.equal(post.cpu(), c["truncated"]) and torch.equal(lens.cpu(), c["sequence_length"])
+    post, lens = S.truncate_response_with_lengths(None, pad, ids)
+    assert torch.equal(post.cpu(), c["ids"]) and torch.equal(lens.cpu(), c["sequence_length_nostop"])
+
+
+def test_masks_large_and_edge(S):
+    """Config-5 sized ids (B=256, T=4096) against the oracle; empty batch; int32 ids; a non-contiguous view."""
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, 151936, (256, 4096), generator=g)
+    ids[::7, 1000] = 151643
+    ids[3, 0] = 151643
+    ids[5, -1] = 151643
+    want = O.completion_mask_from_eos(ids, 151643)
+    mask, eos_idx = S.completion_mask_from_eos(ids.to(DEV), 151643)
+    assert torch.equal(mask.cpu(), want) and torch.equal(eos_idx.cpu(), O.first_true_indices(ids == 151643))
+    assert torch.equal(mask.sum(1).cpu(), torch.clamp(eos_idx.cpu() + 1, max=4096))  # mask length = eos_idx + 1, capped at T
+    post, lens = S.truncate_response_with_lengths(151643, 0, ids.to(DEV))
+    wpost, wlens = O.response_lengths(151643, 0, ids)
+    assert torch.equal(post.cpu(), wpost) and torch.equal(lens.cpu(), wlens)
+    m0, e0 = S.completion_mask_from_eos(torch.zeros(0, 8, dtype=torch.long, device=DEV), 1)
+    assert m0.shape == (0, 8) and e0.shape == (0,)
+    view = ids.to(DEV).to(torch.int32)[:, ::2]  # strided int32 view: converted once, like the reference's `==` would read it
+    mv, ev = S.completion_mask_from_eos(view, 151643)
+    assert torch.equal(mv.cpu(), O.completion_mask_from_eos(ids[:, ::2], 151643))
+
+
+def test_backward_skips_zero_gradient_rows(S):
+    """Backward of selective_log_softmax with masked tokens (upstream gradient exactly 0, e.g. DPO prompt positions):
+    those rows are not read -- their dlogits are zeros even where the logits hold NaN -- and every other row is
+    unchanged against the fp32 oracle."""
+    g = torch.Generator().manual_seed(3)
+    B, T, V = 3, 40, 32768
+    logits = (torch.randn(B, T, V, generator=g) * 2).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    gmask = (torch.rand(B, T, generator=g) > 0.4).float()
+    gtok = torch.randn(B, T, generator=g) * gmask
+    x = logits.float().requires_grad_(True)
+    (O.selective_log_softmax(x, ids) * gtok).sum().backward()
+    want = x.grad.to(torch.bfloat16).float()
+    poisoned = logits.clone()
+    poisoned[gmask == 0] = float("nan")  # masked rows must never be looked at
+    for path in (S.K1_ROW, S.K1_RESIDENT):
+        S.set_k1_path(path)
+        try:
+            xd = (poisoned if path == S.K1_RESIDENT else logits).to(DEV).requires_grad_(True)
+            lp = S.selective_log_softmax(xd, ids.to(DEV))
+            lp.backward(gtok.to(DEV))
+        finally:
+            S.set_k1_path(S.K1_AUTO)
+        got = xd.grad.float().cpu()
+        assert torch.equal(got[gmask == 0], torch.zeros_like(got[gmask == 0]))
+        torch.testing.assert_close(got[gmask != 0], want[gmask != 0], rtol=BF16_ULP, atol=1e-9)

@@ -205,3 +205,18 @@ def test_rloo_loss_vs_reference(i):
     torch.testing.assert_close(stats["approxkl"], c["out"]["approxkl"], rtol=1e-5, atol=1e-8)
     torch.testing.assert_close(stats["entropy"], c["out"]["entropy"].mean(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(stats["ratio"], c["out"]["new_ratio"].mean(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_masks_vs_reference(i):
+    """EOS completion mask (grpo_trainer.py:1812-1817), first_true_indices / truncate_response (utils.py:877-897,
+    1036-1056) and the PPO/RLOO sequence length (ppo_trainer.py:464): bit-exact against the reference's own source."""
+    c = load_golden("masks.pt")[i]
+    ids, eos, pad = c["ids"], c["eos"], c["pad"]
+    assert torch.equal(O.completion_mask_from_eos(ids, eos), c["completion_mask"])
+    assert torch.equal(O.first_true_indices(ids == eos), c["eos_idx"])
+    assert torch.equal(O.truncate_response(eos, pad, ids), c["truncated"])
+    post, lens = O.response_lengths(eos, pad, ids)
+    assert torch.equal(post, c["truncated"]) and torch.equal(lens, c["sequence_length"])
+    assert torch.equal(O.response_lengths(None, pad, ids)[1], c["sequence_length_nostop"])
+    assert torch.equal(O.first_true_indices(c["bools"]), c["first_true"])
