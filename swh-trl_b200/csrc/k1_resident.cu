@@ -857,24 +857,43 @@ struct Geom {
 constexpr int kTwinSlots = 6;
 constexpr int kDenseSlots = 9;  // 9 x 24 KB = 216 KB
 
-Geom pick_geom(int64_t vocab, bool fused) {
+enum Mode { M_FWD, M_BWD, M_FUSED };
+Mode mode_of(const K1Args& a) {
+    const bool fwd = (a.lse_in == nullptr), bwd = (a.dlogits != nullptr);
+    return (fwd && bwd) ? M_FUSED : (fwd ? M_FWD : M_BWD);
+}
+
+Geom pick_geom(int64_t vocab, Mode m) {
     static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense
-    const Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
-    const Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
-    const Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768)), kDenseSlots, 768};
+    Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
+    Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
+    Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768)), kDenseSlots, 768};
+    if (m != M_FUSED) {
+        // forward-only / backward-only: nothing has to stay resident between two sweeps, so a row simply STREAMS
+        // through the ring of one CTA -- no cluster, no DSMEM exchange, any vocabulary.  Measured at config 2
+        // (tools/k1_sweep.sh): forward-only 0.85 ms (2-CTA cluster, dense) -> 0.76 ms = 99.8 % of the copy peak with
+        // two independent 256-consumer CTAs per SM; backward-only 1.69 -> 1.61 ms = 94.6 % with one dense CTA.
+        static const int fwd_cs = env_int("B200TRL_K1_FWD_CS", 1), bwd_cs = env_int("B200TRL_K1_BWD_CS", 1);
+        const int cs = std::max(1, m == M_FWD ? fwd_cs : bwd_cs);
+        wide.cs = std::min(wide.cs ? wide.cs : cs, cs);
+        twin.cs = std::min(twin.cs ? twin.cs : cs, cs);
+        dense.cs = std::min(dense.cs ? dense.cs : cs, cs);
+        if (mode == 1) return wide;
+        if (mode == 2) return twin;
+        if (mode == 3) return dense;
+        return m == M_FWD ? twin : dense;
+    }
     if (mode == 3 && dense.cs && dense.cs <= wide.cs) return dense;
     if (mode == 2 && twin.cs) return twin;
     if (mode == 1 || !twin.cs) return wide;
     // measured (tools/k1_sweep.sh, B200): rows that fit one twin CTA (<= 80 KB, e.g. V = 32000) are fastest with two
-    // drifting CTAs per SM (fused 91.7 %, forward-only 87.6 % of the measured HBM peak); anything that would need a
-    // cluster in twin form is faster with 1 CTA / SM
+    // drifting CTAs per SM (fused 91.7 % of the measured HBM peak); anything that would need a cluster in twin form is
+    // faster with 1 CTA / SM
     if (twin.cs == 1) return twin;
-    const bool dense_ok = dense.cs && dense.cs <= wide.cs;
-    // fused pass: finer 16 KB chunks and a deeper ring beat 24 warps (V = 65 k .. 152 k: +1.5 .. 2.5 %); below ~56 k
-    // the two are equal and dense keeps the shorter tail chunk
-    if (fused && vocab >= 57344) return wide;
-    // forward-only / backward-only: 24 consumer warps hide the fold's latencies better than 16 (forward-only +10 %)
-    if (dense_ok) return dense;
+    // finer 16 KB chunks and a deeper ring beat 24 warps (V = 65 k .. 152 k: +1.5 .. 2.5 %); below ~56 k the two are
+    // equal and dense keeps the shorter tail chunk
+    if (vocab >= 57344) return wide;
+    if (dense.cs && dense.cs <= wide.cs) return dense;
     return wide;
 }
 
@@ -929,25 +948,24 @@ bool k1_resident_supported(const K1Args& a, int dtype) {
                       a.dl_batch_stride % 8 != 0))
         return false;
     if (a.vocab * 2 < 2 * kChunkBytes) return false;  // tiny rows: per-row overheads dominate, use the row kernel
-    return pick_cluster(a.vocab, kMaxSlots) != 0;
+    if (a.vocab * 2 > (int64_t(1) << 30)) return false;  // slice bytes are kept in 32-bit counters
+    return pick_geom(a.vocab, mode_of(a)).cs != 0;
 }
 
-// AUTO policy: clusters of 4 and 8 CTAs are limited by GPC geometry to far fewer co-resident clusters than SMs
-// (measured: V = 262144 forward-only 0.62 ms resident vs 0.41 ms row kernel), so rows that need them go to the row
-// kernel unless the resident path is forced.
-bool k1_resident_preferred(const K1Args& a, int dtype) {
-    return k1_resident_supported(a, dtype) && pick_cluster(a.vocab, kMaxSlots) <= 2;
-}
+// AUTO policy: whenever this kernel can take the call it is the faster one.  Measured fused / forward-only against
+// the row kernel (tools/k1_sweep.sh): V = 200 000 (4-CTA cluster) 1.36 / 0.51 ms vs 1.69 / 0.79 ms; V = 262 144
+// 1.53 / 0.65 vs 2.28 / 0.99; V = 524 288 (8-CTA cluster) 1.66 / 0.65 vs 2.32 / 0.92.
+bool k1_resident_preferred(const K1Args& a, int dtype) { return k1_resident_supported(a, dtype); }
 
 int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
     if (a.n_rows == 0) return B200TRL_OK;
-    const bool fwd = (a.lse_in == nullptr), bwd = (a.dlogits != nullptr);
-    const Geom g = pick_geom(a.vocab, fwd && bwd);
+    const Mode m = mode_of(a);
+    const Geom g = pick_geom(a.vocab, m);
     B200TRL_REQUIRE(g.cs != 0, B200TRL_E_UNSUPPORTED, "k1_resident: vocab %lld too large for an 8-CTA cluster",
                     (long long)a.vocab);
-    if (fwd && bwd) return launch_mode<true, true>(a, g, stream);
-    if (fwd) return launch_mode<true, false>(a, g, stream);
-    B200TRL_REQUIRE(bwd, B200TRL_E_INVALID, "k1_resident: nothing to do");
+    if (m == M_FUSED) return launch_mode<true, true>(a, g, stream);
+    if (m == M_FWD) return launch_mode<true, false>(a, g, stream);
+    B200TRL_REQUIRE(a.dlogits != nullptr, B200TRL_E_INVALID, "k1_resident: nothing to do");
     return launch_mode<false, true>(a, g, stream);
 }
 

@@ -122,8 +122,10 @@ __device__ __forceinline__ Partial block_reduce_partial(Partial p, Partial* smem
     return r;
 }
 
+// 1024-thread CTAs must stay at <= 32 registers so that two of them share an SM (a 52-register build measured 26 %
+// slower forward-only at config 2: one CTA per SM cannot hide the HBM latency of its own row)
 template <typename T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k1_row_kernel(const K1Args a) {
+__global__ void __launch_bounds__(BLOCK, BLOCK == 1024 ? 2 : 1) k1_row_kernel(const K1Args a) {
     constexpr int VN = Vec<T>::N;
     __shared__ Partial s_part[32];
     __shared__ RowScalars s_row;

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kSelBlock) entropy_quantile_kernel(const float
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_rank;
+    __shared__ unsigned int s_wtot[8];
     const int tid = threadIdx.x;
     const int64_t start = static_cast<int64_t>(blockIdx.x) * kSelBlock + tid;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * kSelBlock;
@@ -124,16 +125,27 @@ __global__ void __launch_bounds__(kSelBlock) entropy_quantile_kernel(const float
         if (tid < 256 && hist[tid]) atomicAdd(&ws->hist[pass][tid], hist[tid]);
         __threadfence();
         grid.sync();
-        if (tid == 0) {  // every CTA walks the same global histogram to the same bin
-            const volatile unsigned int* gh = ws->hist[pass];
-            unsigned int rr = r, b = 0;
-            for (; b < 256; ++b) {
-                const unsigned int h = gh[b];
-                if (rr < h) break;
-                rr -= h;
+        // every CTA finds the same bin in the same global histogram: 256 threads fetch one bin each (a serial walk
+        // by one thread costs up to 256 dependent L2 round trips per pass), a two-level shuffle scan gives every
+        // bin its exclusive prefix, and the one bin with prefix <= r < prefix + count publishes the new state
+        if (tid < 256) {
+            const unsigned int h = reinterpret_cast<const volatile unsigned int*>(ws->hist[pass])[tid];
+            unsigned int inc = h;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int up = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((tid & 31) >= o) inc += up;
             }
-            s_rank = rr;
-            s_prefix = prefix | (b << shift);
+            if ((tid & 31) == 31) s_wtot[tid >> 5] = inc;
+            // (only warps 0..7 are in here, so a named barrier over these 256 threads orders the two levels)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            unsigned int base = 0;
+            for (int wv = 0; wv < (tid >> 5); ++wv) base += s_wtot[wv];
+            const unsigned int excl = base + inc - h;
+            if (h != 0u && r >= excl && r < excl + h) {
+                s_rank = r - excl;
+                s_prefix = prefix | (static_cast<uint32_t>(tid) << shift);
+            }
         }
         __syncthreads();
         r = s_rank;

@@ -257,14 +257,16 @@ def entropy_quantile_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold
     _need_cuda(entropies, "entropies")
     e = _f32(entropies, "entropies")
     m = mask.to(torch.int32).contiguous()
-    out = torch.empty(e.shape, dtype=torch.uint8, device=e.device)
+    out = torch.empty(e.shape, dtype=torch.bool, device=e.device)  # the kernel writes 0 / 1 bytes: a bool's storage
     thr = torch.empty(1, dtype=torch.float32, device=e.device)
     if e.numel():
         ws = _workspace(e.device, lib.b200trl_entropy_quantile_workspace_bytes(e.numel()), "quantile", zero=False)
         check(lib.b200trl_entropy_quantile_mask(_ptr(e), _ptr(m), e.numel(), float(threshold), _ptr(ws), _ptr(out),
                                                 _ptr(thr), _stream(e)), "entropy_quantile_mask")
         _count()
-    return out.bool(), thr
+    else:
+        out.zero_()
+    return out, thr
 
 
 # ------------------------------------------------------------------------------------------------ K3

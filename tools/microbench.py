@@ -168,7 +168,24 @@ def main():
         o = S.ppo_loss(xp, rsp, gae["logprobs"], gae["advantages"], gae["returns"], gae["values"], vpp, ln[:mb])
         o.loss.backward()
     ms, n = timeit(ppo_step)
-    add(f"PPO loss step mb={mb} T={Tp} V={Vp} (bf16)", ms, n, 4 * Vp * mb * Tp, "K1 fused(PPO) + K2p; entropy stat is free")
+    add(f"PPO loss step mb={mb} T={Tp} V={Vp} (bf16), eager", ms, n, 4 * Vp * mb * Tp,
+        "K1 fused(PPO) + K2p; entropy stat is free; host-launch-bound at this size (synchronised per step)")
+    # the same step captured once and replayed as a CUDA graph: what the device needs when the host is out of the way
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            ppo_step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    xp.grad = None
+    vpp.grad = None
+    with torch.cuda.graph(graph):
+        o = S.ppo_loss(xp, rsp, gae["logprobs"], gae["advantages"], gae["returns"], gae["values"], vpp, ln[:mb])
+        o.loss.backward()
+    ms, _ = timeit(graph.replay)
+    add(f"PPO loss step mb={mb} T={Tp} V={Vp} (bf16), CUDA graph replay", ms, n, 4 * Vp * mb * Tp,
+        "same kernels, no host work between them")
 
     print(json.dumps(out, indent=1))
 
