@@ -239,6 +239,26 @@ int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidden_row_stri
                                      const int64_t* ids, float inv_temperature, void* workspace, float* logp,
                                      float* entropy, float* lse, b200trl_stream_t stream);
 
+/* ---- a-13: the reference's operator seam as ONE call (grpo_trainer.py:870-886 ctor, :2005-2045 call) ----------
+ * What `self.liger_grpo_loss(_input, lin_weight, selected_token_ids, attention_mask, advantages, bias,
+ * old_per_token_logps, ref_per_token_logps)` computes, forward AND backward, without ever holding the [B,T,V]
+ * logits: per chunk of `chunk_seqs` whole sequences  logits_c = hidden_c W^T (+ bias)  (cuBLASLt GEMM, bf16 in,
+ * fp32 accumulate)  ->  K1 resident kernel in place (logits_c becomes dlogits_c; log-probs, entropies)  ->
+ * dH_c = dlogits_c W  and  dW += dlogits_c^T hidden_c  (cuBLASLt GEMMs, dW accumulated in fp32 inside the GEMM);
+ * then K2 gives the loss and metrics.  cuBLASLt (plain library GEMMs only) is bound with dlopen at first use.
+ * hidden bf16 [B,T,H]; weight bf16 [V,H]; bias bf16 [V] or NULL; H, V multiples of 8.
+ * Outputs: logp, entropy fp32 [B,T]; loss fp32 [1]; metrics fp32 [B200TRL_GRPO_NUM_METRICS] (metrics[B200TRL_M_KL]
+ * and [B200TRL_M_CLIP_REGION] are what grpo_trainer.py:2038-2039 logs); dhidden bf16 [B,T,H], dweight fp32 [V,H],
+ * dbias fp32 [V] — each nullable; all three NULL = forward only.  Gradients are of loss * cfg->grad_scale.
+ * workspace >= b200trl_fused_linear_grpo_workspace_bytes(B, T, V, chunk_seqs) bytes, any contents. */
+int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs);
+int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
+                              int64_t H, int64_t V, const int64_t* ids, const int32_t* mask, const float* advantages,
+                              const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
+                              float inv_temperature, int64_t chunk_seqs, void* workspace, float* logp, float* entropy,
+                              float* loss, float* metrics, void* dhidden, float* dweight, float* dbias,
+                              b200trl_stream_t stream);
+
 /* ---- a-12: masked_mean / masked_var / masked_whiten (trl/core.py:43-76) ------------------------
  * stats fp32 [3] = {mean, unbiased var, count}; out (whitened, fp32 [n]) may be NULL.
  * workspace >= b200trl_masked_workspace_bytes(n), any contents. */

@@ -1,0 +1,297 @@
+// a-13  b200trl_fused_linear_grpo : the reference's one real operator seam, `self.liger_grpo_loss(...)`
+//       (trl/trainer/grpo_trainer.py:870-886 ctor, :2005-2045 call), as ONE C-ABI call.
+//
+// loss(hidden @ W^T + b) forward AND backward without ever holding the [B,T,V] logits: per chunk of whole sequences
+//     logits_c = hidden_c W^T (+ b)          library GEMM (cuBLASLt, bf16 in / fp32 accumulate / bf16 out)
+//     K1 resident kernel, IN PLACE           logits_c -> dlogits_c, emitting log-probs and entropies (one pass)
+//     dH_c  = dlogits_c W                    library GEMM
+//     dW   += dlogits_c^T hidden_c           library GEMM, fp32 accumulator updated inside the GEMM (beta = 1)
+// and K2 turns the log-probs into the loss value and the logged metrics.  The three GEMMs are plain library GEMMs
+// (the one place the rules of this build allow cuBLAS); everything that is not a plain GEMM is this library's own
+// kernel.  cuBLASLt is bound at first use with dlopen, so libb200trl.so itself has no link-time dependency on it
+// (the CPU-side ABI tests load the library on a box without a GPU) and shares the copy the host process (torch)
+// has already loaded.
+#include <cublasLt.h>
+#include <dlfcn.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace b200trl {
+namespace {
+
+// ------------------------------------------------------------------ cuBLASLt, bound lazily
+struct LtApi {
+    void* so = nullptr;
+    decltype(&cublasLtCreate) Create = nullptr;
+    decltype(&cublasLtMatmul) Matmul = nullptr;
+    decltype(&cublasLtMatmulDescCreate) DescCreate = nullptr;
+    decltype(&cublasLtMatmulDescDestroy) DescDestroy = nullptr;
+    decltype(&cublasLtMatmulDescSetAttribute) DescSet = nullptr;
+    decltype(&cublasLtMatrixLayoutCreate) LayoutCreate = nullptr;
+    decltype(&cublasLtMatrixLayoutDestroy) LayoutDestroy = nullptr;
+    decltype(&cublasLtMatmulPreferenceCreate) PrefCreate = nullptr;
+    decltype(&cublasLtMatmulPreferenceDestroy) PrefDestroy = nullptr;
+    decltype(&cublasLtMatmulPreferenceSetAttribute) PrefSet = nullptr;
+    decltype(&cublasLtMatmulAlgoGetHeuristic) Heuristic = nullptr;
+    std::map<int, cublasLtHandle_t> handles;  // one per device
+    bool ok = false;
+};
+
+std::mutex g_lt_mutex;
+LtApi g_lt;
+
+template <typename F>
+bool bind(F& fn, void* so, const char* name) {
+    fn = reinterpret_cast<F>(dlsym(so, name));
+    return fn != nullptr;
+}
+
+LtApi* lt_api() {
+    std::lock_guard<std::mutex> lock(g_lt_mutex);
+    if (g_lt.ok) return &g_lt;
+    if (!g_lt.so) {
+        for (const char* name : {"libcublasLt.so.12", "libcublasLt.so", "/usr/local/cuda/lib64/libcublasLt.so.12"}) {
+            g_lt.so = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (g_lt.so) break;
+        }
+    }
+    if (!g_lt.so) {
+        set_error("fused_linear_grpo: cannot load libcublasLt.so.12 (%s)", dlerror());
+        return nullptr;
+    }
+    LtApi& a = g_lt;
+    a.ok = bind(a.Create, a.so, "cublasLtCreate") && bind(a.Matmul, a.so, "cublasLtMatmul") &&
+           bind(a.DescCreate, a.so, "cublasLtMatmulDescCreate") && bind(a.DescDestroy, a.so, "cublasLtMatmulDescDestroy") &&
+           bind(a.DescSet, a.so, "cublasLtMatmulDescSetAttribute") &&
+           bind(a.LayoutCreate, a.so, "cublasLtMatrixLayoutCreate") &&
+           bind(a.LayoutDestroy, a.so, "cublasLtMatrixLayoutDestroy") &&
+           bind(a.PrefCreate, a.so, "cublasLtMatmulPreferenceCreate") &&
+           bind(a.PrefDestroy, a.so, "cublasLtMatmulPreferenceDestroy") &&
+           bind(a.PrefSet, a.so, "cublasLtMatmulPreferenceSetAttribute") &&
+           bind(a.Heuristic, a.so, "cublasLtMatmulAlgoGetHeuristic");
+    if (!a.ok) {
+        set_error("fused_linear_grpo: libcublasLt lacks an expected symbol");
+        return nullptr;
+    }
+    return &a;
+}
+
+cublasLtHandle_t lt_handle(LtApi* api) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_lt_mutex);
+    auto it = api->handles.find(dev);
+    if (it != api->handles.end()) return it->second;
+    cublasLtHandle_t h = nullptr;
+    if (api->Create(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
+    api->handles[dev] = h;
+    return h;
+}
+
+// One column-major GEMM  D[m,n] = alpha * op(A)[m,k] op(B)[k,n] + beta * D  (+ bias[m] broadcast over columns):
+// bf16 operands, fp32 accumulation, D bf16 or fp32.  Algorithms are chosen once per shape by the library's heuristic.
+struct GemmKey {
+    int ta, tb, dtype, bias;
+    int64_t m, n, k, lda, ldb, ldd;
+    bool operator<(const GemmKey& o) const {
+        return std::tie(ta, tb, dtype, bias, m, n, k, lda, ldb, ldd) <
+               std::tie(o.ta, o.tb, o.dtype, o.bias, o.m, o.n, o.k, o.lda, o.ldb, o.ldd);
+    }
+};
+std::map<std::pair<int, GemmKey>, cublasLtMatmulAlgo_t> g_algos;
+
+int lt_gemm(LtApi* api, cublasLtHandle_t h, cublasOperation_t ta, cublasOperation_t tb, int64_t m, int64_t n, int64_t k,
+            const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd, cudaDataType_t dtype, float beta,
+            const void* bias, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    cublasLtMatmulDesc_t desc = nullptr;
+    cublasLtMatrixLayout_t la = nullptr, lb = nullptr, ld = nullptr;
+    cublasLtMatmulPreference_t pref = nullptr;
+    int rc = B200TRL_E_LAUNCH;
+    bool said = false;  // a specific message has been recorded
+    const float alpha = 1.f;
+    do {
+        if (api->DescCreate(&desc, CUBLAS_COMPUTE_32F, CUDA_R_32F) != CUBLAS_STATUS_SUCCESS) break;
+        api->DescSet(desc, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta));
+        api->DescSet(desc, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb));
+        if (bias) {
+            const cublasLtEpilogue_t ep = CUBLASLT_EPILOGUE_BIAS;
+            if (api->DescSet(desc, CUBLASLT_MATMUL_DESC_EPILOGUE, &ep, sizeof(ep)) != CUBLAS_STATUS_SUCCESS) break;
+            if (api->DescSet(desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)) != CUBLAS_STATUS_SUCCESS) break;
+        }
+        const int64_t a_rows = (ta == CUBLAS_OP_N) ? m : k, a_cols = (ta == CUBLAS_OP_N) ? k : m;
+        const int64_t b_rows = (tb == CUBLAS_OP_N) ? k : n, b_cols = (tb == CUBLAS_OP_N) ? n : k;
+        if (api->LayoutCreate(&la, CUDA_R_16BF, a_rows, a_cols, lda) != CUBLAS_STATUS_SUCCESS) break;
+        if (api->LayoutCreate(&lb, CUDA_R_16BF, b_rows, b_cols, ldb) != CUBLAS_STATUS_SUCCESS) break;
+        if (api->LayoutCreate(&ld, dtype, m, n, ldd) != CUBLAS_STATUS_SUCCESS) break;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const GemmKey key{(int)ta, (int)tb, (int)dtype, bias ? 1 : 0, m, n, k, lda, ldb, ldd};
+        cublasLtMatmulAlgo_t algo;
+        bool have = false;
+        {
+            std::lock_guard<std::mutex> lock(g_lt_mutex);
+            auto it = g_algos.find({dev, key});
+            if (it != g_algos.end()) {
+                algo = it->second;
+                have = true;
+            }
+        }
+        if (!have) {
+            if (api->PrefCreate(&pref) != CUBLAS_STATUS_SUCCESS) break;
+            api->PrefSet(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_bytes, sizeof(ws_bytes));
+            cublasLtMatmulHeuristicResult_t res;
+            int found = 0;
+            if (api->Heuristic(h, desc, la, lb, ld, ld, pref, 1, &res, &found) != CUBLAS_STATUS_SUCCESS || found == 0) {
+                set_error("fused_linear_grpo: cuBLASLt has no algorithm for m=%lld n=%lld k=%lld", (long long)m,
+                          (long long)n, (long long)k);
+                rc = B200TRL_E_UNSUPPORTED;
+                said = true;
+                break;
+            }
+            algo = res.algo;
+            std::lock_guard<std::mutex> lock(g_lt_mutex);
+            g_algos[{dev, key}] = algo;
+        }
+        const cublasStatus_t st = api->Matmul(h, desc, &alpha, A, la, B, lb, &beta, D, ld, D, ld, &algo, ws, ws_bytes, stream);
+        if (st != CUBLAS_STATUS_SUCCESS) {
+            set_error("fused_linear_grpo: cublasLtMatmul failed with status %d", (int)st);
+            said = true;
+            break;
+        }
+        rc = B200TRL_OK;
+    } while (false);
+    if (pref) api->PrefDestroy(pref);
+    if (ld) api->LayoutDestroy(ld);
+    if (lb) api->LayoutDestroy(lb);
+    if (la) api->LayoutDestroy(la);
+    if (desc) api->DescDestroy(desc);
+    if (rc != B200TRL_OK && !said) set_error("fused_linear_grpo: cuBLASLt descriptor setup failed");
+    return rc;
+}
+
+// d(bias)[v] += sum over the chunk's rows of dlogits[r, v]; one thread per column, rows in order => deterministic
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dl, int64_t rows, int64_t V,
+                                                     float* __restrict__ db) {
+    const int64_t v = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (v >= V) return;
+    float s = 0.f;
+    for (int64_t r = 0; r < rows; ++r) s += __bfloat162float(dl[r * V + v]);
+    db[v] += s;
+}
+
+constexpr size_t kLtWorkspace = size_t(64) << 20;
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Layout {
+    size_t logits, row_count, total, k2, lt, end;
+};
+Layout layout(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
+    Layout l;
+    size_t off = 0;
+    l.logits = off;
+    off += align256(static_cast<size_t>(chunk_seqs) * T * V * 2);
+    l.row_count = off;
+    off += align256(static_cast<size_t>(B) * 4);
+    l.total = off;
+    off += 256;
+    l.k2 = off;
+    off += align256(static_cast<size_t>(b200trl_grpo_loss_workspace_bytes(B)));
+    l.lt = off;
+    off += kLtWorkspace;
+    l.end = off;
+    return l;
+}
+
+}  // namespace
+}  // namespace b200trl
+
+using namespace b200trl;
+
+extern "C" int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
+    if (B <= 0 || T <= 0 || V <= 0 || chunk_seqs <= 0) return 0;
+    return static_cast<int64_t>(layout(B, T, V, std::min(chunk_seqs, B)).end);
+}
+
+extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
+                                         int64_t H, int64_t V, const int64_t* ids, const int32_t* mask,
+                                         const float* advantages, const float* old_logp, const float* ref_logp,
+                                         const b200trl_grpo_cfg* cfg, float inv_temperature, int64_t chunk_seqs,
+                                         void* workspace, float* logp, float* entropy, float* loss, float* metrics,
+                                         void* dhidden, float* dweight, float* dbias, b200trl_stream_t stream_) {
+    B200TRL_REQUIRE(hidden && weight && ids && mask && advantages && cfg && workspace && logp && entropy && loss && metrics,
+                    B200TRL_E_INVALID, "fused_linear_grpo: null pointer");
+    B200TRL_REQUIRE(B > 0 && T > 0 && H > 0 && V > 0 && chunk_seqs > 0, B200TRL_E_INVALID, "fused_linear_grpo: bad shape");
+    B200TRL_REQUIRE(H % 8 == 0 && V % 8 == 0, B200TRL_E_UNSUPPORTED,
+                    "fused_linear_grpo: hidden size and vocabulary must be multiples of 8 (16-byte rows)");
+    B200TRL_REQUIRE(!dbias || bias, B200TRL_E_INVALID, "fused_linear_grpo: dbias without bias");
+    B200TRL_REQUIRE(cfg->is_level == B200TRL_IS_TOKEN || old_logp == nullptr, B200TRL_E_UNSUPPORTED,
+                    "fused_linear_grpo: sequence-level importance sampling with old_logp needs the two-phase path");
+    B200TRL_REQUIRE(cfg->beta == 0.f || ref_logp, B200TRL_E_INVALID, "fused_linear_grpo: beta != 0 needs ref_logp");
+    cudaStream_t stream = as_stream(stream_);
+    LtApi* api = lt_api();
+    if (!api) return B200TRL_E_UNSUPPORTED;
+    cublasLtHandle_t h = lt_handle(api);
+    B200TRL_REQUIRE(h != nullptr, B200TRL_E_LAUNCH, "fused_linear_grpo: cublasLtCreate failed");
+
+    chunk_seqs = std::min(chunk_seqs, B);
+    const Layout l = layout(B, T, V, chunk_seqs);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    __nv_bfloat16* logits = reinterpret_cast<__nv_bfloat16*>(ws + l.logits);
+    float* row_count = reinterpret_cast<float*>(ws + l.row_count);
+    float* total = reinterpret_cast<float*>(ws + l.total);
+    void* k2_ws = ws + l.k2;
+    void* lt_ws = ws + l.lt;
+    const bool want_grad = dhidden || dweight || dbias;
+
+    int rc = b200trl_mask_stats(mask, B, T, row_count, total, stream_);
+    if (rc) return rc;
+    if (cudaMemsetAsync(k2_ws, 0, static_cast<size_t>(b200trl_grpo_loss_workspace_bytes(B)), stream) != cudaSuccess)
+        return check_launch("fused_linear_grpo memset");
+    if (dweight && cudaMemsetAsync(dweight, 0, static_cast<size_t>(V) * H * 4, stream) != cudaSuccess)
+        return check_launch("fused_linear_grpo memset");
+    if (dbias && cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream) != cudaSuccess)
+        return check_launch("fused_linear_grpo memset");
+
+    const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
+    __nv_bfloat16* dh = static_cast<__nv_bfloat16*>(dhidden);
+    for (int64_t b0 = 0; b0 < B; b0 += chunk_seqs) {
+        const int64_t nb = std::min(chunk_seqs, B - b0), rows = nb * T, r0 = b0 * T;
+        // row-major logits[rows, V] = hidden_c[rows, H] W[V, H]^T  <=>  column-major D[V, rows] = W^T(T) x hidden_c(N)
+        rc = lt_gemm(api, h, CUBLAS_OP_T, CUBLAS_OP_N, V, rows, H, weight, H, hid + r0 * H, H, logits, V, CUDA_R_16BF, 0.f,
+                     bias, lt_ws, kLtWorkspace, stream);
+        if (rc) return rc;
+        // the loss normalises over the WHOLE batch: grpo / dr_grpo divide by B (grpo_trainer.py:2131, 2135), bnpo by
+        // the batch's token total, which the kernel reads from `total`
+        b200trl_grpo_cfg c = *cfg;
+        c.grad_scale = cfg->grad_scale * (cfg->loss_type == B200TRL_LOSS_BNPO ? 1.f
+                                                                              : static_cast<float>(nb) / static_cast<float>(B));
+        rc = b200trl_grpo_fused_fwd_bwd(logits, B200TRL_BF16, nb, T, V, V, 0, ids + r0, mask + r0, advantages + b0,
+                                        old_logp ? old_logp + r0 : nullptr, ref_logp ? ref_logp + r0 : nullptr, &c,
+                                        inv_temperature, row_count + b0, total, logp + r0, entropy + r0, nullptr,
+                                        want_grad ? logits : nullptr, V, 0, stream_);  // in place: dlogits overwrite logits
+        if (rc) return rc;
+        if (dh) {  // dH_c[rows, H] = dl[rows, V] W[V, H]  <=>  D[H, rows] = W(N)[H, V] x dl(N)[V, rows]
+            rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_N, H, rows, V, weight, H, logits, V, dh + r0 * H, H, CUDA_R_16BF, 0.f,
+                         nullptr, lt_ws, kLtWorkspace, stream);
+            if (rc) return rc;
+        }
+        if (dweight) {  // dW[V, H] += dl^T hidden_c  <=>  D[H, V] += hidden_c(N)[H, rows] x dl(T)[rows, V], fp32 in the GEMM
+            rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_T, H, V, rows, hid + r0 * H, H, logits, V, dweight, H, CUDA_R_32F, 1.f,
+                         nullptr, lt_ws, kLtWorkspace, stream);
+            if (rc) return rc;
+        }
+        if (dbias) {
+            colsum_kernel<<<static_cast<unsigned>((V + 255) / 256), 256, 0, stream>>>(logits, rows, V, dbias);
+            rc = check_launch("colsum_kernel");
+            if (rc) return rc;
+        }
+    }
+    b200trl_grpo_cfg c = *cfg;
+    c.grad_scale = 1.f;
+    return b200trl_grpo_loss(logp, old_logp, ref_logp, advantages, mask, nullptr, entropy, B, T, &c, row_count, total, k2_ws,
+                             loss, metrics, nullptr, stream_);
+}

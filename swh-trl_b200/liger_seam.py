@@ -13,8 +13,9 @@ is what the parity tests check.
 Schedule (grads-in-forward, the full ``[B,T,V]`` logits tensor is never materialised):
 for each chunk of whole sequences: ``logits_c = hidden_c @ W.T`` (library GEMM) → K1 resident kernel turns the chunk
 *in place* into ``dlogits_c`` while emitting log-probs / entropies (one pass) → ``dH_c = dlogits_c @ W`` and
-``dW += dlogits_c.T @ hidden_c`` (library GEMMs).  The three GEMMs are plain cuBLAS calls; everything that is not a
-plain GEMM runs in ``libb200trl``.  Unlike Liger, the entropy mask is the only unsupported option: sequence-level
+``dW += dlogits_c.T @ hidden_c`` (library GEMMs).  For bf16 models the whole loop is ONE C-ABI call,
+``b200trl_fused_linear_grpo`` (cuBLASLt GEMMs, the fp32 ``dW`` accumulated inside the GEMM); other dtypes run the
+same schedule with ``torch.matmul`` as the library GEMM.  Everything that is not a plain GEMM runs in ``libb200trl``.  Unlike Liger, the entropy mask is the only unsupported option: sequence-level
 importance sampling without old log-probs and ``delta`` work (Liger rejects them, grpo_trainer.py:794-802,
 grpo_config.py:615-616).
 """
@@ -28,49 +29,66 @@ import torch
 from . import ops
 
 
+def _chunked_with_torch_gemms(hidden, weight, bias, ids, mask_i32, advantages, old_lp, ref_lp, cfg, inv_temp,
+                              chunk_seqs, need_dh, need_dw, need_db):
+    """The same schedule for fp16 / fp32 models: ``torch.matmul`` is the library GEMM, K1's row kernel works in place."""
+    B, T, H = hidden.shape
+    V = weight.shape[0]
+    want_grad = need_dh or need_dw or need_db
+    _, row_count, total = ops.mask_stats(mask_i32)
+    logp = torch.empty(B, T, dtype=torch.float32, device=hidden.device)
+    ent = torch.empty(B, T, dtype=torch.float32, device=hidden.device)
+    dh = torch.empty_like(hidden) if need_dh else None
+    dw = torch.zeros(V, H, dtype=torch.float32, device=hidden.device) if need_dw else None
+    db = torch.zeros(V, dtype=torch.float32, device=hidden.device) if need_db else None
+    h2 = hidden.reshape(B * T, H)
+    for b0 in range(0, B, chunk_seqs):
+        b1 = min(B, b0 + chunk_seqs)
+        nb = b1 - b0
+        rows = slice(b0 * T, b1 * T)
+        logits = torch.matmul(h2[rows], weight.t())
+        if bias is not None:
+            logits += bias
+        logits = logits.view(nb, T, V)
+        # loss normalisation is over the WHOLE batch: grpo / dr_grpo divide by B (grpo_trainer.py:2131, 2135)
+        cfg.grad_scale = 1.0 if cfg.loss_type == 1 else float(nb) / float(B)  # bnpo divides by the token total
+        lp, en, _, dl = ops.grpo_fused_fwd_bwd(
+            logits, ids[b0:b1], mask_i32[b0:b1], row_count[b0:b1], total, advantages[b0:b1],
+            None if old_lp is None else old_lp[b0:b1], None if ref_lp is None else ref_lp[b0:b1], cfg, inv_temp,
+            want_grad=want_grad, dlogits_out=logits if want_grad else None)  # in place: dlogits overwrite logits
+        logp[b0:b1], ent[b0:b1] = lp, en
+        if want_grad:
+            dl2 = dl.view(nb * T, V)
+            if need_dh:
+                torch.matmul(dl2, weight, out=dh.view(B * T, H)[rows])
+            if need_dw:
+                dw += torch.matmul(dl2.t(), h2[rows])
+            if need_db:
+                db += dl2.float().sum(0)
+        del logits
+    cfg.grad_scale = 1.0
+    loss, metrics, _ = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total, cfg, entropy=ent,
+                                     want_g=False)
+    return loss, metrics, logp, ent, dh, dw, db
+
+
 class _FusedLinearGRPO(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hidden, weight, bias, ids, mask, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs):
         ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
-        B, T, H = hidden.shape
-        V = weight.shape[0]
         need_dh, need_dw = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
         need_db = bias is not None and bool(ctx.needs_input_grad[2])
-        want_grad = need_dh or need_dw or need_db
-        mask_i32, row_count, total = ops.mask_stats(mask)
-        logp = torch.empty(B, T, dtype=torch.float32, device=hidden.device)
-        ent = torch.empty(B, T, dtype=torch.float32, device=hidden.device)
-        dh = torch.empty_like(hidden) if need_dh else None
-        dw = torch.zeros(V, H, dtype=torch.float32, device=hidden.device) if need_dw else None
-        db = torch.zeros(V, dtype=torch.float32, device=hidden.device) if need_db else None
-        h2 = hidden.reshape(B * T, H)
-        for b0 in range(0, B, chunk_seqs):
-            b1 = min(B, b0 + chunk_seqs)
-            nb = b1 - b0
-            rows = slice(b0 * T, b1 * T)
-            logits = torch.matmul(h2[rows], weight.t())  # [rows, V] in the hidden dtype; fp32 accumulate inside cuBLAS
-            if bias is not None:
-                logits += bias
-            logits = logits.view(nb, T, V)
-            # loss normalisation is over the WHOLE batch: grpo / dr_grpo divide by B (grpo_trainer.py:2131, 2135)
-            cfg.grad_scale = 1.0 if cfg.loss_type == 1 else float(nb) / float(B)  # bnpo divides by the token total
-            lp, en, _, dl = ops.grpo_fused_fwd_bwd(
-                logits, ids[b0:b1], mask_i32[b0:b1], row_count[b0:b1], total, advantages[b0:b1],
-                None if old_lp is None else old_lp[b0:b1], None if ref_lp is None else ref_lp[b0:b1], cfg, inv_temp,
-                want_grad=want_grad, dlogits_out=logits if want_grad else None)  # in place: dlogits overwrite logits
-            logp[b0:b1], ent[b0:b1] = lp, en
-            if want_grad:
-                dl2 = dl.view(nb * T, V)
-                if need_dh:
-                    torch.matmul(dl2, weight, out=dh.view(B * T, H)[rows])
-                if need_dw:
-                    dw += torch.matmul(dl2.t(), h2[rows])
-                if need_db:
-                    db += dl2.float().sum(0)
-            del logits
-        cfg.grad_scale = 1.0
-        loss, metrics, _ = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total, cfg,
-                                         entropy=ent, want_g=False)
+        mask_i32 = mask.to(torch.int32).contiguous()
+        if hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16:
+            # the product path: ONE C-ABI call (cuBLASLt GEMMs + K1 in place + K2), fp32 dW accumulated inside the GEMM
+            cfg.grad_scale = 1.0
+            loss, metrics, logp, ent, dh, dw, db = ops.fused_linear_grpo(
+                hidden, weight, bias, ids, mask_i32, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs, need_dh,
+                need_dw, need_db)
+        else:
+            loss, metrics, logp, ent, dh, dw, db = _chunked_with_torch_gemms(
+                hidden, weight, bias, ids, mask_i32, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs, need_dh,
+                need_dw, need_db)
         ctx.grads = (dh, None if dw is None else dw.to(weight.dtype), None if db is None else db.to(bias.dtype))
         ctx.mark_non_differentiable(metrics, logp, ent)
         return loss.reshape(()), metrics, logp, ent

@@ -464,3 +464,39 @@ def fused_linear_logprob_fwd(hidden: torch.Tensor, weight: torch.Tensor, ids: to
                                                    _stream(h2)), "fused_linear_logprob_fwd")
         _count(2)
     return logp, ent, lse
+
+
+# ------------------------------------------------------------------------------------------------ a-13: the seam
+def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ids: torch.Tensor,
+                      mask_i32: torch.Tensor, advantages: torch.Tensor, old_logp: Optional[torch.Tensor],
+                      ref_logp: Optional[torch.Tensor], cfg: GrpoCfg, inv_temperature: float, chunk_seqs: int,
+                      need_dh: bool, need_dw: bool, need_db: bool):
+    """``(loss[1], metrics[8], logp, entropy, dH|None, dW fp32|None, db fp32|None)`` — ``b200trl_fused_linear_grpo``:
+    the whole chunked lm_head + GRPO loss forward/backward in one C call (cuBLASLt GEMMs + K1 in place + K2)."""
+    _need_cuda(hidden, "_input")
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError("fused_linear_grpo needs bf16 hidden states and weights")
+    B, T, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    h = hidden.contiguous()
+    w = weight.contiguous()
+    b = None if bias is None else bias.to(torch.bfloat16).contiguous()
+    idx = ids.to(torch.int64).contiguous()
+    logp = torch.empty(B, T, dtype=torch.float32, device=dev)
+    ent = torch.empty(B, T, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    metrics = torch.empty(_lib.NUM_GRPO_METRICS, dtype=torch.float32, device=dev)
+    dh = torch.empty_like(h) if need_dh else None
+    dw = torch.empty(V, H, dtype=torch.float32, device=dev) if need_dw else None
+    db = torch.empty(V, dtype=torch.float32, device=dev) if need_db else None
+    ws = _workspace(dev, lib.b200trl_fused_linear_grpo_workspace_bytes(B, T, V, int(chunk_seqs)), "fused_linear_grpo",
+                    zero=False)
+    check(lib.b200trl_fused_linear_grpo(
+        _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), _ptr(_f32(advantages, "advantages")),
+        _ptr(_f32(old_logp, "old_per_token_logps")), _ptr(_f32(ref_logp, "ref_per_token_logps")), C.byref(cfg),
+        float(inv_temperature), int(chunk_seqs), _ptr(ws), _ptr(logp), _ptr(ent), _ptr(loss), _ptr(metrics), _ptr(dh),
+        _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo")
+    n_chunks = -(-B // max(1, min(int(chunk_seqs), B)))
+    _count(2 + n_chunks + 1)  # mask stats (memset + kernel), K1 per chunk, K2; the GEMMs are library launches
+    return loss, metrics, logp, ent, dh, dw, db

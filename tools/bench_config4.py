@@ -58,7 +58,7 @@ def main():
     h = hidden.clone().requires_grad_(True)
     w = W.clone().requires_grad_(True)
     res = {}
-    for chunk in (1, 2):
+    for chunk in (1, 2, 4):
         fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
 
         def ours():
