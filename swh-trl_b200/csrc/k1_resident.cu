@@ -27,7 +27,9 @@ namespace {
 constexpr int kMaxConsumers = 768;  // consumer threads per CTA: 768 or 512 (1 CTA / SM), 256 (2 CTAs / SM)
 constexpr int kChunkBytes = 16384;  // default chunk; per-geometry value: chunk_bytes_for()
 constexpr int kMaxSlots = 13;
-__host__ __device__ constexpr int chunk_bytes_for(int consumers) { return consumers == 768 ? 24576 : 16384; }
+__host__ __device__ constexpr int chunk_bytes_for(int consumers) {
+    return (consumers == 768 || consumers == 640) ? consumers * 32 : 16384;
+}
 constexpr int kMaxCluster = 8;
 constexpr int kStoreLag = 2;     // bulk stores allowed to be still reading shared memory
 constexpr float kSlack = 6.0f;   // reference point may trail the running max by 2^6
@@ -846,7 +848,8 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     return check_launch("k1_resident_kernel");
 }
 
-// Three CTA geometries:
+// Four CTA geometries:
+//   mid   : 640 consumers, 11 x 20 KB slots (220 KB), 1 CTA / SM  — the fused pass at V >= 57 k
 //   wide  : 512 consumers, 13 x 16 KB slots (208 KB), 1 CTA / SM  — a row slice of up to 12 chunks per CTA
 //   dense : 768 consumers,  9 x 24 KB slots (216 KB), 1 CTA / SM  — more warps to hide the fold's latencies
 //   twin  : 256 consumers,  6 x 16 KB slots ( 96 KB), 2 CTAs / SM — slices of up to 5 chunks; the two CTAs of an SM
@@ -856,6 +859,7 @@ struct Geom {
 };
 constexpr int kTwinSlots = 6;
 constexpr int kDenseSlots = 9;  // 9 x 24 KB = 216 KB
+constexpr int kMidSlots = 11;   // 11 x 20 KB = 220 KB
 
 enum Mode { M_FWD, M_BWD, M_FUSED };
 Mode mode_of(const K1Args& a) {
@@ -864,10 +868,11 @@ Mode mode_of(const K1Args& a) {
 }
 
 Geom pick_geom(int64_t vocab, Mode m) {
-    static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense
+    static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense, 4 mid
     Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
     Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
     Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768)), kDenseSlots, 768};
+    const Geom mid{pick_cluster(vocab, kMidSlots, chunk_bytes_for(640)), kMidSlots, 640};
     if (m != M_FUSED) {
         // forward-only / backward-only: nothing has to stay resident between two sweeps, so a row simply STREAMS
         // through the ring of one CTA -- no cluster, no DSMEM exchange, any vocabulary.  Measured at config 2
@@ -883,6 +888,7 @@ Geom pick_geom(int64_t vocab, Mode m) {
         if (mode == 3) return dense;
         return m == M_FWD ? twin : dense;
     }
+    if (mode == 4 && mid.cs) return mid;
     if (mode == 3 && dense.cs && dense.cs <= wide.cs) return dense;
     if (mode == 2 && twin.cs) return twin;
     if (mode == 1 || !twin.cs) return wide;
@@ -890,8 +896,11 @@ Geom pick_geom(int64_t vocab, Mode m) {
     // drifting CTAs per SM (fused 91.7 % of the measured HBM peak); anything that would need a cluster in twin form is
     // faster with 1 CTA / SM
     if (twin.cs == 1) return twin;
-    // finer 16 KB chunks and a deeper ring beat 24 warps (V = 65 k .. 152 k: +1.5 .. 2.5 %); below ~56 k the two are
-    // equal and dense keeps the shorter tail chunk
+    // 1 CTA / SM: 20 consumer warps with 20 KB chunks and an 11-slot ring are the best balance of warps against ring
+    // depth and tail-chunk waste -- fused, % of the measured HBM peak for 512 / 640 / 768 consumers: V = 151 936
+    // 90.3 / 93.1 / 88.9, 128 256 89.6 / 89.7 / 87.4, 100 352 82.4 / 94.5 / 82.9, 65 536 92.0 / 92.1 / 90.9; below
+    // ~56 k the shapes are equal and dense keeps the shorter tail chunk
+    if (vocab >= 57344 && mid.cs && mid.cs <= wide.cs) return mid;
     if (vocab >= 57344) return wide;
     if (dense.cs && dense.cs <= wide.cs) return dense;
     return wide;
@@ -931,6 +940,9 @@ int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
     if (g.nc == 256)
         return dual ? launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream)
                     : launch_mode_t<F, Bk, false, 256>(a, g.cs, g.slots, stream);
+    if (g.nc == 640)  // fused pass only (pick_geom); the other modes never ask for it
+        return dual ? launch_mode_t<F, Bk, true, (F && Bk) ? 640 : 512>(a, g.cs, g.slots, stream)
+                    : launch_mode_t<F, Bk, false, (F && Bk) ? 640 : 512>(a, g.cs, g.slots, stream);
     if (g.nc == 768)
         return dual ? launch_mode_t<F, Bk, true, 768>(a, g.cs, g.slots, stream)
                     : launch_mode_t<F, Bk, false, 768>(a, g.cs, g.slots, stream);

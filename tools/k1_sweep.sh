@@ -1,14 +1,10 @@
 #!/bin/bash
 run() { env "$@" python tools/k1_variants.py; }
-run KV_TAG=v50304_twin KV_V=50304 KV_B=32 B200TRL_K1_GEOM=2
-run KV_TAG=v50304_default KV_V=50304 KV_B=32
-run KV_TAG=v40960_twin KV_V=40960 KV_B=32 B200TRL_K1_GEOM=2
-run KV_TAG=v40960_default KV_V=40960 KV_B=32
-run KV_TAG=v57344_twin KV_V=57344 KV_B=32 B200TRL_K1_GEOM=2
-run KV_TAG=v57344_default KV_V=57344 KV_B=32
-run KV_TAG=v262144_row KV_V=262144 KV_B=8 KV_ROW=1
-run KV_TAG=v262144_res KV_V=262144 KV_B=8
-run KV_TAG=v524288_row KV_V=524288 KV_B=4 KV_ROW=1
-run KV_TAG=v524288_res KV_V=524288 KV_B=4
-run KV_TAG=v200000_row KV_V=200000 KV_B=8 KV_ROW=1
-run KV_TAG=v200000_res KV_V=200000 KV_B=8
+for v in 151936 152064 128256 100352 65536; do
+  b=16; [ $v -lt 70000 ] && b=32
+  run KV_TAG=v${v}_wide512 KV_V=$v KV_B=$b B200TRL_K1_GEOM=1
+  run KV_TAG=v${v}_576 KV_V=$v KV_B=$b B200TRL_K1_GEOM=5
+  run KV_TAG=v${v}_640 KV_V=$v KV_B=$b B200TRL_K1_GEOM=4
+  run KV_TAG=v${v}_704 KV_V=$v KV_B=$b B200TRL_K1_GEOM=6
+  run KV_TAG=v${v}_768 KV_V=$v KV_B=$b B200TRL_K1_GEOM=3
+done
