@@ -72,9 +72,12 @@ def test_patch_trl_rebinds_every_importer():
     grpo_mod.GRPOTrainer = GRPOTrainer
     core = types.ModuleType("faketrl.core")
     core.masked_whiten = orig
+    ppo_mod = types.ModuleType("faketrl.trainer.ppo_trainer")  # ppo_trainer.py:54-71 binds the mask helpers too
+    ppo_mod.first_true_indices = orig
+    ppo_mod.truncate_response = orig
     other = types.ModuleType("faketrl.other")
     mods = {"faketrl": pkg, "faketrl.trainer.utils": utils, "faketrl.trainer.grpo_trainer": grpo_mod,
-            "faketrl.core": core, "faketrl.other": other}
+            "faketrl.core": core, "faketrl.trainer.ppo_trainer": ppo_mod, "faketrl.other": other}
     sys.modules.update(mods)
     try:
         report = S.patch_trl("faketrl")
@@ -87,5 +90,7 @@ def test_patch_trl_rebinds_every_importer():
     assert core.masked_whiten is S.masked_whiten
     assert GRPOTrainer._compute_loss is S.compute_loss
     assert GRPOTrainer._trl_original_compute_loss(None, None, None) == "reference"
+    assert ppo_mod.first_true_indices is S.first_true_indices and ppo_mod.truncate_response is S.truncate_response
+    assert ppo_mod._trl_original_truncate_response is orig
     assert "faketrl.other" not in report and set(report) == {"faketrl.trainer.utils", "faketrl.trainer.grpo_trainer",
-                                                              "faketrl.core"}
+                                                              "faketrl.core", "faketrl.trainer.ppo_trainer"}
