@@ -901,3 +901,67 @@ def test_backward_skips_zero_gradient_rows(S):
         got = xd.grad.float().cpu()
         assert torch.equal(got[gmask == 0], torch.zeros_like(got[gmask == 0]))
         torch.testing.assert_close(got[gmask != 0], want[gmask != 0], rtol=BF16_ULP, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,T,V,level", [(16, 1024, 151936, "token"),      # BASELINE config 2, full size
+                                         (4, 4096, 151936, "token"),       # one micro-batch of config 5
+                                         (16, 1024, 151936, "sequence")])  # the fork's GSPO setting: two-phase schedule
+def test_full_size_properties(S, B, T, V, level):
+    """BASELINE sizes through size-independent properties: (a) fused / two-phase log-probs equal the forward-only
+    pass; (b) the loss and metrics K2 reports equal the oracle's loss block evaluated on those log-probs (CPU, [B,T]
+    work only); (c) dlogits are zero where masked and every row sums to ~0 (softmax gradient); (d) sampled rows
+    against the fp32 oracle gradient; (e) no NaN / inf anywhere."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.empty(B, T, V, dtype=torch.bfloat16, device=DEV)
+    for b in range(B):
+        x[b] = (torch.randn(T, V, generator=g, device=DEV) * 1.5).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g, device=DEV)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g, device=DEV)
+    lens[1] = 0
+    lens[2] = T
+    mask = (torch.arange(T, device=DEV).unsqueeze(0) < lens.unsqueeze(1)).int()
+    adv = torch.randn(B, generator=g, device=DEV)
+    lp0, ent0 = S.logprobs_and_entropy(x, ids)
+    old = lp0 + torch.randn(B, T, generator=g, device=DEV) * 0.3
+    ref = lp0 + torch.randn(B, T, generator=g, device=DEV) * 0.1
+    loss_fn = S.GRPOLoss(beta=0.04, loss_type="grpo", importance_sampling_level=level, max_completion_length=T)
+    xx = x.requires_grad_(True)
+    out = loss_fn(xx, ids, mask, adv, old, ref)
+    out.loss.backward()
+    grad = xx.grad
+    assert out.schedule == ("fused" if level == "token" else "two-phase")
+    # (a)
+    torch.testing.assert_close(out.per_token_logps, lp0, rtol=0, atol=5e-6)
+    torch.testing.assert_close(out.entropies, ent0, rtol=0, atol=5e-6)
+    # (b) K2 at full size against the oracle's loss block on the same log-probs
+    cfg = O.GRPOConfigLite(beta=0.04, loss_type="grpo", importance_sampling_level=level, max_completion_length=T)
+    want_loss, want_m = O.grpo_loss(out.per_token_logps.cpu(), out.entropies.cpu(), mask.cpu(), adv.cpu(), cfg, old.cpu(),
+                                    ref.cpu())
+    assert out.loss.item() == pytest.approx(float(want_loss), rel=1e-4, abs=1e-7)
+    from swh_trl_b200.grpo import METRIC_INDEX as MI
+    m = out.metrics.cpu()
+    for name in ("kl", "entropy", "clip_ratio/low", "clip_ratio/high", "clip_ratio/region"):
+        assert float(m[MI[name]]) == pytest.approx(float(want_m[name]), rel=1e-4, abs=1e-6), name
+    # (c), (e) — row by row slabs to keep the fp32 temporaries small
+    assert torch.count_nonzero(grad[mask == 0]) == 0
+    worst = 0.0
+    for b in range(B):
+        gb = grad[b].float()
+        assert bool(torch.isfinite(gb).all())
+        rs, sc = gb.sum(-1), gb.abs().sum(-1).clamp(min=1e-20)
+        worst = max(worst, float((rs.abs() / sc).max()))
+    assert worst < 2e-2  # bf16 rounding noise of 152k terms
+    assert bool(torch.isfinite(out.per_token_logps).all()) and bool((out.per_token_logps <= 0).all())
+    # (d) sampled rows against the fp32 oracle: d loss / d logp from autograd of the oracle's loss block, then the
+    # softmax Jacobian of that row
+    lp_leaf = out.per_token_logps.detach().cpu().clone().requires_grad_(True)
+    l2, _ = O.grpo_loss(lp_leaf, out.entropies.cpu(), mask.cpu(), adv.cpu(), cfg, old.cpu(), ref.cpu())
+    l2.backward()
+    for b, t in [(0, 0), (2, T - 1), (3, int(lens[3]) - 1), (B - 1, 5)]:
+        if mask[b, t] == 0:
+            continue
+        xr = x[b, t].detach().float().cpu()
+        p = torch.softmax(xr, -1)
+        want = -p * lp_leaf.grad[b, t]
+        want[ids[b, t]] += lp_leaf.grad[b, t]
+        torch.testing.assert_close(grad[b, t].float().cpu(), want.to(torch.bfloat16).float(), rtol=2 * BF16_ULP, atol=1e-12)
