@@ -1,21 +1,24 @@
 // K1 "resident" implementation (the product path for bf16 logits): every logit row is read from HBM
 // exactly once and dlogits written exactly once.
 //
-//   * a row is split over a thread-block cluster (1/2/4/8 CTAs, picked so a slice fits one CTA's
-//     shared memory); each CTA pulls its slice with 16 KB TMA bulk copies (cp.async.bulk ->
-//     UBLKCP) into a ring of shared-memory slots, signalled through mbarriers;
-//   * 16 consumer warps fold the chunks into an online (reference, sum, sum*delta) partial as they
-//     land (packed bf16 max, f32x2 FMA/ADD, MUFU ex2), the CTAs of the cluster swap partials
-//     through distributed shared memory, and the row's log-prob / entropy / lse come out;
-//   * the per-token d(loss)/d(logp) is evaluated inline (GRPO or PPO surrogate, see k1_args.cuh),
-//     the still-resident slice is rewritten in place as dlogits (bf16) and leaves through TMA
-//     bulk stores; a slot is refilled with the next row's chunk as soon as its store has drained,
-//     so loads of row r+1 overlap the stores of row r.
+//   * each CTA pulls its share of a row with 16-24 KB TMA bulk copies (cp.async.bulk -> UBLKCP) into a
+//     ring of shared-memory slots, signalled through mbarriers; one DMA warp (one elected lane) issues
+//     every bulk copy;
+//   * 8-24 consumer warps fold the chunks into an online (reference, sum, sum*delta) partial as they
+//     land (packed bf16 max, f32x2 FMA/ADD, MUFU ex2); a reducer warp finishes the row: log-prob,
+//     entropy, lse and the per-token d(loss)/d(logp) (GRPO or PPO surrogate, see k1_args.cuh);
+//   * FUSED pass (forward + dlogits in one read): the row must stay on chip between the two sweeps,
+//     so it is split over a thread-block cluster (1/2/4/8 CTAs, picked so a slice fits one CTA's
+//     shared memory); the CTAs swap their partials with one st.async DSMEM message per peer, and the
+//     consumers turn the still-resident slice into dlogits that leave straight from registers
+//     (st.global.cs), releasing each slot for the next row's chunk as soon as it has been read;
+//   * FORWARD-ONLY and BACKWARD-ONLY passes keep nothing resident: a row streams through the ring of
+//     a single CTA (no cluster, any vocabulary); backward-only rewrites chunks in place and stores
+//     them with TMA bulk stores.
 //
-// One DMA warp (one elected lane) issues every bulk copy; consumers never touch global memory
-// except for a handful of per-row scalars.  Persistent grid: floor(SMs / cluster) clusters loop over
-// rows.  Replaces trl/trainer/utils.py:1430-1490 + grpo_trainer.py:1258 + the autograd backward
-// down to the logits (see include/b200trl.h).
+// Persistent grid: clusters (or single CTAs) loop over rows with a static stride.  Replaces
+// trl/trainer/utils.py:1430-1490 + grpo_trainer.py:1258 + the autograd backward down to the logits
+// (see include/b200trl.h).  Measured behaviour, the phase trace and what was tried: DESIGN.md §3.
 #include <algorithm>
 #include <cstdlib>
 
@@ -24,14 +27,13 @@
 namespace b200trl {
 namespace {
 
-constexpr int kMaxConsumers = 768;  // consumer threads per CTA: 768 or 512 (1 CTA / SM), 256 (2 CTAs / SM)
+constexpr int kMaxConsumers = 768;  // consumer threads per CTA: 768 / 640 / 512 (1 CTA / SM), 256 (2 CTAs / SM)
 constexpr int kChunkBytes = 16384;  // default chunk; per-geometry value: chunk_bytes_for()
 constexpr int kMaxSlots = 13;
 __host__ __device__ constexpr int chunk_bytes_for(int consumers) {
     return (consumers == 768 || consumers == 640) ? consumers * 32 : 16384;
 }
 constexpr int kMaxCluster = 8;
-constexpr int kStoreLag = 2;     // bulk stores allowed to be still reading shared memory
 constexpr float kSlack = 6.0f;   // reference point may trail the running max by 2^6
 
 struct __align__(16) Part4 {
