@@ -128,6 +128,15 @@ int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_t n_rows, i
                                 float inv_temperature, float* logp, float* entropy, float* lse,
                                 b200trl_stream_t stream);
 
+/* The same forward with a row mask (uint8 [n_rows], a torch.bool tensor's storage): rows with row_mask == 0 are NOT
+ * read and get logp = entropy = lse = 0.  This is what the DPO-family consumers compute around the call
+ * (`labels[~loss_mask] = 0; per_token_logps = selective_log_softmax(logits, labels); per_token_logps[~loss_mask] = 0`,
+ * trl/trainer/dpo_trainer.py:1557-1559; likewise kto / bco / cpo / orpo), minus the reads of the prompt rows. */
+int b200trl_masked_logprob_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                               int64_t rows_per_batch, int64_t batch_stride, const int64_t* ids,
+                               const uint8_t* row_mask, float inv_temperature, float* logp, float* entropy, float* lse,
+                               b200trl_stream_t stream);
+
 /* Backward of the gather-log-softmax: dlogits[r,v] = g[r]*inv_T*(1[v==ids[r]] - exp(x[r,v]*inv_T - lse[r])),
  * written in the logits dtype.  What autograd produces for utils.py:1449-1461 + grpo_trainer.py:1258. */
 int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,

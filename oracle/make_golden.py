@@ -268,6 +268,28 @@ def gold_masks():
     save("masks.pt", cases)
 
 
+def gold_dpo():
+    """DPO's per-sequence log-probs (dpo_trainer.py:1557-1571) and their gradient, from the reference's source."""
+    cases = []
+    for i, (B, T, V, dtype) in enumerate([(4, 12, 64, torch.float32), (6, 20, 1032, torch.float32),
+                                          (3, 9, 4104, torch.bfloat16)]):
+        g = torch.Generator().manual_seed(900 + i)
+        logits = (torch.randn(B, T, V, generator=g) * 2).to(dtype)
+        labels = torch.randint(0, V, (B, T), generator=g)
+        start = torch.randint(1, T // 2, (B,), generator=g)
+        end = torch.randint(T // 2, T + 1, (B,), generator=g)
+        pos = torch.arange(T).unsqueeze(0)
+        loss_mask = (pos >= start.unsqueeze(1)) & (pos < end.unsqueeze(1))  # prompt | completion | padding
+        w = torch.randn(B, generator=g)
+        x = logits.float().clone().requires_grad_(True)  # gradient through the reference's fp32 branch
+        all_logps, per_token = R.ref_dpo_sequence_logps(x, labels, loss_mask)
+        (all_logps * w).sum().backward()
+        half = R.ref_dpo_sequence_logps(logits, labels, loss_mask)[0] if dtype != torch.float32 else None
+        cases.append(dict(logits=logits, labels=labels, loss_mask=loss_mask, w=w, all_logps=all_logps.detach(),
+                          per_token_logps=per_token.detach(), grad_logits=x.grad.clone(), all_logps_half_branch=half))
+    save("dpo.pt", cases)
+
+
 def gold_rloo():
     cases = []
     for i, (B, T, k, nr, na, tl) in enumerate([(8, 16, 2, False, False, True), (12, 20, 4, True, True, True),
@@ -315,3 +337,4 @@ if __name__ == "__main__":
     gold_misc()
     gold_rloo()
     gold_masks()
+    gold_dpo()

@@ -120,6 +120,18 @@ def ref_completion_mask(completion_ids, eos_token_id):
     return ns["completion_mask"], ns["eos_idx"]
 
 
+def ref_dpo_sequence_logps(logits, labels, loss_mask):
+    """DPOTrainer.concatenated_forward's log-prob block (dpo_trainer.py:1557-1571), executed verbatim with the
+    reference's own selective_log_softmax; returns (all_logps, per_token_logps)."""
+    ns = dict(_BASE_NS)
+    ns.update(ref_utils())
+    ns.update(logits=logits, labels=labels.clone(), loss_mask=loss_mask.clone(),
+              self=types.SimpleNamespace(padding_free=False))
+    run_lines("trl/trainer/dpo_trainer.py", 1557, 1571, ns, anchor_first="labels[~loss_mask] = 0",
+              anchor_last="all_logps = per_token_logps[:, 1:].sum(-1)")
+    return ns["all_logps"], ns["per_token_logps"]
+
+
 def ref_core():
     return load_defs("trl/core.py", ["masked_mean", "masked_var", "masked_whiten"])
 

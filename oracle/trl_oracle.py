@@ -323,6 +323,15 @@ def first_true_indices(bools: torch.Tensor) -> torch.Tensor:
     return torch.where(bools, pos, torch.full_like(pos, n)).min(dim=-1).values
 
 
+def dpo_sequence_logps(logits, labels, loss_mask):
+    """dpo_trainer.py:1556-1571 (non-padding-free): masked per-token log-probs, rolled right by one, summed from 1."""
+    labels = labels.masked_fill(~loss_mask, 0)                      # :1557
+    per_token = selective_log_softmax(logits, labels)               # :1558
+    per_token = per_token.masked_fill(~loss_mask, 0.0)              # :1559
+    per_token = torch.roll(per_token, shifts=1, dims=1)             # :1560
+    return per_token[:, 1:].sum(-1), per_token                      # :1571
+
+
 def truncate_response(stop_token_id, pad_token_id, responses):
     """utils.py:1036-1056 — everything after the first stop token becomes pad (the stop token stays)."""
     trunc = first_true_indices(responses == stop_token_id).unsqueeze(-1)

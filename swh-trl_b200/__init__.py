@@ -14,9 +14,11 @@ from .functional import (  # noqa: F401
     get_high_entropy_mask,
     logprobs_and_entropy,
     masked_mean,
+    masked_selective_log_softmax,
     masked_var,
     masked_whiten,
     selective_log_softmax,
+    sequence_logps,
 )
 from .grpo import GRPOLoss, GRPOLossOutput, compute_loss, get_per_token_logps_and_entropies  # noqa: F401
 from .liger_seam import B200FusedLinearGRPOLoss  # noqa: F401

@@ -122,6 +122,22 @@ extern "C" int b200trl_logprob_entropy_fwd(const void* logits, int dtype, int64_
     return dispatch(a, dtype, as_stream(stream));
 }
 
+extern "C" int b200trl_masked_logprob_fwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab,
+                                          int64_t row_stride, int64_t rows_per_batch, int64_t batch_stride,
+                                          const int64_t* ids, const uint8_t* row_mask, float inv_temperature,
+                                          float* logp, float* entropy, float* lse, b200trl_stream_t stream) {
+    K1Args a;
+    const int rc = fill_common(a, logits, dtype, n_rows, vocab, row_stride, rows_per_batch, batch_stride, ids,
+                               inv_temperature, "masked_logprob_fwd");
+    if (rc) return rc;
+    B200TRL_REQUIRE(logp && row_mask, B200TRL_E_INVALID, "masked_logprob_fwd: null pointer");
+    a.row_mask = row_mask;
+    a.logp = logp;
+    a.entropy = entropy;
+    a.lse = lse;
+    return dispatch(a, dtype, as_stream(stream));
+}
+
 extern "C" int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
                                    int64_t rows_per_batch, int64_t batch_stride, const int64_t* ids,
                                    float inv_temperature, const float* lse, const float* g, void* dlogits,

@@ -19,6 +19,7 @@ struct K1Args {
     int64_t rows_per_batch;  // 0: flat (row r at r * row_stride); else row r = (b, t) at b * batch_stride + t * row_stride
     int64_t batch_stride;
     const int64_t* ids;
+    const uint8_t* row_mask;  // forward-only, nullable: rows with row_mask[row] == 0 are not read (outputs 0)
     float c;         // inv_temperature * log2(e)
     float inv_temp;
     // forward outputs (nullable)
@@ -67,6 +68,7 @@ __device__ __forceinline__ int64_t dlogits_offset(const K1Args& a, int64_t row) 
 // true when the row's dlogits are known to be zero before reading it: the loss ignores it (fused GRPO / PPO
 // modes) or its upstream gradient is exactly zero (backward of a masked token, e.g. DPO prompt positions)
 __device__ __forceinline__ bool row_is_masked(const K1Args& a, int64_t row) {
+    if (a.row_mask) return a.row_mask[row] == 0;
     if (a.gmode == G_GIVEN) return a.g[row] == 0.f;
     if (a.gmode == G_GRPO) return a.mask[row] == 0;
     if (a.gmode == G_PPO) return (row % a.T) > a.seq_len[row / a.T];

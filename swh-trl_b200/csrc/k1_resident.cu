@@ -915,6 +915,8 @@ int launch_mode_p(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
         return launch_mode_s<F, Bk, DUAL, NC, DIRECT, kFused>(a, cs, num_slots, stream);
     // backward-only with a per-token upstream gradient: rows whose gradient is exactly zero (masked tokens) are not
     // read at all -- their dlogits are zeros whatever the logits hold.  Always on: no output changes.
+    constexpr bool kFwdOnly = F && !Bk;
+    if (kFwdOnly && a.row_mask) return launch_mode_s<F, Bk, DUAL, NC, DIRECT, kFwdOnly>(a, cs, num_slots, stream);
     constexpr bool kBwdOnly = !F && Bk;
     static const int skip_zero = env_int("B200TRL_K1_SKIPZERO", 1);
     if (kBwdOnly && skip_zero && a.gmode == G_GIVEN)

@@ -136,6 +136,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 1024 ? 2 : 1) k1_row_kernel(co
     const T* x = reinterpret_cast<const T*>(a.logits) + logits_offset(a, row);
     const int64_t V = a.vocab;
 
+    if (a.row_mask && !a.dlogits && a.row_mask[row] == 0) {  // masked forward: the row is not read, outputs are 0
+        if (tid == 0) {
+            if (a.logp) a.logp[row] = 0.f;
+            if (a.entropy) a.entropy[row] = 0.f;
+            if (a.lse) a.lse[row] = 0.f;
+        }
+        return;
+    }
     if (a.skip_masked && a.dlogits && a.lse_in == nullptr && row_is_masked(a, row)) {
         // opt-in: a row the loss ignores is not read; outputs are zero (PPO: INVALID_LOGPROB), dlogits are zero
         T* dz = reinterpret_cast<T*>(a.dlogits) + dlogits_offset(a, row);

@@ -42,6 +42,43 @@ class _SelectiveLogSoftmax(torch.autograd.Function):
         return dlogits, None, None, None
 
 
+class _MaskedSelectiveLogSoftmax(torch.autograd.Function):
+    """log_softmax(logits)[index] where ``mask`` is True, exactly 0 elsewhere; masked rows are read neither in the
+    forward nor in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, logits, index, mask):
+        logp, _, lse = ops.masked_logprob_fwd(logits, index, mask)
+        ctx.save_for_backward(logits, index, lse, mask)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g_logp):
+        if g_logp is None:
+            return None, None, None
+        logits, index, lse, mask = ctx.saved_tensors
+        g = g_logp.to(torch.float32) * mask.to(torch.float32)  # the masked outputs are constants
+        return ops.logprob_bwd(logits, index, lse, g.contiguous(), 1.0), None, None
+
+
+def masked_selective_log_softmax(logits: torch.Tensor, index: torch.Tensor, mask: torch.Tensor,
+                                 out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``selective_log_softmax(logits, index)`` with the entries where ``mask`` is False set to 0 — the pattern of the
+    DPO-family trainers (dpo_trainer.py:1557-1559; kto / bco / cpo / orpo alike) — without reading the masked rows
+    (prompt and padding positions) in either pass."""
+    logp = _MaskedSelectiveLogSoftmax.apply(logits, index, mask)
+    return logp if out_dtype is None else logp.to(out_dtype)
+
+
+def sequence_logps(logits: torch.Tensor, labels: torch.Tensor, loss_mask: torch.Tensor):
+    """``(all_logps [B], per_token_logps [B,T])`` as ``DPOTrainer.concatenated_forward`` computes them from the
+    already-shifted ``labels`` / ``loss_mask`` (dpo_trainer.py:1556-1571, the non-padding-free branch): masked
+    per-token log-probs are 0, the tensor is rolled right by one and positions ``1:`` are summed."""
+    per_token = masked_selective_log_softmax(logits, labels, loss_mask)
+    per_token = torch.roll(per_token, shifts=1, dims=1)  # :1560
+    return per_token[:, 1:].sum(-1), per_token          # :1571
+
+
 def logprobs_and_entropy(logits: torch.Tensor, index: torch.Tensor, temperature: float = 1.0,
                          compute_entropy: bool = True):
     """``(log_softmax(logits / temperature)[index], entropy)`` in a single pass (entropy carries no grad).

@@ -163,6 +163,29 @@ def logprob_entropy_fwd(logits: torch.Tensor, ids: torch.Tensor, inv_temperature
     return logp, ent, lse
 
 
+def masked_logprob_fwd(logits: torch.Tensor, ids: torch.Tensor, row_mask: torch.Tensor, inv_temperature: float = 1.0,
+                       want_entropy: bool = False, want_lse: bool = True):
+    """Like ``logprob_entropy_fwd`` but rows with ``row_mask == False`` are not read (outputs 0) —
+    ``b200trl_masked_logprob_fwd``."""
+    r = rows_view(logits)
+    x, n, V = r.t, r.n, r.V
+    _need_cuda(ids, "index")
+    idx = ids.to(torch.int64).contiguous()
+    m = row_mask.to(torch.bool).contiguous().view(torch.uint8)
+    if idx.numel() != n or m.numel() != n:
+        raise ValueError(f"index / mask have {idx.numel()} / {m.numel()} elements, logits has {n} rows")
+    shape = tuple(logits.shape[:-1])
+    logp = torch.empty(shape, dtype=torch.float32, device=x.device)
+    ent = torch.empty(shape, dtype=torch.float32, device=x.device) if want_entropy else None
+    lse = torch.empty(shape, dtype=torch.float32, device=x.device) if want_lse else None
+    if n:
+        check(lib.b200trl_masked_logprob_fwd(_ptr(x), _DTYPES[x.dtype], n, V, r.row_stride, r.rows_per_batch,
+                                             r.batch_stride, _ptr(idx), _ptr(m), float(inv_temperature), _ptr(logp),
+                                             _ptr(ent), _ptr(lse), _stream(x)), "masked_logprob_fwd")
+        _count()
+    return logp, ent, lse
+
+
 def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: torch.Tensor,
                 inv_temperature: float = 1.0) -> torch.Tensor:
     """``dlogits`` (logits dtype, contiguous) for per-token upstream gradient ``g``."""

@@ -965,3 +965,46 @@ def test_full_size_properties(S, B, T, V, level):
         want = -p * lp_leaf.grad[b, t]
         want[ids[b, t]] += lp_leaf.grad[b, t]
         torch.testing.assert_close(grad[b, t].float().cpu(), want.to(torch.bfloat16).float(), rtol=2 * BF16_ULP, atol=1e-12)
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_dpo_sequence_logps_golden(S, i):
+    """f-3: the DPO-family log-prob block (dpo_trainer.py:1557-1571) through the masked forward: values against the
+    reference's fp32 path (1e-5), gradients against its fp32 gradient (bf16 inputs: rounded to bf16, one ulp); masked
+    rows are never read (they hold NaN here) in either pass."""
+    c = load_golden("dpo.pt")[i]
+    logits = c["logits"].clone()
+    poisoned = logits.clone()
+    poisoned[~c["loss_mask"]] = float("nan")
+    for path in (S.K1_ROW, S.K1_AUTO):
+        S.set_k1_path(path)
+        try:
+            x = poisoned.to(DEV).requires_grad_(True)
+            all_logps, per_token = S.sequence_logps(x, c["labels"].to(DEV), c["loss_mask"].to(DEV))
+            (all_logps * c["w"].to(DEV)).sum().backward()
+        finally:
+            S.set_k1_path(S.K1_AUTO)
+        torch.testing.assert_close(per_token.detach().cpu(), c["per_token_logps"], rtol=0, atol=1e-5)
+        torch.testing.assert_close(all_logps.detach().cpu(), c["all_logps"], rtol=1e-5, atol=1e-4)
+        got = x.grad.float().cpu()
+        keep = c["loss_mask"]
+        assert torch.count_nonzero(got[~keep]) == 0 and bool(torch.isfinite(got).all())
+        if logits.dtype == torch.float32:
+            torch.testing.assert_close(got[keep], c["grad_logits"][keep], rtol=1e-4, atol=1e-7)
+        else:
+            torch.testing.assert_close(got[keep], c["grad_logits"][keep].to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-9)
+
+
+def test_masked_forward_large_vocab(S):
+    """The masked forward on the streaming kernel (V=151936 bf16, half the rows masked) against the plain forward."""
+    g = torch.Generator(device=DEV).manual_seed(21)
+    B, T, V = 2, 256, 151936
+    x = torch.randn(B, T, V, generator=g, device=DEV).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g, device=DEV)
+    keep = torch.rand(B, T, generator=g, device=DEV) > 0.5
+    full = S.selective_log_softmax(x, ids)
+    xp = x.clone()
+    xp[~keep] = float("nan")
+    got = S.masked_selective_log_softmax(xp, ids, keep)
+    assert torch.equal(got[~keep], torch.zeros_like(got[~keep]))
+    torch.testing.assert_close(got[keep], full[keep], rtol=0, atol=2e-6)

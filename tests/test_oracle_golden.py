@@ -220,3 +220,14 @@ def test_masks_vs_reference(i):
     assert torch.equal(post, c["truncated"]) and torch.equal(lens, c["sequence_length"])
     assert torch.equal(O.response_lengths(None, pad, ids)[1], c["sequence_length_nostop"])
     assert torch.equal(O.first_true_indices(c["bools"]), c["first_true"])
+
+
+@pytest.mark.parametrize("i", range(3))
+def test_dpo_sequence_logps_vs_reference(i):
+    """DPO's per-sequence log-probs (dpo_trainer.py:1557-1571) and their gradient against the reference's own source."""
+    c = load_golden("dpo.pt")[i]
+    x = c["logits"].float().clone().requires_grad_(True)
+    all_logps, per_token = O.dpo_sequence_logps(x, c["labels"], c["loss_mask"])
+    assert torch.equal(all_logps.detach(), c["all_logps"]) and torch.equal(per_token.detach(), c["per_token_logps"])
+    (all_logps * c["w"]).sum().backward()
+    torch.testing.assert_close(x.grad, c["grad_logits"], rtol=1e-6, atol=1e-7)

@@ -113,6 +113,25 @@ def main():
     add("GRPO fused step (token-level IS) C2", ms, n, 4 * V * N, "mask_stats + K1 + K2 + rescale check")
     x.requires_grad_(False)
 
+    # DPO-family pattern (dpo_trainer.py:1557-1571): per-sequence log-probs with the prompt half masked, fwd + bwd
+    keep = torch.arange(T, device=DEV).unsqueeze(0).expand(B, T) >= T // 2
+    wseq = torch.randn(B, generator=g, device=DEV)
+
+    def dpo_step(masked):
+        x.grad = None
+        if masked:
+            allp, _ = S.sequence_logps(x, ids, keep)
+        else:  # what patch_trl alone gives the reference code: plain op, then the mask
+            allp = (S.selective_log_softmax(x, ids) * keep).sum(-1)
+        (allp * wseq).sum().backward()
+    x.requires_grad_(True)
+    for masked in (False, True):
+        ms, n = timeit(lambda: dpo_step(masked))
+        add(f"DPO sequence log-probs fwd+bwd C2 shape, 50% prompt rows ({'masked forward' if masked else 'plain op + mask'})",
+            ms, n, 6 * V * N, "2R+1W algorithmic for unmasked rows; masked rows are not read"
+            + ("" if masked else " in the backward only"))
+    x.requires_grad_(False)
+
     # K2 alone, quantile mask
     m32, rc, tot = ops.mask_stats(mask)
     cfg = ops.make_cfg(0.04, 0.2, 0.2, None, "bnpo", "token", T)
