@@ -372,14 +372,15 @@ def run_b200(args):
                          "kernel_share_of_step": k1_ms / (elapsed_ms / args.steps)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            nb = 2
+            nb, cpu_steps = 4, 30  # ~11 s of CPU work on the box's cores
             cpu_logits = logits.detach()[:nb].cpu()
             adv = S.group_advantages(rewards_local, weights, G)["advantages"]
             rate, ms = cpu_reference_rate(cpu_logits, ids[:nb].cpu(), mask[:nb].cpu(), adv[:nb].cpu(), old[:nb].cpu(),
-                                          ref[:nb].cpu(), steps=4, warmup=1)
+                                          ref[:nb].cpu(), steps=cpu_steps, warmup=2)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"4 timed steps of 1 sequence (T={T}, V={V}) from the same batch, "
-                                              f"fp32 torch path fwd+bwd, {ms:.0f} ms/step"}
+                                    "sample": f"{cpu_steps} timed steps of 1 sequence each (T={T}, V={V}; {nb} distinct "
+                                              f"sequences of the same batch in turn), fp32 torch path fwd+bwd, "
+                                              f"{ms:.0f} ms/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
