@@ -99,7 +99,7 @@ def main():
         for m in range(n_mb):
             ids, mask, old, ref = make_microbatch(m)  # untimed: stands in for the model forward
             logits.grad = None
-            torch.cuda.synchronize()
+            barrier()  # ranks finish regenerating at different times; the timed region must not wait for that
             e0, e1 = ev(), ev()
             e0.record()
             out = loss_fn(logits, ids, mask, adv[m * MB:(m + 1) * MB], old, ref)
