@@ -893,19 +893,32 @@ Geom pick_geom(int64_t vocab, Mode m) {
     if (mode == 4 && mid.cs) return mid;
     if (mode == 3 && dense.cs && dense.cs <= wide.cs) return dense;
     if (mode == 2 && twin.cs) return twin;
-    if (mode == 1 || !twin.cs) return wide;
+    if (mode == 1) return wide;
     // measured (tools/k1_sweep.sh, B200): rows that fit one twin CTA (<= 80 KB, e.g. V = 32000) are fastest with two
     // drifting CTAs per SM (fused 91.7 % of the measured HBM peak); anything that would need a cluster in twin form is
     // faster with 1 CTA / SM
     if (twin.cs == 1) return twin;
-    // 1 CTA / SM: 20 consumer warps with 20 KB chunks and an 11-slot ring are the best balance of warps against ring
-    // depth and tail-chunk waste -- fused, % of the measured HBM peak for 512 / 640 / 768 consumers: V = 151 936
-    // 90.3 / 93.1 / 88.9, 128 256 89.6 / 89.7 / 87.4, 100 352 82.4 / 94.5 / 82.9, 65 536 92.0 / 92.1 / 90.9; below
-    // ~56 k the shapes are equal and dense keeps the shorter tail chunk
-    if (vocab >= 57344 && mid.cs && mid.cs <= wide.cs) return mid;
-    if (vocab >= 57344) return wide;
-    if (dense.cs && dense.cs <= wide.cs) return dense;
-    return wide;
+    // 1 CTA / SM.  What separates the three shapes is (a) the cluster they need and (b) the time lost in a slice's last,
+    // partial chunk: every chunk is a barrier round, and a partial one costs one or two vector-times whatever it holds.
+    // Take the smallest cluster, then the least tail waste, then (within 1.5 %) 640 > 768 > 512 consumers.  Measured,
+    // fused, % of the HBM peak for 512 / 640 / 768: V = 151 936 90.3 / 93.1 / 88.9, 128 256 89.6 / 89.7 / 87.4, 100 352
+    // 82.4 / 94.5 / 82.9 (only 640 fits one CTA), 65 536 92.0 / 92.1 / 90.9, 50 304 82.0 / 89.9 / 82.7, 49 152 88.9 /
+    // 88.8 / 90.4.
+    auto waste = [&](const Geom& g) {
+        const int chunk = chunk_bytes_for(g.nc);
+        const int64_t slice_vecs = (((vocab + g.cs - 1) / g.cs + 7) & ~int64_t(7)) / 8;
+        const int64_t chunk_vecs = chunk / 16, full = slice_vecs / chunk_vecs, rest = slice_vecs - full * chunk_vecs;
+        const double vpt = static_cast<double>(chunk_vecs) / g.nc;  // vector-times of a full round
+        const double rounds = static_cast<double>(full) + (rest ? static_cast<double>((rest + g.nc - 1) / g.nc) / vpt : 0.0);
+        return rounds * static_cast<double>(chunk_vecs) / static_cast<double>(slice_vecs) - 1.0;
+    };
+    const Geom* order[3] = {&mid, &dense, &wide};
+    const Geom* best = nullptr;
+    for (const Geom* g : order) {
+        if (!g->cs) continue;
+        if (!best || g->cs < best->cs || (g->cs == best->cs && waste(*g) < waste(*best) - 0.015)) best = g;
+    }
+    return best ? *best : wide;
 }
 
 template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT>

@@ -1,10 +1,9 @@
 #!/bin/bash
 run() { env "$@" python tools/k1_variants.py; }
-for v in 151936 152064 128256 100352 65536; do
-  b=16; [ $v -lt 70000 ] && b=32
-  run KV_TAG=v${v}_wide512 KV_V=$v KV_B=$b B200TRL_K1_GEOM=1
-  run KV_TAG=v${v}_576 KV_V=$v KV_B=$b B200TRL_K1_GEOM=5
-  run KV_TAG=v${v}_640 KV_V=$v KV_B=$b B200TRL_K1_GEOM=4
-  run KV_TAG=v${v}_704 KV_V=$v KV_B=$b B200TRL_K1_GEOM=6
-  run KV_TAG=v${v}_768 KV_V=$v KV_B=$b B200TRL_K1_GEOM=3
-done
+run KV_TAG=v151936
+run KV_TAG=v50304 KV_V=50304 KV_B=32
+run KV_TAG=v49152 KV_V=49152 KV_B=32
+run KV_TAG=v100352 KV_V=100352
+run KV_TAG=v128256 KV_V=128256
+run KV_TAG=v524288 KV_V=524288 KV_B=4
+run KV_TAG=v32000 KV_V=32000 KV_B=64
