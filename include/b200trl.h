@@ -108,6 +108,10 @@ int b200trl_set_k1_path(int path); /* returns the previous setting */
  * gradients are unchanged; only the per-token outputs at masked positions differ from the reference (which
  * computes and then discards them).  Returns the previous setting. */
 int b200trl_set_skip_masked(int on);
+/* Which shape the resident K1 kernel takes for a bf16 vocabulary (host-only, no GPU needed): out4 = {consumer threads
+ * per CTA, cluster size, ring slots, chunk bytes}; mode 0 forward-only, 1 backward-only, 2 fused.  Returns
+ * B200TRL_E_UNSUPPORTED (out4 zeroed) when the call would go to the row kernel.  See DESIGN.md §3. */
+int b200trl_k1_geometry(int64_t vocab, int mode, int32_t* out4);
 /* Diagnostics, trace builds only (`make -C swh-trl_b200/csrc trace` -> lib/libb200trl_trace.so; the production
  * library returns B200TRL_E_UNSUPPORTED): while `buffer` (device memory, 4 * 3 * 169 uint64, zeroed by the caller) is
  * set, the resident K1 kernel logs phase timestamps (tag << 56 | row << 40 | chunk << 32 | clock32) of three roles

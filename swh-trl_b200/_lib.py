@@ -52,6 +52,7 @@ PROTOTYPES = {
     "b200trl_last_error": (C.c_char_p, []),
     "b200trl_set_k1_path": (C.c_int, [_i32]),
     "b200trl_set_skip_masked": (C.c_int, [_i32]),
+    "b200trl_k1_geometry": (C.c_int, [_i64, _i32, _p]),
     "b200trl_k1_set_trace": (C.c_int, [_p, _i64]),
     "b200trl_logprob_entropy_fwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p]),
     "b200trl_masked_logprob_fwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _f, _p, _p, _p, _p]),

@@ -93,6 +93,12 @@ extern "C" int b200trl_set_k1_path(int path) {
 
 extern "C" int b200trl_set_skip_masked(int on) { return g_skip_masked.exchange(on ? 1 : 0); }
 
+extern "C" int b200trl_k1_geometry(int64_t vocab, int mode, int32_t* out4) {
+    B200TRL_REQUIRE(out4 != nullptr && mode >= 0 && mode <= 2, B200TRL_E_INVALID, "k1_geometry: bad arguments");
+    k1_resident_geometry(vocab, mode, out4);
+    return out4[0] ? B200TRL_OK : B200TRL_E_UNSUPPORTED;
+}
+
 extern "C" int b200trl_k1_set_trace(void* buffer, int64_t first_row) {
 #ifdef B200TRL_K1_TRACE
     B200TRL_REQUIRE(first_row >= 0, B200TRL_E_INVALID, "k1_set_trace: bad arguments");

@@ -156,5 +156,6 @@ int launch_k1_row(const K1Args& a, int dtype, cudaStream_t stream);
 int launch_k1_resident(const K1Args& a, cudaStream_t stream);
 bool k1_resident_supported(const K1Args& a, int dtype);
 bool k1_resident_preferred(const K1Args& a, int dtype);
+void k1_resident_geometry(int64_t vocab, int mode, int32_t out[4]);
 
 }  // namespace b200trl

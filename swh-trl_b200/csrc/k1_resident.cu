@@ -986,6 +986,19 @@ bool k1_resident_supported(const K1Args& a, int dtype) {
 // 1.53 / 0.65 vs 2.28 / 0.99; V = 524 288 (8-CTA cluster) 1.66 / 0.65 vs 2.32 / 0.92.
 bool k1_resident_preferred(const K1Args& a, int dtype) { return k1_resident_supported(a, dtype); }
 
+// host-only query behind b200trl_k1_geometry: {consumer threads, cluster size, ring slots, chunk bytes}, 0s if the
+// resident kernel cannot take the vocabulary in that mode (0 forward-only, 1 backward-only, 2 fused)
+void k1_resident_geometry(int64_t vocab, int mode, int32_t out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (vocab <= 0 || vocab % 8 != 0 || vocab * 2 < 2 * kChunkBytes || mode < 0 || mode > 2) return;
+    const Geom g = pick_geom(vocab, mode == 0 ? M_FWD : (mode == 1 ? M_BWD : M_FUSED));
+    if (!g.cs) return;
+    out[0] = g.nc;
+    out[1] = g.cs;
+    out[2] = g.slots;
+    out[3] = chunk_bytes_for(g.nc);
+}
+
 int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
     if (a.n_rows == 0) return B200TRL_OK;
     const Mode m = mode_of(a);

@@ -82,3 +82,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("test oracle", ""), os.path.join(dirpath, f)
+
+
+def test_k1_geometry_policy():
+    """The shape the resident kernel takes per vocabulary and mode (host-only logic): streaming modes
+    never need a cluster; the fused pass takes the smallest cluster, then the least tail-chunk waste."""
+    from swh_trl_b200 import _lib
+
+    def geom(vocab, mode):
+        out = (ctypes.c_int32 * 4)()
+        rc = _lib.lib.b200trl_k1_geometry(vocab, mode, out)
+        return rc, tuple(out)
+
+    FWD, BWD, FUSED = 0, 1, 2
+    for v in (32000, 50304, 151936, 262144, 1 << 20):
+        assert geom(v, FWD) == (0, (256, 1, 6, 16384))      # two twin CTAs per SM stream whole rows
+        assert geom(v, BWD) == (0, (768, 1, 9, 24576))
+    assert geom(151936, FUSED) == (0, (640, 2, 11, 20480))   # config 2: half a row per CTA, 8 chunks of 20 KB
+    assert geom(152064, FUSED) == (0, (640, 2, 11, 20480))   # config 4's vocabulary
+    assert geom(100352, FUSED) == (0, (640, 1, 11, 20480))   # the only shape that holds 200 KB in one CTA
+    assert geom(50304, FUSED) == (0, (640, 1, 11, 20480))    # 4.9 chunks of 20 KB vs 4.09 of 24 KB
+    assert geom(49152, FUSED) == (0, (768, 1, 9, 24576))     # exactly four 24 KB chunks
+    assert geom(32000, FUSED) == (0, (256, 1, 6, 16384))     # a whole row fits one twin CTA
+    assert geom(262144, FUSED)[1][1] == 4 and geom(524288, FUSED)[1][1] == 8
+    assert geom(8192, FUSED)[0] == -2 and geom(32001, FWD)[0] == -2  # tiny / unaligned rows go to the row kernel
+    assert geom(1 << 23, FUSED)[0] == -2                             # 16 MB rows exceed an 8-CTA cluster
