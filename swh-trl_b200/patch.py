@@ -40,6 +40,18 @@ def patch_module(mod: types.ModuleType) -> list:
         trainer._compute_loss = grpo.compute_loss
         trainer._get_per_token_logps_and_entropies = grpo.get_per_token_logps_and_entropies
         done.append("GRPOTrainer._compute_loss")
+        # the operator seam: GRPOTrainer.__init__ builds `LigerFusedLinearGRPOLoss(beta=..., ...)` from this module's
+        # global (grpo_trainer.py:82-83, 878-886) behind `is_liger_kernel_available()` (:871); rebinding both makes
+        # `use_liger_loss=True` construct the B200 operator (same keyword arguments), liger-kernel installed or not
+        from .liger_seam import B200FusedLinearGRPOLoss
+        if getattr(mod, "LigerFusedLinearGRPOLoss", None) is not B200FusedLinearGRPOLoss:
+            if hasattr(mod, "LigerFusedLinearGRPOLoss"):
+                mod._trl_original_LigerFusedLinearGRPOLoss = mod.LigerFusedLinearGRPOLoss
+            mod.LigerFusedLinearGRPOLoss = B200FusedLinearGRPOLoss
+            if hasattr(mod, "is_liger_kernel_available"):
+                mod._trl_original_is_liger_kernel_available = mod.is_liger_kernel_available
+                mod.is_liger_kernel_available = lambda *a, **k: True
+            done.append("LigerFusedLinearGRPOLoss")
     return done
 
 

@@ -70,6 +70,7 @@ def test_patch_trl_rebinds_every_importer():
         def _compute_loss(self, model, inputs):
             return "reference"
     grpo_mod.GRPOTrainer = GRPOTrainer
+    grpo_mod.is_liger_kernel_available = lambda: False  # liger-kernel not installed: the name below does not exist
     core = types.ModuleType("faketrl.core")
     core.masked_whiten = orig
     ppo_mod = types.ModuleType("faketrl.trainer.ppo_trainer")  # ppo_trainer.py:54-71 binds the mask helpers too
@@ -89,6 +90,11 @@ def test_patch_trl_rebinds_every_importer():
     assert grpo_mod.get_high_entropy_mask is S.get_high_entropy_mask
     assert core.masked_whiten is S.masked_whiten
     assert GRPOTrainer._compute_loss is S.compute_loss
+    # the seam: `use_liger_loss=True` now constructs the B200 operator with the reference's keyword arguments
+    assert grpo_mod.LigerFusedLinearGRPOLoss is S.B200FusedLinearGRPOLoss and grpo_mod.is_liger_kernel_available()
+    op = grpo_mod.LigerFusedLinearGRPOLoss(beta=0.04, epsilon_low=0.2, epsilon_high=0.28, temperature=0.9,
+                                           use_ref_model=True, loss_type="dr_grpo", max_completion_length=64)
+    assert (op.beta, op.epsilon_high, op.temperature, op.loss_type) == (0.04, 0.28, 0.9, "dr_grpo")
     assert GRPOTrainer._trl_original_compute_loss(None, None, None) == "reference"
     assert ppo_mod.first_true_indices is S.first_true_indices and ppo_mod.truncate_response is S.truncate_response
     assert ppo_mod._trl_original_truncate_response is orig
