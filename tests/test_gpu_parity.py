@@ -1008,3 +1008,31 @@ def test_masked_forward_large_vocab(S):
     got = S.masked_selective_log_softmax(xp, ids, keep)
     assert torch.equal(got[~keep], torch.zeros_like(got[~keep]))
     torch.testing.assert_close(got[keep], full[keep], rtol=0, atol=2e-6)
+
+
+def test_seam_bias_and_upstream_scale(S):
+    """The seam's C call with an lm_head bias (cuBLASLt bias epilogue + dbias column sums) and an upstream gradient
+    that is not 1 (Trainer divides the loss by gradient_accumulation_steps, grpo_trainer.py:1016-1019): gradients are
+    rescaled on the device."""
+    B, T, H, V = 3, 16, 64, 512
+    g = torch.Generator().manual_seed(5)
+    hidden = torch.randn(B, T, H, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g) * 0.2).to(torch.bfloat16)
+    bias = (torch.randn(V, generator=g) * 0.5).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    mask = (torch.arange(T).unsqueeze(0) < torch.tensor([[16], [9], [12]])).int()
+    adv = torch.randn(B, generator=g)
+    hr, Wr, br = (t.float().clone().requires_grad_(True) for t in (hidden, W, bias))
+    logits_r = hr @ Wr.t() + br
+    logits_r = logits_r.detach().to(torch.bfloat16).float() + (logits_r - logits_r.detach())  # bf16 GEMM output
+    cfg = O.GRPOConfigLite(beta=0.0, loss_type="grpo", max_completion_length=T)
+    loss_r, _, _, _ = O.grpo_compute_loss(logits_r, ids, mask, adv, cfg, None, None)
+    (loss_r * 0.25).backward()
+    fn = S.B200FusedLinearGRPOLoss(beta=0.0, loss_type="grpo", max_completion_length=T, chunk_size=2)
+    h, w, b = (t.to(DEV).requires_grad_(True) for t in (hidden, W, bias))
+    loss, _ = fn(h, w, ids.to(DEV), mask.to(DEV), adv.to(DEV), b)
+    (loss * 0.25).backward()
+    assert loss.item() == pytest.approx(loss_r.item(), rel=2e-3, abs=1e-6)
+    for got, want in ((h.grad, hr.grad), (w.grad, Wr.grad), (b.grad, br.grad)):
+        err = (got.float().cpu() - want).norm() / want.norm().clamp(min=1e-12)
+        assert float(err) < 2e-2, float(err)
