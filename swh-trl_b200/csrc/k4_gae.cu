@@ -38,14 +38,16 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, GridWs* ws, int 
     }
     __threadfence();
     grid.sync();
+    // every warp folds the per-CTA partials the same way -- lane-strided sums, then a fixed shuffle tree -- so all
+    // threads of the grid get bit-identical totals; a serial walk by every thread costs gridDim.x dependent L2 reads
     double sa = 0.0, sb = 0.0;
     const volatile double* p = &w->part[0][0];
-    for (unsigned i = 0; i < gridDim.x; ++i) {  // same order in every thread
+    for (unsigned i = threadIdx.x & 31; i < gridDim.x; i += 32) {
         sa += p[2 * i];
         sb += p[2 * i + 1];
     }
-    ta = sa;
-    tb = sb;
+    ta = warp_sum(sa);
+    tb = warp_sum(sb);
 }
 
 // masked_whiten over the whole [n] array (trl/core.py:70-76); values are rewritten in place.
