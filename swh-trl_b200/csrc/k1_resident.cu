@@ -888,6 +888,12 @@ Geom pick_geom(int64_t vocab, Mode m) {
         if (mode == 1) return wide;
         if (mode == 2) return twin;
         if (mode == 3) return dense;
+        // backward-only reads a row and writes it back a ring's depth later: a SHORT ring (96-120 KB in flight per SM)
+        // keeps the read and write streams of an SM close together in time and is both faster and insensitive to how
+        // the two buffers are placed -- 9 / 5 / 4 slots: V = 151 936 1.71 / 1.60 / 1.55 ms, 128 256 1.42 / 1.34 / 1.30,
+        // 65 536 1.44 / 1.34 / 1.37, 32 000 1.43 / 1.42 / 1.43 (tools/k1_sweep.sh, tools/k1_offset_probe.py)
+        static const int bwd_slots = env_int("B200TRL_K1_BWD_SLOTS", 0);
+        if (m == M_BWD) dense.slots = bwd_slots >= 2 && bwd_slots <= kDenseSlots ? bwd_slots : (vocab * 2 >= 200000 ? 4 : 5);
         return m == M_FWD ? twin : dense;
     }
     if (mode == 4 && mid.cs) return mid;

@@ -1,9 +1,8 @@
 #!/bin/bash
 run() { env "$@" python tools/k1_variants.py; }
-run KV_TAG=v151936
-run KV_TAG=v50304 KV_V=50304 KV_B=32
-run KV_TAG=v49152 KV_V=49152 KV_B=32
-run KV_TAG=v100352 KV_V=100352
-run KV_TAG=v128256 KV_V=128256
-run KV_TAG=v524288 KV_V=524288 KV_B=4
-run KV_TAG=v32000 KV_V=32000 KV_B=64
+for v in 151936 128256 65536 32000; do
+  b=16; [ $v -lt 70000 ] && b=32; [ $v -lt 40000 ] && b=64
+  for s in 9 5 4; do
+    run KV_TAG=v${v}_bwdslots$s KV_V=$v KV_B=$b B200TRL_K1_BWD_SLOTS=$s
+  done
+done
