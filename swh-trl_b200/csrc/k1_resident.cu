@@ -924,7 +924,14 @@ Geom pick_geom(int64_t vocab, Mode m) {
         if (!g->cs) continue;
         if (!best || g->cs < best->cs || (g->cs == best->cs && waste(*g) < waste(*best) - 0.015)) best = g;
     }
-    return best ? *best : wide;
+    Geom out = best ? *best : wide;
+    static const int fused_slots = env_int("B200TRL_K1_FUSED_SLOTS", 0);  // tuning knob: shorter ring (>= chunks + 1)
+    if (fused_slots > 0 && fused_slots < out.slots) {
+        const int64_t slice = ((vocab + out.cs - 1) / out.cs + 7) & ~int64_t(7);
+        const int chunks = static_cast<int>((slice * 2 + chunk_bytes_for(out.nc) - 1) / chunk_bytes_for(out.nc));
+        out.slots = std::max(fused_slots, chunks + 1);
+    }
+    return out;
 }
 
 template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT>

@@ -1,8 +1,4 @@
 #!/bin/bash
 run() { env "$@" python tools/k1_variants.py; }
-for v in 151936 128256 65536 32000; do
-  b=16; [ $v -lt 70000 ] && b=32; [ $v -lt 40000 ] && b=64
-  for s in 9 5 4; do
-    run KV_TAG=v${v}_bwdslots$s KV_V=$v KV_B=$b B200TRL_K1_BWD_SLOTS=$s
-  done
-done
+for s in 11 10 9; do run KV_TAG=fused_slots$s B200TRL_K1_FUSED_SLOTS=$s; done
+for s in 13 12 11; do run KV_TAG=wide_slots$s B200TRL_K1_GEOM=1 B200TRL_K1_FUSED_SLOTS=$s; done
