@@ -227,7 +227,6 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import swh_trl_b200 as S
-    from swh_trl_b200 import distributed as D
     from swh_trl_b200 import ops
 
     B, T, V, G = CFG["B"], CFG["T"], CFG["V"], CFG["G"]

@@ -7,7 +7,7 @@ kernel in ``libb200trl.so``.  All wrappers are asynchronous and never synchronis
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 
 import torch
 
-from . import _lib, ops
+from . import ops
 
 INVALID_LOGPROB = 1.0  # ppo_trainer.py:81
 STAT_INDEX = {"loss": 0, "pg_loss": 1, "vf_loss": 2, "pg_clipfrac": 3, "vf_clipfrac": 4, "approxkl": 5, "entropy": 6,

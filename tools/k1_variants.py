@@ -33,6 +33,9 @@ def t(fn, n=20):
 fused = t(lambda: ops.grpo_fused_fwd_bwd(logits, ids, m32, rc, tot, adv, old, ref, cfg, 1.0, dlogits_out=dl))
 fwd = t(lambda: ops.logprob_entropy_fwd(logits, ids, 1.0))
 gtok = torch.randn(B, T, generator=g, device=DEV) * 1e-4
+gz = float(os.environ.get('KV_GZERO', 0))  # fraction of every sequence's tail whose upstream gradient is zero (padding)
+if gz > 0:
+    gtok[:, int(T * (1 - gz)):] = 0
 del dl
 bwd = t(lambda: ops.logprob_bwd(logits, ids, lse0, gtok, 1.0))  # includes torch.empty of the result
 print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("B200TRL") or k.startswith("KV_")}, "fused_ms": fused, "fwd_ms": fwd, "bwd_ms": bwd,
