@@ -1036,3 +1036,36 @@ def test_seam_bias_and_upstream_scale(S):
     for got, want in ((h.grad, hr.grad), (w.grad, Wr.grad), (b.grad, br.grad)):
         err = (got.float().cpu() - want).norm() / want.norm().clamp(min=1e-12)
         assert float(err) < 2e-2, float(err)
+
+
+@pytest.mark.parametrize("V", [32000, 50304, 151936, 262144])  # twin, 1-CTA mid, 2-CTA cluster, 4-CTA cluster
+def test_fused_pass_is_bitwise_reproducible(S, V):
+    """Race hunt (tools/k1_stress.py in small): repeated launches of the fused pass -- cluster exchange over st.async,
+    dlogits stored from registers, slots refilled while the row is still being written back -- give bit-identical
+    log-probs, entropies and dlogits, with and without masked-row skipping."""
+    from swh_trl_b200 import ops
+    B, T = 10, 64
+    g = torch.Generator(device=DEV).manual_seed(V)
+    x = (torch.randn(B, T, V, generator=g, device=DEV) * 2).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g, device=DEV)
+    lens = torch.randint(0, T + 1, (B,), generator=g, device=DEV)
+    mask = (torch.arange(T, device=DEV).unsqueeze(0) < lens.unsqueeze(1)).int()
+    adv = torch.randn(B, generator=g, device=DEV)
+    m32, rc, tot = ops.mask_stats(mask)
+    cfg = ops.make_cfg(0.0, 0.2, 0.2, None, "grpo", "token", T)
+    prev = S.set_k1_path(S.K1_RESIDENT)
+    try:
+        for skip in (False, True):
+            S.set_skip_masked(skip)
+            first = None
+            for _ in range(6):
+                lp, ent, _, dl = ops.grpo_fused_fwd_bwd(x, ids, m32, rc, tot, adv, None, None, cfg, 1.0)
+                cur = (lp.clone(), ent.clone(), dl.clone())
+                if first is None:
+                    first = cur
+                else:
+                    assert all(torch.equal(a, b) for a, b in zip(first, cur))
+            assert torch.count_nonzero(first[2][mask == 0]) == 0 and bool(torch.isfinite(first[2].float()).all())
+    finally:
+        S.set_skip_masked(False)
+        S.set_k1_path(prev)
