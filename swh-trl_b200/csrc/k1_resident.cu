@@ -893,7 +893,15 @@ Geom pick_geom(int64_t vocab, Mode m) {
         // the two buffers are placed -- 9 / 5 / 4 slots: V = 151 936 1.71 / 1.60 / 1.55 ms, 128 256 1.42 / 1.34 / 1.30,
         // 65 536 1.44 / 1.34 / 1.37, 32 000 1.43 / 1.42 / 1.43 (tools/k1_sweep.sh, tools/k1_offset_probe.py)
         static const int bwd_slots = env_int("B200TRL_K1_BWD_SLOTS", 0);
-        if (m == M_BWD) dense.slots = bwd_slots >= 2 && bwd_slots <= kDenseSlots ? bwd_slots : (vocab * 2 >= 200000 ? 4 : 5);
+        if (m == M_BWD) {
+            const int64_t row_bytes = vocab * 2, chunk = chunk_bytes_for(768);
+            const int64_t chunks = (row_bytes + chunk - 1) / chunk, tail = row_bytes % chunk;
+            int slots = row_bytes >= 200000 ? 4 : 5;
+            // a row that fills the ring exactly and ends in a sliver of a chunk (V = 50 304: 4 x 24 KB + 2.3 KB) would
+            // serialise on that sliver's slot: one more slot (measured 1.10 -> 1.00 ms; 57 344 and 49 152 prefer 5)
+            if (chunks <= slots && tail != 0 && tail < chunk / 4) slots = static_cast<int>(chunks) + 1;
+            dense.slots = bwd_slots >= 2 && bwd_slots <= kDenseSlots ? bwd_slots : slots;
+        }
         return m == M_FWD ? twin : dense;
     }
     if (mode == 4 && mid.cs) return mid;

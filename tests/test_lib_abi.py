@@ -97,7 +97,8 @@ def test_k1_geometry_policy():
     FWD, BWD, FUSED = 0, 1, 2
     for v in (32000, 50304, 151936, 262144, 1 << 20):
         assert geom(v, FWD) == (0, (256, 1, 6, 16384))      # two twin CTAs per SM stream whole rows
-        assert geom(v, BWD) == (0, (768, 1, 4 if v * 2 >= 200000 else 5, 24576))  # a short ring: see pick_geom
+        want_slots = 4 if v * 2 >= 200000 else (6 if v == 50304 else 5)  # a short ring: see pick_geom
+        assert geom(v, BWD) == (0, (768, 1, want_slots, 24576))
     assert geom(151936, FUSED) == (0, (640, 2, 11, 20480))   # config 2: half a row per CTA, 8 chunks of 20 KB
     assert geom(152064, FUSED) == (0, (640, 2, 11, 20480))   # config 4's vocabulary
     assert geom(100352, FUSED) == (0, (640, 1, 11, 20480))   # the only shape that holds 200 KB in one CTA
