@@ -1069,3 +1069,52 @@ def test_fused_pass_is_bitwise_reproducible(S, V):
     finally:
         S.set_skip_masked(False)
         S.set_k1_path(prev)
+
+
+@pytest.mark.parametrize("V", [32000, 65536, 151936])  # twin / 512-consumer / 640-consumer cluster geometry
+@pytest.mark.parametrize("cfg", [
+    dict(beta=0.0, loss_type="grpo", delta=None, epsilon_high=0.2, temperature=1.0, with_old=False),
+    dict(beta=0.04, loss_type="dr_grpo", delta=2.0, epsilon_high=0.28, temperature=0.7, with_old=True),
+    dict(beta=0.1, loss_type="bnpo", delta=None, epsilon_high=0.4, temperature=1.3, with_old=True),
+])
+def test_resident_fused_matches_oracle_across_options(S, V, cfg):
+    """Every loss option the fused pass evaluates inline (delta clamp, asymmetric clip, temperature, the three
+    normalisations, KL) on each CTA geometry of the resident kernel, against the oracle's loss on the same bf16
+    logits and against the row kernel."""
+    B, T = 3, 6
+    g = torch.Generator().manual_seed(V + int(cfg["beta"] * 100))
+    logits = (torch.randn(B, T, V, generator=g) * 2).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    mask = (torch.arange(T).unsqueeze(0) < torch.tensor([[6], [3], [5]])).int()
+    adv = torch.tensor([1.2, -0.7, 0.4])
+    temp = cfg["temperature"]
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax(logits.float() / temp, ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.4 if cfg["with_old"] else None
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1 if cfg["beta"] else None
+    ocfg = O.GRPOConfigLite(beta=cfg["beta"], epsilon_low=0.2, epsilon_high=cfg["epsilon_high"], delta=cfg["delta"],
+                            loss_type=cfg["loss_type"], max_completion_length=T, temperature=temp)
+    xr = logits.float().requires_grad_(True)
+    loss_r, met_r, _, _ = O.grpo_compute_loss(xr, ids, mask, adv, ocfg, old, ref)
+    loss_r.backward()
+    fn = S.GRPOLoss(beta=cfg["beta"], epsilon_low=0.2, epsilon_high=cfg["epsilon_high"], delta=cfg["delta"],
+                    loss_type=cfg["loss_type"], max_completion_length=T, temperature=temp)
+    grads = {}
+    for path in (S.K1_ROW, S.K1_RESIDENT):
+        prev = S.set_k1_path(path)
+        try:
+            x = logits.to(DEV).requires_grad_(True)
+            out = fn(x, ids.to(DEV), mask.to(DEV), adv.to(DEV), None if old is None else old.to(DEV),
+                     None if ref is None else ref.to(DEV))
+            out.loss.backward()
+        finally:
+            S.set_k1_path(prev)
+        assert out.schedule == "fused"
+        assert out.loss.item() == pytest.approx(loss_r.item(), rel=1e-4, abs=1e-7)
+        from swh_trl_b200.grpo import METRIC_INDEX as MI
+        m = out.metrics.cpu()
+        for name in ("entropy", "clip_ratio/low", "clip_ratio/high", "clip_ratio/region") + (("kl",) if cfg["beta"] else ()):
+            assert float(m[MI[name]]) == pytest.approx(float(met_r[name]), rel=1e-4, abs=1e-5), name
+        grads[path] = x.grad.float().cpu()
+        torch.testing.assert_close(grads[path], xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-10)
+    torch.testing.assert_close(grads[S.K1_ROW], grads[S.K1_RESIDENT], rtol=BF16_ULP, atol=1e-10)
