@@ -374,9 +374,10 @@ def test_config2_properties(S):
     torch.testing.assert_close(g2.float(), g_res.float() * 2, rtol=0, atol=0)
 
 
-def test_ppo_fused_large_vocab(S):
-    """PPO fused pass on the resident kernel (V=32768 bf16) vs the oracle."""
-    mb, T, V = 3, 9, 32768
+@pytest.mark.parametrize("V", [32768, 50304, 151936])  # twin / one 640-consumer CTA / 2-CTA cluster
+def test_ppo_fused_large_vocab(S, V):
+    """PPO fused pass on every resident-kernel geometry (bf16) vs the oracle."""
+    mb, T = 3, 9
     g = torch.Generator().manual_seed(12)
     logits = (torch.randn(mb, T, V, generator=g) * 2).to(torch.bfloat16)
     responses = torch.randint(0, V, (mb, T), generator=g)
