@@ -1119,3 +1119,42 @@ def test_resident_fused_matches_oracle_across_options(S, V, cfg):
         grads[path] = x.grad.float().cpu()
         torch.testing.assert_close(grads[path], xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-10)
     torch.testing.assert_close(grads[S.K1_ROW], grads[S.K1_RESIDENT], rtol=BF16_ULP, atol=1e-10)
+
+
+def test_seam_and_masks_capture_in_a_cuda_graph(S):
+    """The seam call (cuBLASLt GEMMs with a caller-owned workspace + K1 + K2) and the mask kernels neither allocate
+    nor synchronise once warmed up: captured in a CUDA graph and replayed on new data they reproduce the eager run."""
+    from swh_trl_b200 import ops
+    B, T, H, V = 2, 8, 64, 512
+    g = torch.Generator().manual_seed(8)
+    hidden = torch.randn(B, T, H, generator=g).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(V, H, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    ids = torch.randint(0, V, (B, T), generator=g).to(DEV)
+    adv = torch.tensor([0.7, -1.1], device=DEV)
+    cfg = ops.make_cfg(0.0, 0.2, 0.2, None, "bnpo", "token", T)
+    side = torch.cuda.Stream()
+
+    def step():
+        mask, eos_idx = S.completion_mask_from_eos(ids, 3)
+        out = ops.fused_linear_grpo(hidden, W, None, ids, mask, adv, None, None, cfg, 1.0, 1, True, True, False)
+        return out[0], out[4], out[5], mask
+
+    with torch.cuda.stream(side):
+        for _ in range(2):  # warm-up on the capture stream: cuBLASLt handle / heuristics, workspaces
+            step()
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            loss, dh, dw, mask = step()
+    torch.cuda.current_stream().wait_stream(side)
+    hidden.copy_(torch.randn(B, T, H, generator=g).to(torch.bfloat16))
+    ids.copy_(torch.randint(0, V, (B, T), generator=g))
+    graph.replay()
+    torch.cuda.synchronize()
+    got = (loss.clone(), dh.clone(), dw.clone(), mask.clone())
+    with torch.cuda.stream(side):
+        want = step()
+    side.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
