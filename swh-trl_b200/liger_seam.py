@@ -115,12 +115,12 @@ class B200FusedLinearGRPOLoss:
     def __init__(self, beta: float = 0.04, epsilon_low: float = 0.2, epsilon_high: float = 0.2,
                  temperature: float = 1.0, use_ref_model: bool = True, loss_type: str = "bnpo",
                  max_completion_length: Optional[int] = None, importance_sampling_level: str = "token",
-                 delta: Optional[float] = None, chunk_size: int = 1):
+                 delta: Optional[float] = None, chunk_size: int = 2):
         self.beta, self.epsilon_low, self.epsilon_high = beta, epsilon_low, epsilon_high
         self.temperature, self.use_ref_model, self.loss_type = temperature, use_ref_model, loss_type
         self.max_completion_length = max_completion_length
         self.importance_sampling_level, self.delta = importance_sampling_level, delta
-        self.chunk_size = max(1, int(chunk_size))  # sequences per logits chunk
+        self.chunk_size = max(1, int(chunk_size))  # sequences per logits chunk (config 4: 1 / 2 / 4 -> 43.6 / 42.0 / 42.5 ms)
         ops.make_cfg(beta, epsilon_low, epsilon_high, delta, loss_type, importance_sampling_level,
                      max_completion_length or 1)  # validates enums like the reference (ValueError)
 
