@@ -850,12 +850,12 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     return check_launch("k1_resident_kernel");
 }
 
-// Four CTA geometries:
-//   mid   : 640 consumers, 11 x 20 KB slots (220 KB), 1 CTA / SM  — the fused pass at V >= 57 k
+// Four CTA geometries (which one serves a call: pick_geom below):
+//   mid   : 640 consumers, 11 x 20 KB slots (220 KB), 1 CTA / SM  — the fused pass's usual shape
 //   wide  : 512 consumers, 13 x 16 KB slots (208 KB), 1 CTA / SM  — a row slice of up to 12 chunks per CTA
-//   dense : 768 consumers,  9 x 24 KB slots (216 KB), 1 CTA / SM  — more warps to hide the fold's latencies
-//   twin  : 256 consumers,  6 x 16 KB slots ( 96 KB), 2 CTAs / SM — slices of up to 5 chunks; the two CTAs of an SM
-//           drift apart, so one computes while the other waits on its row hand-off or on HBM
+//   dense : 768 consumers,  9 x 24 KB slots (216 KB), 1 CTA / SM  — backward-only streams through 4-6 of them
+//   twin  : 256 consumers,  6 x 16 KB slots ( 96 KB), 2 CTAs / SM — forward-only at any vocabulary, fused for rows
+//           <= 80 KB; the two CTAs of an SM drift apart, so one computes while the other waits on a barrier or on HBM
 struct Geom {
     int cs, slots, nc;
 };
@@ -878,8 +878,9 @@ Geom pick_geom(int64_t vocab, Mode m) {
     if (m != M_FUSED) {
         // forward-only / backward-only: nothing has to stay resident between two sweeps, so a row simply STREAMS
         // through the ring of one CTA -- no cluster, no DSMEM exchange, any vocabulary.  Measured at config 2
-        // (tools/k1_sweep.sh): forward-only 0.85 ms (2-CTA cluster, dense) -> 0.76 ms = 99.8 % of the copy peak with
-        // two independent 256-consumer CTAs per SM; backward-only 1.69 -> 1.61 ms = 94.6 % with one dense CTA.
+        // (tools/k1_sweep.sh): forward-only 0.85 ms (2-CTA cluster, dense) -> 0.76 ms = 100 % of the copy peak with
+        // two independent 256-consumer CTAs per SM; backward-only 1.69 -> 1.61 ms with one dense CTA (-> 1.55 ms with
+        // the short ring below).
         static const int fwd_cs = env_int("B200TRL_K1_FWD_CS", 1), bwd_cs = env_int("B200TRL_K1_BWD_CS", 1);
         const int cs = std::max(1, m == M_FWD ? fwd_cs : bwd_cs);
         wide.cs = std::min(wide.cs ? wide.cs : cs, cs);
