@@ -1158,3 +1158,26 @@ def test_seam_and_masks_capture_in_a_cuda_graph(S):
     side.synchronize()
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_half_branch_output_dtype(S):
+    """`out_dtype=logits.dtype` returns the fp32 result rounded once to the input dtype.  The reference's half-precision
+    branch (utils.py:1455-1461: per-row F.log_softmax in the input dtype, then gather) rounds inside torch's half
+    log_softmax as well, so its native output (stored in the goldens, produced by torch on the CPU) and ours may fall
+    on either side of a rounding boundary: every element is within one ulp of the reference's native output, and
+    ours is the correctly rounded value of the reference's own fp32 path."""
+    seen = 0
+    for case in load_golden("logprob_entropy.pt"):
+        if case["dtype"] not in (torch.bfloat16, torch.float16):
+            continue
+        logits = _regen(case).to(DEV)
+        got = S.selective_log_softmax(logits, case["ids"].to(DEV), out_dtype=case["dtype"]).cpu()
+        want = case["logp_native"]
+        assert got.dtype == want.dtype == case["dtype"]
+        ulp = 2.0 ** (-7 if case["dtype"] == torch.bfloat16 else -10)
+        torch.testing.assert_close(got.float(), want.float(), rtol=ulp, atol=0)
+        # correctly rounded from the fp32 path (the tiny fp32 differences may flip a tie in a handful of elements)
+        exact = case["logp_fp32"].to(case["dtype"])
+        assert (got == exact).float().mean().item() > 0.99
+        seen += 1
+    assert seen >= 3
