@@ -132,6 +132,30 @@ def main():
             + ("" if masked else " in the backward only"))
     x.requires_grad_(False)
 
+    # For context: the reference's ALGORITHM in torch eager on this same GPU (what a user of the reference runs today).
+    # Restated inline from trl/trainer/utils.py:1455-1461 (half branch: per-row log_softmax + gather), :1483-1490
+    # (entropy per row, no grad), grpo_trainer.py:1258 (temperature copy) and :2084-2133 (k3 KL, clipped surrogate,
+    # bnpo reduction).  Not a parity check (tests/ does that against the pinned oracle) -- a speed reference only.
+    def torch_eager_reference_step():
+        xg = x.detach().requires_grad_(True)
+        lg = xg / 1.0                                                                       # :1258
+        lps = torch.stack([torch.log_softmax(row, dim=-1).gather(-1, i.unsqueeze(-1)).squeeze(-1)
+                           for row, i in zip(lg, ids)])                                     # utils.py:1457-1461
+        with torch.no_grad():                                                               # :1265-1267
+            ents = torch.stack([-(torch.softmax(row, -1) * torch.log_softmax(row, -1)).sum(-1) for row in lg])
+        lp = lps.float()
+        kl = torch.exp(ref - lp) - (ref - lp) - 1                                           # :2087-2089
+        c1 = torch.exp(lp - old)                                                            # :2113
+        c2 = torch.clamp(c1, 0.8, 1.2)                                                      # :2114
+        a = adv.unsqueeze(1)
+        ptl = -torch.min(c1 * a, c2 * a) + 0.04 * kl                                        # :2120-2126
+        loss = (ptl * mask).sum() / mask.sum().clamp(min=1.0)                               # :2133 (bnpo)
+        loss.backward()
+        return ents
+    ms, _ = timeit(torch_eager_reference_step, warmup=2, iters=5)
+    add("reference algorithm in torch eager on the same GPU, C2 (context, not the CPU baseline)", ms, 0, 4 * V * N,
+        "per-row log_softmax + gather, per-row entropy, elementwise loss, autograd backward")
+
     # K2 alone, quantile mask
     m32, rc, tot = ops.mask_stats(mask)
     cfg = ops.make_cfg(0.04, 0.2, 0.2, None, "bnpo", "token", T)
