@@ -252,6 +252,22 @@ int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidden_row_stri
                                      const int64_t* ids, float inv_temperature, void* workspace, float* logp,
                                      float* entropy, float* lse, b200trl_stream_t stream);
 
+/* ---- K7: the three contractions of the Liger seam on tcgen05 (CTA-pair MMA, TMA, TMEM accumulators) -----------
+ * D[M,N] = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulation: what `LigerFusedLinearGRPOLoss` contracts per chunk
+ * (grpo_trainer.py:2005-2045): logits_c = hidden_c W^T, dH_c = dlogits_c W, dW += dlogits_c^T hidden_c.
+ * a_layout / b_layout: 0 = the operand is stored [rows, K] (K contiguous), 1 = stored [K, rows] (rows contiguous);
+ * lda / ldb / ldd: elements between stored rows (multiples of 8).  out_kind B200TRL_TC_OUT_BF16: out = bf16 [M, ldd],
+ * D (+ bias[N], bf16, nullable) rounded once; B200TRL_TC_OUT_F32_ACC: out = fp32 [M, ldd], out += D.
+ * Supported (a_layout, b_layout, out_kind): (0,0,BF16) (0,1,BF16) (1,1,F32_ACC).  m_fastest: work order, 1 = clusters
+ * running at the same time share the B tile, 0 = the A tile (pick the operand that does not fit L2). */
+enum { B200TRL_TC_OUT_BF16 = 1, B200TRL_TC_OUT_F32_ACC = 2 };
+int b200trl_tc_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb, int64_t M,
+                    int64_t N, int64_t K, int out_kind, void* out, int64_t ldd, const void* bias, int m_fastest,
+                    b200trl_stream_t stream);
+/* Which implementation the seam's three GEMMs use: bit 0 = logits, bit 1 = dH, bit 2 = dW; a set bit = the tcgen05
+ * kernel above, a clear bit = cuBLASLt.  Returns the previous mask; mask < 0 only queries. */
+int b200trl_set_seam_gemm_mask(int mask);
+
 /* ---- a-13: the reference's operator seam as ONE call (grpo_trainer.py:870-886 ctor, :2005-2045 call) ----------
  * What `self.liger_grpo_loss(_input, lin_weight, selected_token_ids, attention_mask, advantages, bias,
  * old_per_token_logps, ref_per_token_logps)` computes, forward AND backward, without ever holding the [B,T,V]

@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace b200trl {
 namespace {
@@ -365,7 +366,8 @@ using namespace b200trl;
 extern "C" int64_t b200trl_fused_linear_workspace_bytes(int64_t n_rows, int64_t vocab) {
     if (n_rows <= 0 || vocab <= 0) return 0;
     const int64_t padded = ((n_rows + kBM - 1) / kBM) * kBM;
-    return static_cast<int64_t>(groups_for(n_rows, vocab)) * padded * static_cast<int64_t>(sizeof(float4));
+    const int64_t v1 = static_cast<int64_t>(groups_for(n_rows, vocab)) * padded * static_cast<int64_t>(sizeof(float4));
+    return std::max(v1, tc_stats_workspace_bytes(n_rows, vocab));
 }
 
 extern "C" int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidden_row_stride, const void* weight,
@@ -380,6 +382,17 @@ extern "C" int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidd
                     B200TRL_E_UNSUPPORTED, "fused_linear: bf16 operands need 16-byte aligned rows (hidden %% 8 == 0)");
     B200TRL_REQUIRE(inv_temperature > 0.f && std::isfinite(inv_temperature), B200TRL_E_INVALID,
                     "fused_linear: inv_temperature must be positive and finite");
+    // The product path is the CTA-pair kernel (k7_tc_gemm.cu: cta_group::2, half the B tile per SM);
+    // B200TRL_K5_IMPL=1 keeps the single-CTA kernel below for A/B measurements and as a cross-check in the tests.
+    static const int impl = env_int5("B200TRL_K5_IMPL", 2);
+    if (impl != 1) {
+        const float c = static_cast<float>(static_cast<double>(inv_temperature) * 1.4426950408889634);
+        int n_groups = 0;
+        int rc2 = tc_gemm(0, 0, TC_EPI_STATS, hidden, hidden_row_stride, weight, weight_row_stride, n_rows, vocab,
+                          hidden_size, nullptr, 0, nullptr, ids, c, workspace, &n_groups, 1, as_stream(stream));
+        if (rc2) return rc2;
+        return tc_merge_stats(workspace, n_groups, n_rows, c, logp, entropy, lse, as_stream(stream));
+    }
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, hidden, n_rows, hidden_size, hidden_row_stride, kBM);
     if (rc) return rc;

@@ -14,11 +14,14 @@
 #include <cublasLt.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
+
 #include <map>
 #include <mutex>
 #include <tuple>
 
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace b200trl {
 namespace {
@@ -183,6 +186,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     db[v] += s;
 }
 
+// bit 0 = logits GEMM, bit 1 = dH, bit 2 = dW on the CTA-pair tcgen05 kernel (k7_tc_gemm.cu); clear = cuBLASLt
+int default_gemm_mask() {
+    const char* v = getenv("B200TRL_SEAM_GEMM");
+    return v ? atoi(v) : 0;
+}
+int g_gemm_mask = default_gemm_mask();
+
 constexpr size_t kLtWorkspace = size_t(64) << 20;
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -211,6 +221,12 @@ Layout layout(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
 
 using namespace b200trl;
 
+extern "C" int b200trl_set_seam_gemm_mask(int mask) {
+    const int prev = g_gemm_mask;
+    if (mask >= 0) g_gemm_mask = mask & 7;
+    return prev;
+}
+
 extern "C" int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
     if (B <= 0 || T <= 0 || V <= 0 || chunk_seqs <= 0) return 0;
     return static_cast<int64_t>(layout(B, T, V, std::min(chunk_seqs, B)).end);
@@ -232,10 +248,12 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
                     "fused_linear_grpo: sequence-level importance sampling with old_logp needs the two-phase path");
     B200TRL_REQUIRE(cfg->beta == 0.f || ref_logp, B200TRL_E_INVALID, "fused_linear_grpo: beta != 0 needs ref_logp");
     cudaStream_t stream = as_stream(stream_);
-    LtApi* api = lt_api();
-    if (!api) return B200TRL_E_UNSUPPORTED;
-    cublasLtHandle_t h = lt_handle(api);
-    B200TRL_REQUIRE(h != nullptr, B200TRL_E_LAUNCH, "fused_linear_grpo: cublasLtCreate failed");
+    const int mask_tc = g_gemm_mask;
+    const bool need_lt = !(mask_tc & 1) || (dhidden && !(mask_tc & 2)) || (dweight && !(mask_tc & 4));
+    LtApi* api = need_lt ? lt_api() : nullptr;
+    if (need_lt && !api) return B200TRL_E_UNSUPPORTED;
+    cublasLtHandle_t h = api ? lt_handle(api) : nullptr;
+    B200TRL_REQUIRE(!need_lt || h != nullptr, B200TRL_E_LAUNCH, "fused_linear_grpo: cublasLtCreate failed");
 
     chunk_seqs = std::min(chunk_seqs, B);
     const Layout l = layout(B, T, V, chunk_seqs);
@@ -261,8 +279,12 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
     for (int64_t b0 = 0; b0 < B; b0 += chunk_seqs) {
         const int64_t nb = std::min(chunk_seqs, B - b0), rows = nb * T, r0 = b0 * T;
         // row-major logits[rows, V] = hidden_c[rows, H] W[V, H]^T  <=>  column-major D[V, rows] = W^T(T) x hidden_c(N)
-        rc = lt_gemm(api, h, CUBLAS_OP_T, CUBLAS_OP_N, V, rows, H, weight, H, hid + r0 * H, H, logits, V, CUDA_R_16BF, 0.f,
-                     bias, lt_ws, kLtWorkspace, stream);
+        if (mask_tc & 1)  // hidden_c and W both K-major; all row blocks of one W tile run at the same time
+            rc = tc_gemm(0, 0, TC_EPI_STORE, hid + r0 * H, H, weight, H, rows, V, H, logits, V, bias, nullptr, 0.f, nullptr,
+                         nullptr, 1, stream);
+        else
+            rc = lt_gemm(api, h, CUBLAS_OP_T, CUBLAS_OP_N, V, rows, H, weight, H, hid + r0 * H, H, logits, V, CUDA_R_16BF,
+                         0.f, bias, lt_ws, kLtWorkspace, stream);
         if (rc) return rc;
         // the loss normalises over the WHOLE batch: grpo / dr_grpo divide by B (grpo_trainer.py:2131, 2135), bnpo by
         // the batch's token total, which the kernel reads from `total`
@@ -275,13 +297,22 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
                                         want_grad ? logits : nullptr, V, 0, stream_);  // in place: dlogits overwrite logits
         if (rc) return rc;
         if (dh) {  // dH_c[rows, H] = dl[rows, V] W[V, H]  <=>  D[H, rows] = W(N)[H, V] x dl(N)[V, rows]
-            rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_N, H, rows, V, weight, H, logits, V, dh + r0 * H, H, CUDA_R_16BF, 0.f,
-                         nullptr, lt_ws, kLtWorkspace, stream);
+            if (mask_tc & 2)  // A = dl (K = V contiguous), B[n = h, k = v] = W[v, h] is MN-major
+                rc = tc_gemm(0, 1, TC_EPI_STORE, logits, V, weight, H, rows, H, V, dh + r0 * H, H, nullptr, nullptr, 0.f,
+                             nullptr, nullptr, 1, stream);
+            else
+                rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_N, H, rows, V, weight, H, logits, V, dh + r0 * H, H, CUDA_R_16BF,
+                             0.f, nullptr, lt_ws, kLtWorkspace, stream);
             if (rc) return rc;
         }
         if (dweight) {  // dW[V, H] += dl^T hidden_c  <=>  D[H, V] += hidden_c(N)[H, rows] x dl(T)[rows, V], fp32 in the GEMM
-            rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_T, H, V, rows, hid + r0 * H, H, logits, V, dweight, H, CUDA_R_32F, 1.f,
-                         nullptr, lt_ws, kLtWorkspace, stream);
+            if (mask_tc & 4)  // A[m = v, k = r] = dl[r, v] and B[n = h, k = r] = hidden[r, h]: both MN-major; the dl
+                              // tile is the operand that does not fit L2, so consecutive clusters share it
+                rc = tc_gemm(1, 1, TC_EPI_ACCUM, logits, V, hid + r0 * H, H, V, H, rows, dweight, H, nullptr, nullptr, 0.f,
+                             nullptr, nullptr, 0, stream);
+            else
+                rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_T, H, V, rows, hid + r0 * H, H, logits, V, dweight, H, CUDA_R_32F,
+                             1.f, nullptr, lt_ws, kLtWorkspace, stream);
             if (rc) return rc;
         }
         if (dbias) {

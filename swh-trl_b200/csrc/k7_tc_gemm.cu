@@ -1,0 +1,535 @@
+// K7: the CTA-pair tcgen05 GEMM family (BASELINE config 4: hidden 3584 -> V = 152064).
+//
+//   D[M, N] = A[M, K] * B[N, K]^T      bf16 operands, fp32 accumulation in tensor memory
+//
+// One kernel template, three epilogues, operands K-major or MN-major:
+//   EPI_STATS  nothing is stored: every 128 x 256 accumulator tile is folded into the per-row online-softmax
+//              statistics (m, S, U, selected logit) -> log-probs / entropies of hidden @ W^T with the logits never
+//              leaving the SM (grpo_trainer.py:1163-1203 + :1258-1267 for the no-grad old / ref passes);
+//   EPI_STORE  D is rounded to bf16 (+ bias) and stored row-major; optionally the same rounded values are folded into
+//              the row statistics, i.e. exactly what a pass over the stored logits would compute
+//              (the lm_head GEMM of the Liger seam, grpo_trainer.py:2005-2045; dH = dlogits W);
+//   EPI_ACCUM  D is added into an fp32 matrix (dW += dlogits^T hidden across chunks of sequences).
+//
+// Execution model (Blackwell-native, no legacy mma.sync anywhere):
+//   * thread-block clusters of 2 CTAs on one TPC issue ONE tcgen05.mma.cta_group::2 per 256 x 256 x 16 step: each CTA
+//     holds 128 rows of A and HALF of the B tile (128 of its 256 rows), so every SM stages 32 KB per 64-deep k-block
+//     instead of 48 KB and reads 8 KB instead of 12 KB of shared memory per MMA;
+//   * warp 0 (one lane) of each CTA: TMA producer, cp.async.bulk.tensor.2d.cta_group::2 into a 6-stage ring; the bytes
+//     of BOTH CTAs complete the transaction barrier of the pair's leader;
+//   * warp 1 (one lane) of the leader CTA: MMA issuer; tcgen05.commit ... multicast::cluster releases a stage in both
+//     CTAs / publishes an accumulator to both epilogues;
+//   * warp 2: allocates / frees the 512 TMEM columns (two 128 x 256 fp32 accumulators per CTA, ping-pong);
+//   * warps 4-7: epilogue, tcgen05.ld 32 lanes x 32 columns, thread == accumulator row; overlaps the next tile's MMAs.
+//   Persistent: cluster c takes work items c, c + n_clusters, ...; an item is (256-row block, run of n-tiles).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+#include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace b200trl {
+namespace {
+
+using namespace tc;
+
+constexpr int kTileM = 128;  // accumulator rows per CTA (the pair covers 256)
+constexpr int kTileN = 256;  // accumulator columns per tile
+constexpr int kHalfN = 128;  // B rows staged by each CTA
+constexpr int kTileK = 64;   // k-block: one 128-byte swizzle row of bf16
+constexpr int kUmmaK = 16;
+constexpr int kStages = 6;
+constexpr int kOperandBytes = 128 * kTileK * 2;  // 16 KB: a 128 x 64 bf16 operand slab (either major)
+constexpr int kStageBytes = 2 * kOperandBytes;   // per CTA
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr float kSlack = 6.0f;  // the running reference moves only when the tile maximum exceeds it by 2^6
+
+enum { EPI_STATS = TC_EPI_STATS, EPI_STORE = TC_EPI_STORE, EPI_ACCUM = TC_EPI_ACCUM };
+
+struct Bars {
+    uint64_t full[kStages];   // leader CTA: both CTAs' TMA bytes of a stage have landed
+    uint64_t empty[kStages];  // each CTA: the MMAs reading this stage have completed
+    uint64_t tmem_full[2];    // each CTA: accumulator complete
+    uint64_t tmem_empty[2];   // leader CTA: both epilogues have drained the accumulator (8 warp arrivals)
+    uint32_t tmem_base;
+};
+
+struct GemmArgs {
+    int64_t m_rows, n_cols, k_len;
+    int n_mpairs, n_ntiles, n_groups, tiles_per_group, m_fastest;
+    // statistics (EPI_STATS always; EPI_STORE when partial != nullptr)
+    const int64_t* ids;
+    float c;          // inv_T * log2(e)
+    float4* partial;  // [n_groups][n_mpairs * 256] : (m, S, U, selected logit or NaN)
+    // output (EPI_STORE: bf16 [m_rows, ldd]; EPI_ACCUM: fp32 [m_rows, ldd], += )
+    void* out;
+    int64_t ldd;
+    const __nv_bfloat16* bias;  // EPI_STORE only, per column, may be null
+};
+
+struct RowFold {
+    float m, S, U, xsel;
+};
+
+// fold 32 logits of one row (columns cj .. cj + 31, `valid` of them real) into the row's running statistics
+__device__ __forceinline__ void fold32(RowFold& f, const float* v, int valid, float c, int64_t id, int64_t cj) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < valid) ? v[i] : -INFINITY);
+    mx *= c;
+    if (mx > f.m + kSlack) {
+        const float d = f.m - mx, s = ex2(d);
+        f.U = s * fmaf(d, f.S, f.U);
+        f.S *= s;
+        f.m = mx;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float d = fmaf(v[i], c, -f.m);
+        const float e = (i < valid) ? ex2(d) : 0.f;
+        f.S += e;
+        f.U = (i < valid) ? fmaf(e, d, f.U) : f.U;
+    }
+    if (id >= cj && id < cj + 32) {
+        const int want = static_cast<int>(id - cj);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i == want) f.xsel = v[i];
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <int kAMn, int kBMn, int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment in the shared window (1 KB of slack is allocated); both CTAs of the
+    // pair compute the same offset, which the pair MMA relies on
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_items = a.n_mpairs * a.n_groups;
+    const int kblocks = static_cast<int>((a.k_len + kTileK - 1) / kTileK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars.full[s], 1);
+            mbar_init(&bars.empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars.tmem_full[b], 1);
+            mbar_init(&bars.tmem_empty[b], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        mbar_fence_init_cluster();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    fence_before_sync();
+    cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+    fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars.tmem_base);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int g = a.m_fastest ? item / a.n_mpairs : item % a.n_groups;
+                const int mp = a.m_fastest ? item % a.n_mpairs : item / a.n_groups;
+                const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
+                const int m0 = mp * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    const int n0 = nt * kTileN + static_cast<int>(rank) * kHalfN;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&bars.empty[stage], phase ^ 1u);
+                        unsigned char* sa = smem + stage * kStageBytes;
+                        unsigned char* sb = sa + kOperandBytes;
+                        const uint32_t full_leader = map_to_rank(smem_u32(&bars.full[stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&bars.full[stage], 2 * kStageBytes);
+                        if (kAMn) {  // rows = k, 64 m-elements per 128-byte row: two 64 x 64 boxes
+                            tma_load_2d_pair(sa, &map_a, m0, kb * kTileK, full_leader);
+                            tma_load_2d_pair(sa + kOperandBytes / 2, &map_a, m0 + 64, kb * kTileK, full_leader);
+                        } else {
+                            tma_load_2d_pair(sa, &map_a, kb * kTileK, m0, full_leader);
+                        }
+                        if (kBMn) {
+                            tma_load_2d_pair(sb, &map_b, n0, kb * kTileK, full_leader);
+                            tma_load_2d_pair(sb + kOperandBytes / 2, &map_b, n0 + 64, kb * kTileK, full_leader);
+                        } else {
+                            tma_load_2d_pair(sb, &map_b, kb * kTileK, n0, full_leader);
+                        }
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+            // drain: every multicast commit aimed at this CTA's `empty` barriers has landed before the CTA may exit
+            for (int s = 0; s < kStages; ++s) {
+                mbar_wait(&bars.empty[stage], phase ^ 1u);
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = instr_desc_bf16(2 * kTileM, kTileN, kAMn, kBMn);
+            // K-major: 16 k-elements = 32 B inside the 128-byte swizzle row; MN-major: 16 k-rows = 2048 B
+            constexpr uint64_t a_step = kAMn ? (16 * 128) >> 4 : 32 >> 4;
+            constexpr uint64_t b_step = kBMn ? (16 * 128) >> 4 : 32 >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            int buf = 0;
+            uint32_t acc_phase = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int g = a.m_fastest ? item / a.n_mpairs : item % a.n_groups;
+                const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    mbar_wait_cluster(&bars.tmem_empty[buf], acc_phase ^ 1u);  // both epilogues drained this buffer
+                    fence_after_sync();
+                    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * kTileN);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&bars.full[stage], phase);
+                        fence_after_sync();
+                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                        const uint64_t adesc = smem_desc_sw128(sa, kAMn ? kOperandBytes / 2 : 16);
+                        const uint64_t bdesc = smem_desc_sw128(sa + kOperandBytes, kBMn ? kOperandBytes / 2 : 16);
+#pragma unroll
+                        for (int k = 0; k < kTileK / kUmmaK; ++k)
+                            mma_pair_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        commit_pair_multicast(&bars.empty[stage], 3);  // both CTAs may refill the stage
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    commit_pair_multicast(&bars.tmem_full[buf], 3);  // accumulator complete -> both epilogues
+                    buf ^= 1;
+                    if (buf == 0) acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (both CTAs): thread == accumulator row
+        const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        const int row_in_tile = ew * 32 + lane;
+        const float c = a.c;
+        const bool want_stats = (kEpi == EPI_STATS) || (kEpi == EPI_STORE && a.partial != nullptr);
+        int buf = 0;
+        uint32_t acc_phase = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int g = a.m_fastest ? item / a.n_mpairs : item % a.n_groups;
+            const int mp = a.m_fastest ? item % a.n_mpairs : item / a.n_groups;
+            const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
+            const int64_t row = static_cast<int64_t>(mp) * (2 * kTileM) + static_cast<int64_t>(rank) * kTileM + row_in_tile;
+            const bool row_ok = row < a.m_rows;
+            const int64_t id = (want_stats && row_ok) ? a.ids[row] : -1;
+            RowFold f{kNegBig, 0.f, 0.f, __int_as_float(0x7fc00000)};
+            for (int nt = nt0; nt < nt1; ++nt) {
+                mbar_wait(&bars.tmem_full[buf], acc_phase);
+                fence_after_sync();
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(buf * kTileN);
+                const int64_t col0 = static_cast<int64_t>(nt) * kTileN;
+#pragma unroll 1
+                for (int j = 0; j < kTileN / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
+                    const int64_t cj = col0 + j * 32;
+                    const int64_t left = a.n_cols - cj;
+                    const int valid = left < 32 ? static_cast<int>(left) : 32;  // columns past N are padding
+                    if (valid <= 0) continue;
+                    if (kEpi == EPI_STORE) {
+                        if (a.bias) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < valid) v[i] += __bfloat162float(a.bias[cj + i]);
+                        }
+                        uint32_t p[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                        if (row_ok) {
+                            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + row * a.ldd + cj;
+                            if (valid == 32) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    *reinterpret_cast<uint4*>(o + 8 * q) =
+                                        make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+                            } else {
+                                for (int i = 0; i < valid; ++i)
+                                    o[i] = __ushort_as_bfloat16(static_cast<unsigned short>((p[i >> 1] >> ((i & 1) * 16)) & 0xffffu));
+                            }
+                        }
+                        if (want_stats) {  // statistics of the ROUNDED logits: what a pass over the stored tile would see
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                v[2 * i] = __uint_as_float(p[i] << 16);
+                                v[2 * i + 1] = __uint_as_float(p[i] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (kEpi == EPI_ACCUM) {
+                        if (row_ok) {
+                            float* o = static_cast<float*>(a.out) + row * a.ldd + cj;
+                            if (valid == 32) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    float4 t = *reinterpret_cast<float4*>(o + 4 * q);
+                                    t.x += v[4 * q];
+                                    t.y += v[4 * q + 1];
+                                    t.z += v[4 * q + 2];
+                                    t.w += v[4 * q + 3];
+                                    *reinterpret_cast<float4*>(o + 4 * q) = t;
+                                }
+                            } else {
+                                for (int i = 0; i < valid; ++i) o[i] += v[i];
+                            }
+                        }
+                    }
+                    if (want_stats) fold32(f, v, valid, c, id, cj);
+                }
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank(smem_u32(&bars.tmem_empty[buf]), 0));
+                buf ^= 1;
+                if (buf == 0) acc_phase ^= 1u;
+            }
+            if (want_stats && row_ok)
+                a.partial[static_cast<int64_t>(g) * a.n_mpairs * (2 * kTileM) + row] = make_float4(f.m, f.S, f.U, f.xsel);
+        }
+    }
+    fence_before_sync();
+    cluster_sync_all();  // the peer's remote arrives and this CTA's multicast commits have all been consumed
+    if (warp == 2) {
+        fence_after_sync();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+__global__ void tc_merge_kernel(const float4* __restrict__ partial, int n_groups, int64_t padded_rows, int64_t n_rows,
+                                float c, float* __restrict__ logp, float* __restrict__ entropy,
+                                float* __restrict__ lse) {
+    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (row >= n_rows) return;
+    Partial tot = partial_empty();
+    float xsel = __int_as_float(0x7fc00000);
+    for (int g = 0; g < n_groups; ++g) {
+        const float4 p = partial[static_cast<int64_t>(g) * padded_rows + row];
+        tot = partial_merge(tot, Partial{p.x, p.y, p.z});
+        if (!isnan(p.w)) xsel = p.w;
+    }
+    const RowStats st = finish_row(tot, xsel, c);
+    if (logp) logp[row] = st.logp;
+    if (entropy) entropy[row] = st.entropy;
+    if (lse) lse[row] = st.lse;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// A bf16 matrix stored row-major as [outer, inner] with `ld` elements between rows; one box = 64 inner elements
+// (128 bytes, SWIZZLE_128B) x `box_outer` rows.  K-major operand: inner = k, box_outer = 128 (m / n rows).
+// MN-major operand: inner = m / n, box_outer = 64 (k rows).
+int make_map(CUtensorMap* map, const void* base, int64_t outer, int64_t inner, int64_t ld, int box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
+        return B200TRL_E_LAUNCH;
+    }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_outer)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+        return B200TRL_E_INVALID;
+    }
+    return B200TRL_OK;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+int n_clusters_for_device() { return std::max(1, num_sms() / 2); }
+
+// Static round-robin of (256-row block, run of n-tiles) items over the clusters: pick the run length whose slowest
+// cluster finishes first (an item costs its tiles plus ~0.15 tile of pipeline restart and partial write).
+int plan_tiles_per_group(int n_mpairs, int n_ntiles, int n_clusters) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int> cache;
+    const auto key = std::make_tuple(n_mpairs, n_ntiles, n_clusters);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    const int forced = env_int("B200TRL_K7_TPG", 0);
+    const int lo = std::min(n_ntiles, 4);
+    int best = std::max(lo, std::min(n_ntiles, forced));
+    if (forced <= 0) {
+        double best_cost = 1e300;
+        for (int tpg = lo; tpg <= n_ntiles; ++tpg) {
+            const int groups = (n_ntiles + tpg - 1) / tpg;
+            const int last = n_ntiles - (groups - 1) * tpg;
+            const int64_t items = static_cast<int64_t>(groups) * n_mpairs;
+            if (items > 65536) continue;
+            double worst = 0;
+            for (int cl = 0; cl < std::min<int64_t>(n_clusters, items); ++cl) {
+                double t = 0;
+                for (int64_t i = cl; i < items; i += n_clusters) t += ((i / n_mpairs == groups - 1) ? last : tpg) + 0.15;
+                worst = std::max(worst, t);
+            }
+            if (worst < best_cost - 1e-9) {
+                best_cost = worst;
+                best = tpg;
+            }
+        }
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    cache[key] = best;
+    return best;
+}
+
+template <int kAMn, int kBMn, int kEpi>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, cudaStream_t s) {
+    const size_t smem = static_cast<size_t>(kStages) * kStageBytes + sizeof(Bars) + 1024;
+    auto kern = tc_gemm_kernel<kAMn, kBMn, kEpi>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+        set_error("tc_gemm: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
+        return B200TRL_E_LAUNCH;
+    }
+    const int64_t items = static_cast<int64_t>(a.n_mpairs) * a.n_groups;
+    const int clusters = static_cast<int>(std::min<int64_t>(n_clusters_for_device(), items));
+    kern<<<2 * clusters, kThreads, smem, s>>>(ma, mb, a);
+    return check_launch("tc_gemm_kernel");
+}
+
+}  // namespace
+
+// D = A B^T with the epilogue of `epi`; shared by the C entry points of this file and k6 (the seam).
+//   a_mn / b_mn: 0 = the operand is stored [rows, k] (k contiguous), 1 = stored [k, rows] (rows contiguous)
+int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
+            int64_t K, void* out, int64_t ldd, const void* bias, const int64_t* ids, float c, void* partial,
+            int* n_groups_out, int m_fastest, cudaStream_t s) {
+    B200TRL_REQUIRE(M > 0 && N > 0 && K > 0, B200TRL_E_INVALID, "tc_gemm: bad shape");
+    B200TRL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                    B200TRL_E_UNSUPPORTED, "tc_gemm: bf16 operands need 16-byte aligned rows");
+    B200TRL_REQUIRE(epi != EPI_STATS || (partial && ids), B200TRL_E_INVALID, "tc_gemm: statistics need ids and a workspace");
+    B200TRL_REQUIRE(epi == EPI_STATS || (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0),
+                    B200TRL_E_UNSUPPORTED, "tc_gemm: output rows must be 16-byte aligned");
+    CUtensorMap ma, mb;
+    int rc = a_mn ? make_map(&ma, A, K, M, lda, 64) : make_map(&ma, A, M, K, lda, 128);
+    if (rc) return rc;
+    rc = b_mn ? make_map(&mb, B, K, N, ldb, 64) : make_map(&mb, B, N, K, ldb, 128);
+    if (rc) return rc;
+    GemmArgs a{};
+    a.m_rows = M;
+    a.n_cols = N;
+    a.k_len = K;
+    a.n_mpairs = static_cast<int>((M + 2 * kTileM - 1) / (2 * kTileM));
+    a.n_ntiles = static_cast<int>((N + kTileN - 1) / kTileN);
+    const bool stats = partial != nullptr;
+    if (stats) {
+        a.tiles_per_group = plan_tiles_per_group(a.n_mpairs, a.n_ntiles, n_clusters_for_device());
+        a.m_fastest = 1;
+    } else {
+        a.tiles_per_group = 1;
+        a.m_fastest = m_fastest;
+    }
+    a.n_groups = (a.n_ntiles + a.tiles_per_group - 1) / a.tiles_per_group;
+    a.ids = ids;
+    a.c = c;
+    a.partial = static_cast<float4*>(partial);
+    a.out = out;
+    a.ldd = ldd;
+    a.bias = static_cast<const __nv_bfloat16*>(bias);
+    if (n_groups_out) *n_groups_out = a.n_groups;
+#define B200TRL_TC_CASE(AM, BM, EP) \
+    if (a_mn == AM && b_mn == BM && epi == EP) return launch<AM, BM, EP>(ma, mb, a, s);
+    B200TRL_TC_CASE(0, 0, EPI_STATS)
+    B200TRL_TC_CASE(0, 0, EPI_STORE)
+    B200TRL_TC_CASE(0, 1, EPI_STORE)
+    B200TRL_TC_CASE(1, 1, EPI_ACCUM)
+#undef B200TRL_TC_CASE
+    set_error("tc_gemm: unsupported operand layout / epilogue combination (%d, %d, %d)", a_mn, b_mn, epi);
+    return B200TRL_E_UNSUPPORTED;
+}
+
+int64_t tc_stats_workspace_bytes(int64_t n_rows, int64_t n_cols) {
+    if (n_rows <= 0 || n_cols <= 0) return 0;
+    const int64_t padded = ((n_rows + 2 * kTileM - 1) / (2 * kTileM)) * (2 * kTileM);
+    const int64_t n_ntiles = (n_cols + kTileN - 1) / kTileN;
+    const int64_t max_groups = (n_ntiles + 3) / 4 + 1;  // plan_tiles_per_group never goes below runs of 4 (or all)
+    return max_groups * padded * static_cast<int64_t>(sizeof(float4));
+}
+
+int tc_merge_stats(const void* partial, int n_groups, int64_t n_rows, float c, float* logp, float* entropy, float* lse,
+                   cudaStream_t s) {
+    const int64_t padded = ((n_rows + 2 * kTileM - 1) / (2 * kTileM)) * (2 * kTileM);
+    tc_merge_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, s>>>(static_cast<const float4*>(partial), n_groups,
+                                                                               padded, n_rows, c, logp, entropy, lse);
+    return check_launch("tc_merge_kernel");
+}
+
+}  // namespace b200trl
+
+using namespace b200trl;
+
+extern "C" int b200trl_tc_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb,
+                               int64_t M, int64_t N, int64_t K, int out_kind, void* out, int64_t ldd, const void* bias,
+                               int m_fastest, b200trl_stream_t stream) {
+    B200TRL_REQUIRE(A && B && out, B200TRL_E_INVALID, "tc_gemm: null pointer");
+    B200TRL_REQUIRE(out_kind == B200TRL_TC_OUT_BF16 || out_kind == B200TRL_TC_OUT_F32_ACC, B200TRL_E_INVALID,
+                    "tc_gemm: unknown out_kind %d", out_kind);
+    B200TRL_REQUIRE(!bias || out_kind == B200TRL_TC_OUT_BF16, B200TRL_E_INVALID, "tc_gemm: bias needs the bf16 output");
+    return tc_gemm(a_layout, b_layout, out_kind == B200TRL_TC_OUT_BF16 ? TC_EPI_STORE : TC_EPI_ACCUM, A, lda, B, ldb, M, N,
+                   K, out, ldd, bias, nullptr, 0.f, nullptr, nullptr, m_fastest, as_stream(stream));
+}

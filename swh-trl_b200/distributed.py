@@ -53,6 +53,20 @@ def gather_metrics(metrics: torch.Tensor, accelerator=None) -> torch.Tensor:
     return g.reshape(-1, m.shape[1]).float().cpu()
 
 
+def gather_metric_rows(rows: torch.Tensor, accelerator=None) -> torch.Tensor:
+    """``[world, steps, n_metrics]`` on the host for a ``[steps, n_metrics]`` device ring: one collective and one
+    device->host read for every deferred step (``grpo.flush_metrics``, ``ppo.PPOStatsRing``)."""
+    m = rows.detach().reshape(1, rows.shape[0], -1).contiguous()
+    if accelerator is not None and hasattr(accelerator, "gather"):
+        g = accelerator.gather(m)
+    elif world() > 1:
+        g = torch.empty((world(),) + tuple(m.shape[1:]), dtype=m.dtype, device=m.device)
+        dist.all_gather_into_tensor(g, m)
+    else:
+        g = m
+    return g.reshape(-1, m.shape[1], m.shape[2]).float().cpu()
+
+
 def reduce_metrics(gathered: torch.Tensor) -> dict:
     """The reference's logged scalars from the gathered per-rank means (grpo_trainer.py:2150-2172)."""
     from .grpo import METRIC_INDEX as mi, _nanmax, _nanmin

@@ -131,28 +131,75 @@ def get_high_entropy_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold
 
 
 # ---------------------------------------------------------------------------------------- trl/core.py
+class _MaskedMean(torch.autograd.Function):
+    """Global masked mean on the library, differentiable wrt ``values``: the unmodified reference PPO loop builds its
+    loss out of ``masked_mean`` (ppo_trainer.py:574, 583-585) and calls ``accelerator.backward`` on it, so the
+    patched binding has to carry a ``grad_fn``.  d mean / d values = mask / count."""
+
+    @staticmethod
+    def forward(ctx, values, mask):
+        m = (mask != 0).expand_as(values)
+        _, stats = ops.masked_whiten(values, m, want_out=False)
+        ctx.save_for_backward(m, stats)
+        ctx.in_dtype = values.dtype
+        return stats[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        m, stats = ctx.saved_tensors
+        return (m * (g / stats[2])).to(ctx.in_dtype), None
+
+
+def _like_input(x: torch.Tensor, values: torch.Tensor) -> torch.Tensor:
+    # the reference computes in the dtype of ``values`` (bool masks promote to it); the kernel accumulates in
+    # fp32 / double and the result is rounded once
+    return x.to(values.dtype) if values.is_floating_point() and values.dtype != torch.float32 else x
+
+
+def _wants_grad(values: torch.Tensor) -> bool:
+    return values.requires_grad and torch.is_grad_enabled()
+
+
 def masked_mean(values: torch.Tensor, mask: torch.Tensor, axis: Optional[int] = None) -> torch.Tensor:
-    """trl/core.py:43-48.  The global form runs on the library; the per-axis form is a tiny torch reduction."""
+    """trl/core.py:43-48.  The global form runs on the library (differentiable wrt ``values``); the per-axis form
+    is a tiny torch reduction."""
     if axis is not None:
         return (values * mask).sum(axis=axis) / mask.sum(axis=axis)
-    _, stats = ops.masked_whiten(values, mask != 0, want_out=False)
-    return stats[0]
+    return _like_input(_MaskedMean.apply(values, mask), values)
+
+
+def _empty_mask_error():
+    return ValueError(
+        "The sum of the mask is zero, which can happen when `mini_batch_size=1`;"
+        "try increase the `mini_batch_size` or `gradient_accumulation_steps`")
 
 
 def masked_var(values: torch.Tensor, mask: torch.Tensor, unbiased: bool = True) -> torch.Tensor:
     """trl/core.py:51-67; raises the reference's ValueError on an empty mask (this is the reference's host sync)."""
+    if _wants_grad(values):
+        # differentiable form: the reference's own composition (core.py:53-66) over the differentiable mean
+        mean = masked_mean(values, mask)
+        variance = masked_mean((values - mean) ** 2, mask)
+        if unbiased:
+            mask_sum = mask.sum()
+            if mask_sum == 0:
+                raise _empty_mask_error()
+            variance = variance * (mask_sum / (mask_sum - 1))
+        return variance
     _, stats = ops.masked_whiten(values, mask != 0, want_out=False)
     if unbiased:
         if float(stats[2]) == 0:
-            raise ValueError(
-                "The sum of the mask is zero, which can happen when `mini_batch_size=1`;"
-                "try increase the `mini_batch_size` or `gradient_accumulation_steps`")
-        return stats[1]
+            raise _empty_mask_error()
+        return _like_input(stats[1], values)
     n = stats[2]
-    return stats[1] * ((n - 1) / n)
+    return _like_input(stats[1] * ((n - 1) / n), values)
 
 
 def masked_whiten(values: torch.Tensor, mask: torch.Tensor, shift_mean: bool = True) -> torch.Tensor:
     """trl/core.py:70-76."""
+    if _wants_grad(values):
+        mean, var = masked_mean(values, mask), masked_var(values, mask)
+        whitened = (values - mean) * torch.rsqrt(var + 1e-8)
+        return whitened if shift_mean else whitened + mean
     out, _ = ops.masked_whiten(values, mask != 0, shift_mean=shift_mean)
-    return out.view_as(values)
+    return _like_input(out.view_as(values), values)

@@ -21,6 +21,7 @@ from typing import Optional
 import torch
 
 from . import _lib, ops
+from ._nvtx import nvtx_range
 
 METRIC_INDEX = {"loss": 0, "kl": 1, "entropy": 2, "clip_ratio/low": 3, "clip_ratio/high": 4, "clip_ratio/region": 5,
                 "num_tokens": 6}
@@ -256,25 +257,66 @@ def compute_loss(self, model, inputs):
     loss_fn = GRPOLoss(self.beta, self.epsilon_low, self.epsilon_high, getattr(self.args, "delta", None),
                        self.loss_type, self.importance_sampling_level, self.max_completion_length, self.temperature,
                        self.top_entropy_quantile)
-    grad_scale = 1.0 / float(getattr(self, "current_gradient_accumulation_steps", 1) or 1) \
-        if getattr(self, "_b200_prescale", False) else 1.0
-    out = loss_fn(logits, completion_ids, completion_mask, inputs["advantages"], inputs.get("old_per_token_logps"),
-                  inputs.get("ref_per_token_logps") if self.beta != 0.0 else None, grad_scale=grad_scale,
-                  logits_to_keep=T)
+    # HF Trainer.training_step divides the loss by `current_gradient_accumulation_steps` before backward (GRPOTrainer
+    # sets `model_accepts_loss_kwargs = False`, grpo_trainer.py:1018-1019), so that is the upstream gradient the fused
+    # pass folds in; any other upstream value (fp16 GradScaler ...) is fixed on the device by `rescale_if_needed`.
+    # `_b200_prescale = False` switches the fold off.
+    grad_scale = 1.0
+    if getattr(self, "_b200_prescale", True) and torch.is_grad_enabled():
+        grad_scale = 1.0 / float(getattr(self, "current_gradient_accumulation_steps", 1) or 1)
+    with nvtx_range("b200trl.grpo_loss"):
+        out = loss_fn(logits, completion_ids, completion_mask, inputs["advantages"], inputs.get("old_per_token_logps"),
+                      inputs.get("ref_per_token_logps") if self.beta != 0.0 else None, grad_scale=grad_scale,
+                      logits_to_keep=T)
 
     mode = "train" if self.model.training else "eval"
-    g = gather_metrics(out.metrics, getattr(self, "accelerator", None))  # [world, 8] on host, one sync
-    mi = METRIC_INDEX
-    if self.beta != 0.0:
-        self._metrics[mode]["kl"].append(_nanmean(g[:, mi["kl"]]))
-    self._metrics[mode]["entropy"].append(_nanmean(g[:, mi["entropy"]]))
-    low, high, region = g[:, mi["clip_ratio/low"]], g[:, mi["clip_ratio/high"]], g[:, mi["clip_ratio/region"]]
-    self._metrics[mode]["clip_ratio/low_mean"].append(_nanmean(low))
-    self._metrics[mode]["clip_ratio/low_min"].append(_nanmin(low))
-    self._metrics[mode]["clip_ratio/high_mean"].append(_nanmean(high))
-    self._metrics[mode]["clip_ratio/high_max"].append(_nanmax(high))
-    self._metrics[mode]["clip_ratio/region_mean"].append(_nanmean(region))
+    if getattr(self, "_b200_deferred_metrics", False):
+        # no host sync here: the packed row waits on the device until `log()` (patched by patch_trl) flushes the ring
+        pending = self.__dict__.setdefault("_b200_pending_metrics", [])
+        pending.append((mode, out.metrics, self.beta != 0.0))
+    else:
+        g = gather_metrics(out.metrics, getattr(self, "accelerator", None))  # [world, 8] on host, one sync
+        _append_metrics(self._metrics[mode], g, self.beta != 0.0)
     return out.loss
+
+
+def _append_metrics(store, g: torch.Tensor, has_kl: bool) -> None:
+    """One step's logged scalars from the gathered per-rank rows ``g [world, 8]`` (grpo_trainer.py:2150-2172)."""
+    mi = METRIC_INDEX
+    if has_kl:
+        store["kl"].append(_nanmean(g[:, mi["kl"]]))
+    store["entropy"].append(_nanmean(g[:, mi["entropy"]]))
+    low, high, region = g[:, mi["clip_ratio/low"]], g[:, mi["clip_ratio/high"]], g[:, mi["clip_ratio/region"]]
+    store["clip_ratio/low_mean"].append(_nanmean(low))
+    store["clip_ratio/low_min"].append(_nanmin(low))
+    store["clip_ratio/high_mean"].append(_nanmean(high))
+    store["clip_ratio/high_max"].append(_nanmax(high))
+    store["clip_ratio/region_mean"].append(_nanmean(region))
+
+
+def flush_metrics(self) -> int:
+    """Move the deferred metric rows of ``compute_loss`` into ``self._metrics``: ONE ``[steps, 8]`` exchange and ONE
+    device->host read per ``log()`` call instead of one per micro-step (the reference pays five gathers and seven
+    ``.item()`` syncs per micro-step, grpo_trainer.py:2150-2172).  Per-step values are identical to the eager path:
+    each row is reduced over ranks separately, in the order the steps ran.  Returns the number of rows flushed."""
+    from .distributed import gather_metric_rows
+
+    pending = self.__dict__.get("_b200_pending_metrics") or []
+    if not pending:
+        return 0
+    self._b200_pending_metrics = []
+    rows = torch.stack([m for _, m, _ in pending])                       # [steps, 8] on the device
+    g = gather_metric_rows(rows, getattr(self, "accelerator", None))     # [world, steps, 8] on the host
+    for i, (mode, _, has_kl) in enumerate(pending):
+        _append_metrics(self._metrics[mode], g[:, i], has_kl)
+    return len(pending)
+
+
+def log(self, logs, start_time=None):
+    """``GRPOTrainer.log`` with the deferred metric rows flushed first (grpo_trainer.py:2184-2193 reads
+    ``self._metrics`` there and nowhere else)."""
+    flush_metrics(self)
+    return type(self)._trl_original_log(self, logs, start_time)
 
 
 def _nanmean(x: torch.Tensor) -> float:

@@ -45,6 +45,27 @@ def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     return t.detach().to(torch.float32).contiguous()
 
 
+class _Keep:
+    """Owns the fp32 / contiguous temporaries of one C call.
+
+    ``_ptr(_f32(x))`` alone would hand the library a pointer whose tensor CPython frees before the call is made:
+    two same-sized temporaries in one argument list then alias in the caching allocator (e.g. bf16 ``old`` and
+    ``ref`` log-probs).  Every converted tensor is therefore parked here until the wrapper returns; after that the
+    allocator's stream ordering keeps the block valid for the launched kernel.
+    """
+
+    __slots__ = ("held",)
+
+    def __init__(self):
+        self.held = []
+
+    def f32(self, t: Optional[torch.Tensor], name: str):
+        x = _f32(t, name)
+        if x is not None:
+            self.held.append(x)
+        return _ptr(x)
+
+
 def collapse_rows(shape, strides) -> Optional[int]:
     """Row stride (in elements) if a ``(..., V)`` layout is addressable as ``base + r * row_stride``, else None.
 
@@ -189,13 +210,14 @@ def masked_logprob_fwd(logits: torch.Tensor, ids: torch.Tensor, row_mask: torch.
 def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: torch.Tensor,
                 inv_temperature: float = 1.0) -> torch.Tensor:
     """``dlogits`` (logits dtype, contiguous) for per-token upstream gradient ``g``."""
+    k = _Keep()
     r = rows_view(logits)
     x, n, V = r.t, r.n, r.V
     idx = ids.to(torch.int64).contiguous()
     out = torch.empty(logits.shape, dtype=x.dtype, device=x.device)
     if n:
         check(lib.b200trl_logprob_bwd(_ptr(x), _DTYPES[x.dtype], n, V, r.row_stride, r.rows_per_batch, r.batch_stride,
-                                      _ptr(idx), float(inv_temperature), _ptr(_f32(lse, "lse")), _ptr(_f32(g, "g")),
+                                      _ptr(idx), float(inv_temperature), k.f32(lse, "lse"), k.f32(g, "g"),
                                       _ptr(out), V, 0, _stream(x)), "logprob_bwd")
         _count()
     return out
@@ -216,6 +238,7 @@ def mask_stats(mask: torch.Tensor):
 def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages, old_logp, ref_logp, cfg: GrpoCfg,
                        inv_temperature: float, want_grad: bool = True, dlogits_out: Optional[torch.Tensor] = None):
     """One pass: ``(logp, entropy, lse, dlogits|None)``; see ``b200trl_grpo_fused_fwd_bwd``."""
+    k = _Keep()
     B, T = mask_i32.shape
     r = rows_view(logits, rows_per_batch=T)
     x, n, V = r.t, r.n, r.V
@@ -234,8 +257,8 @@ def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages
         dl_rs, dl_bs = d[0], d[2]
     check(lib.b200trl_grpo_fused_fwd_bwd(
         _ptr(x), _DTYPES[x.dtype], B, T, V, r.row_stride, r.batch_stride, _ptr(idx), _ptr(mask_i32),
-        _ptr(_f32(advantages, "advantages")), _ptr(_f32(old_logp, "old_per_token_logps")),
-        _ptr(_f32(ref_logp, "ref_per_token_logps")), C.byref(cfg), float(inv_temperature), _ptr(row_count),
+        k.f32(advantages, "advantages"), k.f32(old_logp, "old_per_token_logps"),
+        k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg), float(inv_temperature), _ptr(row_count),
         _ptr(total_count), _ptr(logp), _ptr(ent), _ptr(lse), _ptr(dl), dl_rs, dl_bs, _stream(x)),
         "grpo_fused_fwd_bwd")
     _count()
@@ -259,6 +282,7 @@ def _workspace(device, nbytes: int, key: str, zero: bool) -> torch.Tensor:
 def grpo_loss(logp, old_logp, ref_logp, advantages, mask_i32, row_count, total_count, cfg: GrpoCfg,
               ent_mask: Optional[torch.Tensor] = None, entropy: Optional[torch.Tensor] = None, want_g: bool = False):
     """``(loss[1], metrics[8], g[B,T]|None)`` — ``b200trl_grpo_loss``."""
+    k = _Keep()
     B, T = mask_i32.shape
     dev = mask_i32.device
     ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(B), "grpo_loss", zero=True)
@@ -267,9 +291,9 @@ def grpo_loss(logp, old_logp, ref_logp, advantages, mask_i32, row_count, total_c
     g = torch.empty(B, T, dtype=torch.float32, device=dev) if want_g else None
     em = None if ent_mask is None else ent_mask.to(torch.uint8).contiguous()
     check(lib.b200trl_grpo_loss(
-        _ptr(_f32(logp, "per_token_logps")), _ptr(_f32(old_logp, "old_per_token_logps")),
-        _ptr(_f32(ref_logp, "ref_per_token_logps")), _ptr(_f32(advantages, "advantages")), _ptr(mask_i32), _ptr(em),
-        _ptr(_f32(entropy, "entropies")), B, T, C.byref(cfg), _ptr(row_count), _ptr(total_count), _ptr(ws), _ptr(loss),
+        k.f32(logp, "per_token_logps"), k.f32(old_logp, "old_per_token_logps"),
+        k.f32(ref_logp, "ref_per_token_logps"), k.f32(advantages, "advantages"), _ptr(mask_i32), _ptr(em),
+        k.f32(entropy, "entropies"), B, T, C.byref(cfg), _ptr(row_count), _ptr(total_count), _ptr(ws), _ptr(loss),
         _ptr(metrics), _ptr(g), _stream(mask_i32)), "grpo_loss")
     _count()
     return loss, metrics, g
@@ -348,6 +372,7 @@ def ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl
 def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advantages, inv_temperature, cliprange,
                       grad_scale: float = 1.0, want_grad: bool = True):
     """``(new_logprobs, entropy, lse, dlogits|None)`` — ``b200trl_ppo_fused_fwd_bwd``."""
+    k = _Keep()
     mb, T = responses.shape
     r = rows_view(logits, rows_per_batch=T)
     x, n, V = r.t, r.n, r.V
@@ -361,8 +386,8 @@ def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advanta
     lse = torch.empty(mb, T, dtype=torch.float32, device=dev)
     dl = torch.empty((mb, T, V), dtype=x.dtype, device=dev) if want_grad else None
     check(lib.b200trl_ppo_fused_fwd_bwd(_ptr(x), _DTYPES[x.dtype], mb, T, V, r.row_stride, r.batch_stride, _ptr(idx),
-                                        _ptr(sl), _ptr(_f32(old_logprobs, "old_logprobs")),
-                                        _ptr(_f32(advantages, "advantages")), float(inv_temperature), float(cliprange),
+                                        _ptr(sl), k.f32(old_logprobs, "old_logprobs"),
+                                        k.f32(advantages, "advantages"), float(inv_temperature), float(cliprange),
                                         float(grad_scale), _ptr(nlp), _ptr(ent), _ptr(lse), _ptr(dl), V, 0,
                                         _stream(x)), "ppo_fused_fwd_bwd")
     _count()
@@ -372,6 +397,7 @@ def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advanta
 def ppo_loss(new_logprobs, old_logprobs, advantages, returns, values, vpred, entropy, sequence_lengths, cliprange,
              cliprange_value, vf_coef, grad_scale: float = 1.0, want_dvpred: bool = True):
     """``(stats[8], dvpred|None)`` — ``b200trl_ppo_loss``."""
+    k = _Keep()
     nlp = _f32(new_logprobs, "new_logprobs")
     mb, T = nlp.shape
     dev = nlp.device
@@ -379,9 +405,9 @@ def ppo_loss(new_logprobs, old_logprobs, advantages, returns, values, vpred, ent
     ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(mb), "ppo_loss", zero=True)
     stats = torch.empty(_lib.NUM_PPO_STATS, dtype=torch.float32, device=dev)
     dvp = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_dvpred else None
-    check(lib.b200trl_ppo_loss(_ptr(nlp), _ptr(_f32(old_logprobs, "old_logprobs")), _ptr(_f32(advantages, "advantages")),
-                               _ptr(_f32(returns, "returns")), _ptr(_f32(values, "values")), _ptr(_f32(vpred, "vpred")),
-                               _ptr(_f32(entropy, "entropy")), _ptr(sl), mb, T, float(cliprange),
+    check(lib.b200trl_ppo_loss(_ptr(nlp), k.f32(old_logprobs, "old_logprobs"), k.f32(advantages, "advantages"),
+                               k.f32(returns, "returns"), k.f32(values, "values"), k.f32(vpred, "vpred"),
+                               k.f32(entropy, "entropy"), _ptr(sl), mb, T, float(cliprange),
                                float(cliprange_value), float(vf_coef), float(grad_scale), _ptr(ws), _ptr(stats),
                                _ptr(dvp), _stream(nlp)), "ppo_loss")
     _count()
@@ -444,6 +470,7 @@ def rloo_rewards_advantages(logprobs, ref_logprobs, scores, sequence_lengths, kl
 def rloo_loss(new_logprobs, old_logprobs, advantages, entropy, sequence_lengths, cliprange, grad_scale: float = 1.0,
               want_g: bool = True):
     """``(stats[8], g[mb,T]|None)`` — ``b200trl_rloo_loss``."""
+    k = _Keep()
     nlp = _f32(new_logprobs, "new_logprobs")
     mb, T = nlp.shape
     dev = nlp.device
@@ -451,8 +478,8 @@ def rloo_loss(new_logprobs, old_logprobs, advantages, entropy, sequence_lengths,
     ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(mb), "rloo_loss", zero=True)
     stats = torch.empty(8, dtype=torch.float32, device=dev)
     g = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_g else None
-    check(lib.b200trl_rloo_loss(_ptr(nlp), _ptr(_f32(old_logprobs, "old_logprobs")),
-                                _ptr(_f32(advantages, "advantages")), _ptr(_f32(entropy, "entropy")), _ptr(sl), mb, T,
+    check(lib.b200trl_rloo_loss(_ptr(nlp), k.f32(old_logprobs, "old_logprobs"),
+                                k.f32(advantages, "advantages"), k.f32(entropy, "entropy"), _ptr(sl), mb, T,
                                 float(cliprange), float(grad_scale), _ptr(ws), _ptr(stats), _ptr(g), _stream(nlp)),
           "rloo_loss")
     _count()
@@ -496,6 +523,7 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
                       need_dh: bool, need_dw: bool, need_db: bool):
     """``(loss[1], metrics[8], logp, entropy, dH|None, dW fp32|None, db fp32|None)`` — ``b200trl_fused_linear_grpo``:
     the whole chunked lm_head + GRPO loss forward/backward in one C call (cuBLASLt GEMMs + K1 in place + K2)."""
+    k = _Keep()
     _need_cuda(hidden, "_input")
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise TypeError("fused_linear_grpo needs bf16 hidden states and weights")
@@ -516,10 +544,53 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     ws = _workspace(dev, lib.b200trl_fused_linear_grpo_workspace_bytes(B, T, V, int(chunk_seqs)), "fused_linear_grpo",
                     zero=False)
     check(lib.b200trl_fused_linear_grpo(
-        _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), _ptr(_f32(advantages, "advantages")),
-        _ptr(_f32(old_logp, "old_per_token_logps")), _ptr(_f32(ref_logp, "ref_per_token_logps")), C.byref(cfg),
+        _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), k.f32(advantages, "advantages"),
+        k.f32(old_logp, "old_per_token_logps"), k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg),
         float(inv_temperature), int(chunk_seqs), _ptr(ws), _ptr(logp), _ptr(ent), _ptr(loss), _ptr(metrics), _ptr(dh),
         _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo")
     n_chunks = -(-B // max(1, min(int(chunk_seqs), B)))
     _count(2 + n_chunks + 1)  # mask stats (memset + kernel), K1 per chunk, K2; the GEMMs are library launches
     return loss, metrics, logp, ent, dh, dw, db
+
+
+# ------------------------------------------------------------------------------------------------ K7: tcgen05 GEMMs
+TC_OUT_BF16, TC_OUT_F32_ACC = 1, 2
+
+
+def tc_gemm(a: torch.Tensor, b: torch.Tensor, a_layout: int = 0, b_layout: int = 0,
+            out: Optional[torch.Tensor] = None, accumulate: bool = False, bias: Optional[torch.Tensor] = None,
+            m_fastest: bool = True) -> torch.Tensor:
+    """``D = A @ B.T`` on the CTA-pair tcgen05 kernel — ``b200trl_tc_gemm``.
+
+    ``a`` is stored ``[M, K]`` (``a_layout=0``) or ``[K, M]`` (``a_layout=1``), ``b`` ``[N, K]`` or ``[K, N]``
+    likewise; bf16, last dim contiguous.  ``accumulate=False``: bf16 ``[M, N]`` result (+ ``bias``);
+    ``accumulate=True``: ``out`` (fp32 ``[M, N]``) ``+= D``.
+    """
+    _need_cuda(a, "a")
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2:
+        raise TypeError("tc_gemm needs 2-D bf16 operands")
+    if a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("tc_gemm operands must be contiguous in their last dimension")
+    M, K = (a.shape[1], a.shape[0]) if a_layout else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_layout else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError(f"tc_gemm: contraction lengths differ ({K} vs {Kb})")
+    if accumulate:
+        if out is None or out.dtype != torch.float32 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+            raise ValueError("tc_gemm(accumulate=True) needs an fp32 [M, N] `out`")
+    elif out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    elif out.dtype != torch.bfloat16 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise ValueError("tc_gemm needs a bf16 [M, N] `out`")
+    bb = None if bias is None else bias.to(torch.bfloat16).contiguous()
+    check(lib.b200trl_tc_gemm(_ptr(a), int(a_layout), a.stride(0), _ptr(b), int(b_layout), b.stride(0), M, N, K,
+                              TC_OUT_F32_ACC if accumulate else TC_OUT_BF16, _ptr(out), out.stride(0), _ptr(bb),
+                              int(bool(m_fastest)), _stream(a)), "tc_gemm")
+    _count()
+    return out
+
+
+def set_seam_gemm_mask(mask: int) -> int:
+    """Bit 0 / 1 / 2 = logits / dH / dW GEMM of ``fused_linear_grpo`` on the tcgen05 kernel (clear = cuBLASLt);
+    returns the previous mask, ``mask < 0`` only queries."""
+    return int(lib.b200trl_set_seam_gemm_mask(int(mask)))
