@@ -199,7 +199,7 @@ size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 struct Layout {
     size_t logits, row_count, total, k2, lt, end;
 };
-Layout layout(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
+Layout layout(int64_t B, int64_t T, int64_t H, int64_t V, int64_t chunk_seqs) {
     Layout l;
     size_t off = 0;
     l.logits = off;
@@ -210,8 +210,9 @@ Layout layout(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
     off += 256;
     l.k2 = off;
     off += align256(static_cast<size_t>(b200trl_grpo_loss_workspace_bytes(B)));
-    l.lt = off;
-    off += kLtWorkspace;
+    l.lt = off;  // cuBLASLt scratch, or the fp32 split-K planes of the tcgen05 dH GEMM (never both at once)
+    off += std::max<size_t>(kLtWorkspace, align256(static_cast<size_t>(
+                                              b200trl_tc_gemm_workspace_bytes(chunk_seqs * T, H, V, B200TRL_TC_OUT_BF16))));
     l.end = off;
     return l;
 }
@@ -227,9 +228,10 @@ extern "C" int b200trl_set_seam_gemm_mask(int mask) {
     return prev;
 }
 
-extern "C" int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t T, int64_t V, int64_t chunk_seqs) {
-    if (B <= 0 || T <= 0 || V <= 0 || chunk_seqs <= 0) return 0;
-    return static_cast<int64_t>(layout(B, T, V, std::min(chunk_seqs, B)).end);
+extern "C" int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t V,
+                                                             int64_t chunk_seqs) {
+    if (B <= 0 || T <= 0 || H <= 0 || V <= 0 || chunk_seqs <= 0) return 0;
+    return static_cast<int64_t>(layout(B, T, H, V, std::min(chunk_seqs, B)).end);
 }
 
 extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
@@ -256,7 +258,7 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
     B200TRL_REQUIRE(!need_lt || h != nullptr, B200TRL_E_LAUNCH, "fused_linear_grpo: cublasLtCreate failed");
 
     chunk_seqs = std::min(chunk_seqs, B);
-    const Layout l = layout(B, T, V, chunk_seqs);
+    const Layout l = layout(B, T, H, V, chunk_seqs);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     __nv_bfloat16* logits = reinterpret_cast<__nv_bfloat16*>(ws + l.logits);
     float* row_count = reinterpret_cast<float*>(ws + l.row_count);
@@ -281,7 +283,7 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
         // row-major logits[rows, V] = hidden_c[rows, H] W[V, H]^T  <=>  column-major D[V, rows] = W^T(T) x hidden_c(N)
         if (mask_tc & 1)  // hidden_c and W both K-major; all row blocks of one W tile run at the same time
             rc = tc_gemm(0, 0, TC_EPI_STORE, hid + r0 * H, H, weight, H, rows, V, H, logits, V, bias, nullptr, 0.f, nullptr,
-                         nullptr, 1, stream);
+                         nullptr, 1, nullptr, 0, stream);
         else
             rc = lt_gemm(api, h, CUBLAS_OP_T, CUBLAS_OP_N, V, rows, H, weight, H, hid + r0 * H, H, logits, V, CUDA_R_16BF,
                          0.f, bias, lt_ws, kLtWorkspace, stream);
@@ -299,7 +301,7 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
         if (dh) {  // dH_c[rows, H] = dl[rows, V] W[V, H]  <=>  D[H, rows] = W(N)[H, V] x dl(N)[V, rows]
             if (mask_tc & 2)  // A = dl (K = V contiguous), B[n = h, k = v] = W[v, h] is MN-major
                 rc = tc_gemm(0, 1, TC_EPI_STORE, logits, V, weight, H, rows, H, V, dh + r0 * H, H, nullptr, nullptr, 0.f,
-                             nullptr, nullptr, 1, stream);
+                             nullptr, nullptr, 1, lt_ws, static_cast<int64_t>(l.end - l.lt), stream);
             else
                 rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_N, H, rows, V, weight, H, logits, V, dh + r0 * H, H, CUDA_R_16BF,
                              0.f, nullptr, lt_ws, kLtWorkspace, stream);
@@ -309,7 +311,7 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
             if (mask_tc & 4)  // A[m = v, k = r] = dl[r, v] and B[n = h, k = r] = hidden[r, h]: both MN-major; the dl
                               // tile is the operand that does not fit L2, so consecutive clusters share it
                 rc = tc_gemm(1, 1, TC_EPI_ACCUM, logits, V, hid + r0 * H, H, V, H, rows, dweight, H, nullptr, nullptr, 0.f,
-                             nullptr, nullptr, 0, stream);
+                             nullptr, nullptr, 0, nullptr, 0, stream);
             else
                 rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_T, H, V, rows, hid + r0 * H, H, logits, V, dweight, H, CUDA_R_32F,
                              1.f, nullptr, lt_ws, kLtWorkspace, stream);

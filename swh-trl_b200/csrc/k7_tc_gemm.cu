@@ -9,7 +9,11 @@
 //   EPI_STORE  D is rounded to bf16 (+ bias) and stored row-major; optionally the same rounded values are folded into
 //              the row statistics, i.e. exactly what a pass over the stored logits would compute
 //              (the lm_head GEMM of the Liger seam, grpo_trainer.py:2005-2045; dH = dlogits W);
-//   EPI_ACCUM  D is added into an fp32 matrix (dW += dlogits^T hidden across chunks of sequences).
+//   EPI_ACCUM  D is added into an fp32 matrix (dW += dlogits^T hidden across chunks of sequences) with TMA
+//              reduce-add stores: the read-modify-write happens in L2, the SM only writes;
+//   EPI_PARTIAL  split-K: the item's k-slice of D goes to its own fp32 plane (plain TMA store); a second small kernel
+//              adds the planes in a fixed order and rounds to bf16 -> deterministic, and a contraction with few output
+//              tiles and a huge K (dH: 224 tiles over 74 clusters, K = 152064) fills the last wave.
 //
 // Execution model (Blackwell-native, no legacy mma.sync anywhere):
 //   * thread-block clusters of 2 CTAs on one TPC issue ONE tcgen05.mma.cta_group::2 per 256 x 256 x 16 step: each CTA
@@ -21,6 +25,9 @@
 //     CTAs / publishes an accumulator to both epilogues;
 //   * warp 2: allocates / frees the 512 TMEM columns (two 128 x 256 fp32 accumulators per CTA, ping-pong);
 //   * warps 4-7: epilogue, tcgen05.ld 32 lanes x 32 columns, thread == accumulator row; overlaps the next tile's MMAs.
+//     Stored tiles leave through shared memory: each warp writes its 32 rows into a private 128-byte-swizzled 4 KB box
+//     (conflict-free) and one lane issues a TMA store / reduce-add, so global memory sees whole 128-byte rows
+//     (direct st.global of the thread == row layout wrote 64-byte fragments and cost 5 % of the tensor time).
 //   Persistent: cluster c takes work items c, c + n_clusters, ...; an item is (256-row block, run of n-tiles).
 #include <cuda.h>
 
@@ -47,11 +54,12 @@ constexpr int kUmmaK = 16;
 constexpr int kStages = 6;
 constexpr int kOperandBytes = 128 * kTileK * 2;  // 16 KB: a 128 x 64 bf16 operand slab (either major)
 constexpr int kStageBytes = 2 * kOperandBytes;   // per CTA
+constexpr int kStagingBytes = 4 * 2 * 4096;      // epilogue: per warp two 32-row x 128-byte boxes
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr float kSlack = 6.0f;  // the running reference moves only when the tile maximum exceeds it by 2^6
 
-enum { EPI_STATS = TC_EPI_STATS, EPI_STORE = TC_EPI_STORE, EPI_ACCUM = TC_EPI_ACCUM };
+enum { EPI_STATS = TC_EPI_STATS, EPI_STORE = TC_EPI_STORE, EPI_ACCUM = TC_EPI_ACCUM, EPI_PARTIAL = 3 };
 
 struct Bars {
     uint64_t full[kStages];   // leader CTA: both CTAs' TMA bytes of a stage have landed
@@ -64,13 +72,15 @@ struct Bars {
 struct GemmArgs {
     int64_t m_rows, n_cols, k_len;
     int n_mpairs, n_ntiles, n_groups, tiles_per_group, m_fastest;
+    int sb_mpairs;  // 256-row blocks per super-block: the A rows that are walked together stay resident in L2
+    int k_splits, kb_per_split;  // EPI_PARTIAL: item = (k-slice, row block, n-tile), slice-major so that all clusters
+                                 // walk the same k-range at the same time (operands shared through L2)
     // statistics (EPI_STATS always; EPI_STORE when partial != nullptr)
     const int64_t* ids;
     float c;          // inv_T * log2(e)
     float4* partial;  // [n_groups][n_mpairs * 256] : (m, S, U, selected logit or NaN)
-    // output (EPI_STORE: bf16 [m_rows, ldd]; EPI_ACCUM: fp32 [m_rows, ldd], += )
-    void* out;
-    int64_t ldd;
+    // output goes through the third tensor map (EPI_STORE: bf16 [m_rows, n_cols]; EPI_ACCUM: fp32, +=; EPI_PARTIAL:
+    // fp32 [k_splits, m_rows, n_cols])
     const __nv_bfloat16* bias;  // EPI_STORE only, per column, may be null
 };
 
@@ -105,6 +115,25 @@ __device__ __forceinline__ void fold32(RowFold& f, const float* v, int valid, fl
     }
 }
 
+// Work order.  m_fastest: super-block of `sb_mpairs` row blocks -> run of n-tiles -> row block, so that clusters
+// running at the same time share the B tile and re-read an A super-block that fits L2 (at config 4 the whole
+// hidden matrix, 117 MB, does not: walking all of it per n-tile costs 30 % of the tensor throughput).  Otherwise
+// row block -> run of n-tiles: clusters running at the same time share the A tile.
+__device__ __host__ __forceinline__ void decode_item(int item, int n_mpairs, int n_groups, int sb_mpairs, int m_fastest,
+                                                     int& g, int& mp) {
+    if (m_fastest) {
+        const int per_sb = sb_mpairs * n_groups;
+        const int sb = item / per_sb, r = item - sb * per_sb;
+        const int rest = n_mpairs - sb * sb_mpairs;
+        const int mps = rest < sb_mpairs ? rest : sb_mpairs;
+        g = r / mps;
+        mp = sb * sb_mpairs + (r - g * mps);
+    } else {
+        mp = item / n_groups;
+        g = item - mp * n_groups;
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -113,17 +142,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 template <int kAMn, int kBMn, int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs a) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_d, const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment in the shared window (1 KB of slack is allocated); both CTAs of the
     // pair compute the same offset, which the pair MMA relies on
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
+    unsigned char* staging = smem + kStages * kStageBytes;
+    Bars& bars = *reinterpret_cast<Bars*>(staging + kStagingBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int n_items = a.n_mpairs * a.n_groups;
+    const int items_per_split = a.n_mpairs * a.n_groups;
+    const int n_items = items_per_split * a.k_splits;
     const int kblocks = static_cast<int>((a.k_len + kTileK - 1) / kTileK);
 
     if (threadIdx.x == 0) {
@@ -140,6 +172,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (kEpi != EPI_STATS) tma_prefetch_desc(&map_d);
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
@@ -158,13 +191,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const int g = a.m_fastest ? item / a.n_mpairs : item % a.n_groups;
-                const int mp = a.m_fastest ? item % a.n_mpairs : item / a.n_groups;
+                int g, mp;
+                const int ks = item / items_per_split;
+                decode_item(item - ks * items_per_split, a.n_mpairs, a.n_groups, a.sb_mpairs, a.m_fastest, g, mp);
+                const int kb0 = ks * a.kb_per_split, kb1 = min(kblocks, kb0 + a.kb_per_split);
                 const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
                 const int m0 = mp * (2 * kTileM) + static_cast<int>(rank) * kTileM;
                 for (int nt = nt0; nt < nt1; ++nt) {
                     const int n0 = nt * kTileN + static_cast<int>(rank) * kHalfN;
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&bars.empty[stage], phase ^ 1u);
                         unsigned char* sa = smem + stage * kStageBytes;
                         unsigned char* sb = sa + kOperandBytes;
@@ -210,13 +245,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int buf = 0;
             uint32_t acc_phase = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters) {
-                const int g = a.m_fastest ? item / a.n_mpairs : item % a.n_groups;
+                int g, mp;
+                const int ks = item / items_per_split;
+                decode_item(item - ks * items_per_split, a.n_mpairs, a.n_groups, a.sb_mpairs, a.m_fastest, g, mp);
+                const int kb0 = ks * a.kb_per_split, kb1 = min(kblocks, kb0 + a.kb_per_split);
                 const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
                 for (int nt = nt0; nt < nt1; ++nt) {
                     mbar_wait_cluster(&bars.tmem_empty[buf], acc_phase ^ 1u);  // both epilogues drained this buffer
                     fence_after_sync();
                     const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * kTileN);
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&bars.full[stage], phase);
                         fence_after_sync();
                         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -224,7 +262,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t bdesc = smem_desc_sw128(sa + kOperandBytes, kBMn ? kOperandBytes / 2 : 16);
 #pragma unroll
                         for (int k = 0; k < kTileK / kUmmaK; ++k)
-                            mma_pair_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            mma_pair_f16(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                         commit_pair_multicast(&bars.empty[stage], 3);  // both CTAs may refill the stage
                         if (++stage == kStages) {
                             stage = 0;
@@ -240,16 +278,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (both CTAs): thread == accumulator row
         const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
-        const int row_in_tile = ew * 32 + lane;
         const float c = a.c;
         const bool want_stats = (kEpi == EPI_STATS) || (kEpi == EPI_STORE && a.partial != nullptr);
+        // this warp's two staging boxes (32 rows x 128 bytes, SWIZZLE_128B: 16-byte chunk q of row r sits at q ^ (r & 7))
+        const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(ew) * 8192u;
+        const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        uint32_t box = 0;
         int buf = 0;
         uint32_t acc_phase = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
-            const int g = a.m_fastest ? item / a.n_mpairs : item % a.n_groups;
-            const int mp = a.m_fastest ? item % a.n_mpairs : item / a.n_groups;
+            int g, mp;
+            const int ks = item / items_per_split;
+            decode_item(item - ks * items_per_split, a.n_mpairs, a.n_groups, a.sb_mpairs, a.m_fastest, g, mp);
             const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
-            const int64_t row = static_cast<int64_t>(mp) * (2 * kTileM) + static_cast<int64_t>(rank) * kTileM + row_in_tile;
+            const int row0 = mp * (2 * kTileM) + static_cast<int>(rank) * kTileM + ew * 32;  // this warp's first row
+            const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < a.m_rows;
             const int64_t id = (want_stats && row_ok) ? a.ids[row] : -1;
             RowFold f{kNegBig, 0.f, 0.f, __int_as_float(0x7fc00000)};
@@ -257,16 +301,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(&bars.tmem_full[buf], acc_phase);
                 fence_after_sync();
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(buf * kTileN);
-                const int64_t col0 = static_cast<int64_t>(nt) * kTileN;
+                const int col0 = nt * kTileN;
 #pragma unroll 1
                 for (int j = 0; j < kTileN / 32; ++j) {
-                    float v[32];
-                    tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
-                    const int64_t cj = col0 + j * 32;
+                    const int cj = col0 + j * 32;
                     const int64_t left = a.n_cols - cj;
                     const int valid = left < 32 ? static_cast<int>(left) : 32;  // columns past N are padding
-                    if (valid <= 0) continue;
-                    if (kEpi == EPI_STORE) {
+                    if (valid <= 0) break;
+                    float v[32];
+                    if (kEpi == EPI_STATS) {
+                        tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
+                        fold32(f, v, valid, c, id, cj);
+                    } else if (kEpi == EPI_STORE) {
+                        // a bf16 box is 64 columns: two TMEM loads fill its two halves
+                        const uint32_t dst = stg + (box & 1u) * 4096u + my_row;
+                        if ((j & 1) == 0) {
+                            if (lane == 0) bulk_wait_read<1>();  // the store that last read this box has finished
+                            __syncwarp();
+                        }
+                        tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
                         if (a.bias) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
@@ -275,45 +328,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         uint32_t p[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-                        if (row_ok) {
-                            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a.out) + row * a.ldd + cj;
-                            if (valid == 32) {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    *reinterpret_cast<uint4*>(o + 8 * q) =
-                                        make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
-                            } else {
-                                for (int i = 0; i < valid; ++i)
-                                    o[i] = __ushort_as_bfloat16(static_cast<unsigned short>((p[i >> 1] >> ((i & 1) * 16)) & 0xffffu));
-                            }
-                        }
+                        for (int q = 0; q < 4; ++q)
+                            st_shared_v4(dst + ((static_cast<uint32_t>((j & 1) * 4 + q) ^ sw) << 4), p[4 * q], p[4 * q + 1],
+                                         p[4 * q + 2], p[4 * q + 3]);
                         if (want_stats) {  // statistics of the ROUNDED logits: what a pass over the stored tile would see
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 v[2 * i] = __uint_as_float(p[i] << 16);
                                 v[2 * i + 1] = __uint_as_float(p[i] & 0xffff0000u);
                             }
+                            fold32(f, v, valid, c, id, cj);
                         }
-                    }
-                    if (kEpi == EPI_ACCUM) {
-                        if (row_ok) {
-                            float* o = static_cast<float*>(a.out) + row * a.ldd + cj;
-                            if (valid == 32) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    float4 t = *reinterpret_cast<float4*>(o + 4 * q);
-                                    t.x += v[4 * q];
-                                    t.y += v[4 * q + 1];
-                                    t.z += v[4 * q + 2];
-                                    t.w += v[4 * q + 3];
-                                    *reinterpret_cast<float4*>(o + 4 * q) = t;
-                                }
-                            } else {
-                                for (int i = 0; i < valid; ++i) o[i] += v[i];
+                        if ((j & 1) == 1 || cj + 32 >= a.n_cols) {  // box complete (or the row ends inside it)
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && row0 < a.m_rows) {
+                                tma_store_2d(&map_d, cj & ~63, row0, staging + ew * 8192 + (box & 1u) * 4096u);
+                                bulk_commit();
                             }
+                            ++box;
                         }
+                    } else {  // EPI_ACCUM / EPI_PARTIAL: an fp32 box is 32 columns
+                        const uint32_t dst = stg + (box & 1u) * 4096u + my_row;
+                        if (lane == 0) bulk_wait_read<1>();
+                        __syncwarp();
+                        tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            st_shared_v4(dst + ((static_cast<uint32_t>(q) ^ sw) << 4), __float_as_uint(v[4 * q]),
+                                         __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                                         __float_as_uint(v[4 * q + 3]));
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && row0 < a.m_rows) {
+                            const void* src = staging + ew * 8192 + (box & 1u) * 4096u;
+                            if (kEpi == EPI_ACCUM)
+                                tma_reduce_add_2d(&map_d, cj, row0, src);
+                            else
+                                tma_store_3d(&map_d, cj, row0, ks, src);
+                            bulk_commit();
+                        }
+                        ++box;
                     }
-                    if (want_stats) fold32(f, v, valid, c, id, cj);
                 }
                 fence_before_sync();
                 __syncwarp();
@@ -324,6 +381,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (want_stats && row_ok)
                 a.partial[static_cast<int64_t>(g) * a.n_mpairs * (2 * kTileM) + row] = make_float4(f.m, f.S, f.U, f.xsel);
         }
+        if (kEpi != EPI_STATS && lane == 0) bulk_wait<0>();  // every store of this warp has reached global memory
     }
     fence_before_sync();
     cluster_sync_all();  // the peer's remote arrives and this CTA's multicast commits have all been consumed
@@ -391,6 +449,57 @@ int make_map(CUtensorMap* map, const void* base, int64_t outer, int64_t inner, i
     return B200TRL_OK;
 }
 
+// Output maps: boxes of 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), SWIZZLE_128B; rank 3 = [plane, row, col].
+int make_out_map(CUtensorMap* map, bool fp32, const void* base, int64_t planes, int64_t rows, int64_t cols, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
+        return B200TRL_E_LAUNCH;
+    }
+    const cuuint64_t esz = fp32 ? 4 : 2;
+    const cuuint32_t rank = planes > 0 ? 3 : 2;
+    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                                static_cast<cuuint64_t>(std::max<int64_t>(planes, 1))};
+    const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * esz, static_cast<cuuint64_t>(rows) * ld * esz};
+    const cuuint32_t box[3] = {fp32 ? 32u : 64u, 32u, 1u};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                          const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled failed for the output (%d)", static_cast<int>(r));
+        return B200TRL_E_INVALID;
+    }
+    return B200TRL_OK;
+}
+
+// bf16 out[r, c] = sum over the k-slices (in slice order) of the fp32 planes (+ bias[c]); 8 columns per thread
+__global__ void __launch_bounds__(256) tc_splitk_finish_kernel(const float* __restrict__ ws, int splits, int64_t rows,
+                                                               int64_t cols, __nv_bfloat16* __restrict__ out, int64_t ldd,
+                                                               const __nv_bfloat16* __restrict__ bias) {
+    const int64_t per_row = cols / 8;
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= rows * per_row) return;
+    const int64_t r = idx / per_row, c8 = (idx - r * per_row) * 8;
+    const int64_t plane = rows * cols;
+    const float* p = ws + r * cols + c8;
+    float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+    for (int s = 1; s < splits; ++s) {
+        const float4 a = *reinterpret_cast<const float4*>(p + s * plane), b = *reinterpret_cast<const float4*>(p + s * plane + 4);
+        lo.x += a.x, lo.y += a.y, lo.z += a.z, lo.w += a.w;
+        hi.x += b.x, hi.y += b.y, hi.z += b.z, hi.w += b.w;
+    }
+    if (bias) {
+        const uint4 bb = *reinterpret_cast<const uint4*>(bias + c8);
+        lo.x += __uint_as_float(bb.x << 16), lo.y += __uint_as_float(bb.x & 0xffff0000u);
+        lo.z += __uint_as_float(bb.y << 16), lo.w += __uint_as_float(bb.y & 0xffff0000u);
+        hi.x += __uint_as_float(bb.z << 16), hi.y += __uint_as_float(bb.z & 0xffff0000u);
+        hi.z += __uint_as_float(bb.w << 16), hi.w += __uint_as_float(bb.w & 0xffff0000u);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldd + c8) =
+        make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -400,10 +509,10 @@ int n_clusters_for_device() { return std::max(1, num_sms() / 2); }
 
 // Static round-robin of (256-row block, run of n-tiles) items over the clusters: pick the run length whose slowest
 // cluster finishes first (an item costs its tiles plus ~0.15 tile of pipeline restart and partial write).
-int plan_tiles_per_group(int n_mpairs, int n_ntiles, int n_clusters) {
+int plan_tiles_per_group(int n_mpairs, int n_ntiles, int n_clusters, int sb_mpairs) {
     static std::mutex mu;
-    static std::map<std::tuple<int, int, int>, int> cache;
-    const auto key = std::make_tuple(n_mpairs, n_ntiles, n_clusters);
+    static std::map<std::tuple<int, int, int, int>, int> cache;
+    const auto key = std::make_tuple(n_mpairs, n_ntiles, n_clusters, sb_mpairs);
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -422,7 +531,11 @@ int plan_tiles_per_group(int n_mpairs, int n_ntiles, int n_clusters) {
             double worst = 0;
             for (int cl = 0; cl < std::min<int64_t>(n_clusters, items); ++cl) {
                 double t = 0;
-                for (int64_t i = cl; i < items; i += n_clusters) t += ((i / n_mpairs == groups - 1) ? last : tpg) + 0.15;
+                for (int64_t i = cl; i < items; i += n_clusters) {
+                    int g, mp;
+                    decode_item(static_cast<int>(i), n_mpairs, groups, sb_mpairs, 1, g, mp);
+                    t += ((g == groups - 1) ? last : tpg) + 0.15;
+                }
                 worst = std::max(worst, t);
             }
             if (worst < best_cost - 1e-9) {
@@ -437,18 +550,41 @@ int plan_tiles_per_group(int n_mpairs, int n_ntiles, int n_clusters) {
 }
 
 template <int kAMn, int kBMn, int kEpi>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, cudaStream_t s) {
-    const size_t smem = static_cast<size_t>(kStages) * kStageBytes + sizeof(Bars) + 1024;
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const GemmArgs& a, cudaStream_t s) {
+    const size_t smem = static_cast<size_t>(kStages) * kStageBytes + kStagingBytes + sizeof(Bars) + 1024;
     auto kern = tc_gemm_kernel<kAMn, kBMn, kEpi>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) {
         set_error("tc_gemm: cannot reserve %zu B shared memory: %s", smem, cudaGetErrorString(e));
         return B200TRL_E_LAUNCH;
     }
-    const int64_t items = static_cast<int64_t>(a.n_mpairs) * a.n_groups;
+    const int64_t items = static_cast<int64_t>(a.n_mpairs) * a.n_groups * a.k_splits;
     const int clusters = static_cast<int>(std::min<int64_t>(n_clusters_for_device(), items));
-    kern<<<2 * clusters, kThreads, smem, s>>>(ma, mb, a);
+    kern<<<2 * clusters, kThreads, smem, s>>>(ma, mb, md, a);
     return check_launch("tc_gemm_kernel");
+}
+
+// Split-K decision for a stored GEMM: with `tiles` output tiles over `clusters` clusters the last wave of whole tiles
+// may be nearly empty (dH at config 4: 224 tiles on 74 clusters = 3.03 waves, paid as 4).  Splitting K into S slices
+// gives S * tiles items of 1/S the length; the planes cost S * M * N * 8 bytes of extra traffic.  Returns S (1 = none).
+int plan_k_splits(int64_t tiles, int clusters, int kblocks, int64_t M, int64_t N, int64_t ws_bytes) {
+    static const int forced = env_int("B200TRL_K7_SPLITK", 0);
+    const double tile_s = 2.0 * 256 * 256 * kblocks * kTileK / (2 * 10.5e12);  // one tile on one CTA pair
+    int best = 1;
+    double best_t = static_cast<double>((tiles + clusters - 1) / clusters) * tile_s;
+    for (int S = 2; S <= 16; ++S) {
+        if (kblocks / S < 32 || S * M * N * 4 > ws_bytes) break;
+        const int kbs = (kblocks + S - 1) / S;
+        const int S_eff = (kblocks + kbs - 1) / kbs;
+        const double rounds = static_cast<double>((tiles * S_eff + clusters - 1) / clusters);
+        const double t = rounds * tile_s * kbs / kblocks + S_eff * M * N * 8.0 / 6.0e12 + 4e-6;
+        if ((forced == S) || (forced <= 0 && t < best_t * 0.985)) {
+            best_t = t;
+            best = S;
+            if (forced == S) break;
+        }
+    }
+    return best;
 }
 
 }  // namespace
@@ -457,7 +593,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, cuda
 //   a_mn / b_mn: 0 = the operand is stored [rows, k] (k contiguous), 1 = stored [k, rows] (rows contiguous)
 int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
             int64_t K, void* out, int64_t ldd, const void* bias, const int64_t* ids, float c, void* partial,
-            int* n_groups_out, int m_fastest, cudaStream_t s) {
+            int* n_groups_out, int m_fastest, void* splitk_ws, int64_t splitk_ws_bytes, cudaStream_t s) {
     B200TRL_REQUIRE(M > 0 && N > 0 && K > 0, B200TRL_E_INVALID, "tc_gemm: bad shape");
     B200TRL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(B) & 15) == 0,
@@ -476,9 +612,17 @@ int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void*
     a.k_len = K;
     a.n_mpairs = static_cast<int>((M + 2 * kTileM - 1) / (2 * kTileM));
     a.n_ntiles = static_cast<int>((N + kTileN - 1) / kTileN);
+    // A super-block = the 256-row blocks whose A rows (sb_mpairs * 256 * K bf16) fit a 32 MB share of L2, evened out
+    {
+        static const int budget_mb = std::max(1, env_int("B200TRL_K7_SB_MB", 32));
+        const int64_t per_mpair = 2 * kTileM * K * 2;
+        const int fit = static_cast<int>(std::max<int64_t>(1, (static_cast<int64_t>(budget_mb) << 20) / per_mpair));
+        const int n_sb = (a.n_mpairs + fit - 1) / fit;
+        a.sb_mpairs = (a.n_mpairs + n_sb - 1) / n_sb;
+    }
     const bool stats = partial != nullptr;
     if (stats) {
-        a.tiles_per_group = plan_tiles_per_group(a.n_mpairs, a.n_ntiles, n_clusters_for_device());
+        a.tiles_per_group = plan_tiles_per_group(a.n_mpairs, a.n_ntiles, n_clusters_for_device(), a.sb_mpairs);
         a.m_fastest = 1;
     } else {
         a.tiles_per_group = 1;
@@ -488,12 +632,40 @@ int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void*
     a.ids = ids;
     a.c = c;
     a.partial = static_cast<float4*>(partial);
-    a.out = out;
-    a.ldd = ldd;
     a.bias = static_cast<const __nv_bfloat16*>(bias);
+    a.k_splits = 1;
+    a.kb_per_split = static_cast<int>((K + kTileK - 1) / kTileK);
     if (n_groups_out) *n_groups_out = a.n_groups;
+    CUtensorMap md = ma;  // EPI_STATS stores nothing
+    if (epi == EPI_STORE && splitk_ws && !stats && N % 8 == 0 && a_mn == 0) {
+        const int kblocks = a.kb_per_split;
+        const int S = plan_k_splits(static_cast<int64_t>(a.n_mpairs) * a.n_ntiles, n_clusters_for_device(), kblocks, M, N,
+                                    splitk_ws_bytes);
+        if (S > 1) {
+            a.kb_per_split = (kblocks + S - 1) / S;
+            a.k_splits = (kblocks + a.kb_per_split - 1) / a.kb_per_split;
+            a.bias = nullptr;  // added once, by the finishing kernel
+            rc = make_out_map(&md, true, splitk_ws, a.k_splits, M, N, N);
+            if (rc) return rc;
+            rc = B200TRL_E_UNSUPPORTED;
+            if (a_mn == 0 && b_mn == 0) rc = launch<0, 0, EPI_PARTIAL>(ma, mb, md, a, s);
+            if (a_mn == 0 && b_mn == 1) rc = launch<0, 1, EPI_PARTIAL>(ma, mb, md, a, s);
+            if (rc) {
+                if (rc == B200TRL_E_UNSUPPORTED) set_error("tc_gemm: split-K is not built for this operand layout");
+                return rc;
+            }
+            const int64_t n_thr = M * (N / 8);
+            tc_splitk_finish_kernel<<<static_cast<unsigned>((n_thr + 255) / 256), 256, 0, s>>>(
+                static_cast<const float*>(splitk_ws), a.k_splits, M, N, static_cast<__nv_bfloat16*>(out), ldd,
+                static_cast<const __nv_bfloat16*>(bias));
+            return check_launch("tc_splitk_finish_kernel");
+        }
+    }
+    if (epi == EPI_STORE) rc = make_out_map(&md, false, out, 0, M, N, ldd);
+    if (epi == EPI_ACCUM) rc = make_out_map(&md, true, out, 0, M, N, ldd);
+    if (rc) return rc;
 #define B200TRL_TC_CASE(AM, BM, EP) \
-    if (a_mn == AM && b_mn == BM && epi == EP) return launch<AM, BM, EP>(ma, mb, a, s);
+    if (a_mn == AM && b_mn == BM && epi == EP) return launch<AM, BM, EP>(ma, mb, md, a, s);
     B200TRL_TC_CASE(0, 0, EPI_STATS)
     B200TRL_TC_CASE(0, 0, EPI_STORE)
     B200TRL_TC_CASE(0, 1, EPI_STORE)
@@ -523,13 +695,20 @@ int tc_merge_stats(const void* partial, int n_groups, int64_t n_rows, float c, f
 
 using namespace b200trl;
 
+extern "C" int64_t b200trl_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int out_kind) {
+    if (M <= 0 || N <= 0 || K <= 0 || out_kind != B200TRL_TC_OUT_BF16) return 0;
+    // room for up to 8 fp32 planes of D, capped at 512 MB: enough for every split the planner would pick
+    return std::min<int64_t>(8 * M * N * 4, int64_t(512) << 20);
+}
+
 extern "C" int b200trl_tc_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb,
                                int64_t M, int64_t N, int64_t K, int out_kind, void* out, int64_t ldd, const void* bias,
-                               int m_fastest, b200trl_stream_t stream) {
+                               int m_fastest, void* workspace, int64_t workspace_bytes, b200trl_stream_t stream) {
     B200TRL_REQUIRE(A && B && out, B200TRL_E_INVALID, "tc_gemm: null pointer");
     B200TRL_REQUIRE(out_kind == B200TRL_TC_OUT_BF16 || out_kind == B200TRL_TC_OUT_F32_ACC, B200TRL_E_INVALID,
                     "tc_gemm: unknown out_kind %d", out_kind);
     B200TRL_REQUIRE(!bias || out_kind == B200TRL_TC_OUT_BF16, B200TRL_E_INVALID, "tc_gemm: bias needs the bf16 output");
     return tc_gemm(a_layout, b_layout, out_kind == B200TRL_TC_OUT_BF16 ? TC_EPI_STORE : TC_EPI_ACCUM, A, lda, B, ldb, M, N,
-                   K, out, ldd, bias, nullptr, 0.f, nullptr, nullptr, m_fastest, as_stream(stream));
+                   K, out, ldd, bias, nullptr, 0.f, nullptr, nullptr, m_fastest, workspace, workspace ? workspace_bytes : 0,
+                   as_stream(stream));
 }

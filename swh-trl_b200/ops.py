@@ -541,7 +541,7 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     dh = torch.empty_like(h) if need_dh else None
     dw = torch.empty(V, H, dtype=torch.float32, device=dev) if need_dw else None
     db = torch.empty(V, dtype=torch.float32, device=dev) if need_db else None
-    ws = _workspace(dev, lib.b200trl_fused_linear_grpo_workspace_bytes(B, T, V, int(chunk_seqs)), "fused_linear_grpo",
+    ws = _workspace(dev, lib.b200trl_fused_linear_grpo_workspace_bytes(B, T, H, V, int(chunk_seqs)), "fused_linear_grpo",
                     zero=False)
     check(lib.b200trl_fused_linear_grpo(
         _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), k.f32(advantages, "advantages"),
@@ -559,12 +559,13 @@ TC_OUT_BF16, TC_OUT_F32_ACC = 1, 2
 
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, a_layout: int = 0, b_layout: int = 0,
             out: Optional[torch.Tensor] = None, accumulate: bool = False, bias: Optional[torch.Tensor] = None,
-            m_fastest: bool = True) -> torch.Tensor:
+            m_fastest: bool = True, split_k: bool = True) -> torch.Tensor:
     """``D = A @ B.T`` on the CTA-pair tcgen05 kernel — ``b200trl_tc_gemm``.
 
     ``a`` is stored ``[M, K]`` (``a_layout=0``) or ``[K, M]`` (``a_layout=1``), ``b`` ``[N, K]`` or ``[K, N]``
     likewise; bf16, last dim contiguous.  ``accumulate=False``: bf16 ``[M, N]`` result (+ ``bias``);
-    ``accumulate=True``: ``out`` (fp32 ``[M, N]``) ``+= D``.
+    ``accumulate=True``: ``out`` (fp32 ``[M, N]``) ``+= D``.  ``split_k``: hand the kernel an fp32 scratch so that
+    it may split K when the output has too few tiles to fill the machine (bf16 output only).
     """
     _need_cuda(a, "a")
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2:
@@ -583,10 +584,15 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, a_layout: int = 0, b_layout: int =
     elif out.dtype != torch.bfloat16 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
         raise ValueError("tc_gemm needs a bf16 [M, N] `out`")
     bb = None if bias is None else bias.to(torch.bfloat16).contiguous()
-    check(lib.b200trl_tc_gemm(_ptr(a), int(a_layout), a.stride(0), _ptr(b), int(b_layout), b.stride(0), M, N, K,
-                              TC_OUT_F32_ACC if accumulate else TC_OUT_BF16, _ptr(out), out.stride(0), _ptr(bb),
-                              int(bool(m_fastest)), _stream(a)), "tc_gemm")
-    _count()
+    kind = TC_OUT_F32_ACC if accumulate else TC_OUT_BF16
+    ws, ws_bytes = None, 0
+    if split_k and not accumulate:
+        ws_bytes = int(lib.b200trl_tc_gemm_workspace_bytes(M, N, K, kind))
+        ws = _workspace(a.device, ws_bytes, "tc_gemm", zero=False) if ws_bytes else None
+    check(lib.b200trl_tc_gemm(_ptr(a), int(a_layout), a.stride(0), _ptr(b), int(b_layout), b.stride(0), M, N, K, kind,
+                              _ptr(out), out.stride(0), _ptr(bb), int(bool(m_fastest)), _ptr(ws), ws_bytes, _stream(a)),
+          "tc_gemm")
+    _count(2 if ws is not None else 1)
     return out
 
 

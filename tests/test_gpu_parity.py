@@ -542,11 +542,90 @@ def test_fused_linear_grpo_seam(S, dtype, V, H, loss_type, beta, with_old, level
         torch.testing.assert_close(h.grad.cpu(), hr.grad, rtol=1e-3, atol=1e-6)
         torch.testing.assert_close(w.grad.cpu(), Wr.grad, rtol=1e-3, atol=1e-6)
     else:
-        assert loss.item() == pytest.approx(loss_r.item(), rel=2e-3, abs=1e-6)
-        # bf16 GEMM operands (dlogits rounded to bf16): compare in aggregate, 2% of the gradient norm
+        # bf16 model: the oracle above rounds the logits to bf16 exactly where a bf16 lm_head does, so the loss is
+        # held to north_star's 1e-4; see _seam_bf16_oracle for the element-level bars on the gradients
+        assert loss.item() == pytest.approx(loss_r.item(), rel=1e-4, abs=1e-6)
         for got, want in ((h.grad, hr.grad), (w.grad, Wr.grad)):
             err = (got.float().cpu() - want).norm() / want.norm().clamp(min=1e-12)
-            assert float(err) < 2e-2, float(err)
+            assert float(err) < 6e-3, float(err)  # dlogits rounded once to bf16 (2^-9 rms) before the two GEMMs
+
+
+def _seam_bf16_oracle(hidden, W, ids, mask, adv, old, ref, cfg):
+    """The reference with a bf16 model, restated on the CPU with every rounding point the bf16 path has:
+    ``logits = bf16(hidden @ W.T)`` (fp32 accumulation, what a bf16 ``lm_head`` / Liger's chunk GEMM emit), the
+    reference's fp32 loss on them (grpo_trainer.py:2084-2137), ``dlogits`` rounded to bf16 (autograd's gradient of a
+    bf16 tensor), then ``dH = bf16(dlogits @ W)`` and ``dW = dlogits.T @ hidden`` accumulated in fp32."""
+    logits32 = hidden.float() @ W.float().t()
+    logits = logits32.to(torch.bfloat16).float().requires_grad_(True)
+    loss, met, lp, ent = O.grpo_compute_loss(logits, ids, mask, adv, cfg, old, ref)
+    loss.backward()
+    dl = logits.grad.to(torch.bfloat16).float().reshape(-1, W.shape[0])
+    dH = (dl @ W.float()).reshape(hidden.shape)
+    dW = dl.t() @ hidden.float().reshape(-1, hidden.shape[-1])
+    return loss.detach(), met, lp.detach(), ent.detach(), dH, dW, logits.detach()
+
+
+def _check_seam_against_bf16_oracle(S, B, T, H, V, chunk, seed, wscale):
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(B, T, H, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g) * wscale).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T).unsqueeze(0) < lens.unsqueeze(1)).int()
+    adv = torch.randn(B, generator=g)
+    cfg = O.GRPOConfigLite(beta=0.04, loss_type="bnpo", importance_sampling_level="token", max_completion_length=T)
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax((hidden.float() @ W.float().t()).to(torch.bfloat16).float(), ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.3
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1
+    loss_r, met_r, lp_r, ent_r, dH_r, dW_r, logits_r = _seam_bf16_oracle(hidden, W, ids, mask, adv, old, ref, cfg)
+
+    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
+    h = hidden.to(DEV).requires_grad_(True)
+    w = W.to(DEV).requires_grad_(True)
+    loss, metrics = fn(h, w, ids.to(DEV), mask.to(DEV), adv.to(DEV), None, old.to(DEV), ref.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    # loss and logged metrics: north_star's 1e-4 relative
+    assert loss.item() == pytest.approx(loss_r.item(), rel=1e-4, abs=1e-6)
+    assert metrics[0].item() == pytest.approx(met_r["kl"].item(), rel=1e-4, abs=1e-7)
+    assert metrics[-1].item() == pytest.approx(met_r["clip_ratio/region"].item(), abs=1e-6)
+    # log-probs: 1e-5 wherever the tensor core's accumulation order rounds the selected logit (and the row's large
+    # logits) to the same bf16 value as the CPU product; where a rounding flips, the difference is one bf16 ulp of
+    # that logit -- rare (the two fp32 sums differ by ~1e-6 relative, a bf16 rounding boundary is 2^-8 wide)
+    d = (fn.last_per_token_logps.cpu() - lp_r).abs()
+    assert float((d > 2e-5).float().mean()) < 2e-3, float((d > 2e-5).float().mean())
+    assert float(d.max()) <= 2.0 ** -7 * float(logits_r.abs().max()) + 1e-5
+    de = (fn.last_entropies.cpu() - ent_r).abs()
+    assert float((de > 1e-4).float().mean()) < 2e-3
+    # dW: accumulated in fp32 over the chunks, handed to autograd in the weight's dtype (bf16) like the reference's
+    # `.grad`; every rounding point is reproduced by the oracle, what is left are dlogits elements whose bf16 rounding
+    # flips (fp32 round-off of the exponentials) -- one bf16 ulp on a small fraction of the elements
+    want_w = dW_r.to(torch.bfloat16).float()
+    ew = (w.grad.float().cpu() - want_w).norm() / want_w.norm()
+    assert float(ew) < 1e-3, float(ew)
+    torch.testing.assert_close(w.grad.float().cpu(), want_w, rtol=2 * BF16_ULP, atol=4e-3 * float(want_w.abs().max()))
+    # dH is emitted in bf16: against the oracle's value rounded the same way, one bf16 ulp
+    want_h = dH_r.to(torch.bfloat16).float()
+    eh = (h.grad.float().cpu() - want_h).norm() / want_h.norm()
+    assert float(eh) < 4e-3, float(eh)
+    torch.testing.assert_close(h.grad.float().cpu(), want_h, rtol=2 * BF16_ULP, atol=4e-3 * float(want_h.abs().max()))
+    return float(ew), float(eh)
+
+
+@pytest.mark.parametrize("B,T,H,V,chunk", [(4, 64, 128, 32768, 2), (3, 96, 256, 50304, 1)])
+def test_seam_bf16_rounding_points(S, B, T, H, V, chunk):
+    """a-13 with a bf16 model against the CPU restatement that rounds where the bf16 reference rounds."""
+    _check_seam_against_bf16_oracle(S, B, T, H, V, chunk, seed=V + H, wscale=0.1)
+
+
+@pytest.mark.timeout(1500)
+def test_seam_config4_width(S):
+    """BASELINE config 4's contraction width (hidden 3584 -> V = 152064, Qwen2.5-7B lm_head) on 2 048 rows: loss,
+    metrics, log-probs, dH and dW of the seam operator against the CPU oracle with the bf16 rounding points."""
+    ew, eh = _check_seam_against_bf16_oracle(S, B=2, T=1024, H=3584, V=152064, chunk=1, seed=4, wscale=0.02)
+    print(f"config-4 width: dW rel-norm error {ew:.2e}, dH rel-norm error vs bf16-rounded oracle {eh:.2e}")
 
 
 # ------------------------------------------------------------------------------------------------ edge cases

@@ -56,7 +56,7 @@ def test_argument_validation_without_gpu():
     # the production build carries no trace hooks (they cost the hot kernel 20 %): the entry point says so
     assert lib.b200trl_k1_set_trace(None, 0) == -2 and b"trace" in lib.b200trl_last_error()
     # the seam call validates before it touches cuBLASLt or the device
-    assert lib.b200trl_fused_linear_grpo_workspace_bytes(8, 2048, 152064, 2) > 2 * 2048 * 152064 * 2
+    assert lib.b200trl_fused_linear_grpo_workspace_bytes(8, 2048, 3584, 152064, 2) > 2 * 2048 * 152064 * 2
     rc = lib.b200trl_fused_linear_grpo(None, None, None, 1, 1, 8, 8, None, None, None, None, None, None, 1.0, 1, None,
                                        None, None, None, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.b200trl_last_error()

@@ -79,7 +79,7 @@ def timing():
         ("logits", lambda: ops.tc_gemm(hid, W, out=logits), lambda: torch.matmul(hid, W.t(), out=logits)),
         ("dH", lambda: ops.tc_gemm(dl, W, b_layout=1, out=dh), lambda: torch.matmul(dl, W, out=dh)),
         ("dW", lambda: ops.tc_gemm(dl, hid, a_layout=1, b_layout=1, out=dw, accumulate=True, m_fastest=False),
-         lambda: dw.addmm_(dl.t().float()[:1, :1], hid.float()[:1, :1]) if False else torch.matmul(dl.t(), hid)),
+         lambda: torch.matmul(dl.t(), hid)),
     ]:
         say(name, "...")
         ms_o, ms_l = t(ours), t(lib)
@@ -93,6 +93,28 @@ def timing():
     say(json.dumps(res))
 
 
+def ncu_target():
+    """A handful of launches of each contraction at the config-4 chunk shape, for `ncu --set full -k regex:tc_gemm`."""
+    R, H, V = 4096, 3584, 152064
+    g = torch.Generator(device=DEV).manual_seed(0)
+    hid = torch.randn(R, H, generator=g, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g, device=DEV) * 0.02).to(torch.bfloat16)
+    dl = (torch.randn(R, V, generator=g, device=DEV) * 0.01).to(torch.bfloat16)
+    logits = torch.empty(R, V, dtype=torch.bfloat16, device=DEV)
+    dh = torch.empty(R, H, dtype=torch.bfloat16, device=DEV)
+    dw = torch.zeros(V, H, dtype=torch.float32, device=DEV)
+    ids = torch.randint(0, V, (R,), generator=g, device=DEV)
+    for _ in range(2):
+        ops.tc_gemm(hid, W, out=logits)
+        ops.tc_gemm(dl, W, b_layout=1, out=dh)
+        ops.tc_gemm(dl, hid, a_layout=1, b_layout=1, out=dw, accumulate=True, m_fastest=False)
+        ops.fused_linear_logprob_fwd(hid, W, ids, 1.0)
+    torch.cuda.synchronize()
+    say("ncu target done")
+
+
+if mode == "ncu":
+    ncu_target()
 if mode in ("check", "all"):
     check()
 if mode in ("time", "all"):
