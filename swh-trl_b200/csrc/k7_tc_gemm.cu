@@ -54,8 +54,8 @@ constexpr int kUmmaK = 16;
 constexpr int kStages = 6;
 constexpr int kOperandBytes = 128 * kTileK * 2;  // 16 KB: a 128 x 64 bf16 operand slab (either major)
 constexpr int kStageBytes = 2 * kOperandBytes;   // per CTA
-constexpr int kStagingBytes = 4 * 2 * 4096;      // epilogue: per warp two 32-row x 128-byte boxes
-constexpr int kThreads = 256;
+constexpr int kStagingBytes = 8 * 4096;          // epilogue (EPI_STORE): one 32-row x 128-byte box per warp
+constexpr int kThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: two epilogue warp-groups
 constexpr int kTmemCols = 512;
 constexpr float kSlack = 6.0f;  // the running reference moves only when the tile maximum exceeds it by 2^6
 
@@ -65,7 +65,7 @@ struct Bars {
     uint64_t full[kStages];   // leader CTA: both CTAs' TMA bytes of a stage have landed
     uint64_t empty[kStages];  // each CTA: the MMAs reading this stage have completed
     uint64_t tmem_full[2];    // each CTA: accumulator complete
-    uint64_t tmem_empty[2];   // leader CTA: both epilogues have drained the accumulator (8 warp arrivals)
+    uint64_t tmem_empty[2];   // leader CTA: both epilogues have drained the accumulator (16 warp arrivals)
     uint32_t tmem_base;
 };
 
@@ -78,9 +78,11 @@ struct GemmArgs {
     // statistics (EPI_STATS always; EPI_STORE when partial != nullptr)
     const int64_t* ids;
     float c;          // inv_T * log2(e)
-    float4* partial;  // [n_groups][n_mpairs * 256] : (m, S, U, selected logit or NaN)
-    // output goes through the third tensor map (EPI_STORE: bf16 [m_rows, n_cols]; EPI_ACCUM: fp32, +=; EPI_PARTIAL:
-    // fp32 [k_splits, m_rows, n_cols])
+    float4* partial;  // [n_groups * 2 column halves][n_mpairs * 256] : (m, S, U, selected logit or NaN)
+    // output: EPI_STORE goes through the third tensor map (bf16 [m_rows, n_cols]); EPI_ACCUM: fp32 [m_rows, ldd], +=;
+    // EPI_PARTIAL: fp32 planes [k_splits][m_rows, ldd], plane_stride elements apart
+    void* out;
+    int64_t ldd, plane_stride;
     const __nv_bfloat16* bias;  // EPI_STORE only, per column, may be null
 };
 
@@ -165,14 +167,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars.tmem_full[b], 1);
-            mbar_init(&bars.tmem_empty[b], 8);  // 4 epilogue warps x 2 CTAs
+            mbar_init(&bars.tmem_empty[b], 16);  // 8 epilogue warps x 2 CTAs
         }
         mbar_fence_init_cluster();
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        if (kEpi != EPI_STATS) tma_prefetch_desc(&map_d);
+        if (kEpi == EPI_STORE) tma_prefetch_desc(&map_d);
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
@@ -277,14 +279,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (both CTAs): thread == accumulator row
-        const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        // two warp-groups: warps 4-7 take columns [0, 128) of the tile, warps 8-11 columns [128, 256); a warp may
+        // only read the TMEM lane quarter warp % 4
+        const int ew = warp - 4;
+        const int quarter = ew & 3, half = ew >> 2;
         const float c = a.c;
         const bool want_stats = (kEpi == EPI_STATS) || (kEpi == EPI_STORE && a.partial != nullptr);
-        // this warp's two staging boxes (32 rows x 128 bytes, SWIZZLE_128B: 16-byte chunk q of row r sits at q ^ (r & 7))
-        const uint32_t stg = smem_u32(staging) + static_cast<uint32_t>(ew) * 8192u;
-        const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
+        // this warp's staging box (32 rows x 128 bytes, SWIZZLE_128B: 16-byte chunk q of row r sits at q ^ (r & 7))
+        unsigned char* my_box = staging + ew * 4096;
+        const uint32_t dst = smem_u32(my_box) + static_cast<uint32_t>(lane) * 128u;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        uint32_t box = 0;
         int buf = 0;
         uint32_t acc_phase = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters) {
@@ -292,34 +296,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int ks = item / items_per_split;
             decode_item(item - ks * items_per_split, a.n_mpairs, a.n_groups, a.sb_mpairs, a.m_fastest, g, mp);
             const int nt0 = g * a.tiles_per_group, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_group);
-            const int row0 = mp * (2 * kTileM) + static_cast<int>(rank) * kTileM + ew * 32;  // this warp's first row
+            const int row0 = mp * (2 * kTileM) + static_cast<int>(rank) * kTileM + quarter * 32;  // this warp's first row
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < a.m_rows;
             const int64_t id = (want_stats && row_ok) ? a.ids[row] : -1;
             RowFold f{kNegBig, 0.f, 0.f, __int_as_float(0x7fc00000)};
             for (int nt = nt0; nt < nt1; ++nt) {
+                const int col0 = nt * kTileN;
+                float* out32 = nullptr;
+                if (kEpi == EPI_ACCUM || kEpi == EPI_PARTIAL)
+                    out32 = static_cast<float*>(a.out) + (kEpi == EPI_PARTIAL ? ks * a.plane_stride : 0) + row * a.ldd;
+                float old[32];
+                if (kEpi == EPI_ACCUM) {  // the running sum of this thread's first 32 columns: in flight while the
+                                          // tile's MMAs are still running
+                    const int cj = col0 + half * 128;
+                    if (row_ok && cj + 32 <= a.n_cols) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = *reinterpret_cast<const float4*>(out32 + cj + 4 * q);
+                            old[4 * q] = t.x, old[4 * q + 1] = t.y, old[4 * q + 2] = t.z, old[4 * q + 3] = t.w;
+                        }
+                    }
+                }
                 mbar_wait(&bars.tmem_full[buf], acc_phase);
                 fence_after_sync();
-                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(buf * kTileN);
-                const int col0 = nt * kTileN;
+                const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTileN);
 #pragma unroll 1
-                for (int j = 0; j < kTileN / 32; ++j) {
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = half * 4 + jj;
                     const int cj = col0 + j * 32;
                     const int64_t left = a.n_cols - cj;
                     const int valid = left < 32 ? static_cast<int>(left) : 32;  // columns past N are padding
                     if (valid <= 0) break;
                     float v[32];
+                    tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
                     if (kEpi == EPI_STATS) {
-                        tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
                         fold32(f, v, valid, c, id, cj);
                     } else if (kEpi == EPI_STORE) {
                         // a bf16 box is 64 columns: two TMEM loads fill its two halves
-                        const uint32_t dst = stg + (box & 1u) * 4096u + my_row;
-                        if ((j & 1) == 0) {
-                            if (lane == 0) bulk_wait_read<1>();  // the store that last read this box has finished
+                        if ((jj & 1) == 0) {
+                            if (lane == 0) bulk_wait_read<0>();  // the store that last read this box has finished
                             __syncwarp();
                         }
-                        tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
                         if (a.bias) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
@@ -330,7 +348,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int i = 0; i < 16; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            st_shared_v4(dst + ((static_cast<uint32_t>((j & 1) * 4 + q) ^ sw) << 4), p[4 * q], p[4 * q + 1],
+                            st_shared_v4(dst + ((static_cast<uint32_t>((jj & 1) * 4 + q) ^ sw) << 4), p[4 * q], p[4 * q + 1],
                                          p[4 * q + 2], p[4 * q + 3]);
                         if (want_stats) {  // statistics of the ROUNDED logits: what a pass over the stored tile would see
 #pragma unroll
@@ -340,36 +358,51 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                             fold32(f, v, valid, c, id, cj);
                         }
-                        if ((j & 1) == 1 || cj + 32 >= a.n_cols) {  // box complete (or the row ends inside it)
+                        if ((jj & 1) == 1 || cj + 32 >= a.n_cols) {  // box complete (or the row ends inside it)
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0 && row0 < a.m_rows) {
-                                tma_store_2d(&map_d, cj & ~63, row0, staging + ew * 8192 + (box & 1u) * 4096u);
+                                tma_store_2d(&map_d, cj & ~63, row0, my_box);
                                 bulk_commit();
                             }
-                            ++box;
                         }
-                    } else {  // EPI_ACCUM / EPI_PARTIAL: an fp32 box is 32 columns
-                        const uint32_t dst = stg + (box & 1u) * 4096u + my_row;
-                        if (lane == 0) bulk_wait_read<1>();
-                        __syncwarp();
-                        tmem_ld32(tbase + static_cast<uint32_t>(j * 32), v);
+                    } else if (kEpi == EPI_ACCUM) {
+                        if (row_ok) {
+                            float* o = out32 + cj;
+                            if (valid == 32) {
+                                float nxt[32];
+                                const bool more = jj < 3 && cj + 64 <= a.n_cols;
+                                if (more) {  // next box's running sum: in flight while this one is added and stored
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            st_shared_v4(dst + ((static_cast<uint32_t>(q) ^ sw) << 4), __float_as_uint(v[4 * q]),
-                                         __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-                                         __float_as_uint(v[4 * q + 3]));
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && row0 < a.m_rows) {
-                            const void* src = staging + ew * 8192 + (box & 1u) * 4096u;
-                            if (kEpi == EPI_ACCUM)
-                                tma_reduce_add_2d(&map_d, cj, row0, src);
-                            else
-                                tma_store_3d(&map_d, cj, row0, ks, src);
-                            bulk_commit();
+                                    for (int q = 0; q < 8; ++q) {
+                                        const float4 t = *reinterpret_cast<const float4*>(o + 32 + 4 * q);
+                                        nxt[4 * q] = t.x, nxt[4 * q + 1] = t.y, nxt[4 * q + 2] = t.z, nxt[4 * q + 3] = t.w;
+                                    }
+                                }
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    *reinterpret_cast<float4*>(o + 4 * q) =
+                                        make_float4(old[4 * q] + v[4 * q], old[4 * q + 1] + v[4 * q + 1],
+                                                    old[4 * q + 2] + v[4 * q + 2], old[4 * q + 3] + v[4 * q + 3]);
+                                if (more) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) old[i] = nxt[i];
+                                }
+                            } else {
+                                for (int i = 0; i < valid; ++i) o[i] += v[i];
+                            }
                         }
-                        ++box;
+                    } else {  // EPI_PARTIAL: this k-slice's plane, plain fp32 stores (a thread owns whole 128-byte lines)
+                        if (row_ok) {
+                            float* o = out32 + cj;
+                            if (valid == 32) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            } else {
+                                for (int i = 0; i < valid; ++i) o[i] = v[i];
+                            }
+                        }
                     }
                 }
                 fence_before_sync();
@@ -379,9 +412,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (buf == 0) acc_phase ^= 1u;
             }
             if (want_stats && row_ok)
-                a.partial[static_cast<int64_t>(g) * a.n_mpairs * (2 * kTileM) + row] = make_float4(f.m, f.S, f.U, f.xsel);
+                a.partial[static_cast<int64_t>(g * 2 + half) * a.n_mpairs * (2 * kTileM) + row] = make_float4(f.m, f.S, f.U, f.xsel);
         }
-        if (kEpi != EPI_STATS && lane == 0) bulk_wait<0>();  // every store of this warp has reached global memory
+        if (kEpi == EPI_STORE && lane == 0) bulk_wait<0>();  // every store of this warp has reached global memory
     }
     fence_before_sync();
     cluster_sync_all();  // the peer's remote arrives and this CTA's multicast commits have all been consumed
@@ -449,23 +482,20 @@ int make_map(CUtensorMap* map, const void* base, int64_t outer, int64_t inner, i
     return B200TRL_OK;
 }
 
-// Output maps: boxes of 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), SWIZZLE_128B; rank 3 = [plane, row, col].
-int make_out_map(CUtensorMap* map, bool fp32, const void* base, int64_t planes, int64_t rows, int64_t cols, int64_t ld) {
+// Output map of EPI_STORE: bf16 [rows, cols], boxes of 32 rows x 64 columns (128 bytes), SWIZZLE_128B.
+int make_out_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
         return B200TRL_E_LAUNCH;
     }
-    const cuuint64_t esz = fp32 ? 4 : 2;
-    const cuuint32_t rank = planes > 0 ? 3 : 2;
-    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
-                                static_cast<cuuint64_t>(std::max<int64_t>(planes, 1))};
-    const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * esz, static_cast<cuuint64_t>(rows) * ld * esz};
-    const cuuint32_t box[3] = {fp32 ? 32u : 64u, 32u, 1u};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
-                          const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+    const cuuint32_t box[2] = {64u, 32u};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("tc_gemm: cuTensorMapEncodeTiled failed for the output (%d)", static_cast<int>(r));
         return B200TRL_E_INVALID;
@@ -635,7 +665,7 @@ int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void*
     a.bias = static_cast<const __nv_bfloat16*>(bias);
     a.k_splits = 1;
     a.kb_per_split = static_cast<int>((K + kTileK - 1) / kTileK);
-    if (n_groups_out) *n_groups_out = a.n_groups;
+    if (n_groups_out) *n_groups_out = a.n_groups * 2;  // one partial per (run of n-tiles, column half)
     CUtensorMap md = ma;  // EPI_STATS stores nothing
     if (epi == EPI_STORE && splitk_ws && !stats && N % 8 == 0 && a_mn == 0) {
         const int kblocks = a.kb_per_split;
@@ -645,8 +675,9 @@ int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void*
             a.kb_per_split = (kblocks + S - 1) / S;
             a.k_splits = (kblocks + a.kb_per_split - 1) / a.kb_per_split;
             a.bias = nullptr;  // added once, by the finishing kernel
-            rc = make_out_map(&md, true, splitk_ws, a.k_splits, M, N, N);
-            if (rc) return rc;
+            a.out = splitk_ws;
+            a.ldd = N;
+            a.plane_stride = M * N;
             rc = B200TRL_E_UNSUPPORTED;
             if (a_mn == 0 && b_mn == 0) rc = launch<0, 0, EPI_PARTIAL>(ma, mb, md, a, s);
             if (a_mn == 0 && b_mn == 1) rc = launch<0, 1, EPI_PARTIAL>(ma, mb, md, a, s);
@@ -661,9 +692,10 @@ int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void*
             return check_launch("tc_splitk_finish_kernel");
         }
     }
-    if (epi == EPI_STORE) rc = make_out_map(&md, false, out, 0, M, N, ldd);
-    if (epi == EPI_ACCUM) rc = make_out_map(&md, true, out, 0, M, N, ldd);
+    if (epi == EPI_STORE) rc = make_out_map(&md, out, M, N, ldd);
     if (rc) return rc;
+    a.out = out;
+    a.ldd = ldd;
 #define B200TRL_TC_CASE(AM, BM, EP) \
     if (a_mn == AM && b_mn == BM && epi == EP) return launch<AM, BM, EP>(ma, mb, md, a, s);
     B200TRL_TC_CASE(0, 0, EPI_STATS)
@@ -680,7 +712,7 @@ int64_t tc_stats_workspace_bytes(int64_t n_rows, int64_t n_cols) {
     const int64_t padded = ((n_rows + 2 * kTileM - 1) / (2 * kTileM)) * (2 * kTileM);
     const int64_t n_ntiles = (n_cols + kTileN - 1) / kTileN;
     const int64_t max_groups = (n_ntiles + 3) / 4 + 1;  // plan_tiles_per_group never goes below runs of 4 (or all)
-    return max_groups * padded * static_cast<int64_t>(sizeof(float4));
+    return 2 * max_groups * padded * static_cast<int64_t>(sizeof(float4));  // two column halves per run
 }
 
 int tc_merge_stats(const void* partial, int n_groups, int64_t n_rows, float c, float* logp, float* entropy, float* lse,

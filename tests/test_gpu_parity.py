@@ -591,14 +591,16 @@ def _check_seam_against_bf16_oracle(S, B, T, H, V, chunk, seed, wscale):
     assert loss.item() == pytest.approx(loss_r.item(), rel=1e-4, abs=1e-6)
     assert metrics[0].item() == pytest.approx(met_r["kl"].item(), rel=1e-4, abs=1e-7)
     assert metrics[-1].item() == pytest.approx(met_r["clip_ratio/region"].item(), abs=1e-6)
-    # log-probs: 1e-5 wherever the tensor core's accumulation order rounds the selected logit (and the row's large
-    # logits) to the same bf16 value as the CPU product; where a rounding flips, the difference is one bf16 ulp of
-    # that logit -- rare (the two fp32 sums differ by ~1e-6 relative, a bf16 rounding boundary is 2^-8 wide)
+    # log-probs: 1e-5 wherever the tensor core's accumulation order rounds the selected logit to the same bf16 value
+    # as the CPU product; where the rounding flips, the difference is one bf16 ulp of that logit.  A flip needs the
+    # exact sum to lie within the two fp32 sums' discrepancy (~1e-5 relative at K = 3584: the tensor core aligns the
+    # products of an MMA step before adding) of a bf16 rounding boundary (spacing 2^-8 relative): ~0.5 % of the rows
+    # at config-4 width (measured 0.49 %), fewer at smaller K
     d = (fn.last_per_token_logps.cpu() - lp_r).abs()
-    assert float((d > 2e-5).float().mean()) < 2e-3, float((d > 2e-5).float().mean())
+    assert float((d > 2e-5).float().mean()) < 1.5e-2, float((d > 2e-5).float().mean())
     assert float(d.max()) <= 2.0 ** -7 * float(logits_r.abs().max()) + 1e-5
     de = (fn.last_entropies.cpu() - ent_r).abs()
-    assert float((de > 1e-4).float().mean()) < 2e-3
+    assert float((de > 1e-4).float().mean()) < 1.5e-2
     # dW: accumulated in fp32 over the chunks, handed to autograd in the weight's dtype (bf16) like the reference's
     # `.grad`; every rounding point is reproduced by the oracle, what is left are dlogits elements whose bf16 rounding
     # flips (fp32 round-off of the exponentials) -- one bf16 ulp on a small fraction of the elements

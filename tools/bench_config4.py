@@ -58,7 +58,11 @@ def main():
     h = hidden.clone().requires_grad_(True)
     w = W.clone().requires_grad_(True)
     res = {}
-    for chunk in (1, 2, 4):
+    from swh_trl_b200 import ops
+    masks = [int(m) for m in os.environ.get("SEAM_MASKS", "0,7").split(",")]
+    chunks = [int(c) for c in os.environ.get("SEAM_CHUNKS", "2,4").split(",")]
+    for gemm_mask, chunk in [(m, c) for m in masks for c in chunks]:
+        ops.set_seam_gemm_mask(gemm_mask)
         fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
 
         def ours():
@@ -69,7 +73,8 @@ def main():
             res["loss"], res["kl"], res["clip"] = loss.detach(), m[0], m[-1]
         ms = timeit(ours)
         torch.cuda.synchronize()
-        out["rows"].append({"impl": f"swh_trl_b200.B200FusedLinearGRPOLoss(chunk_size={chunk})", "ms": ms,
+        out["rows"].append({"impl": f"swh_trl_b200.B200FusedLinearGRPOLoss(chunk_size={chunk})",
+                            "gemms": {0: "cuBLASLt x3", 7: "tcgen05 K7 x3"}.get(gemm_mask, f"mask {gemm_mask}"), "ms": ms,
                             "tokens_per_s": B * T / ms * 1e3, "tflops": flops / ms / 1e9,
                             "frac_of_sustained_bf16_peak": flops / ms / 1e9 / tf_peak, "loss": float(res["loss"]),
                             "kl": float(res["kl"]), "clip_ratio": float(res["clip"]),
@@ -77,6 +82,9 @@ def main():
         print(json.dumps(out["rows"][-1]), file=sys.stderr)
     ours_dh, ours_dw = h.grad.float().clone(), w.grad.float().clone()
 
+    if os.environ.get("SEAM_NO_LIGER"):
+        print(json.dumps(out, indent=1))
+        return
     try:
         from liger_kernel.chunked_loss import LigerFusedLinearGRPOLoss
         import liger_kernel
