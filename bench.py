@@ -18,8 +18,15 @@ One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one
               launch / its CUDA-event duration measured inside the timed region, against MEASURED_PEAKS.json;
 * ``cpu_baseline``  the CPU oracle (torch restatement of the reference path, fp32) on a bounded sample, rank 0, N=1.
 
-``--impl reference`` times that CPU path alone (the reference is pure Python and cannot travel to the GPU box;
-the oracle port, pinned on the reference's own outputs, is what runs).
+``--impl reference`` times the reference's own CPU implementation alone: ``GRPOTrainer._compute_loss`` as lifted
+verbatim into ``oracle/_ref`` by ``oracle/build_ref.py`` (``kind: "reference"``); if that directory did not travel, the
+vectorised port ``oracle/trl_oracle.py`` (``kind: "port"``).
+
+The line also carries ``extra`` — every other BASELINE config measured in the same process with CUDA events and the
+same clock sampler: config 1, the two-phase (sequence-level IS) step, config 3 (PPO), config 4 (the Liger seam:
+ms, TFLOP/s against the measured sustained bf16 peak, and the no-logits tcgen05 forward) and config 5 (B=256, T=4096
+strong scaling over the N ranks) — and ``parity_check``: outside the timed region every rank compares its K3
+advantages with the CPU oracle's on the gathered rewards, and sampled log-probs with the oracle's.
 """
 from __future__ import annotations
 
@@ -41,6 +48,17 @@ METRIC = "fwd+bwd logit-tokens/s for fused logprob+GRPO loss; % of HBM roofline"
 UNIT = "logit-tokens/s"
 
 
+def static_config(n_gpus: int) -> dict:
+    """The workload description: identical, key for key, in the B200 arm and the reference arm (run-specific values
+    such as the loss or the measured padding fraction live in ``run``)."""
+    B, T, V, G = CFG["B"], CFG["T"], CFG["V"], CFG["G"]
+    return {"workload": WORKLOAD, "loss_type": CFG["loss_type"], "importance_sampling_level": CFG["level"],
+            "beta": CFG["beta"], "epsilon": CFG["epsilon"], "old_per_token_logps": True, "global_batch": B * n_gpus,
+            "seq_len": T, "vocab": V, "num_generations": G,
+            "parallelism": f"sequence-sharded x{n_gpus}, no V-sized collective",
+            "l2": "inputs 4.98 GB per GPU per step >> 126 MB L2, no flush needed"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -49,13 +67,24 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tflops():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
 def ncu_traffic():
-    """dram bytes per K1 launch from the committed ncu --set full capture, if any."""
+    """(dram bytes per K1 launch, provenance) from the committed ``ncu --set full`` capture: a STATIC number read from
+    ``profiles/k1_traffic.json``, not measured by this run."""
     path = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
-    return None
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch"), f"static: ncu --set full capture {d.get('captured', 'round 1')} (profiles/k1_traffic.json)"
+    return None, "no capture committed"
 
 
 # ------------------------------------------------------------------------------------------------ synthetic data
@@ -133,53 +162,77 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.time()
 
-    def stop(self):
+    def summarise(self, t0, t1):
+        """Clock / power / throttle summary of the samples taken in [t0, t1] (wall clock)."""
         if self._thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no sampler"]}
-        self._stop.set()
-        self._thread.join(timeout=2)
         rows = list(self.rows)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
-        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
         where = "timed region"
         if not inside:  # region shorter than the polling period: take the sample closest to it
-            mid = 0.5 * ((self.t0 or rows[-1][0]) + (self.t1 or rows[-1][0]))
+            mid = 0.5 * ((t0 or rows[-1][0]) + (t1 or rows[-1][0]))
             inside = [min(rows, key=lambda r: abs(r[0] - mid))]
             where = "nearest sample to the timed region"
         reasons = sorted({n for r in inside for n in r[3]})
         return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": self.max_sm, "reasons": reasons,
                 "power_w_max": max(r[2] for r in inside), "samples": len(inside), "window": where, "source": "nvml"}
 
+    def stop(self):
+        out = self.summarise(self.t0, self.t1)
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        return out
+
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_reference_rate(logits_bf16_cpu, ids, mask, adv, old, ref, steps, warmup):
-    """logit-tokens/s of the oracle (reference fp32 torch path, all host threads) fwd+bwd on [b,T,V] samples."""
+    """``(logit-tokens/s, ms/step, kind)`` of the reference's CPU path fwd+bwd on ``[b, T, V]`` samples, all host threads.
+
+    ``kind == "reference"``: the reference's own ``GRPOTrainer._compute_loss`` (its per-row Python loops and temporaries),
+    lifted verbatim into ``oracle/_ref`` by ``oracle/build_ref.py`` and driven by ``oracle/ref_runner.py``.
+    ``kind == "port"``: the vectorised restatement ``oracle/trl_oracle.py`` (when ``oracle/_ref`` did not travel).
+    Either way the fp32 path: the bf16 logits are upcast outside the timed step (in the reference they come out of the
+    model), the step is loss forward + backward to the logits gradient."""
+    from oracle import ref_runner as R
     from oracle import trl_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.GRPOConfigLite(beta=CFG["beta"], epsilon_low=CFG["epsilon"], epsilon_high=CFG["epsilon"],
-                           loss_type=CFG["loss_type"], importance_sampling_level=CFG["level"],
-                           max_completion_length=CFG["T"], temperature=CFG["temperature"])
-    nb = logits_bf16_cpu.shape[0]
+    nb, T = logits_bf16_cpu.shape[0], logits_bf16_cpu.shape[1]
+    kind = "reference" if R.available() else "port"
+    if kind == "reference":
+        mod = R.load()
+        trainer = R.make_trainer(mod, beta=CFG["beta"], epsilon_low=CFG["epsilon"], epsilon_high=CFG["epsilon"], delta=None,
+                                 loss_type=CFG["loss_type"], importance_sampling_level=CFG["level"],
+                                 max_completion_length=T, temperature=CFG["temperature"])
+    else:
+        cfg = O.GRPOConfigLite(beta=CFG["beta"], epsilon_low=CFG["epsilon"], epsilon_high=CFG["epsilon"],
+                               loss_type=CFG["loss_type"], importance_sampling_level=CFG["level"],
+                               max_completion_length=T, temperature=CFG["temperature"])
     times = []
     for s in range(warmup + steps):
         b = s % nb
-        t0 = time.perf_counter()
-        x = logits_bf16_cpu[b:b + 1].float().requires_grad_(True)  # the reference fp32 path: upcast, then torch eager
-        loss, _, _, _ = O.grpo_compute_loss(x, ids[b:b + 1], mask[b:b + 1], adv[b:b + 1], cfg, old[b:b + 1],
-                                            ref[b:b + 1])
+        if kind == "reference":
+            x = R.model_logits(logits_bf16_cpu[b:b + 1].float()).requires_grad_(True)
+            t0 = time.perf_counter()
+            loss = R.compute_loss(trainer, mod, x, ids[b:b + 1], mask[b:b + 1], adv[b:b + 1], old[b:b + 1], ref[b:b + 1])
+        else:
+            x = logits_bf16_cpu[b:b + 1].float().requires_grad_(True)
+            t0 = time.perf_counter()
+            loss, _, _, _ = O.grpo_compute_loss(x, ids[b:b + 1], mask[b:b + 1], adv[b:b + 1], cfg, old[b:b + 1],
+                                                ref[b:b + 1])
         loss.backward()
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
         del x, loss
-    tokens = logits_bf16_cpu.shape[1]
     total = sum(times)
-    return tokens * len(times) / total, total / len(times) * 1e3
+    return T * len(times) / total, total / len(times) * 1e3, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation (oracle port) on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -196,19 +249,301 @@ def run_reference(args):
         lp0 = torch.cat([O.selective_log_softmax(logits[b:b + 1].float(), ids[b:b + 1]) for b in range(B)])
     old = lp0 + torch.randn(B, T, generator=gen) * 0.3
     ref = lp0 + torch.randn(B, T, generator=gen) * 0.1
-    rate, ms = cpu_reference_rate(logits, ids, mask, adv, old, ref, args.steps, args.warmup)
+    rate, ms, kind = cpu_reference_rate(logits, ids, mask, adv, old, ref, args.steps, args.warmup)
     cores = os.cpu_count() or 1
-    sample = f"each step = 1 sequence (T={T}, V={V}) of the config-2 batch, fp32 torch path fwd+bwd"
+    sample = (f"each step = 1 sequence (T={T}, V={V}) of the config-2 batch, fp32 torch path fwd+bwd, "
+              + ("the reference's own GRPOTrainer._compute_loss (oracle/_ref)" if kind == "reference"
+                 else "vectorised port (oracle/trl_oracle.py)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_path": "CPU torch eager (oracle port of grpo_trainer.py:2058-2137)",
-                   "host_threads": cores},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": static_config(args.gpus),
+        "run": {"reference_path": "CPU torch eager, grpo_trainer.py:2058-2137 (" + kind + ")", "host_threads": cores},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ helpers of the GPU arm
+def event_ms(fn, iters, warmup=3):
+    """Mean CUDA-event milliseconds of ``fn`` over ``iters`` back-to-back calls after ``warmup`` untimed ones."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, (t0, time.time())
+
+
+def gpu_affinity(local_rank):
+    """CPUs and NUMA node next to this rank's GPU (sysfs of its PCI function); (None, None) if the box does not say."""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber: resolve through the UUID
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:  # noqa: BLE001
+            h = N.nvmlDeviceGetHandleByIndex(local_rank)
+        bdf = N.nvmlDeviceGetPciInfo(h).busId
+        bdf = bdf.decode() if isinstance(bdf, bytes) else str(bdf)
+    except Exception:  # noqa: BLE001
+        return None, None
+    bdf = bdf.lower()
+    if len(bdf.split(":")[0]) == 8:  # NVML pads the domain to 8 hex digits, sysfs uses 4
+        bdf = bdf[4:]
+    base = f"/sys/bus/pci/devices/{bdf}"
+    try:
+        node = int(open(base + "/numa_node").read())
+        cpus = open(base + "/local_cpulist").read().strip()
+    except OSError:
+        return None, None
+    ids = set()
+    for part in cpus.split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            ids.update(range(int(a), int(b) + 1))
+        elif part:
+            ids.add(int(part))
+    return (node if node >= 0 else None), (sorted(ids) or None)
+
+
+def pinned_near_gpu(shape, dtype, local_rank):
+    """A pinned host tensor whose pages are first touched on the CPUs next to this rank's GPU: the thread is bound to
+    them while ``cudaHostAlloc`` allocates and pins, so that on a multi-socket host the H2D copies of the N ranks do
+    not all cross to one socket's memory.  Returns ``(tensor, {numa_node, cpus})``."""
+    node, cpus = gpu_affinity(local_rank)
+    info = {"numa_node": node, "cpus_near_gpu": (f"{cpus[0]}-{cpus[-1]}" if cpus else None)}
+    old = None
+    if cpus:
+        try:
+            old = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, set(cpus) & old or old)
+        except OSError:
+            old = None
+    try:
+        t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        t.view(torch.uint8).reshape(-1)[::4096].fill_(0)  # touch every page from here
+    finally:
+        if old is not None:
+            os.sched_setaffinity(0, old)
+    return t, info
+
+
+# ------------------------------------------------------------------------------------------------ extras (other configs)
+def extra_config1(S, ops, dev, hbm_peak):
+    """BASELINE configs[0] on the GPU: B=4, T=256, V=32000, G=4 (the reference's CPU-runnable case)."""
+    B, T, V = 4, 256, 32000
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(B, T, V, generator=g, device=dev).to(torch.bfloat16).requires_grad_(True)
+    ids = torch.randint(0, V, (B, T), generator=g, device=dev)
+    mask = torch.ones(B, T, dtype=torch.int32, device=dev)
+    adv = S.group_advantages(torch.randn(B, 1, generator=g, device=dev), torch.ones(1, device=dev), 4, gathered=True,
+                             local_batch=B)["advantages"]
+    with torch.no_grad():
+        lp0, _ = S.logprobs_and_entropy(x.detach(), ids, 1.0, compute_entropy=False)
+    old = lp0 + 0.1
+    fn = S.GRPOLoss(beta=0.0, max_completion_length=T)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)  # 256 MB > L2: the 65 MB input would otherwise sit in L2
+
+    def step():
+        flush.add_(1.0)
+        x.grad = None
+        fn(x, ids, mask, adv, old, None).loss.backward()
+
+    def flush_only():
+        flush.add_(1.0)
+    ms_all, win = event_ms(step, 30)
+    ms_flush, _ = event_ms(flush_only, 30)
+    ms = ms_all - ms_flush
+    return {"workload": "configs[0]: B=4 T=256 V=32000 G=4, fused logprob + GRPO loss fwd+bwd", "us_per_step": ms * 1e3,
+            "logit_tokens_per_s": B * T / (ms * 1e-3), "frac_of_hbm_roofline": 4 * V * B * T / (ms * 1e-3) / 1e9 / hbm_peak,
+            "l2": "256 MB flush write between steps (its own time, measured alone, subtracted)"}, win
+
+
+def extra_config3(S, ops, dev):
+    """BASELINE configs[2]: PPO reward shaping + GAE (B=64, T=512) and the clipped policy / value loss."""
+    B, T = 64, 512
+    g = torch.Generator(device=dev).manual_seed(13)
+    lp = -torch.rand(B, T, generator=g, device=dev) * 5
+    rlp = -torch.rand(B, T, generator=g, device=dev) * 5
+    val = torch.randn(B, T, generator=g, device=dev)
+    sc = torch.randn(B, generator=g, device=dev)
+    ln = torch.randint(T // 2, T, (B,), generator=g, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    out = {}
+    n0 = ops.launch_count
+    gae = ops.ppo_rewards_gae(lp, rlp, val, sc, ln, 0.05, "k1", 1.0, 0.95, True)
+    launches_gae = ops.launch_count - n0
+
+    def gae_step():
+        flush.add_(1.0)
+        ops.ppo_rewards_gae(lp, rlp, val, sc, ln, 0.05, "k1", 1.0, 0.95, True)
+
+    def flush_only():
+        flush.add_(1.0)
+    ms_f, _ = event_ms(flush_only, 30)
+    ms_g, win = event_ms(gae_step, 30)
+    out["rewards_gae_whiten_us"] = (ms_g - ms_f) * 1e3
+    out["rewards_gae_launches"] = launches_gae
+    newlp = gae["logprobs"] + 0.05 * torch.randn(B, T, generator=g, device=dev)
+    ent = torch.rand(B, T, generator=g, device=dev)
+    vpred = gae["values"] + 0.1
+    n0 = ops.launch_count
+    ops.ppo_loss(newlp, gae["logprobs"], gae["advantages"], gae["returns"], gae["values"], vpred, ent, ln, 0.2, 0.2, 0.1)
+    launches_loss = ops.launch_count - n0
+
+    def loss_step():
+        flush.add_(1.0)
+        ops.ppo_loss(newlp, gae["logprobs"], gae["advantages"], gae["returns"], gae["values"], vpred, ent, ln, 0.2, 0.2, 0.1)
+    ms_l, _ = event_ms(loss_step, 30)
+    out["clipped_losses_us"] = (ms_l - ms_f) * 1e3
+    out["clipped_losses_launches"] = launches_loss
+    # the V-sized part of a PPO micro-batch (ppo_trainer.py:557-605): mb=8, V=50304 bf16 logits, fwd+bwd
+    mb, V = 8, 50304
+    x = (torch.randn(mb, T, V, generator=g, device=dev) * 2).to(torch.bfloat16).requires_grad_(True)
+    rsp = torch.randint(0, V, (mb, T), generator=g, device=dev)
+    vp = (gae["values"][:mb] + 0.1).requires_grad_(True)
+
+    def ppo_step():
+        x.grad = None
+        vp.grad = None
+        S.ppo_loss(x, rsp, gae["logprobs"][:mb], gae["advantages"][:mb], gae["returns"][:mb], gae["values"][:mb], vp,
+                   ln[:mb]).loss.backward()
+    n0 = ops.launch_count
+    ppo_step()
+    out["microbatch_step_launches"] = ops.launch_count - n0
+    ms_s, _ = event_ms(ppo_step, 20)
+    out["microbatch_step_us"] = ms_s * 1e3
+    out["microbatch_step_shape"] = f"mb={mb} T={T} V={V} bf16 (412 MB logits > L2)"
+    out["workload"] = "configs[2]: PPO per-token KL reward + GAE (gamma=1, lam=0.95) + whitening, clipped policy/value loss, B=64 T=512"
+    out["l2"] = "256 MB flush write before each small-kernel call (its own time subtracted)"
+    return out, win
+
+
+def extra_config4(S, ops, dev):
+    """BASELINE configs[3]: chunked lm_head (3584 -> 152064) fused with the GRPO loss, B=8, T=2048, no [B,T,V] logits."""
+    B, T, H, V = 8, 2048, 3584, 152064
+    g = torch.Generator(device=dev).manual_seed(17)
+    hidden = torch.randn(B, T, H, generator=g, device=dev).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g, device=dev) * 0.02).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g, device=dev)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g, device=dev)
+    mask = (torch.arange(T, device=dev).unsqueeze(0) < lens.unsqueeze(1)).int()
+    adv = torch.randn(B, generator=g, device=dev)
+    burst, sustained, src = measured_tflops()
+    # the no-logits forward (K5 on the CTA-pair tcgen05 kernel): old / ref log-prob passes
+    out = {"workload": "configs[3]: chunked lm_head (hidden 3584 -> V=152064) fused with online log-softmax on tcgen05, "
+                       "B=8 T=2048, no materialised logits"}
+    ms_f, win = event_ms(lambda: ops.fused_linear_logprob_fwd(hidden, W, ids, 1.0), 5, warmup=2)
+    fl = 2.0 * B * T * H * V
+    out["forward_no_logits"] = {"ms": ms_f, "tflops": fl / ms_f / 1e9, "frac_of_bf16_burst_peak": fl / ms_f / 1e9 / burst,
+                                "frac_of_bf16_sustained_peak": fl / ms_f / 1e9 / sustained,
+                                "kernel": "tc_gemm_kernel<K-major, K-major, statistics> (tcgen05.mma.cta_group::2)"}
+    with torch.no_grad():
+        lp0, _, _ = ops.fused_linear_logprob_fwd(hidden, W, ids, 1.0, want_entropy=False)
+    old = lp0 + torch.randn(B, T, generator=g, device=dev) * 0.3
+    ref = lp0 + torch.randn(B, T, generator=g, device=dev) * 0.1
+    h = hidden.clone().requires_grad_(True)
+    w = W.clone().requires_grad_(True)
+    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=2)
+
+    def seam():
+        h.grad = None
+        w.grad = None
+        loss, _ = fn(h, w, ids, mask, adv, None, old, ref)
+        loss.backward()
+    n0 = ops.launch_count
+    seam()
+    launches = ops.launch_count - n0
+    ms, win2 = event_ms(seam, 5, warmup=1)
+    fl3 = 6.0 * B * T * H * V
+    names = {0: "cuBLASLt", 1: "tcgen05 K7"}
+    m = ops.set_seam_gemm_mask(-1)
+    out["fwd_bwd"] = {"ms": ms, "tokens_per_s": B * T / (ms * 1e-3), "tflops": fl3 / ms / 1e9,
+                      "frac_of_bf16_sustained_peak": fl3 / ms / 1e9 / sustained, "peak_source": src,
+                      "gemms": {"logits": names[m & 1], "dH": names[(m >> 1) & 1], "dW": names[(m >> 2) & 1]},
+                      "our_launches": launches, "chunk_sequences": 2}
+    del h, w, hidden, W
+    torch.cuda.empty_cache()
+    return out, (win[0], win2[1])
+
+
+def extra_two_phase(S, x, ids, mask, adv, old, ref, T, V, hbm_peak):
+    """The fork's production setting (examples/scripts/grpo_train.py:491-514): sequence-level importance sampling with
+    old log-probs -> K1 forward, K2 with the per-token gradient, K1 backward (2R + 1W of the logits)."""
+    fn = S.GRPOLoss(beta=CFG["beta"], epsilon_low=CFG["epsilon"], epsilon_high=CFG["epsilon"], loss_type=CFG["loss_type"],
+                    importance_sampling_level="sequence", max_completion_length=T, temperature=CFG["temperature"])
+
+    def step():
+        x.grad = None
+        fn(x, ids, mask, adv, old, ref).loss.backward()
+    ms, win = event_ms(step, 10)
+    n = ids.numel()
+    return {"workload": "config-2 tensors, importance_sampling_level='sequence' with old_per_token_logps (two-phase schedule)",
+            "ms_per_step": ms, "logit_tokens_per_s": n / (ms * 1e-3),
+            "frac_of_4V_roofline": 4 * V * n / (ms * 1e-3) / 1e9 / hbm_peak,
+            "ceiling": "0.667 of the 4V roofline: the logits are read twice"}, win
+
+
+def extra_config5(S, ops, dist, world, rank, dev, x, ids, mask, old, ref, hbm_peak):
+    """BASELINE configs[4]: B=256, T=4096, V=151936, G=8 over the N ranks -- STRONG scaling.  Rank r owns 256/N
+    sequences and streams them as micro-batches of 4 sequences (16 384 logit-tokens; the config-2 buffer viewed as
+    [4, 4096, V] is reused for every micro-batch: synthetic data, so nothing is regenerated inside the region).  One
+    reward all-gather + K3 per batch, no host sync between micro-batches, the packed metric rows of ALL micro-batches
+    leave in one exchange at the end."""
+    from swh_trl_b200 import distributed as D
+    Bg, T5, V, G, MB = 256, 4096, CFG["V"], 8, 4
+    b_local = Bg // world
+    n_mb = b_local // MB
+    gen = torch.Generator(device=dev).manual_seed(5000 + rank)
+    rewards_local = torch.randn(b_local, 1, generator=gen, device=dev)
+    weights = torch.ones(1, device=dev)
+    x5 = x.detach().view(MB, T5, V).requires_grad_(True)
+    ids5, mask5, old5, ref5 = ids.view(MB, T5), mask.view(MB, T5), old.view(MB, T5), ref.view(MB, T5)
+    fn = S.GRPOLoss(beta=CFG["beta"], epsilon_low=CFG["epsilon"], epsilon_high=CFG["epsilon"], loss_type=CFG["loss_type"],
+                    importance_sampling_level="token", max_completion_length=T5, temperature=CFG["temperature"])
+    ring = torch.empty(n_mb, 8, device=dev)
+
+    def batch():
+        adv = S.group_advantages(rewards_local, weights, G)["advantages"]  # NCCL all-gather + K3, once per batch
+        for m in range(n_mb):
+            x5.grad = None
+            o = fn(x5, ids5, mask5, adv[m * MB:(m + 1) * MB], old5, ref5, grad_scale=1.0 / n_mb)
+            o.loss.backward()
+            ring[m].copy_(o.metrics)
+        return D.gather_metric_rows(ring) if world > 1 else ring  # ONE exchange for the whole batch
+
+    batch()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    batch()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    return {"workload": "configs[4]: GRPO sequence-sharded, B=256 T=4096 V=151936 G=8, NCCL reward all-gather, strong scaling",
+            "n_gpus": world, "scaling": "strong", "sequences_per_rank": b_local, "micro_batches_per_rank": n_mb,
+            "micro_batch": "4 sequences x 4096 tokens (16 384 logit-tokens, 4.98 GB logits + 4.98 GB dlogits)",
+            "ms_per_batch": ms, "value": Bg * T5 / (ms * 1e-3), "unit": UNIT,
+            "frac_of_hbm_roofline_per_gpu": 4 * V * b_local * T5 / (ms * 1e-3) / 1e9 / hbm_peak,
+            "exchanges_per_batch": "1 reward all-gather + 1 packed [micro_batches, 8] metric all-gather; no host sync in between",
+            "timing": "CUDA events around the whole batch, max over ranks"}, (t0, time.time())
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -280,6 +615,15 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
+    # pre-burn: >= 1 s of the same step so that the timed region reads steady-state clocks and power even when the
+    # driver asks for only 20 steps (33 ms)
+    burn_steps, t_burn = 0, time.time()
+    while time.time() - t_burn < args.burn_s:
+        for _ in range(25):
+            step()
+        burn_steps += 25
+        torch.cuda.synchronize()
+    barrier()
     loss_val = float(out.loss.detach())
 
     launches0 = ops.launch_count
@@ -300,31 +644,30 @@ def run_b200(args):
         torch.cuda.profiler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     launches = ops.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
     k1_ms = statistics.mean(a.elapsed_time(b) for a, b in k1_events)
 
     # ---- e2e: pinned host logits -> H2D -> loss fwd+bwd -> D2H of loss / metrics / log-probs, every step
-    host_logits = torch.empty(B, T, V, dtype=torch.bfloat16, pin_memory=True)
-    host_logits.copy_(logits.detach())
-    host_small = torch.empty(8 + 1 + B * T, dtype=torch.float32, pin_memory=True)
-    dev_logits = torch.empty_like(logits).requires_grad_(True)
-    h2d = host_logits.numel() * 2
-    d2h = host_small.numel() * 4
-
-    def e2e_step():
-        dev_logits.grad = None
-        with torch.no_grad():
-            dev_logits.copy_(host_logits, non_blocking=True)
-        adv = S.group_advantages(rewards_local, weights, G)["advantages"]
-        o = loss_fn(dev_logits, ids, mask, adv, old, ref)
-        o.loss.backward()
-        packed = torch.cat([o.metrics, o.loss.detach().reshape(1), o.per_token_logps.reshape(-1)])
-        host_small.copy_(packed, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller needs the loss on the host
-
     e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
-    e2e_s = float("nan")
+    e2e_s, copy_s, pin_info = float("nan"), float("nan"), {}
+    h2d = B * T * V * 2
+    d2h = (8 + 1 + B * T) * 4
     if e2e_steps:
+        host_logits, pin_info = pinned_near_gpu((B, T, V), torch.bfloat16, local_rank)
+        host_logits.copy_(logits.detach())
+        host_small = torch.empty(8 + 1 + B * T, dtype=torch.float32, pin_memory=True)
+        dev_logits = torch.empty_like(logits).requires_grad_(True)
+
+        def e2e_step():
+            dev_logits.grad = None
+            with torch.no_grad():
+                dev_logits.copy_(host_logits, non_blocking=True)
+            adv = S.group_advantages(rewards_local, weights, G)["advantages"]
+            o = loss_fn(dev_logits, ids, mask, adv, old, ref)
+            o.loss.backward()
+            packed = torch.cat([o.metrics, o.loss.detach().reshape(1), o.per_token_logps.reshape(-1)])
+            host_small.copy_(packed, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller needs the loss on the host
+
         for _ in range(2):
             e2e_step()
         barrier()
@@ -333,50 +676,104 @@ def run_b200(args):
             e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
-    del host_logits, dev_logits
+        # the platform's ceiling for this leg: the same host->device copy alone, all ranks at the same time
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            with torch.no_grad():
+                dev_logits.copy_(host_logits, non_blocking=True)
+        barrier()
+        copy_s = (time.perf_counter() - t0) / 3
+        del host_logits, dev_logits
+
+    # ---- parity check, outside every timed region: this rank's K3 advantages against the CPU oracle on the gathered
+    # rewards (bound of tests/test_gpu_parity.py::test_group_advantages_golden), and sampled log-probs of the fused pass
+    from oracle import trl_oracle as O
+    from swh_trl_b200 import distributed as D
+    res = S.group_advantages(rewards_local, weights, G)
+    full_rewards = D.gather_rewards(rewards_local).cpu()
+    want_loc, want_all, _, want_std, _, _ = O.group_advantages(full_rewards, torch.ones(1), G, True, rank * B, B)
+    bound = 2e-5 * want_all.abs() + 3e-7 / (want_std.repeat_interleave(G) + 1e-4)
+    adv_ok = bool(((res["all"].cpu() - want_all).abs() <= bound).all()) and \
+        torch.equal(res["advantages"].cpu(), res["all"].cpu()[rank * B:(rank + 1) * B])
+    rows = slice(0, 64)
+    lp_dev = out.per_token_logps[3, rows].cpu()
+    lp_cpu = O.selective_log_softmax(logits.detach()[3:4, rows].float().cpu(), ids[3:4, rows].cpu())[0]
+    lp_err = float((lp_dev - lp_cpu).abs().max())
+    ok = torch.tensor([1.0 if (adv_ok and lp_err <= 1e-5) else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    parity = {"ok": bool(ok.item() == 1.0), "advantages_vs_oracle_all_ranks": True if ok.item() == 1.0 else adv_ok,
+              "max_abs_logp_err_sampled_rows": lp_err, "rows_sampled": 64,
+              "what": "K3 group advantages of every rank vs the CPU oracle on the NCCL-gathered rewards (values within the "
+                      "test bound, local slice bit-equal to the global order); 64 fused-pass log-probs vs the oracle, 1e-5"}
+
+    # ---- the other BASELINE configs, same process, CUDA events, same clock sampler
+    hbm_peak, peak_src = measured_peaks()
+    extra, windows = {}, {}
+    if not args.no_extras:
+        adv_now = res["advantages"]
+        extra["two_phase_sequence_is"], windows["two_phase_sequence_is"] = extra_two_phase(S, x, ids, mask, adv_now, old,
+                                                                                        ref, T, V, hbm_peak)
+        extra["config5_strong_scaling"], windows["config5_strong_scaling"] = extra_config5(
+            S, ops, dist, world, rank, dev, x, ids, mask, old, ref, hbm_peak)
+        if rank == 0:
+            extra["config1"], windows["config1"] = extra_config1(S, ops, dev, hbm_peak)
+            extra["config3_ppo"], windows["config3_ppo"] = extra_config3(S, ops, dev)
+            extra["config4_liger_seam"], windows["config4_liger_seam"] = extra_config4(S, ops, dev)
+        if sampler:
+            for k, (a, b) in windows.items():
+                if k in extra:
+                    c = sampler.summarise(a, b)
+                    extra[k]["clocks"] = {"sm_mhz": c.get("sm_mhz"), "power_w_max": c.get("power_w_max"),
+                                          "reasons": c.get("reasons")}
+    clocks = sampler.stop() if sampler else None
 
     # ---- max over ranks
-    t = torch.tensor([elapsed_ms, k1_ms, e2e_s], device=dev, dtype=torch.float64)
+    t = torch.tensor([elapsed_ms, k1_ms, e2e_s, copy_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, k1_ms, e2e_s = [float(v) for v in t]
+    elapsed_ms, k1_ms, e2e_s, copy_s = [float(v) for v in t]
 
     if rank == 0:
         tokens_per_step = B * T * world
         value = tokens_per_step * args.steps / (elapsed_ms * 1e-3)
-        peak, peak_src = measured_peaks()
         alg_bytes = 4 * V * B * T  # per K1 launch (one GPU): bf16 logits read once + bf16 dlogits written once
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "loss_type": CFG["loss_type"], "importance_sampling_level": CFG["level"],
-                       "beta": CFG["beta"], "epsilon": CFG["epsilon"], "old_per_token_logps": True,
-                       "global_batch": B * world, "seq_len": T, "vocab": V, "num_generations": G,
-                       "parallelism": f"sequence-sharded x{world}, no V-sized collective",
-                       "l2": "inputs 4.98 GB per GPU per step >> 126 MB L2, no flush needed",
-                       "metric_readback": "packed metrics all-gathered on device every step; host read deferred",
-                       "skip_masked_rows": bool(args.skip_masked),
-                       "masked_token_fraction": float(1.0 - mask.float().mean()),
-                       "loss": loss_val},
+            "config": static_config(world),
+            "run": {"loss": loss_val, "masked_token_fraction": float(1.0 - mask.float().mean()),
+                    "skip_masked_rows": bool(args.skip_masked), "pre_burn_steps": burn_steps, "pre_burn_s": args.burn_s,
+                    "metric_readback": "packed metrics all-gathered on device every step; host read deferred"},
             "clocks": clocks,
             "e2e": ({"value": tokens_per_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                     "d2h_bytes_per_step": d2h, "steps": e2e_steps} if e2e_steps else None),
+                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                     "h2d_gbs_per_gpu_in_step": h2d / (e2e_s / e2e_steps) / 1e9,
+                     "h2d_copy_alone_gbs_per_gpu": h2d / copy_s / 1e9,
+                     "platform_ceiling": "h2d_copy_alone = the same pinned-host -> device copy with nothing else in the "
+                                         "step, all ranks copying at once (max over ranks): what PCIe / host DRAM allow",
+                     "pinned_buffer": pin_info} if e2e_steps else None),
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k1_resident_kernel<fwd,bwd> (fused log-prob + entropy + dlogits)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+            "parity_check": parity,
+            "roofline": {"bound": "hbm", "kernel": "k1_resident_kernel<fwd,bwd> (fused log-prob + entropy + dlogits)",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k1_ms,
                          "frac_of_nominal_8TBps": achieved / 8000.0,
                          "kernel_share_of_step": k1_ms / (elapsed_ms / args.steps)},
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             nb, cpu_steps = 4, 30  # ~11 s of CPU work on the box's cores
             cpu_logits = logits.detach()[:nb].cpu()
-            adv = S.group_advantages(rewards_local, weights, G)["advantages"]
-            rate, ms = cpu_reference_rate(cpu_logits, ids[:nb].cpu(), mask[:nb].cpu(), adv[:nb].cpu(), old[:nb].cpu(),
-                                          ref[:nb].cpu(), steps=cpu_steps, warmup=2)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            adv = res["advantages"]
+            rate, ms, kind = cpu_reference_rate(cpu_logits, ids[:nb].cpu(), mask[:nb].cpu(), adv[:nb].cpu(), old[:nb].cpu(),
+                                                ref[:nb].cpu(), steps=cpu_steps, warmup=2)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
                                     "sample": f"{cpu_steps} timed steps of 1 sequence each (T={T}, V={V}; {nb} distinct "
                                               f"sequences of the same batch in turn), fp32 torch path fwd+bwd, "
                                               f"{ms:.0f} ms/step"}
@@ -393,6 +790,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (profiling runs)")
+    ap.add_argument("--burn-s", type=float, default=1.0, help="seconds of untimed steps before the timed region")
     ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region")
     ap.add_argument("--skip-masked", action="store_true",
                     help="opt-in: do not read rows with completion_mask == 0 (reported in config; NOT the default)")

@@ -257,17 +257,19 @@ int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidden_row_stri
  * (grpo_trainer.py:2005-2045): logits_c = hidden_c W^T, dH_c = dlogits_c W, dW += dlogits_c^T hidden_c.
  * a_layout / b_layout: 0 = the operand is stored [rows, K] (K contiguous), 1 = stored [K, rows] (rows contiguous);
  * lda / ldb / ldd: elements between stored rows (multiples of 8).  out_kind B200TRL_TC_OUT_BF16: out = bf16 [M, ldd],
- * D (+ bias[N], bf16, nullable) rounded once; B200TRL_TC_OUT_F32_ACC: out = fp32 [M, ldd], out += D.
- * Supported (a_layout, b_layout, out_kind): (0,0,BF16) (0,1,BF16) (1,1,F32_ACC).  m_fastest: work order, 1 = clusters
+ * D (+ bias[N], bf16, nullable) (+ addend fp32 [M, ld_addend], nullable) rounded once; B200TRL_TC_OUT_F32_ACC: out =
+ * fp32 [M, ldd], out += D; B200TRL_TC_OUT_F32: out = D.
+ * Supported (a_layout, b_layout, out_kind): (0,0,BF16) (0,1,BF16) (1,1,BF16) (1,1,F32_ACC) (1,1,F32).  m_fastest: work order, 1 = clusters
  * running at the same time share the B tile, 0 = the A tile (pick the operand that does not fit L2).
  * workspace (nullable, b200trl_tc_gemm_workspace_bytes, any contents): fp32 scratch for the bf16 output.  With it, a
  * contraction that has too few output tiles to fill the 74 CTA pairs (dH: 16 x 14 tiles, K = 152064) is split along
  * K; the slices' partial products land in planes of the scratch and are added in slice order (deterministic). */
-enum { B200TRL_TC_OUT_BF16 = 1, B200TRL_TC_OUT_F32_ACC = 2 };
+enum { B200TRL_TC_OUT_BF16 = 1, B200TRL_TC_OUT_F32_ACC = 2, B200TRL_TC_OUT_F32 = 3 };
 int64_t b200trl_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int out_kind);
 int b200trl_tc_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb, int64_t M,
-                    int64_t N, int64_t K, int out_kind, void* out, int64_t ldd, const void* bias, int m_fastest,
-                    void* workspace, int64_t workspace_bytes, b200trl_stream_t stream);
+                    int64_t N, int64_t K, int out_kind, void* out, int64_t ldd, const void* bias, const float* addend,
+                    int64_t ld_addend, int m_fastest, void* workspace, int64_t workspace_bytes,
+                    b200trl_stream_t stream);
 /* Which implementation the seam's three GEMMs use: bit 0 = logits, bit 1 = dH, bit 2 = dW; a set bit = the tcgen05
  * kernel above, a clear bit = cuBLASLt.  Returns the previous mask; mask < 0 only queries. */
 int b200trl_set_seam_gemm_mask(int mask);
@@ -281,16 +283,19 @@ int b200trl_set_seam_gemm_mask(int mask);
  * then K2 gives the loss and metrics.  cuBLASLt (plain library GEMMs only) is bound with dlopen at first use.
  * hidden bf16 [B,T,H]; weight bf16 [V,H]; bias bf16 [V] or NULL; H, V multiples of 8.
  * Outputs: logp, entropy fp32 [B,T]; loss fp32 [1]; metrics fp32 [B200TRL_GRPO_NUM_METRICS] (metrics[B200TRL_M_KL]
- * and [B200TRL_M_CLIP_REGION] are what grpo_trainer.py:2038-2039 logs); dhidden bf16 [B,T,H], dweight fp32 [V,H],
- * dbias fp32 [V] — each nullable; all three NULL = forward only.  Gradients are of loss * cfg->grad_scale.
+ * and [B200TRL_M_CLIP_REGION] are what grpo_trainer.py:2038-2039 logs); dhidden bf16 [B,T,H], dweight fp32 [V,H]
+ * (the accumulator over the chunks: written by the first chunk, no pre-zeroing), dweight_bf16 bf16 [V,H] (the final
+ * dW rounded once to the weight's dtype — with the tcgen05 dW GEMM the last chunk's epilogue emits it as
+ * bf16(dweight + D) and dweight itself is then left one chunk short; dweight may be NULL when B <= chunk_seqs),
+ * dbias fp32 [V] — each nullable; all NULL = forward only.  Gradients are of loss * cfg->grad_scale.
  * workspace >= b200trl_fused_linear_grpo_workspace_bytes(B, T, H, V, chunk_seqs) bytes, any contents. */
 int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t T, int64_t H, int64_t V, int64_t chunk_seqs);
 int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
                               int64_t H, int64_t V, const int64_t* ids, const int32_t* mask, const float* advantages,
                               const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
                               float inv_temperature, int64_t chunk_seqs, void* workspace, float* logp, float* entropy,
-                              float* loss, float* metrics, void* dhidden, float* dweight, float* dbias,
-                              b200trl_stream_t stream);
+                              float* loss, float* metrics, void* dhidden, float* dweight, void* dweight_bf16,
+                              float* dbias, b200trl_stream_t stream);
 
 /* ---- a-12: masked_mean / masked_var / masked_whiten (trl/core.py:43-76) ------------------------
  * stats fp32 [3] = {mean, unbiased var, count}; out (whitened, fp32 [n]) may be NULL.

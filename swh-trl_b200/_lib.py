@@ -78,12 +78,12 @@ PROTOTYPES = {
     "b200trl_fused_linear_workspace_bytes": (_i64, [_i64, _i64]),
     "b200trl_fused_linear_logprob_fwd": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _i64, _p, _f, _p, _p, _p, _p, _p]),
     "b200trl_tc_gemm_workspace_bytes": (_i64, [_i64, _i64, _i64, _i32]),
-    "b200trl_tc_gemm": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _i64, _p, _i32, _p, _i64,
-                                  _p]),
+    "b200trl_tc_gemm": (C.c_int, [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _i64, _p, _p, _i64, _i32, _p,
+                                  _i64, _p]),
     "b200trl_set_seam_gemm_mask": (C.c_int, [_i32]),
     "b200trl_fused_linear_grpo_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "b200trl_fused_linear_grpo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, C.POINTER(GrpoCfg),
-                                            _f, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+                                            _f, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200trl_masked_workspace_bytes": (_i64, [_i64]),
     "b200trl_masked_whiten": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p]),
     "b200trl_first_true_indices": (C.c_int, [_p, _i64, _i64, _p, _p]),

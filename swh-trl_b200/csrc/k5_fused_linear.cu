@@ -388,8 +388,12 @@ extern "C" int b200trl_fused_linear_logprob_fwd(const void* hidden, int64_t hidd
     if (impl != 1) {
         const float c = static_cast<float>(static_cast<double>(inv_temperature) * 1.4426950408889634);
         int n_groups = 0;
-        int rc2 = tc_gemm(0, 0, TC_EPI_STATS, hidden, hidden_row_stride, weight, weight_row_stride, n_rows, vocab,
-                          hidden_size, nullptr, 0, nullptr, ids, c, workspace, &n_groups, 1, nullptr, 0, as_stream(stream));
+        TcGemmParams p;
+        p.epi = TC_EPI_STATS;
+        p.A = hidden, p.lda = hidden_row_stride, p.B = weight, p.ldb = weight_row_stride;
+        p.M = n_rows, p.N = vocab, p.K = hidden_size;
+        p.ids = ids, p.c = c, p.partial = workspace, p.n_groups_out = &n_groups;
+        int rc2 = tc_gemm(p, as_stream(stream));
         if (rc2) return rc2;
         return tc_merge_stats(workspace, n_groups, n_rows, c, logp, entropy, lse, as_stream(stream));
     }

@@ -234,12 +234,25 @@ extern "C" int64_t b200trl_fused_linear_grpo_workspace_bytes(int64_t B, int64_t 
     return static_cast<int64_t>(layout(B, T, H, V, std::min(chunk_seqs, B)).end);
 }
 
+// fp32 -> bf16, 8 elements per thread: only needed when the LIBRARY produced the last chunk of dW (our own kernel
+// rounds inside its epilogue)
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            int64_t n8) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    __nv_bfloat162 r[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+    reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<uint4*>(r);
+}
+
 extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
                                          int64_t H, int64_t V, const int64_t* ids, const int32_t* mask,
                                          const float* advantages, const float* old_logp, const float* ref_logp,
                                          const b200trl_grpo_cfg* cfg, float inv_temperature, int64_t chunk_seqs,
                                          void* workspace, float* logp, float* entropy, float* loss, float* metrics,
-                                         void* dhidden, float* dweight, float* dbias, b200trl_stream_t stream_) {
+                                         void* dhidden, float* dweight, void* dweight_bf16, float* dbias,
+                                         b200trl_stream_t stream_) {
     B200TRL_REQUIRE(hidden && weight && ids && mask && advantages && cfg && workspace && logp && entropy && loss && metrics,
                     B200TRL_E_INVALID, "fused_linear_grpo: null pointer");
     B200TRL_REQUIRE(B > 0 && T > 0 && H > 0 && V > 0 && chunk_seqs > 0, B200TRL_E_INVALID, "fused_linear_grpo: bad shape");
@@ -249,15 +262,19 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
     B200TRL_REQUIRE(cfg->is_level == B200TRL_IS_TOKEN || old_logp == nullptr, B200TRL_E_UNSUPPORTED,
                     "fused_linear_grpo: sequence-level importance sampling with old_logp needs the two-phase path");
     B200TRL_REQUIRE(cfg->beta == 0.f || ref_logp, B200TRL_E_INVALID, "fused_linear_grpo: beta != 0 needs ref_logp");
+    chunk_seqs = std::min(chunk_seqs, B);
+    const int64_t n_chunks = (B + chunk_seqs - 1) / chunk_seqs;
+    B200TRL_REQUIRE(!dweight_bf16 || dweight || n_chunks == 1, B200TRL_E_INVALID,
+                    "fused_linear_grpo: dweight_bf16 over several chunks needs the fp32 dweight accumulator as well");
+    const bool want_dw = dweight || dweight_bf16;
     cudaStream_t stream = as_stream(stream_);
     const int mask_tc = g_gemm_mask;
-    const bool need_lt = !(mask_tc & 1) || (dhidden && !(mask_tc & 2)) || (dweight && !(mask_tc & 4));
+    const bool need_lt = !(mask_tc & 1) || (dhidden && !(mask_tc & 2)) || (want_dw && !(mask_tc & 4));
     LtApi* api = need_lt ? lt_api() : nullptr;
     if (need_lt && !api) return B200TRL_E_UNSUPPORTED;
     cublasLtHandle_t h = api ? lt_handle(api) : nullptr;
     B200TRL_REQUIRE(!need_lt || h != nullptr, B200TRL_E_LAUNCH, "fused_linear_grpo: cublasLtCreate failed");
 
-    chunk_seqs = std::min(chunk_seqs, B);
     const Layout l = layout(B, T, H, V, chunk_seqs);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     __nv_bfloat16* logits = reinterpret_cast<__nv_bfloat16*>(ws + l.logits);
@@ -265,28 +282,32 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
     float* total = reinterpret_cast<float*>(ws + l.total);
     void* k2_ws = ws + l.k2;
     void* lt_ws = ws + l.lt;
-    const bool want_grad = dhidden || dweight || dbias;
+    const bool want_grad = dhidden || want_dw || dbias;
 
     int rc = b200trl_mask_stats(mask, B, T, row_count, total, stream_);
     if (rc) return rc;
     if (cudaMemsetAsync(k2_ws, 0, static_cast<size_t>(b200trl_grpo_loss_workspace_bytes(B)), stream) != cudaSuccess)
         return check_launch("fused_linear_grpo memset");
-    if (dweight && cudaMemsetAsync(dweight, 0, static_cast<size_t>(V) * H * 4, stream) != cudaSuccess)
-        return check_launch("fused_linear_grpo memset");
     if (dbias && cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream) != cudaSuccess)
         return check_launch("fused_linear_grpo memset");
+    // dW is not zeroed: the first chunk's contraction writes it (beta = 0), the following ones accumulate
 
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dh = static_cast<__nv_bfloat16*>(dhidden);
-    for (int64_t b0 = 0; b0 < B; b0 += chunk_seqs) {
+    int64_t chunk = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk_seqs, ++chunk) {
         const int64_t nb = std::min(chunk_seqs, B - b0), rows = nb * T, r0 = b0 * T;
+        const bool first = chunk == 0, last = chunk == n_chunks - 1;
         // row-major logits[rows, V] = hidden_c[rows, H] W[V, H]^T  <=>  column-major D[V, rows] = W^T(T) x hidden_c(N)
-        if (mask_tc & 1)  // hidden_c and W both K-major; all row blocks of one W tile run at the same time
-            rc = tc_gemm(0, 0, TC_EPI_STORE, hid + r0 * H, H, weight, H, rows, V, H, logits, V, bias, nullptr, 0.f, nullptr,
-                         nullptr, 1, nullptr, 0, stream);
-        else
+        if (mask_tc & 1) {  // hidden_c and W both K-major; all row blocks of one W tile run at the same time
+            TcGemmParams p;
+            p.A = hid + r0 * H, p.lda = H, p.B = weight, p.ldb = H, p.M = rows, p.N = V, p.K = H;
+            p.out = logits, p.ldd = V, p.bias = bias, p.m_fastest = 1;
+            rc = tc_gemm(p, stream);
+        } else {
             rc = lt_gemm(api, h, CUBLAS_OP_T, CUBLAS_OP_N, V, rows, H, weight, H, hid + r0 * H, H, logits, V, CUDA_R_16BF,
                          0.f, bias, lt_ws, kLtWorkspace, stream);
+        }
         if (rc) return rc;
         // the loss normalises over the WHOLE batch: grpo / dr_grpo divide by B (grpo_trainer.py:2131, 2135), bnpo by
         // the batch's token total, which the kernel reads from `total`
@@ -299,22 +320,45 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
                                         want_grad ? logits : nullptr, V, 0, stream_);  // in place: dlogits overwrite logits
         if (rc) return rc;
         if (dh) {  // dH_c[rows, H] = dl[rows, V] W[V, H]  <=>  D[H, rows] = W(N)[H, V] x dl(N)[V, rows]
-            if (mask_tc & 2)  // A = dl (K = V contiguous), B[n = h, k = v] = W[v, h] is MN-major
-                rc = tc_gemm(0, 1, TC_EPI_STORE, logits, V, weight, H, rows, H, V, dh + r0 * H, H, nullptr, nullptr, 0.f,
-                             nullptr, nullptr, 1, lt_ws, static_cast<int64_t>(l.end - l.lt), stream);
-            else
+            if (mask_tc & 2) {  // A = dl (K = V contiguous), B[n = h, k = v] = W[v, h] is MN-major; few tiles -> split-K
+                TcGemmParams p;
+                p.b_mn = 1;
+                p.A = logits, p.lda = V, p.B = weight, p.ldb = H, p.M = rows, p.N = H, p.K = V;
+                p.out = dh + r0 * H, p.ldd = H, p.m_fastest = 1;
+                p.splitk_ws = lt_ws, p.splitk_ws_bytes = static_cast<int64_t>(l.end - l.lt);
+                rc = tc_gemm(p, stream);
+            } else {
                 rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_N, H, rows, V, weight, H, logits, V, dh + r0 * H, H, CUDA_R_16BF,
                              0.f, nullptr, lt_ws, kLtWorkspace, stream);
+            }
             if (rc) return rc;
         }
-        if (dweight) {  // dW[V, H] += dl^T hidden_c  <=>  D[H, V] += hidden_c(N)[H, rows] x dl(T)[rows, V], fp32 in the GEMM
-            if (mask_tc & 4)  // A[m = v, k = r] = dl[r, v] and B[n = h, k = r] = hidden[r, h]: both MN-major; the dl
-                              // tile is the operand that does not fit L2, so consecutive clusters share it
-                rc = tc_gemm(1, 1, TC_EPI_ACCUM, logits, V, hid + r0 * H, H, V, H, rows, dweight, H, nullptr, nullptr, 0.f,
-                             nullptr, nullptr, 0, nullptr, 0, stream);
-            else
+        if (want_dw) {  // dW[V, H] (+)= dl^T hidden_c  <=>  D[H, V] (+)= hidden_c(N)[H, rows] x dl(T)[rows, V]
+            if (mask_tc & 4) {
+                // A[m = v, k = r] = dl[r, v] and B[n = h, k = r] = hidden[r, h]: both MN-major; the dl tile is the
+                // operand that does not fit L2, so clusters running together share it.  First chunk: plain fp32 store;
+                // middle chunks: fp32 accumulate; last chunk with a bf16 destination: bf16(dW_fp32 + D) in the epilogue
+                TcGemmParams p;
+                p.a_mn = p.b_mn = 1;
+                p.A = logits, p.lda = V, p.B = hid + r0 * H, p.ldb = H, p.M = V, p.N = H, p.K = rows;
+                p.m_fastest = 0;
+                if (last && dweight_bf16) {
+                    p.epi = TC_EPI_STORE, p.out = dweight_bf16, p.ldd = H;
+                    if (!first) p.addend = dweight, p.ld_addend = H;
+                } else {
+                    p.epi = first ? TC_EPI_STORE_F32 : TC_EPI_ACCUM, p.out = dweight, p.ldd = H;
+                }
+                rc = tc_gemm(p, stream);
+            } else {
                 rc = lt_gemm(api, h, CUBLAS_OP_N, CUBLAS_OP_T, H, V, rows, hid + r0 * H, H, logits, V, dweight, H, CUDA_R_32F,
-                             1.f, nullptr, lt_ws, kLtWorkspace, stream);
+                             first ? 0.f : 1.f, nullptr, lt_ws, kLtWorkspace, stream);
+                if (!rc && last && dweight_bf16) {
+                    const int64_t n8 = V * H / 8;
+                    cast_f32_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+                        dweight, static_cast<__nv_bfloat16*>(dweight_bf16), n8);
+                    rc = check_launch("cast_f32_bf16_kernel");
+                }
+            }
             if (rc) return rc;
         }
         if (dbias) {

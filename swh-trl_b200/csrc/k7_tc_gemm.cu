@@ -84,6 +84,8 @@ struct GemmArgs {
     void* out;
     int64_t ldd, plane_stride;
     const __nv_bfloat16* bias;  // EPI_STORE only, per column, may be null
+    const float* addend;        // EPI_STORE only: fp32 [m_rows, ld_addend] added before the rounding, may be null
+    int64_t ld_addend;          //   (the last chunk of dW: bf16(dW_fp32 + dlogits_c^T hidden_c) without a cast pass)
 };
 
 struct RowFold {
@@ -287,6 +289,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool want_stats = (kEpi == EPI_STATS) || (kEpi == EPI_STORE && a.partial != nullptr);
         // this warp's staging box (32 rows x 128 bytes, SWIZZLE_128B: 16-byte chunk q of row r sits at q ^ (r & 7))
         unsigned char* my_box = staging + ew * 4096;
+        const uint64_t stream_policy = l2_policy_evict_first();
         const uint32_t dst = smem_u32(my_box) + static_cast<uint32_t>(lane) * 128u;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
         int buf = 0;
@@ -313,7 +316,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (row_ok && cj + 32 <= a.n_cols) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const float4 t = *reinterpret_cast<const float4*>(out32 + cj + 4 * q);
+                            const float4 t = ld_stream_f4(out32 + cj + 4 * q);
                             old[4 * q] = t.x, old[4 * q + 1] = t.y, old[4 * q + 2] = t.z, old[4 * q + 3] = t.w;
                         }
                     }
@@ -343,6 +346,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             for (int i = 0; i < 32; ++i)
                                 if (i < valid) v[i] += __bfloat162float(a.bias[cj + i]);
                         }
+                        if (a.addend && row_ok) {
+                            const float* ad = a.addend + row * a.ld_addend + cj;
+                            if (valid == 32) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 t = ld_stream_f4(ad + 4 * q);
+                                    v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (i < valid) v[i] += ad[i];
+                            }
+                        }
                         uint32_t p[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) p[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -362,7 +379,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0 && row0 < a.m_rows) {
-                                tma_store_2d(&map_d, cj & ~63, row0, my_box);
+                                tma_store_2d_hint(&map_d, cj & ~63, row0, my_box, stream_policy);  // written once, read later
                                 bulk_commit();
                             }
                         }
@@ -375,15 +392,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 if (more) {  // next box's running sum: in flight while this one is added and stored
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) {
-                                        const float4 t = *reinterpret_cast<const float4*>(o + 32 + 4 * q);
+                                        const float4 t = ld_stream_f4(o + 32 + 4 * q);
                                         nxt[4 * q] = t.x, nxt[4 * q + 1] = t.y, nxt[4 * q + 2] = t.z, nxt[4 * q + 3] = t.w;
                                     }
                                 }
 #pragma unroll
                                 for (int q = 0; q < 8; ++q)
-                                    *reinterpret_cast<float4*>(o + 4 * q) =
-                                        make_float4(old[4 * q] + v[4 * q], old[4 * q + 1] + v[4 * q + 1],
-                                                    old[4 * q + 2] + v[4 * q + 2], old[4 * q + 3] + v[4 * q + 3]);
+                                    st_stream_f4(o + 4 * q, old[4 * q] + v[4 * q], old[4 * q + 1] + v[4 * q + 1],
+                                                 old[4 * q + 2] + v[4 * q + 2], old[4 * q + 3] + v[4 * q + 3]);
                                 if (more) {
 #pragma unroll
                                     for (int i = 0; i < 32; ++i) old[i] = nxt[i];
@@ -397,8 +413,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             float* o = out32 + cj;
                             if (valid == 32) {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                                for (int q = 0; q < 8; ++q) st_stream_f4(o + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                             } else {
                                 for (int i = 0; i < valid; ++i) o[i] = v[i];
                             }
@@ -619,22 +634,26 @@ int plan_k_splits(int64_t tiles, int clusters, int kblocks, int64_t M, int64_t N
 
 }  // namespace
 
-// D = A B^T with the epilogue of `epi`; shared by the C entry points of this file and k6 (the seam).
-//   a_mn / b_mn: 0 = the operand is stored [rows, k] (k contiguous), 1 = stored [k, rows] (rows contiguous)
-int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
-            int64_t K, void* out, int64_t ldd, const void* bias, const int64_t* ids, float c, void* partial,
-            int* n_groups_out, int m_fastest, void* splitk_ws, int64_t splitk_ws_bytes, cudaStream_t s) {
+// D = A B^T with the epilogue of `p.epi`; shared by the C entry points of this file, k5 and k6 (the seam).
+int tc_gemm(const TcGemmParams& p, cudaStream_t s) {
+    const int64_t M = p.M, N = p.N, K = p.K;
     B200TRL_REQUIRE(M > 0 && N > 0 && K > 0, B200TRL_E_INVALID, "tc_gemm: bad shape");
-    B200TRL_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+    B200TRL_REQUIRE(p.lda % 8 == 0 && p.ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.B) & 15) == 0,
                     B200TRL_E_UNSUPPORTED, "tc_gemm: bf16 operands need 16-byte aligned rows");
-    B200TRL_REQUIRE(epi != EPI_STATS || (partial && ids), B200TRL_E_INVALID, "tc_gemm: statistics need ids and a workspace");
-    B200TRL_REQUIRE(epi == EPI_STATS || (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0),
+    B200TRL_REQUIRE(p.epi != TC_EPI_STATS || (p.partial && p.ids), B200TRL_E_INVALID,
+                    "tc_gemm: statistics need ids and a workspace");
+    const bool f32_out = p.epi == TC_EPI_ACCUM || p.epi == TC_EPI_STORE_F32;
+    B200TRL_REQUIRE(p.epi == TC_EPI_STATS ||
+                        (p.out && p.ldd % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0),
                     B200TRL_E_UNSUPPORTED, "tc_gemm: output rows must be 16-byte aligned");
+    B200TRL_REQUIRE(!p.addend || (p.epi == TC_EPI_STORE && p.ld_addend % 4 == 0 &&
+                                  (reinterpret_cast<uintptr_t>(p.addend) & 15) == 0),
+                    B200TRL_E_UNSUPPORTED, "tc_gemm: the fp32 addend needs the bf16 output and 16-byte aligned rows");
     CUtensorMap ma, mb;
-    int rc = a_mn ? make_map(&ma, A, K, M, lda, 64) : make_map(&ma, A, M, K, lda, 128);
+    int rc = p.a_mn ? make_map(&ma, p.A, K, M, p.lda, 64) : make_map(&ma, p.A, M, K, p.lda, 128);
     if (rc) return rc;
-    rc = b_mn ? make_map(&mb, B, K, N, ldb, 64) : make_map(&mb, B, N, K, ldb, 128);
+    rc = p.b_mn ? make_map(&mb, p.B, K, N, p.ldb, 64) : make_map(&mb, p.B, N, K, p.ldb, 128);
     if (rc) return rc;
     GemmArgs a{};
     a.m_rows = M;
@@ -650,60 +669,61 @@ int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void*
         const int n_sb = (a.n_mpairs + fit - 1) / fit;
         a.sb_mpairs = (a.n_mpairs + n_sb - 1) / n_sb;
     }
-    const bool stats = partial != nullptr;
+    const bool stats = p.partial != nullptr;
     if (stats) {
         a.tiles_per_group = plan_tiles_per_group(a.n_mpairs, a.n_ntiles, n_clusters_for_device(), a.sb_mpairs);
         a.m_fastest = 1;
     } else {
         a.tiles_per_group = 1;
-        a.m_fastest = m_fastest;
+        a.m_fastest = p.m_fastest;
     }
     a.n_groups = (a.n_ntiles + a.tiles_per_group - 1) / a.tiles_per_group;
-    a.ids = ids;
-    a.c = c;
-    a.partial = static_cast<float4*>(partial);
-    a.bias = static_cast<const __nv_bfloat16*>(bias);
+    a.ids = p.ids;
+    a.c = p.c;
+    a.partial = static_cast<float4*>(p.partial);
+    a.bias = static_cast<const __nv_bfloat16*>(p.bias);
+    a.addend = p.addend;
+    a.ld_addend = p.ld_addend;
     a.k_splits = 1;
     a.kb_per_split = static_cast<int>((K + kTileK - 1) / kTileK);
-    if (n_groups_out) *n_groups_out = a.n_groups * 2;  // one partial per (run of n-tiles, column half)
-    CUtensorMap md = ma;  // EPI_STATS stores nothing
-    if (epi == EPI_STORE && splitk_ws && !stats && N % 8 == 0 && a_mn == 0) {
+    if (p.n_groups_out) *p.n_groups_out = a.n_groups * 2;  // one partial per (run of n-tiles, column half)
+    CUtensorMap md = ma;  // only EPI_STORE stores through a tensor map
+    if (p.epi == TC_EPI_STORE && p.splitk_ws && !stats && !p.addend && N % 8 == 0 && p.a_mn == 0) {
         const int kblocks = a.kb_per_split;
         const int S = plan_k_splits(static_cast<int64_t>(a.n_mpairs) * a.n_ntiles, n_clusters_for_device(), kblocks, M, N,
-                                    splitk_ws_bytes);
+                                    p.splitk_ws_bytes);
         if (S > 1) {
             a.kb_per_split = (kblocks + S - 1) / S;
             a.k_splits = (kblocks + a.kb_per_split - 1) / a.kb_per_split;
             a.bias = nullptr;  // added once, by the finishing kernel
-            a.out = splitk_ws;
+            a.out = p.splitk_ws;
             a.ldd = N;
             a.plane_stride = M * N;
-            rc = B200TRL_E_UNSUPPORTED;
-            if (a_mn == 0 && b_mn == 0) rc = launch<0, 0, EPI_PARTIAL>(ma, mb, md, a, s);
-            if (a_mn == 0 && b_mn == 1) rc = launch<0, 1, EPI_PARTIAL>(ma, mb, md, a, s);
-            if (rc) {
-                if (rc == B200TRL_E_UNSUPPORTED) set_error("tc_gemm: split-K is not built for this operand layout");
-                return rc;
-            }
+            rc = p.b_mn ? launch<0, 1, EPI_PARTIAL>(ma, mb, md, a, s) : launch<0, 0, EPI_PARTIAL>(ma, mb, md, a, s);
+            if (rc) return rc;
             const int64_t n_thr = M * (N / 8);
             tc_splitk_finish_kernel<<<static_cast<unsigned>((n_thr + 255) / 256), 256, 0, s>>>(
-                static_cast<const float*>(splitk_ws), a.k_splits, M, N, static_cast<__nv_bfloat16*>(out), ldd,
-                static_cast<const __nv_bfloat16*>(bias));
+                static_cast<const float*>(p.splitk_ws), a.k_splits, M, N, static_cast<__nv_bfloat16*>(p.out), p.ldd,
+                static_cast<const __nv_bfloat16*>(p.bias));
             return check_launch("tc_splitk_finish_kernel");
         }
     }
-    if (epi == EPI_STORE) rc = make_out_map(&md, out, M, N, ldd);
+    if (p.epi == TC_EPI_STORE) rc = make_out_map(&md, p.out, M, N, p.ldd);
     if (rc) return rc;
-    a.out = out;
-    a.ldd = ldd;
-#define B200TRL_TC_CASE(AM, BM, EP) \
-    if (a_mn == AM && b_mn == BM && epi == EP) return launch<AM, BM, EP>(ma, mb, md, a, s);
-    B200TRL_TC_CASE(0, 0, EPI_STATS)
-    B200TRL_TC_CASE(0, 0, EPI_STORE)
-    B200TRL_TC_CASE(0, 1, EPI_STORE)
-    B200TRL_TC_CASE(1, 1, EPI_ACCUM)
-#undef B200TRL_TC_CASE
-    set_error("tc_gemm: unsupported operand layout / epilogue combination (%d, %d, %d)", a_mn, b_mn, epi);
+    a.out = p.out;
+    a.ldd = p.ldd;
+    a.plane_stride = 0;
+    const int key = p.a_mn * 100 + p.b_mn * 10 + p.epi;
+    switch (key) {
+        case 0 * 100 + 0 * 10 + TC_EPI_STATS: return launch<0, 0, EPI_STATS>(ma, mb, md, a, s);
+        case 0 * 100 + 0 * 10 + TC_EPI_STORE: return launch<0, 0, EPI_STORE>(ma, mb, md, a, s);
+        case 0 * 100 + 1 * 10 + TC_EPI_STORE: return launch<0, 1, EPI_STORE>(ma, mb, md, a, s);
+        case 1 * 100 + 1 * 10 + TC_EPI_STORE: return launch<1, 1, EPI_STORE>(ma, mb, md, a, s);
+        case 1 * 100 + 1 * 10 + TC_EPI_ACCUM: return launch<1, 1, EPI_ACCUM>(ma, mb, md, a, s);
+        case 1 * 100 + 1 * 10 + TC_EPI_STORE_F32: return launch<1, 1, EPI_PARTIAL>(ma, mb, md, a, s);  // one plane, k_splits = 1
+        default: break;
+    }
+    set_error("tc_gemm: unsupported operand layout / epilogue combination (%d, %d, %d)", p.a_mn, p.b_mn, p.epi);
     return B200TRL_E_UNSUPPORTED;
 }
 
@@ -735,12 +755,21 @@ extern "C" int64_t b200trl_tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t
 
 extern "C" int b200trl_tc_gemm(const void* A, int a_layout, int64_t lda, const void* B, int b_layout, int64_t ldb,
                                int64_t M, int64_t N, int64_t K, int out_kind, void* out, int64_t ldd, const void* bias,
-                               int m_fastest, void* workspace, int64_t workspace_bytes, b200trl_stream_t stream) {
+                               const float* addend, int64_t ld_addend, int m_fastest, void* workspace,
+                               int64_t workspace_bytes, b200trl_stream_t stream) {
     B200TRL_REQUIRE(A && B && out, B200TRL_E_INVALID, "tc_gemm: null pointer");
-    B200TRL_REQUIRE(out_kind == B200TRL_TC_OUT_BF16 || out_kind == B200TRL_TC_OUT_F32_ACC, B200TRL_E_INVALID,
-                    "tc_gemm: unknown out_kind %d", out_kind);
-    B200TRL_REQUIRE(!bias || out_kind == B200TRL_TC_OUT_BF16, B200TRL_E_INVALID, "tc_gemm: bias needs the bf16 output");
-    return tc_gemm(a_layout, b_layout, out_kind == B200TRL_TC_OUT_BF16 ? TC_EPI_STORE : TC_EPI_ACCUM, A, lda, B, ldb, M, N,
-                   K, out, ldd, bias, nullptr, 0.f, nullptr, nullptr, m_fastest, workspace, workspace ? workspace_bytes : 0,
-                   as_stream(stream));
+    B200TRL_REQUIRE(out_kind == B200TRL_TC_OUT_BF16 || out_kind == B200TRL_TC_OUT_F32_ACC || out_kind == B200TRL_TC_OUT_F32,
+                    B200TRL_E_INVALID, "tc_gemm: unknown out_kind %d", out_kind);
+    B200TRL_REQUIRE((!bias && !addend) || out_kind == B200TRL_TC_OUT_BF16, B200TRL_E_INVALID,
+                    "tc_gemm: bias / addend need the bf16 output");
+    TcGemmParams p;
+    p.a_mn = a_layout;
+    p.b_mn = b_layout;
+    p.epi = out_kind == B200TRL_TC_OUT_BF16 ? TC_EPI_STORE : out_kind == B200TRL_TC_OUT_F32_ACC ? TC_EPI_ACCUM : TC_EPI_STORE_F32;
+    p.A = A, p.lda = lda, p.B = B, p.ldb = ldb, p.M = M, p.N = N, p.K = K;
+    p.out = out, p.ldd = ldd, p.bias = bias, p.addend = addend, p.ld_addend = ld_addend;
+    p.m_fastest = m_fastest;
+    p.splitk_ws = workspace;
+    p.splitk_ws_bytes = workspace ? workspace_bytes : 0;
+    return tc_gemm(p, as_stream(stream));
 }

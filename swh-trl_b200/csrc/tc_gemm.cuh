@@ -6,18 +6,37 @@
 
 namespace b200trl {
 
-enum TcEpilogue { TC_EPI_STATS = 0, TC_EPI_STORE = 1, TC_EPI_ACCUM = 2 };
+enum TcEpilogue {
+    TC_EPI_STATS = 0,      // nothing stored: per-row online-softmax statistics into `partial`
+    TC_EPI_STORE = 1,      // out = bf16 [M, ldd] = D (+ bias[N]) (+ addend fp32 [M, ld_addend]); with `partial` the
+                           // statistics of the rounded values as well
+    TC_EPI_ACCUM = 2,      // out = fp32 [M, ldd], out += D
+    TC_EPI_STORE_F32 = 4,  // out = fp32 [M, ldd], out = D
+};
 
 // D[M, N] = A[M, K] B[N, K]^T.  a_mn / b_mn = 0: operand stored [rows, k] (k contiguous); 1: stored [k, rows].
-//   TC_EPI_STATS: `partial` (tc_stats_workspace_bytes) receives per-group row statistics, nothing else is written;
-//   TC_EPI_STORE: out = bf16 [M, ldd] (+ bias[N]); with `partial` the statistics of the rounded values as well;
-//   TC_EPI_ACCUM: out = fp32 [M, ldd], accumulated into.
-// `splitk_ws` (nullable): fp32 scratch for TC_EPI_STORE; when the output has too few tiles to fill the machine, K is
-// split into slices whose partial products go to planes of the scratch and are added in slice order (deterministic).
-// `m_fastest`: work order when no statistics are wanted (1: consecutive clusters share the B tile, 0: the A tile).
-int tc_gemm(int a_mn, int b_mn, int epi, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
-            int64_t K, void* out, int64_t ldd, const void* bias, const int64_t* ids, float c, void* partial,
-            int* n_groups_out, int m_fastest, void* splitk_ws, int64_t splitk_ws_bytes, cudaStream_t s);
+struct TcGemmParams {
+    int a_mn = 0, b_mn = 0, epi = TC_EPI_STORE;
+    const void* A = nullptr;
+    int64_t lda = 0;
+    const void* B = nullptr;
+    int64_t ldb = 0;
+    int64_t M = 0, N = 0, K = 0;
+    void* out = nullptr;
+    int64_t ldd = 0;
+    const void* bias = nullptr;     // bf16 [N], TC_EPI_STORE only
+    const float* addend = nullptr;  // fp32 [M, ld_addend], TC_EPI_STORE only
+    int64_t ld_addend = 0;
+    const int64_t* ids = nullptr;   // statistics: selected column per row
+    float c = 0.f;                  // statistics: inv_T * log2(e)
+    void* partial = nullptr;        // statistics workspace (tc_stats_workspace_bytes)
+    int* n_groups_out = nullptr;    // statistics: number of partials per row, for tc_merge_stats
+    int m_fastest = 1;              // work order without statistics: 1 = clusters running together share the B tile
+                                    // (and an L2-sized super-block of A rows), 0 = they share the A tile
+    void* splitk_ws = nullptr;      // TC_EPI_STORE: fp32 scratch; with it a contraction with too few output tiles is
+    int64_t splitk_ws_bytes = 0;    // split along K (planes added in slice order -> deterministic)
+};
+int tc_gemm(const TcGemmParams& p, cudaStream_t s);
 int64_t tc_stats_workspace_bytes(int64_t n_rows, int64_t n_cols);
 int tc_merge_stats(const void* partial, int n_groups, int64_t n_rows, float c, float* logp, float* entropy, float* lse,
                    cudaStream_t s);

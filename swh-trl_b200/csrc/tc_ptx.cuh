@@ -94,6 +94,26 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int x,
                  "r"(smem_u32(src)), "r"(x), "r"(y)
                  : "memory");
 }
+// Streaming (evict-first) global accesses for data that is touched once per launch: the fp32 read-modify-write of
+// dW and the split-K planes must not push the operand panels, which ARE re-read, out of L2.
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, int x, int y, const void* src, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(x), "r"(y), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // at most N of this thread's committed groups may still be READING their shared-memory source
 template <int N>

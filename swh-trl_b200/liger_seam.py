@@ -80,7 +80,8 @@ class _FusedLinearGRPO(torch.autograd.Function):
         need_db = bias is not None and bool(ctx.needs_input_grad[2])
         mask_i32 = mask.to(torch.int32).contiguous()
         if hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16:
-            # the product path: ONE C-ABI call (cuBLASLt GEMMs + K1 in place + K2), fp32 dW accumulated inside the GEMM
+            # the product path: ONE C-ABI call (GEMMs + K1 in place + K2); dW is accumulated in fp32 inside the GEMM
+            # and comes back already rounded to bf16
             cfg.grad_scale = 1.0
             loss, metrics, logp, ent, dh, dw, db = ops.fused_linear_grpo(
                 hidden, weight, bias, ids, mask_i32, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs, need_dh,

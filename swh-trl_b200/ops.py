@@ -521,8 +521,9 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
                       mask_i32: torch.Tensor, advantages: torch.Tensor, old_logp: Optional[torch.Tensor],
                       ref_logp: Optional[torch.Tensor], cfg: GrpoCfg, inv_temperature: float, chunk_seqs: int,
                       need_dh: bool, need_dw: bool, need_db: bool):
-    """``(loss[1], metrics[8], logp, entropy, dH|None, dW fp32|None, db fp32|None)`` — ``b200trl_fused_linear_grpo``:
-    the whole chunked lm_head + GRPO loss forward/backward in one C call (cuBLASLt GEMMs + K1 in place + K2)."""
+    """``(loss[1], metrics[8], logp, entropy, dH|None, dW bf16|None, db fp32|None)`` — ``b200trl_fused_linear_grpo``:
+    the whole chunked lm_head + GRPO loss forward/backward in one C call (GEMMs + K1 in place + K2).  ``dW`` is
+    accumulated over the chunks in fp32 and handed back rounded once to the weight's dtype."""
     k = _Keep()
     _need_cuda(hidden, "_input")
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -539,7 +540,9 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     metrics = torch.empty(_lib.NUM_GRPO_METRICS, dtype=torch.float32, device=dev)
     dh = torch.empty_like(h) if need_dh else None
-    dw = torch.empty(V, H, dtype=torch.float32, device=dev) if need_dw else None
+    n_chunks = -(-B // max(1, min(int(chunk_seqs), B)))
+    dw = torch.empty(V, H, dtype=torch.bfloat16, device=dev) if need_dw else None
+    dw_acc = torch.empty(V, H, dtype=torch.float32, device=dev) if need_dw and n_chunks > 1 else None
     db = torch.empty(V, dtype=torch.float32, device=dev) if need_db else None
     ws = _workspace(dev, lib.b200trl_fused_linear_grpo_workspace_bytes(B, T, H, V, int(chunk_seqs)), "fused_linear_grpo",
                     zero=False)
@@ -547,24 +550,25 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
         _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), k.f32(advantages, "advantages"),
         k.f32(old_logp, "old_per_token_logps"), k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg),
         float(inv_temperature), int(chunk_seqs), _ptr(ws), _ptr(logp), _ptr(ent), _ptr(loss), _ptr(metrics), _ptr(dh),
-        _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo")
-    n_chunks = -(-B // max(1, min(int(chunk_seqs), B)))
+        _ptr(dw_acc), _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo")
     _count(2 + n_chunks + 1)  # mask stats (memset + kernel), K1 per chunk, K2; the GEMMs are library launches
     return loss, metrics, logp, ent, dh, dw, db
 
 
 # ------------------------------------------------------------------------------------------------ K7: tcgen05 GEMMs
-TC_OUT_BF16, TC_OUT_F32_ACC = 1, 2
+TC_OUT_BF16, TC_OUT_F32_ACC, TC_OUT_F32 = 1, 2, 3
 
 
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, a_layout: int = 0, b_layout: int = 0,
             out: Optional[torch.Tensor] = None, accumulate: bool = False, bias: Optional[torch.Tensor] = None,
-            m_fastest: bool = True, split_k: bool = True) -> torch.Tensor:
+            m_fastest: bool = True, split_k: bool = True, addend: Optional[torch.Tensor] = None,
+            out_fp32: bool = False) -> torch.Tensor:
     """``D = A @ B.T`` on the CTA-pair tcgen05 kernel — ``b200trl_tc_gemm``.
 
     ``a`` is stored ``[M, K]`` (``a_layout=0``) or ``[K, M]`` (``a_layout=1``), ``b`` ``[N, K]`` or ``[K, N]``
     likewise; bf16, last dim contiguous.  ``accumulate=False``: bf16 ``[M, N]`` result (+ ``bias``);
-    ``accumulate=True``: ``out`` (fp32 ``[M, N]``) ``+= D``.  ``split_k``: hand the kernel an fp32 scratch so that
+    ``accumulate=True``: ``out`` (fp32 ``[M, N]``) ``+= D``; ``out_fp32=True``: fp32 result, plain store;
+    ``addend``: fp32 ``[M, N]`` added before the bf16 rounding.  ``split_k``: hand the kernel an fp32 scratch so that
     it may split K when the output has too few tiles to fill the machine (bf16 output only).
     """
     _need_cuda(a, "a")
@@ -576,7 +580,9 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, a_layout: int = 0, b_layout: int =
     N, Kb = (b.shape[1], b.shape[0]) if b_layout else (b.shape[0], b.shape[1])
     if K != Kb:
         raise ValueError(f"tc_gemm: contraction lengths differ ({K} vs {Kb})")
-    if accumulate:
+    if accumulate or out_fp32:
+        if out is None and out_fp32 and not accumulate:
+            out = torch.empty(M, N, dtype=torch.float32, device=a.device)
         if out is None or out.dtype != torch.float32 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
             raise ValueError("tc_gemm(accumulate=True) needs an fp32 [M, N] `out`")
     elif out is None:
@@ -584,14 +590,19 @@ def tc_gemm(a: torch.Tensor, b: torch.Tensor, a_layout: int = 0, b_layout: int =
     elif out.dtype != torch.bfloat16 or tuple(out.shape) != (M, N) or out.stride(1) != 1:
         raise ValueError("tc_gemm needs a bf16 [M, N] `out`")
     bb = None if bias is None else bias.to(torch.bfloat16).contiguous()
-    kind = TC_OUT_F32_ACC if accumulate else TC_OUT_BF16
+    kind = TC_OUT_F32_ACC if accumulate else (TC_OUT_F32 if out_fp32 else TC_OUT_BF16)
+    ad = None
+    if addend is not None:
+        if addend.dtype != torch.float32 or tuple(addend.shape) != (M, N) or addend.stride(1) != 1:
+            raise ValueError("tc_gemm needs an fp32 [M, N] `addend`")
+        ad = addend
     ws, ws_bytes = None, 0
-    if split_k and not accumulate:
+    if split_k and kind == TC_OUT_BF16 and ad is None:
         ws_bytes = int(lib.b200trl_tc_gemm_workspace_bytes(M, N, K, kind))
         ws = _workspace(a.device, ws_bytes, "tc_gemm", zero=False) if ws_bytes else None
     check(lib.b200trl_tc_gemm(_ptr(a), int(a_layout), a.stride(0), _ptr(b), int(b_layout), b.stride(0), M, N, K, kind,
-                              _ptr(out), out.stride(0), _ptr(bb), int(bool(m_fastest)), _ptr(ws), ws_bytes, _stream(a)),
-          "tc_gemm")
+                              _ptr(out), out.stride(0), _ptr(bb), _ptr(ad), ad.stride(0) if ad is not None else 0,
+                              int(bool(m_fastest)), _ptr(ws), ws_bytes, _stream(a)), "tc_gemm")
     _count(2 if ws is not None else 1)
     return out
 

@@ -26,7 +26,8 @@ def test_reference_arm_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert d["vs_baseline"] is None and d["config"]["workload"].startswith("configs[1]")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    lifted = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "trl_hotpath.py"))  # oracle/build_ref.py's output
+    assert cb["kind"] == ("reference" if lifted else "port") and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

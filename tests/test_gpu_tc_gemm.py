@@ -100,6 +100,13 @@ def test_tc_gemm_mnmajor_accumulate(S, M, N, K):
     torch.testing.assert_close(out.cpu().double(), want + 0.25, rtol=1e-5, atol=tol)
     ops.tc_gemm(a.t().contiguous().to(DEV), b.t().contiguous().to(DEV), a_layout=1, b_layout=1, out=out, accumulate=True)
     torch.testing.assert_close(out.cpu().double(), 2 * want + 0.25, rtol=1e-5, atol=2 * tol)
+    # first chunk of dW: plain fp32 store; last chunk: bf16(accumulator + D) rounded in the epilogue
+    at, bt = a.t().contiguous().to(DEV), b.t().contiguous().to(DEV)
+    first = ops.tc_gemm(at, bt, a_layout=1, b_layout=1, out_fp32=True, m_fastest=False)
+    torch.testing.assert_close(first.cpu().double(), want, rtol=1e-5, atol=tol)
+    final = ops.tc_gemm(at, bt, a_layout=1, b_layout=1, addend=first, m_fastest=False)
+    assert final.dtype == torch.bfloat16
+    torch.testing.assert_close(final.float().cpu(), (2 * want).to(torch.bfloat16).float(), rtol=BF16_ULP, atol=2 * tol)
 
 
 def test_fused_forward_pair_vs_single_cta(S):
@@ -156,7 +163,7 @@ def test_seam_on_tcgen05_gemms(S, mask):
     assert loss1.item() == pytest.approx(loss0.item(), rel=1e-3, abs=1e-6)
     torch.testing.assert_close(lp1, lp0, rtol=0, atol=2e-2)  # one bf16 ulp of a logit of magnitude ~2
     assert (dh1.float() - dh0.float()).norm() <= 1e-2 * dh0.float().norm()
-    assert (dw1 - dw0).norm() <= 1e-2 * dw0.norm()
+    assert (dw1.float() - dw0.float()).norm() <= 1e-2 * dw0.float().norm()
     # the oracle: reference loss on bf16-rounded logits of the same operands (what a bf16 model hands the loss)
     logits = (hidden.float().cpu() @ W.float().cpu().t()).to(torch.bfloat16).float()
     ocfg = O.GRPOConfigLite(beta=0.0, loss_type="bnpo", max_completion_length=T)

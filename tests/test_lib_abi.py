@@ -58,7 +58,7 @@ def test_argument_validation_without_gpu():
     # the seam call validates before it touches cuBLASLt or the device
     assert lib.b200trl_fused_linear_grpo_workspace_bytes(8, 2048, 3584, 152064, 2) > 2 * 2048 * 152064 * 2
     rc = lib.b200trl_fused_linear_grpo(None, None, None, 1, 1, 8, 8, None, None, None, None, None, None, 1.0, 1, None,
-                                       None, None, None, None, None, None, None, None)
+                                       None, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"null" in lib.b200trl_last_error()
     rc = lib.b200trl_completion_mask(None, 2, 4, 0, None, None, None)
     assert rc == -1

@@ -109,6 +109,7 @@ def ncu_target():
         ops.tc_gemm(dl, W, b_layout=1, out=dh)
         ops.tc_gemm(dl, hid, a_layout=1, b_layout=1, out=dw, accumulate=True, m_fastest=False)
         ops.fused_linear_logprob_fwd(hid, W, ids, 1.0)
+        ops.tc_gemm(dl, hid, a_layout=1, b_layout=1, out=dw, out_fp32=True, m_fastest=False)
     torch.cuda.synchronize()
     say("ncu target done")
 
