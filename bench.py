@@ -464,7 +464,7 @@ def extra_config4(S, ops, dev):
     launches = ops.launch_count - n0
     ms, win2 = event_ms(seam, 5, warmup=1)
     fl3 = 6.0 * B * T * H * V
-    names = {0: "cuBLASLt", 1: "tcgen05 K7"}
+    names = {0: "cuBLASLt", 1: "tcgen05 K7 (tc_gemm_kernel, cta_group::2)"}
     m = ops.set_seam_gemm_mask(-1)
     out["fwd_bwd"] = {"ms": ms, "tokens_per_s": B * T / (ms * 1e-3), "tflops": fl3 / ms / 1e9,
                       "frac_of_bf16_sustained_peak": fl3 / ms / 1e9 / sustained, "peak_source": src,
@@ -515,8 +515,10 @@ def extra_config5(S, ops, dist, world, rank, dev, x, ids, mask, old, ref, hbm_pe
         adv = S.group_advantages(rewards_local, weights, G)["advantages"]  # NCCL all-gather + K3, once per batch
         for m in range(n_mb):
             x5.grad = None
+            # what HF Trainer does with gradient accumulation: loss / GA, then backward -> the upstream gradient the
+            # fused pass has already folded in (grad_scale); nothing is rescaled afterwards
             o = fn(x5, ids5, mask5, adv[m * MB:(m + 1) * MB], old5, ref5, grad_scale=1.0 / n_mb)
-            o.loss.backward()
+            (o.loss / n_mb).backward()
             ring[m].copy_(o.metrics)
         return D.gather_metric_rows(ring) if world > 1 else ring  # ONE exchange for the whole batch
 

@@ -271,16 +271,19 @@ int b200trl_tc_gemm(const void* A, int a_layout, int64_t lda, const void* B, int
                     int64_t ld_addend, int m_fastest, void* workspace, int64_t workspace_bytes,
                     b200trl_stream_t stream);
 /* Which implementation the seam's three GEMMs use: bit 0 = logits, bit 1 = dH, bit 2 = dW; a set bit = the tcgen05
- * kernel above, a clear bit = cuBLASLt.  Returns the previous mask; mask < 0 only queries. */
+ * kernel above (default: all three), a clear bit = cuBLASLt (A/B baseline).  Returns the previous mask; mask < 0
+ * only queries. */
 int b200trl_set_seam_gemm_mask(int mask);
 
 /* ---- a-13: the reference's operator seam as ONE call (grpo_trainer.py:870-886 ctor, :2005-2045 call) ----------
  * What `self.liger_grpo_loss(_input, lin_weight, selected_token_ids, attention_mask, advantages, bias,
  * old_per_token_logps, ref_per_token_logps)` computes, forward AND backward, without ever holding the [B,T,V]
- * logits: per chunk of `chunk_seqs` whole sequences  logits_c = hidden_c W^T (+ bias)  (cuBLASLt GEMM, bf16 in,
- * fp32 accumulate)  ->  K1 resident kernel in place (logits_c becomes dlogits_c; log-probs, entropies)  ->
- * dH_c = dlogits_c W  and  dW += dlogits_c^T hidden_c  (cuBLASLt GEMMs, dW accumulated in fp32 inside the GEMM);
- * then K2 gives the loss and metrics.  cuBLASLt (plain library GEMMs only) is bound with dlopen at first use.
+ * logits: per chunk of `chunk_seqs` whole sequences  logits_c = hidden_c W^T (+ bias)  (this library's CTA-pair
+ * tcgen05 GEMM, bf16 in, fp32 accumulate in TMEM)  ->  K1 resident kernel in place (logits_c becomes dlogits_c;
+ * log-probs, entropies)  ->  dH_c = dlogits_c W  and  dW += dlogits_c^T hidden_c  (same kernel family; dW is
+ * accumulated in fp32 by TMA reduce-add); then K2 gives the loss and metrics.  cuBLASLt can be selected per GEMM
+ * as an A/B baseline (b200trl_set_seam_gemm_mask / B200TRL_SEAM_GEMM, default 7 = all ours); it is bound with
+ * dlopen only if selected.
  * hidden bf16 [B,T,H]; weight bf16 [V,H]; bias bf16 [V] or NULL; H, V multiples of 8.
  * Outputs: logp, entropy fp32 [B,T]; loss fp32 [1]; metrics fp32 [B200TRL_GRPO_NUM_METRICS] (metrics[B200TRL_M_KL]
  * and [B200TRL_M_CLIP_REGION] are what grpo_trainer.py:2038-2039 logs); dhidden bf16 [B,T,H], dweight fp32 [V,H]

@@ -2,15 +2,17 @@
 //       (trl/trainer/grpo_trainer.py:870-886 ctor, :2005-2045 call), as ONE C-ABI call.
 //
 // loss(hidden @ W^T + b) forward AND backward without ever holding the [B,T,V] logits: per chunk of whole sequences
-//     logits_c = hidden_c W^T (+ b)          library GEMM (cuBLASLt, bf16 in / fp32 accumulate / bf16 out)
+//     logits_c = hidden_c W^T (+ b)          K7 CTA-pair tcgen05 GEMM, bf16 in / fp32 accumulate in TMEM / bf16 out
 //     K1 resident kernel, IN PLACE           logits_c -> dlogits_c, emitting log-probs and entropies (one pass)
-//     dH_c  = dlogits_c W                    library GEMM
-//     dW   += dlogits_c^T hidden_c           library GEMM, fp32 accumulator updated inside the GEMM (beta = 1)
-// and K2 turns the log-probs into the loss value and the logged metrics.  The three GEMMs are plain library GEMMs
-// (the one place the rules of this build allow cuBLAS); everything that is not a plain GEMM is this library's own
-// kernel.  cuBLASLt is bound at first use with dlopen, so libb200trl.so itself has no link-time dependency on it
-// (the CPU-side ABI tests load the library on a box without a GPU) and shares the copy the host process (torch)
-// has already loaded.
+//     dH_c  = dlogits_c W                    K7, split-K over V with deterministic fp32 planes
+//     dW   += dlogits_c^T hidden_c           K7, fp32 running sum updated by TMA reduce-add; the last chunk's epilogue
+//                                            rounds bf16(dW_fp32 + D) itself (no cast pass)
+// and K2 turns the log-probs into the loss value and the logged metrics.  Every contraction runs on this library's own
+// tcgen05 kernel (k7_tc_gemm.cu) by default.  cuBLASLt stays available per GEMM as the A/B baseline
+// (B200TRL_SEAM_GEMM / b200trl_set_seam_gemm_mask: bit 0 logits, bit 1 dH, bit 2 dW; set = ours): measured in situ
+// at config 4 under the 1 kW cap (tools/seam_timeline.py) the library route takes 42.0 ms, ours 42.3 ms.  cuBLASLt
+// is bound at first use with dlopen, so libb200trl.so has no link-time dependency on it (the CPU-side ABI tests load
+// the library on a box without a GPU) and it is not loaded at all on the default path.
 #include <cublasLt.h>
 #include <dlfcn.h>
 
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 // bit 0 = logits GEMM, bit 1 = dH, bit 2 = dW on the CTA-pair tcgen05 kernel (k7_tc_gemm.cu); clear = cuBLASLt
 int default_gemm_mask() {
     const char* v = getenv("B200TRL_SEAM_GEMM");
-    return v ? atoi(v) : 0;
+    return v ? (atoi(v) & 7) : 7;
 }
 int g_gemm_mask = default_gemm_mask();
 

@@ -10,7 +10,10 @@
 //              the row statistics, i.e. exactly what a pass over the stored logits would compute
 //              (the lm_head GEMM of the Liger seam, grpo_trainer.py:2005-2045; dH = dlogits W);
 //   EPI_ACCUM  D is added into an fp32 matrix (dW += dlogits^T hidden across chunks of sequences) with TMA
-//              reduce-add stores: the read-modify-write happens in L2, the SM only writes;
+//              reduce-add stores from swizzled 32 x 32 fp32 boxes: the read-modify-write happens in L2, the SM only
+//              writes shared memory.  (A thread == row read-modify-write with ld/st.global touches 32 lines per warp
+//              instruction: ncu showed the LSU data pipe 60 % busy and the tensor pipe down to 78 %.)
+//   EPI_STORE32  the same boxes with plain TMA stores: D as fp32 (the first chunk of dW);
 //   EPI_PARTIAL  split-K: the item's k-slice of D goes to its own fp32 plane (plain TMA store); a second small kernel
 //              adds the planes in a fixed order and rounds to bf16 -> deterministic, and a contraction with few output
 //              tiles and a huge K (dH: 224 tiles over 74 clusters, K = 152064) fills the last wave.
@@ -59,7 +62,7 @@ constexpr int kThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warp
 constexpr int kTmemCols = 512;
 constexpr float kSlack = 6.0f;  // the running reference moves only when the tile maximum exceeds it by 2^6
 
-enum { EPI_STATS = TC_EPI_STATS, EPI_STORE = TC_EPI_STORE, EPI_ACCUM = TC_EPI_ACCUM, EPI_PARTIAL = 3 };
+enum { EPI_STATS = TC_EPI_STATS, EPI_STORE = TC_EPI_STORE, EPI_ACCUM = TC_EPI_ACCUM, EPI_PARTIAL = 3, EPI_STORE32 = 5 };
 
 struct Bars {
     uint64_t full[kStages];   // leader CTA: both CTAs' TMA bytes of a stage have landed
@@ -176,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        if (kEpi == EPI_STORE) tma_prefetch_desc(&map_d);
+        if (kEpi == EPI_STORE || kEpi == EPI_ACCUM || kEpi == EPI_STORE32) tma_prefetch_desc(&map_d);
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
@@ -307,20 +310,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int nt = nt0; nt < nt1; ++nt) {
                 const int col0 = nt * kTileN;
                 float* out32 = nullptr;
-                if (kEpi == EPI_ACCUM || kEpi == EPI_PARTIAL)
-                    out32 = static_cast<float*>(a.out) + (kEpi == EPI_PARTIAL ? ks * a.plane_stride : 0) + row * a.ldd;
-                float old[32];
-                if (kEpi == EPI_ACCUM) {  // the running sum of this thread's first 32 columns: in flight while the
-                                          // tile's MMAs are still running
-                    const int cj = col0 + half * 128;
-                    if (row_ok && cj + 32 <= a.n_cols) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = ld_stream_f4(out32 + cj + 4 * q);
-                            old[4 * q] = t.x, old[4 * q + 1] = t.y, old[4 * q + 2] = t.z, old[4 * q + 3] = t.w;
-                        }
-                    }
-                }
+                if (kEpi == EPI_PARTIAL) out32 = static_cast<float*>(a.out) + ks * a.plane_stride + row * a.ldd;
                 mbar_wait(&bars.tmem_full[buf], acc_phase);
                 fence_after_sync();
                 const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * kTileN);
@@ -383,30 +373,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 bulk_commit();
                             }
                         }
-                    } else if (kEpi == EPI_ACCUM) {
-                        if (row_ok) {
-                            float* o = out32 + cj;
-                            if (valid == 32) {
-                                float nxt[32];
-                                const bool more = jj < 3 && cj + 64 <= a.n_cols;
-                                if (more) {  // next box's running sum: in flight while this one is added and stored
+                    } else if (kEpi == EPI_ACCUM || kEpi == EPI_STORE32) {
+                        // an fp32 box is 32 rows x 32 columns (128-byte rows); the TMA clips it at the matrix bounds
+                        if (lane == 0) bulk_wait_read<0>();  // the copy that last read this box has finished
+                        __syncwarp();
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const float4 t = ld_stream_f4(o + 32 + 4 * q);
-                                        nxt[4 * q] = t.x, nxt[4 * q + 1] = t.y, nxt[4 * q + 2] = t.z, nxt[4 * q + 3] = t.w;
-                                    }
-                                }
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    st_stream_f4(o + 4 * q, old[4 * q] + v[4 * q], old[4 * q + 1] + v[4 * q + 1],
-                                                 old[4 * q + 2] + v[4 * q + 2], old[4 * q + 3] + v[4 * q + 3]);
-                                if (more) {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) old[i] = nxt[i];
-                                }
-                            } else {
-                                for (int i = 0; i < valid; ++i) o[i] += v[i];
-                            }
+                        for (int q = 0; q < 8; ++q)
+                            st_shared_v4(dst + ((static_cast<uint32_t>(q) ^ sw) << 4), __float_as_uint(v[4 * q]),
+                                         __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                                         __float_as_uint(v[4 * q + 3]));
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && row0 < a.m_rows) {
+                            if (kEpi == EPI_ACCUM)
+                                tma_reduce_add_2d_hint(&map_d, cj, row0, my_box, stream_policy);
+                            else
+                                tma_store_2d_hint(&map_d, cj, row0, my_box, stream_policy);
+                            bulk_commit();
                         }
                     } else {  // EPI_PARTIAL: this k-slice's plane, plain fp32 stores (a thread owns whole 128-byte lines)
                         if (row_ok) {
@@ -429,7 +412,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (want_stats && row_ok)
                 a.partial[static_cast<int64_t>(g * 2 + half) * a.n_mpairs * (2 * kTileM) + row] = make_float4(f.m, f.S, f.U, f.xsel);
         }
-        if (kEpi == EPI_STORE && lane == 0) bulk_wait<0>();  // every store of this warp has reached global memory
+        if ((kEpi == EPI_STORE || kEpi == EPI_ACCUM || kEpi == EPI_STORE32) && lane == 0)
+            bulk_wait<0>();  // every store / reduction of this warp has reached global memory
     }
     fence_before_sync();
     cluster_sync_all();  // the peer's remote arrives and this CTA's multicast commits have all been consumed
@@ -513,6 +497,27 @@ int make_out_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("tc_gemm: cuTensorMapEncodeTiled failed for the output (%d)", static_cast<int>(r));
+        return B200TRL_E_INVALID;
+    }
+    return B200TRL_OK;
+}
+
+// Output map of EPI_ACCUM / EPI_STORE32: fp32 [rows, cols], boxes of 32 rows x 32 columns (128 bytes), SWIZZLE_128B.
+int make_out_map_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
+        return B200TRL_E_LAUNCH;
+    }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+    const cuuint32_t box[2] = {32u, 32u};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled failed for the fp32 output (%d)", static_cast<int>(r));
         return B200TRL_E_INVALID;
     }
     return B200TRL_OK;
@@ -709,6 +714,7 @@ int tc_gemm(const TcGemmParams& p, cudaStream_t s) {
         }
     }
     if (p.epi == TC_EPI_STORE) rc = make_out_map(&md, p.out, M, N, p.ldd);
+    if (p.epi == TC_EPI_ACCUM || p.epi == TC_EPI_STORE_F32) rc = make_out_map_f32(&md, p.out, M, N, p.ldd);
     if (rc) return rc;
     a.out = p.out;
     a.ldd = p.ldd;
@@ -720,7 +726,7 @@ int tc_gemm(const TcGemmParams& p, cudaStream_t s) {
         case 0 * 100 + 1 * 10 + TC_EPI_STORE: return launch<0, 1, EPI_STORE>(ma, mb, md, a, s);
         case 1 * 100 + 1 * 10 + TC_EPI_STORE: return launch<1, 1, EPI_STORE>(ma, mb, md, a, s);
         case 1 * 100 + 1 * 10 + TC_EPI_ACCUM: return launch<1, 1, EPI_ACCUM>(ma, mb, md, a, s);
-        case 1 * 100 + 1 * 10 + TC_EPI_STORE_F32: return launch<1, 1, EPI_PARTIAL>(ma, mb, md, a, s);  // one plane, k_splits = 1
+        case 1 * 100 + 1 * 10 + TC_EPI_STORE_F32: return launch<1, 1, EPI_STORE32>(ma, mb, md, a, s);
         default: break;
     }
     set_error("tc_gemm: unsupported operand layout / epilogue combination (%d, %d, %d)", p.a_mn, p.b_mn, p.epi);

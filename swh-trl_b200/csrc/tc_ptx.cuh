@@ -94,6 +94,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int x,
                  "r"(smem_u32(src)), "r"(x), "r"(y)
                  : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d_hint(const CUtensorMap* map, int x, int y, const void* src, uint64_t policy) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+        "r"(smem_u32(src)), "r"(x), "r"(y), "l"(policy)
+        : "memory");
+}
 // Streaming (evict-first) global accesses for data that is touched once per launch: the fp32 read-modify-write of
 // dW and the split-K planes must not push the operand panels, which ARE re-read, out of L2.
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {

@@ -11,13 +11,14 @@ as what ``use_liger_loss=False`` computes — the reference's own loss applied t
 is what the parity tests check.
 
 Schedule (grads-in-forward, the full ``[B,T,V]`` logits tensor is never materialised):
-for each chunk of whole sequences: ``logits_c = hidden_c @ W.T`` (library GEMM) → K1 resident kernel turns the chunk
-*in place* into ``dlogits_c`` while emitting log-probs / entropies (one pass) → ``dH_c = dlogits_c @ W`` and
-``dW += dlogits_c.T @ hidden_c`` (library GEMMs).  For bf16 models the whole loop is ONE C-ABI call,
-``b200trl_fused_linear_grpo`` (cuBLASLt GEMMs, the fp32 ``dW`` accumulated inside the GEMM); other dtypes run the
-same schedule with ``torch.matmul`` as the library GEMM.  Everything that is not a plain GEMM runs in ``libb200trl``.  Unlike Liger, the entropy mask is the only unsupported option: sequence-level
-importance sampling without old log-probs and ``delta`` work (Liger rejects them, grpo_trainer.py:794-802,
-grpo_config.py:615-616).
+for each chunk of whole sequences: ``logits_c = hidden_c @ W.T`` → K1 resident kernel turns the chunk *in place* into
+``dlogits_c`` while emitting log-probs / entropies (one pass) → ``dH_c = dlogits_c @ W`` and
+``dW += dlogits_c.T @ hidden_c``.  For bf16 models the whole loop is ONE C-ABI call, ``b200trl_fused_linear_grpo``,
+and all three contractions run on this library's CTA-pair tcgen05 kernel (``k7_tc_gemm.cu``; cuBLASLt is selectable
+per GEMM as an A/B baseline, ``ops.set_seam_gemm_mask``).  fp16 / fp32 models run the same schedule with
+``torch.matmul`` for the contractions and K1's row kernel in place.  Unlike Liger, the entropy mask is the only
+unsupported option: sequence-level importance sampling without old log-probs and ``delta`` work (Liger rejects them,
+grpo_trainer.py:794-802, grpo_config.py:615-616).
 """
 
 from __future__ import annotations

@@ -24,6 +24,24 @@ def S():
     return s
 
 
+def assert_logp(got, logits, ids, temp=1.0, where=""):
+    """north_star bar for log-probs: <= 1e-5 abs against the reference's fp32 path.
+
+    That path is itself a rounded computation: its distance from the exact value depends on the host CPU's vector width
+    (torch's CPU reductions), and CPU ``randn`` differs across ISAs, so the seeded instance differs from box to box --
+    one box of the pool measured 1.14e-5 between the row kernel and ITS fp32 reference at V = 32000 where every other
+    box passes 1e-5.  The check is therefore two-sided and per element: (1) <= 1e-5 from the EXACT value (the
+    reference's own code run in fp64, the stricter reading of the bar); (2) <= 1e-5 plus the fp32 reference's own
+    measured distance from exact (triangle inequality) against the fp32 reference."""
+    got = got.detach().double().cpu()
+    exact = O.selective_log_softmax(logits.double() / temp, ids)
+    ref32 = O.selective_log_softmax(logits.float() / temp, ids).double()
+    err = (got - exact).abs().max().item()
+    assert err <= 1e-5, f"{where}: {err:.3e} from the exact (fp64) log-prob"
+    over = ((got - ref32).abs() - (1e-5 + (ref32 - exact).abs())).max().item()
+    assert over <= 0, f"{where}: exceeds 1e-5 + the fp32 reference's own error by {over:.3e}"
+
+
 def _regen(case):
     g = torch.Generator().manual_seed(case["seed"])
     B, T, V = case["shape"]
@@ -66,7 +84,6 @@ def test_entropy_reference_shape(S):
 def test_k1_forward_vs_oracle(S, V, temp, peaked):
     B, T = 2, 5
     logits, ids, _ = O.synth_batch(B, T, V, seed=3, sigma=4.0 if peaked else 1.0, peaked=peaked)
-    want_lp = O.selective_log_softmax(logits.float() / temp, ids)
     # On peaked rows the reference's own fp32 entropy is off by up to 1.3e-4 abs from the exact value (measured
     # against fp64: log_softmax -> exp -> mul -> sum loses digits); the kernel accumulates (y - m) terms and
     # stays within 1e-5 of the exact value, so exact (fp64) is the primary bar and fp32-reference a loose one.
@@ -79,7 +96,7 @@ def test_k1_forward_vs_oracle(S, V, temp, peaked):
             lp, ent = S.logprobs_and_entropy(x, idx, temperature=temp)
         finally:
             S.set_k1_path(prev)
-        torch.testing.assert_close(lp.cpu(), want_lp, rtol=0, atol=1e-5, msg=lambda m: f"path {path}: {m}")
+        assert_logp(lp, logits, ids, temp, where=f"path {path}")
         torch.testing.assert_close(ent.cpu(), want_ent, rtol=1e-5, atol=1e-5, msg=lambda m: f"path {path}: {m}")
         torch.testing.assert_close(ent.cpu(), ref32_ent, rtol=1e-4, atol=5e-4, msg=lambda m: f"path {path}: {m}")
 
@@ -642,9 +659,8 @@ def test_tiny_and_boundary_vocab(S, V):
         ids.view(-1)[-1] = V - 1
         for dt in (torch.float32, torch.bfloat16):
             x = logits.to(dt)
-            want = O.selective_log_softmax(x.float(), ids)
             got = S.selective_log_softmax(x.to(DEV), ids.to(DEV))
-            torch.testing.assert_close(got.cpu(), want, rtol=0, atol=1e-5)
+            assert_logp(got, x, ids, where=f"V={V} {dt}")
             ent = S.entropy_from_logits(x.to(DEV))
             torch.testing.assert_close(ent.cpu(), O.entropy_from_logits(x.double()).float(), rtol=1e-5, atol=1e-5)
 
@@ -680,7 +696,7 @@ def test_large_vocab_clusters(S, V):
         out.loss.backward()
     finally:
         S.set_k1_path(prev)
-    torch.testing.assert_close(out.per_token_logps.cpu(), lp_r.detach(), rtol=0, atol=1e-5)
+    assert_logp(out.per_token_logps, logits, ids, where="resident kernel, ids at the slice edges")
     torch.testing.assert_close(out.entropies.cpu(), O.entropy_from_logits(logits.double()).float(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(x.grad.float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-14)
 
@@ -737,8 +753,7 @@ def test_no_out_of_bounds_writes(S, path):
         assert bool((buf[:margin] == sent.to(DEV)).all()) and bool((buf[margin + n:] == sent.to(DEV)).all())
         pad = buf[margin:margin + n].view(B, T, PADV)[:, :, V:]
         assert bool((pad == sent.to(DEV)).all())
-    want = O.selective_log_softmax(x.float().cpu(), ids.cpu())
-    torch.testing.assert_close(lp.cpu(), want, rtol=0, atol=1e-5)
+    assert_logp(lp, x.cpu(), ids.cpu(), where=f"in-place {path}")
     assert torch.count_nonzero(dl[mask == 0]) == 0 and torch.count_nonzero(dl[mask == 1]) > 0
 
 
@@ -782,8 +797,7 @@ def test_cuda_graph_capture(S):
     idx.copy_(ids2.to(DEV))
     graph.replay()
     torch.cuda.synchronize()
-    want_lp = O.selective_log_softmax(logits2.float(), ids2)
-    torch.testing.assert_close(lp.cpu(), want_lp, rtol=0, atol=1e-5)
+    assert_logp(lp, logits2, ids2, where="graph replay")
     eager_loss, _, eager_adv = step()
     torch.testing.assert_close(loss, eager_loss, rtol=1e-6, atol=1e-8)
     torch.testing.assert_close(adv_ppo, eager_adv, rtol=1e-6, atol=1e-7)
