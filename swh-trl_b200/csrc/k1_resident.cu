@@ -324,6 +324,190 @@ __device__ __forceinline__ Partial acc_to_partial(const Acc& a) {
     return Partial{a.m, s0 + s1, u0 + u1};
 }
 
+// ------------------------------------------------------------------ fast consumer of the fused pass
+// The product path (fused forward + dlogits, direct stores, two accumulation chains) has its own consumer code:
+//   * shared memory is addressed with 32-bit shared-window addresses computed once (the generic-pointer form made
+//     the compiler rebuild the window base for every chunk) and the full chunks run in loops that know nothing about
+//     the partial last chunk: ~40 -> ~12 bookkeeping instructions per chunk and warp, a quarter of all instructions;
+//   * one reference-point check per chunk, driven by a PACKED running maximum (bf16x2): the common case is four
+//     3-input packed max instructions and one integer compare;
+//   Tried and dropped: writing bf16(2^(y - m)) back over the folded logits so that the backward sweep is a multiply
+//   instead of a second exponential (half the MUFU load).  The cached value is rounded (2^-8) before the gradient is
+//   rounded (2^-8): 28 of 884 736 elements of test_ppo_fused_large_vocab left the one-ulp bar (1.16 % vs 0.78 %), and
+//   the pass was 10 % SLOWER (1.86 vs 1.68 ms burst: the write-back competes with the TMA for shared-memory bandwidth).
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_U:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE_U;\n\t"
+        "bra WAIT_LOOP_U;\n\t"
+        "WAIT_DONE_U:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr uint32_t kNegInf2 = 0xff80ff80u;  // bf16x2 (-inf, -inf)
+
+// fold one vector
+__device__ __forceinline__ void fold_words(uint64_t& s2, uint64_t& u2, const uint4& v, uint64_t c2, uint64_t nm2) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+        const uint64_t d2 = ffma2(x2, c2, nm2);
+        float d0, d1;
+        unpack2(d2, d0, d1);
+        const float e0 = ex2(d0), e1 = ex2(d1);
+        const uint64_t e2 = pack2(e0, e1);
+        s2 = fadd2(s2, e2);
+        u2 = ffma2(e2, d2, u2);
+    }
+}
+template <int NC>
+struct FusedConsumer {
+    static constexpr int kChunkBytes = chunk_bytes_for(NC);
+    static constexpr int kChunkElems = kChunkBytes / 2;
+    static constexpr int kVpt = kChunkBytes / 16 / NC;
+    static constexpr uint32_t kVecStride = NC * 16u;
+
+    // geometry
+    uint32_t slots_u32, full0, done0, my_off;
+    int num_slots, tid, lane, tail_vecs;
+    float c;
+    uint64_t c2;
+    // forward state of the row being folded
+    int fslot;
+    uint32_t fpar;
+    float m;
+    uint32_t rmx;
+    uint64_t s2, u2, t2, v2;
+    // backward cursor
+    int bslot;
+
+    __device__ __forceinline__ void row_begin() {
+        m = kNegBig;
+        rmx = kNegInf2;
+        s2 = u2 = t2 = v2 = 0ull;
+    }
+    __device__ __forceinline__ Partial row_partial() const {
+        float s0, s1, u0, u1;
+        unpack2(fadd2(s2, t2), s0, s1);
+        unpack2(fadd2(u2, v2), u0, u1);
+        return Partial{m, s0 + s1, u0 + u1};
+    }
+    __device__ __forceinline__ void move_reference(uint32_t t) {  // the running maximum moved: rare after the first chunk
+        rmx = t;
+        const float cm = fmaxf(__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u)) * c;
+        if (cm > m + kSlack) {
+            const float d = m - cm;
+            const float f = ex2(d);
+            const uint64_t f2 = pack2(f, f), d2 = pack2(d, d);
+            u2 = fmul2(f2, ffma2(d2, s2, u2));
+            s2 = fmul2(s2, f2);
+            v2 = fmul2(f2, ffma2(d2, t2, v2));
+            t2 = fmul2(t2, f2);
+            m = cm;
+        }
+    }
+    __device__ __forceinline__ void fwd_advance() {
+        if (++fslot == num_slots) {
+            fslot = 0;
+            fpar ^= 1u;
+        }
+    }
+    // a chunk of a masked row (masked-row skipping): nothing was loaded, the DMA warp arrived on the barrier itself
+    __device__ __forceinline__ void fwd_skip() {
+        mbar_wait_u32(full0 + static_cast<uint32_t>(fslot) * 8u, fpar);
+        fwd_advance();
+    }
+    // a full chunk: every thread folds kVpt vectors
+    __device__ __forceinline__ void fwd_full() {
+        mbar_wait_u32(full0 + static_cast<uint32_t>(fslot) * 8u, fpar);
+        const uint32_t base = slots_u32 + static_cast<uint32_t>(fslot) * kChunkBytes + my_off;
+        uint4 v[kVpt];
+        uint32_t t = rmx;
+#pragma unroll
+        for (int k = 0; k < kVpt; ++k) {
+            v[k] = lds128(base + k * kVecStride);
+            t = bf16x2_max(t, vec_max(v[k]));
+        }
+        if (t != rmx) move_reference(t);
+        const uint64_t nm2 = pack2(-m, -m);
+#pragma unroll
+        for (int k = 0; k < kVpt; k += 2) {
+            fold_words(s2, u2, v[k], c2, nm2);
+            fold_words(t2, v2, v[k + 1], c2, nm2);
+        }
+        fwd_advance();
+    }
+    // the partial last chunk of a slice: vector v of it belongs to thread v % NC; once per row
+    __device__ __forceinline__ void fwd_tail() {
+        mbar_wait_u32(full0 + static_cast<uint32_t>(fslot) * 8u, fpar);
+        const uint32_t base = slots_u32 + static_cast<uint32_t>(fslot) * kChunkBytes + my_off;
+        uint32_t t = rmx;
+#pragma unroll
+        for (int k = 0; k < kVpt; ++k)
+            if (tid + k * NC < tail_vecs) t = bf16x2_max(t, vec_max(lds128(base + k * kVecStride)));
+        if (t != rmx) move_reference(t);
+        const uint64_t nm2 = pack2(-m, -m);
+#pragma unroll
+        for (int k = 0; k < kVpt; ++k) {
+            if (tid + k * NC < tail_vecs) {
+                const uint4 v = lds128(base + k * kVecStride);
+                if (k & 1)
+                    fold_words(t2, v2, v, c2, nm2);
+                else
+                    fold_words(s2, u2, v, c2, nm2);
+            }
+        }
+        fwd_advance();
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void fwd() {
+        if (FULL)
+            fwd_full();
+        else
+            fwd_tail();
+    }
+    // one chunk of dlogits: gv = this CTA's slice of the row at this chunk
+    template <bool FULL>
+    __device__ __forceinline__ void bwd(uint4* gv, uint64_t nl2, uint64_t ng2) {
+        const uint32_t base = slots_u32 + static_cast<uint32_t>(bslot) * kChunkBytes + my_off;
+        uint4 v[kVpt];
+#pragma unroll
+        for (int k = 0; k < kVpt; ++k) {
+            v[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (FULL || (tid + k * NC < tail_vecs)) v[k] = lds128(base + k * kVecStride);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(done0 + static_cast<uint32_t>(bslot) * 8u);  // read: the slot may be refilled
+#pragma unroll
+        for (int k = 0; k < kVpt; ++k)
+            if (FULL || (tid + k * NC < tail_vecs))
+                st_global_cs(gv + tid + k * NC, grad_vec(v[k], c2, nl2, ng2));
+        if (++bslot == num_slots) bslot = 0;
+    }
+    template <bool FULL>
+    __device__ __forceinline__ void bwd_zero(uint4* gv) {
+        if (lane == 0) mbar_arrive_u32(done0 + static_cast<uint32_t>(bslot) * 8u);
+#pragma unroll
+        for (int k = 0; k < kVpt; ++k)
+            if (FULL || (tid + k * NC < tail_vecs)) st_global_cs(gv + tid + k * NC, make_uint4(0u, 0u, 0u, 0u));
+        if (++bslot == num_slots) bslot = 0;
+    }
+};
+
 // ------------------------------------------------------------------ the kernel
 // Warp roles: 0..15 consumers, 16 DMA (one lane), 17 reducer (row statistics + cluster exchange).
 //
@@ -345,9 +529,11 @@ struct Cursor {
     }
 };
 
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP>
+// FAST: 0 = generic consumer code; 1 = FusedConsumer
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST>
 __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
     k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag, const int l2_prefetch) {
+    static_assert(FAST == 0 || (HAS_FWD && HAS_BWD && DUAL && DIRECT), "the fast consumer is the fused pass");
     constexpr int kConsumers = NC;
     constexpr int kWarps = NC / 32;
     // chunk geometry of this instantiation: 512 and 256 consumers use 16 KB chunks (2 / 4 vectors per thread),
@@ -596,6 +782,80 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             }
             tr.finish();
         }
+    } else if (FAST != 0) {
+        // =========================== consumers, fused pass (FusedConsumer) ===========================
+        using FC = FusedConsumer<NC>;
+        FC fc;
+        fc.slots_u32 = smem_u32(slots);
+        fc.full0 = smem_u32(&sm.full_bar[0]);
+        fc.done0 = smem_u32(&sm.done_bar[0]);
+        fc.my_off = static_cast<uint32_t>(tid) * 16u;
+        fc.num_slots = num_slots;
+        fc.tid = tid;
+        fc.lane = lane;
+        fc.c = a.c;
+        fc.c2 = pack2(a.c, a.c);
+        fc.fslot = 0;
+        fc.fpar = 0u;
+        fc.bslot = 0;
+        const int n_full = (last_bytes == kChunkBytes) ? C : C - 1;  // chunks every thread has kVpt vectors of
+        fc.tail_vecs = (n_full < C) ? (last_bytes >> 4) : 0;
+        const int pre_full = min(k_pre, n_full);
+        const bool pre_tail = (k_pre == C) && (n_full < C);    // the early-folded chunks include the partial one
+        const bool main_tail = (k_pre < C) && (n_full < C);
+        // masked-row skipping (SKIP): the flag of the row being folded and of the one after it, fetched ahead
+        auto masked_at = [&](int r) {
+            return SKIP && r < n_my_rows && row_is_masked(a, first_row + static_cast<int64_t>(r) * row_step);
+        };
+        bool cur_masked = masked_at(0), nxt_masked = masked_at(1);
+        auto fold_early = [&](bool masked) {  // chunks [0, k_pre)
+            if (SKIP && masked) {
+                for (int cidx = 0; cidx < k_pre; ++cidx) fc.fwd_skip();
+            } else {
+                for (int cidx = 0; cidx < pre_full; ++cidx) fc.template fwd<true>();
+                if (pre_tail) fc.template fwd<false>();
+            }
+        };
+        fc.row_begin();
+        if (n_my_rows > 0) fold_early(cur_masked);
+        for (int i = 0; i < n_my_rows; ++i) {
+            const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
+            const int par = i & 1;
+            const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
+            const bool nn_masked = masked_at(i + 2);
+            if (SKIP && cur_masked) {
+                for (int cidx = k_pre; cidx < C; ++cidx) fc.fwd_skip();
+            } else {
+                for (int cidx = k_pre; cidx < n_full; ++cidx) fc.template fwd<true>();
+                if (main_tail) fc.template fwd<false>();
+            }
+            const Partial p = partial_warp_reduce_fast(fc.row_partial());
+            if (lane == 0) {
+                sm.warp_part[par][warp] = Part4{p.m, p.s, p.u, 0.f};
+                mbar_arrive(&sm.part_bar[par]);
+            }
+            fc.row_begin();
+            if (i + 1 < n_my_rows) fold_early(nxt_masked);
+            cur_masked = nxt_masked;
+            nxt_masked = nn_masked;
+            mbar_wait(&sm.res_bar[par], rpar);
+            const RowResult rr = sm.result[par];
+            const uint64_t nl2 = pack2(-rr.lse2, -rr.lse2);
+            const uint64_t ng2 = pack2(rr.ng, rr.ng);
+            uint4* gv = reinterpret_cast<uint4*>(dlogits + dlogits_offset(a, row) + e_begin);
+            if (rr.ng == 0.f) {  // masked token: the row's dlogits are zero
+                for (int cidx = 0; cidx < n_full; ++cidx) fc.template bwd_zero<true>(gv + static_cast<int64_t>(cidx) * (kChunkBytes / 16));
+                if (n_full < C) fc.template bwd_zero<false>(gv + static_cast<int64_t>(n_full) * (kChunkBytes / 16));
+            } else {
+                for (int cidx = 0; cidx < n_full; ++cidx)
+                    fc.template bwd<true>(gv + static_cast<int64_t>(cidx) * (kChunkBytes / 16), nl2, ng2);
+                if (n_full < C) fc.template bwd<false>(gv + static_cast<int64_t>(n_full) * (kChunkBytes / 16), nl2, ng2);
+                // the selected id: g' * (1 - p_id); the thread that wrote the vector holding it patches it
+                if (rr.id_vec >= 0 && (rr.id_vec % kConsumers) == tid)
+                    reinterpret_cast<__nv_bfloat16*>(gv + static_cast<int64_t>(rr.id_chunk) * (kChunkBytes / 16))[rr.id_elem] =
+                        __float2bfloat16_rn(rr.patch);
+            }
+        }
     } else {
         // =========================== consumers ===========================
         const float c = a.c;
@@ -790,9 +1050,9 @@ int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP>
-int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP>;
+template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST>
+int launch_mode_f(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP, FAST>;
     constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
     static_assert(chunk_bytes_for(NC) % (NC * 16) == 0, "a full chunk must give every consumer the same vector count");
     constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
@@ -848,6 +1108,18 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
         return B200TRL_E_LAUNCH;
     }
     return check_launch("k1_resident_kernel");
+}
+
+// The fused pass with direct stores and two chains runs on FusedConsumer (B200TRL_K1_FAST=0: generic consumer code).
+template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP>
+int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+#ifndef B200TRL_K1_TRACE
+    if constexpr (F && Bk && DUAL && DIRECT) {
+        static const int fast = env_int("B200TRL_K1_FAST", 1);
+        if (fast != 0) return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 1>(a, cs, num_slots, stream);
+    }
+#endif
+    return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 0>(a, cs, num_slots, stream);
 }
 
 // Four CTA geometries (which one serves a call: pick_geom below):

@@ -7,9 +7,15 @@
 // segment, a 5-step shuffle scan composes the 32 segment maps, then each lane replays its segment with the
 // true carry-in.  Global masked statistics use per-CTA partials + grid.sync() and are folded in CTA order in
 // double precision, so results are deterministic.
+//
+// Batches of up to 131 072 tokens (config 3 is 32 768) do not need the grid at all: ppo_gae_cluster_kernel keeps
+// rewards / values / advantages of the whole batch in the shared memory of ONE 8-CTA thread-block cluster, reads every
+// input once and writes every output once, and replaces the four to seven grid.sync() rounds (3-5 us each, 31-41 us
+// in total at config 3) by cluster barriers with the partial sums exchanged through distributed shared memory.
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -200,6 +206,177 @@ __global__ void __launch_bounds__(kBlock) ppo_gae_kernel(const GaeArgs a) {
     grid_whiten(grid, a.ws, 2, a.adv, n, keep_p0, /*shift_mean=*/true, /*zero_masked=*/true, red, nullptr);
 }
 
+
+// ------------------------------------------------------------------ single-cluster variant (small batches)
+constexpr int kClusterCtas = 8;
+constexpr int kClBlock = 1024;
+constexpr int kClMaxElems = 16384;  // per CTA: 3 fp32 arrays of this many elements = 192 KB of shared memory
+
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(const double* local, uint32_t rank, double v) {
+    uint32_t addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(addr)
+                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(local))), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// sum of (a, b) over the cluster: block tree, every CTA posts its partial into every CTA's exchange row (DSMEM),
+// one cluster barrier, then everybody adds the 8 partials in rank order -> bit-identical totals in all threads
+__device__ __forceinline__ void cluster_sum2(double (*xch)[2], float a, float b, double& ta, double& tb, float* red) {
+    float v[2] = {a, b};
+    block_sum<2, kClBlock>(v, red);
+    const uint32_t me = cl_rank();
+    if (threadIdx.x < kClusterCtas) {
+        st_cluster_f64(&xch[me][0], threadIdx.x, static_cast<double>(v[0]));
+        st_cluster_f64(&xch[me][1], threadIdx.x, static_cast<double>(v[1]));
+    }
+    cl_sync();
+    ta = 0.0;
+    tb = 0.0;
+#pragma unroll
+    for (int r = 0; r < kClusterCtas; ++r) {
+        ta += xch[r][0];
+        tb += xch[r][1];
+    }
+}
+
+// masked_whiten of x[0, n_loc) (shared memory) with statistics over the whole cluster; keep(i) takes the LOCAL index
+template <typename KeepFn>
+__device__ __forceinline__ void cluster_whiten(double (*xch)[kClusterCtas][2], int slot0, float* x, int n_loc, KeepFn keep,
+                                               bool shift_mean, float* red) {
+    const int tid = threadIdx.x;
+    float s = 0.f, c = 0.f;
+    for (int i = tid; i < n_loc; i += kClBlock) {
+        const float k = keep(i) ? 1.f : 0.f;
+        s += x[i] * k;
+        c += k;
+    }
+    double ts, tc, tq, unused;
+    cluster_sum2(xch[slot0], s, c, ts, tc, red);
+    const float mean = static_cast<float>(ts / tc);
+    float q = 0.f;
+    for (int i = tid; i < n_loc; i += kClBlock) {
+        const float d = x[i] - mean;
+        q += keep(i) ? d * d : 0.f;
+    }
+    cluster_sum2(xch[slot0 + 1], q, 0.f, tq, unused, red);
+    const float var = static_cast<float>((tq / tc) * (tc / (tc - 1.0)));
+    const float inv = rsqrtf(var + 1e-8f);
+    for (int i = tid; i < n_loc; i += kClBlock) {
+        float o = (x[i] - mean) * inv;
+        if (!shift_mean) o += mean;
+        if (!keep(i)) o = 0.f;
+        x[i] = o;
+    }
+    __syncthreads();
+}
+
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClBlock, 1)
+    ppo_gae_cluster_kernel(const GaeArgs a, const int rows_per_cta) {
+    extern __shared__ __align__(16) float sm_dyn[];
+    __shared__ float red[2 * 32];
+    __shared__ double xch[4][kClusterCtas][2];  // one exchange row set per reduction: never reused within a launch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = static_cast<int>(a.T);
+    const int64_t row0 = static_cast<int64_t>(cl_rank()) * rows_per_cta;
+    const int64_t row1 = (row0 + rows_per_cta < a.B) ? row0 + rows_per_cta : a.B;
+    const int rows = row1 > row0 ? static_cast<int>(row1 - row0) : 0;
+    const int n_loc = rows * T;
+    float* r_s = sm_dyn;                                          // rewards
+    float* v_s = sm_dyn + static_cast<size_t>(rows_per_cta) * T;  // filled values
+    float* a_s = v_s + static_cast<size_t>(rows_per_cta) * T;     // advantages
+    const int64_t g0 = row0 * T;                                  // global index of local element 0
+
+    // ---- phase 1: pad fills, KL reward, score at actual_end  (:500-516)
+    for (int i = tid; i < n_loc; i += kClBlock) {
+        const int rl = i / T, t = i - rl * T;
+        const int64_t b = row0 + rl, gi = g0 + i;
+        const int64_t len = a.seq_len[b];
+        const int64_t end = (len + 1 < T) ? len + 1 : len;  // :515
+        const bool pad = t > len, pad1 = t > len + 1;
+        const float lp = pad ? 1.0f : a.lp[gi];      // INVALID_LOGPROB (:502)
+        const float rlp = pad ? 1.0f : a.rlp[gi];    // :503
+        const float v = pad1 ? 0.f : a.values[gi];   // :506
+        const float logr = rlp - lp;                 // :510
+        const float kl = (a.estimator == B200TRL_KL_K1) ? -logr : (expf(logr) - 1.f) - logr;  // :511
+        float r = -a.kl_coef * kl;                   // :512
+        if (t == end) r += a.scores[b];              // :516
+        r_s[i] = r;
+        v_s[i] = v;
+        if (a.lp_f) a.lp_f[gi] = lp;
+        if (a.rlp_f) a.rlp_f[gi] = rlp;
+        if (a.val_f) a.val_f[gi] = v;
+    }
+    __syncthreads();
+    const int64_t* sl = a.seq_len;
+    auto keep_p1 = [sl, T, row0](int i) { return (i % T) <= sl[row0 + i / T] + 1; };  // ~padding_mask_p1
+    auto keep_p0 = [sl, T, row0](int i) { return (i % T) <= sl[row0 + i / T]; };      // ~padding_mask
+    if (a.whiten_rewards)  // :519-521
+        cluster_whiten(xch, 0, r_s, n_loc, keep_p1, /*shift_mean=*/false, red);
+    for (int i = tid; i < n_loc; i += kClBlock) a.rewards[g0 + i] = r_s[i];
+
+    // ---- phase 2: reverse GAE, one warp per row, 32 steps per round  (:523-533)
+    {
+        const float k = a.gamma * a.lam;
+        for (int rl = warp; rl < rows; rl += kClBlock / 32) {
+            const float* r = r_s + rl * T;
+            const float* v = v_s + rl * T;
+            float carry = 0.f;  // A_{t+1} of the chunk's last step
+            for (int c0 = ((T - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+                const int t = c0 + lane;
+                float Q = 0.f, P = 1.f;  // identity map for steps past the row's end
+                if (t < T) {
+                    const float nv = (t + 1 < T) ? v[t + 1] : 0.f;
+                    Q = r[t] + a.gamma * nv - v[t];
+                    P = k;
+                }
+                // reverse inclusive scan of the affine maps A -> Q + P * A over the 32 lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float nQ = __shfl_down_sync(0xffffffffu, Q, o);
+                    const float nP = __shfl_down_sync(0xffffffffu, P, o);
+                    if (lane + o < 32) {
+                        Q = Q + P * nQ;
+                        P = P * nP;
+                    }
+                }
+                const float A = Q + P * carry;
+                if (t < T) a_s[rl * T + t] = A;
+                carry = __shfl_sync(0xffffffffu, A, 0);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_loc; i += kClBlock) a.returns[g0 + i] = a_s[i] + v_s[i];  // :533
+    // ---- phase 3: advantage whitening, pads to zero (:534-535)
+    cluster_whiten(xch, 2, a_s, n_loc, keep_p0, /*shift_mean=*/true, red);
+    for (int i = tid; i < n_loc; i += kClBlock) a.adv[g0 + i] = a_s[i];
+    cl_sync();  // no CTA leaves while a peer may still write into its exchange rows
+}
+
+int launch_gae_cluster(const GaeArgs& a, int rows_per_cta, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(3) * rows_per_cta * a.T * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(ppo_gae_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(3 * kClMaxElems * sizeof(float))) != cudaSuccess) {
+            set_error("ppo_gae_cluster_kernel: cannot reserve shared memory");
+            return B200TRL_E_LAUNCH;
+        }
+        configured = true;
+    }
+    ppo_gae_cluster_kernel<<<kClusterCtas, kClBlock, smem, stream>>>(a, rows_per_cta);
+    return check_launch("ppo_gae_cluster_kernel");
+}
+
 struct WhitenArgs {
     const float* values;
     const uint8_t* mask;
@@ -288,6 +465,11 @@ extern "C" int b200trl_ppo_rewards_gae(const float* logprobs, const float* ref_l
     GaeArgs a{logprobs, ref_logprobs, values, scores, sequence_lengths, B, T, kl_coef, kl_estimator, gamma, lam,
               whiten_rewards, static_cast<GridWs*>(workspace), rewards, advantages, returns, logprobs_f,
               ref_logprobs_f, values_f};
+    // one 8-CTA cluster when the batch fits its shared memory (B200TRL_GAE_CLUSTER=0: always the cooperative grid)
+    static const bool use_cluster = !(getenv("B200TRL_GAE_CLUSTER") && atoi(getenv("B200TRL_GAE_CLUSTER")) == 0);
+    const int64_t rows_per_cta = (B + kClusterCtas - 1) / kClusterCtas;
+    if (use_cluster && rows_per_cta * T <= kClMaxElems)
+        return launch_gae_cluster(a, static_cast<int>(rows_per_cta), as_stream(stream));
     return coop_launch(ppo_gae_kernel, a, B, as_stream(stream), "ppo_gae_kernel");
 }
 

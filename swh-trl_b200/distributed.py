@@ -53,6 +53,16 @@ def gather_metrics(metrics: torch.Tensor, accelerator=None) -> torch.Tensor:
     return g.reshape(-1, m.shape[1]).float().cpu()
 
 
+def gather_metric_rows_device(rows: torch.Tensor) -> torch.Tensor:
+    """``[world, steps, n_metrics]`` on the DEVICE for a ``[steps, n_metrics]`` ring: the exchange alone, no host read."""
+    m = rows.detach().reshape(1, rows.shape[0], -1).contiguous()
+    if world() == 1:
+        return m
+    g = torch.empty((world(),) + tuple(m.shape[1:]), dtype=m.dtype, device=m.device)
+    dist.all_gather_into_tensor(g, m)
+    return g
+
+
 def gather_metric_rows(rows: torch.Tensor, accelerator=None) -> torch.Tensor:
     """``[world, steps, n_metrics]`` on the host for a ``[steps, n_metrics]`` device ring: one collective and one
     device->host read for every deferred step (``grpo.flush_metrics``, ``ppo.PPOStatsRing``)."""

@@ -26,30 +26,42 @@ _FUNCTIONS = {
 
 
 def patch_module(mod: types.ModuleType) -> list:
-    """Replace every hot-path global that ``mod`` holds; returns the names replaced."""
+    """Replace every hot-path global that ``mod`` holds; returns the names replaced.  Only the module's own namespace
+    is inspected (``vars``): ``trl`` and ``trl.trainer`` are lazy modules whose ``__getattr__`` would import half of
+    the package."""
     done = []
+    ns = vars(mod)
     for name, fn in _FUNCTIONS.items():
-        cur = getattr(mod, name, None)
+        cur = ns.get(name)
         if cur is not None and callable(cur) and cur is not fn:
             setattr(mod, "_trl_original_" + name, cur)
             setattr(mod, name, fn)
             done.append(name)
-    trainer = getattr(mod, "GRPOTrainer", None)
+    # PPO / RLOO have no seam: their train() is rewritten in place (train_patch.py); a reference whose train() does not
+    # contain the expected blocks raises TrainPatchError rather than running half-patched
+    from . import train_patch
+    for cls_name, blocks in (("PPOTrainer", train_patch.PPO_BLOCKS), ("RLOOTrainer", train_patch.RLOO_BLOCKS)):
+        cls = ns.get(cls_name)
+        if isinstance(cls, type) and train_patch.patch_trainer_class(cls, blocks):
+            done.append(cls_name + ".train")
+    trainer = ns.get("GRPOTrainer")
     if isinstance(trainer, type) and "_compute_loss" in trainer.__dict__:
-        trainer._trl_original_compute_loss = trainer._compute_loss
-        trainer._compute_loss = grpo.compute_loss
-        trainer._get_per_token_logps_and_entropies = grpo.get_per_token_logps_and_entropies
-        done.append("GRPOTrainer._compute_loss")
-        # the operator seam: GRPOTrainer.__init__ builds `LigerFusedLinearGRPOLoss(beta=..., ...)` from this module's
-        # global (grpo_trainer.py:82-83, 878-886) behind `is_liger_kernel_available()` (:871); rebinding both makes
-        # `use_liger_loss=True` construct the B200 operator (same keyword arguments), liger-kernel installed or not
+        if trainer.__dict__["_compute_loss"] is not grpo.compute_loss:  # the class may be reachable from several modules
+            trainer._trl_original_compute_loss = trainer._compute_loss
+            trainer._compute_loss = grpo.compute_loss
+            trainer._get_per_token_logps_and_entropies = grpo.get_per_token_logps_and_entropies
+            done.append("GRPOTrainer._compute_loss")
+        # the operator seam: GRPOTrainer.__init__ builds `LigerFusedLinearGRPOLoss(beta=..., ...)` from ITS module's
+        # global (grpo_trainer.py:82-83, 878-886) behind `is_liger_kernel_available()` (:871); rebinding both there
+        # makes `use_liger_loss=True` construct the B200 operator (same keyword arguments), liger-kernel installed or not
         from .liger_seam import B200FusedLinearGRPOLoss
-        if getattr(mod, "LigerFusedLinearGRPOLoss", None) is not B200FusedLinearGRPOLoss:
-            if hasattr(mod, "LigerFusedLinearGRPOLoss"):
-                mod._trl_original_LigerFusedLinearGRPOLoss = mod.LigerFusedLinearGRPOLoss
+        is_home = trainer.__module__ == mod.__name__ or "is_liger_kernel_available" in ns or "LigerFusedLinearGRPOLoss" in ns
+        if is_home and ns.get("LigerFusedLinearGRPOLoss") is not B200FusedLinearGRPOLoss:
+            if "LigerFusedLinearGRPOLoss" in ns:
+                mod._trl_original_LigerFusedLinearGRPOLoss = ns["LigerFusedLinearGRPOLoss"]
             mod.LigerFusedLinearGRPOLoss = B200FusedLinearGRPOLoss
-            if hasattr(mod, "is_liger_kernel_available"):
-                mod._trl_original_is_liger_kernel_available = mod.is_liger_kernel_available
+            if "is_liger_kernel_available" in ns:
+                mod._trl_original_is_liger_kernel_available = ns["is_liger_kernel_available"]
                 mod.is_liger_kernel_available = lambda *a, **k: True
             done.append("LigerFusedLinearGRPOLoss")
     return done

@@ -79,3 +79,56 @@ def ppo_loss(logits, mb_responses, mb_logprobs, mb_advantage, mb_return, mb_valu
                                       sequence_lengths, inv_temp, float(cliprange), float(cliprange_value),
                                       float(vf_coef), float(grad_scale))
     return PPOLossOutput(loss, stats, nlp)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Helpers named by the rewritten ``PPOTrainer.train`` / ``RLOOTrainer.train`` (train_patch.py)
+# ------------------------------------------------------------------------------------------------------------------
+def kl_terms(logprobs, ref_logprobs, kl_coef: float, kl_estimator: str = "k1"):
+    """``(kl, non_score_reward)`` as ppo_trainer.py:510-512 defines them on the pad-filled log-probs: only the two
+    logged row sums (``objective/kl``, ``objective/non_score_reward``, :618-620) still need these ``[B, T]`` tensors
+    once per rollout; the rewards themselves come out of ``ppo_rewards_gae``."""
+    logr = ref_logprobs - logprobs
+    kl = -logr if kl_estimator == "k1" else (logr.exp() - 1) - logr
+    return kl, -kl_coef * kl
+
+
+def backward_scale(accelerator) -> float:
+    """The upstream gradient ``accelerator.backward(loss)`` hands to the loss: accelerate divides by its
+    ``gradient_accumulation_steps``.  Folding it into the fused pass saves the rescale of the dlogits buffer."""
+    return 1.0 / float(max(1, int(getattr(accelerator, "gradient_accumulation_steps", 1) or 1)))
+
+
+def _packed_row(named: dict, var_of: torch.Tensor) -> torch.Tensor:
+    """This rank's ``[1, len(named) + 3]`` float64 row: local means, then (n, sum, sum of squares) of ``var_of``."""
+    vals = [v.detach().to(torch.float64).mean() for v in named.values()]
+    x = var_of.detach().to(torch.float64).reshape(-1)
+    vals += [torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device), x.sum(), (x * x).sum()]
+    return torch.stack([v.reshape(()) for v in vals]).reshape(1, -1)
+
+
+def packed_metrics(accelerator, eps: int, named: dict, var_of: torch.Tensor) -> dict:
+    """The logged scalars of one PPO / RLOO update from ONE exchange and ONE device->host read.
+
+    The reference pays one ``gather_for_metrics(...)`` collective and one ``.item()`` sync per metric
+    (ppo_trainer.py:618-633: 13 of each; rloo_trainer.py:525-543: 12).  Every one of them is the mean over ranks of a
+    local mean (equal local sizes), except ``val/ratio_var``: the unbiased variance over the gathered ``ratio_stats``
+    elements, which is rebuilt exactly from per-rank ``(n, sum, sum of squares)`` in float64.  ``named`` maps the
+    metric name to a tensor (its local mean is taken); the insertion order is the reference's order."""
+    from . import distributed as D
+
+    row = _packed_row(named, var_of)
+    if accelerator is not None and hasattr(accelerator, "gather"):
+        g = accelerator.gather(row)
+    elif D.world() > 1:
+        g = torch.empty((D.world(), row.shape[1]), dtype=row.dtype, device=row.device)
+        torch.distributed.all_gather_into_tensor(g, row.contiguous())
+    else:
+        g = row
+    g = g.reshape(-1, row.shape[1]).cpu()  # the one sync
+    out = {"eps": eps}
+    for i, name in enumerate(named):
+        out[name] = g[:, i].mean().item()
+    n, s1, s2 = g[:, -3].sum().item(), g[:, -2].sum().item(), g[:, -1].sum().item()
+    out["val/ratio_var"] = (s2 - s1 * s1 / n) / (n - 1) if n > 1 else float("nan")
+    return out

@@ -59,3 +59,10 @@ def rloo_loss(logits, mb_responses, mb_logprobs, mb_advantage, sequence_lengths,
     loss, stats, lp = _RLOOLoss.apply(logits, mb_responses, mb_logprobs, mb_advantage, sequence_lengths,
                                       1.0 / (float(temperature) + 1e-7), float(cliprange))
     return RLOOLossOutput(loss, stats, lp)
+
+
+def normalized_scores(scores: torch.Tensor, reward_clip_range: float) -> torch.Tensor:
+    """rloo_trainer.py:407-409: the reference rebinds ``scores`` to the normalised, clipped ones and logs their mean
+    (``objective/scores``, :533); ``rloo_rewards_advantages`` normalises internally, this only serves the log line."""
+    scores = (scores - scores.mean()) / (scores.std() + 1e-8)
+    return torch.clamp(scores, -reward_clip_range, reward_clip_range)

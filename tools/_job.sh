@@ -1,8 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-lscpu | grep -E "Model name|^CPU\(s\)" > gpurun_out/s2_lscpu.log
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s2_gputest_b.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s2_gputest_b.log
-SUSTAIN_ONLY=dW timeout 300 python tools/tc_gemm_sustained.py > gpurun_out/s2_sus_dw.log 2>&1
-SEAM_MASKS=0,1,4,7 timeout 600 python tools/seam_timeline.py > gpurun_out/s2_seam_timeline_a.jsonl 2> gpurun_out/s2_seam_timeline_a.err
-tail -5 gpurun_out/s2_gputest_b.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s2_gputest_e.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s2_gputest_e.log
+timeout 600 python tools/k1_stress.py > gpurun_out/s2_k1_stress3.log 2>&1; echo "stress rc=$?" >> gpurun_out/s2_k1_stress3.log
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/s2_bench_b.json 2> gpurun_out/s2_bench_b.err; echo "bench rc=$?"
+tail -3 gpurun_out/s2_gputest_e.log
