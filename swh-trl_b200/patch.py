@@ -11,7 +11,30 @@ from __future__ import annotations
 import sys
 import types
 
+import torch
+
 from . import functional, grpo, masks
+
+def _ref_dtype_binding(name: str, original):
+    """The binding ``patch_trl`` installs for ``selective_log_softmax`` / ``entropy_from_logits``: the reference's dtype
+    contract (utils.py:1455-1461 returns the logits dtype, bf16 for a bf16 model — DPO / KTO / ORPO callers depend on
+    it), and CPU or fp64 inputs (eval utilities, unit tests) go to the reference's own function instead of raising.
+    The GRPO path does not come through here: ``grpo.compute_loss`` keeps fp32 log-probs."""
+    ours = getattr(functional, name)
+
+    def bound(logits, *args, **kwargs):
+        if not logits.is_cuda or logits.dtype == torch.float64:
+            return original(logits, *args, **kwargs)
+        kwargs.setdefault("out_dtype", logits.dtype)
+        return ours(logits, *args, **kwargs)
+
+    bound.__name__ = bound.__qualname__ = name
+    bound.__doc__ = ours.__doc__
+    bound._b200trl_patched = True
+    return bound
+
+
+_REF_DTYPE = ("selective_log_softmax", "entropy_from_logits")
 
 _FUNCTIONS = {
     "selective_log_softmax": functional.selective_log_softmax,
@@ -33,9 +56,9 @@ def patch_module(mod: types.ModuleType) -> list:
     ns = vars(mod)
     for name, fn in _FUNCTIONS.items():
         cur = ns.get(name)
-        if cur is not None and callable(cur) and cur is not fn:
+        if cur is not None and callable(cur) and cur is not fn and not getattr(cur, "_b200trl_patched", False):
             setattr(mod, "_trl_original_" + name, cur)
-            setattr(mod, name, fn)
+            setattr(mod, name, _ref_dtype_binding(name, cur) if name in _REF_DTYPE else fn)
             done.append(name)
     # PPO / RLOO have no seam: their train() is rewritten in place (train_patch.py); a reference whose train() does not
     # contain the expected blocks raises TrainPatchError rather than running half-patched

@@ -26,10 +26,10 @@ report = S.patch_trl()
 ppo, rloo, grpo_mod = (mods["trl.trainer.ppo_trainer"], mods["trl.trainer.rloo_trainer"], mods["trl.trainer.grpo_trainer"])
 out = {
     "report": report,
-    "ppo_sls_is_ours": ppo.selective_log_softmax is functional.selective_log_softmax,
+    "ppo_sls_is_ours": getattr(ppo.selective_log_softmax, "_b200trl_patched", False),
     "ppo_masked_whiten_is_ours": ppo.masked_whiten is functional.masked_whiten,
     "ppo_first_true_is_ours": ppo.first_true_indices is masks.first_true_indices,
-    "rloo_sls_is_ours": rloo.selective_log_softmax is functional.selective_log_softmax,
+    "rloo_sls_is_ours": getattr(rloo.selective_log_softmax, "_b200trl_patched", False),
     "grpo_compute_loss_is_ours": grpo_mod.GRPOTrainer._compute_loss is grpo.compute_loss,
     "grpo_liger_is_ours": grpo_mod.LigerFusedLinearGRPOLoss is S.B200FusedLinearGRPOLoss,
     "ppo_train_patched": bool(getattr(ppo.PPOTrainer, "_b200_train_patched", False)),

@@ -1276,3 +1276,28 @@ def test_half_branch_output_dtype(S):
         assert (got == exact).float().mean().item() > 0.99
         seen += 1
     assert seen >= 3
+
+
+def test_patched_leaf_binding_keeps_reference_dtype(S):
+    """Under ``patch_trl()`` the leaf bindings follow the reference's dtype contract (utils.py:1455-1461: bf16 logits ->
+    bf16 log-probs; DPO / KTO / ORPO callers rely on it), while CPU and fp64 inputs reach the reference's own function;
+    ``S.selective_log_softmax`` itself (what the GRPO path uses) stays fp32."""
+    from swh_trl_b200 import patch as P
+
+    calls = []
+
+    def reference(logits, index):
+        calls.append(logits.dtype)
+        return torch.gather(logits.log_softmax(-1), -1, index.unsqueeze(-1)).squeeze(-1)
+
+    bound = P._ref_dtype_binding("selective_log_softmax", reference)
+    case = next(c for c in load_golden("logprob_entropy.pt") if c["dtype"] == torch.bfloat16)
+    logits, ids = _regen(case).to(DEV), case["ids"].to(DEV)
+    got = bound(logits, ids)
+    assert got.dtype == torch.bfloat16 and not calls
+    assert torch.equal(got, S.selective_log_softmax(logits, ids, out_dtype=torch.bfloat16))
+    assert S.selective_log_softmax(logits, ids).dtype == torch.float32
+    assert bound(logits.double(), ids).dtype == torch.float64 and calls == [torch.float64]
+    assert bound(logits.float().cpu(), ids.cpu()).dtype == torch.float32 and len(calls) == 2
+    ent = P._ref_dtype_binding("entropy_from_logits", lambda x, chunk_size=1: None)(logits)
+    assert ent.dtype == torch.bfloat16

@@ -57,7 +57,7 @@ def test_schedule_choice():
 def test_patch_trl_rebinds_every_importer():
     """Ten reference modules bind selective_log_softmax at import time."""
     def orig(logits, index):
-        return None
+        return "reference"
     pkg = types.ModuleType("faketrl")
     utils = types.ModuleType("faketrl.trainer.utils")
     utils.selective_log_softmax = orig
@@ -85,8 +85,12 @@ def test_patch_trl_rebinds_every_importer():
     finally:
         for k in mods:
             sys.modules.pop(k)
-    assert utils.selective_log_softmax is S.selective_log_softmax
-    assert grpo_mod.selective_log_softmax is S.selective_log_softmax
+    # the leaf bindings keep the reference's dtype contract (out_dtype defaults to the logits dtype) and hand CPU /
+    # fp64 inputs to the reference's own function instead of raising
+    for bound in (utils.selective_log_softmax, grpo_mod.selective_log_softmax, utils.entropy_from_logits):
+        assert bound._b200trl_patched and bound is not orig
+        assert bound(torch.zeros(2, 4), torch.zeros(2, dtype=torch.long)) == "reference"
+    assert utils._trl_original_selective_log_softmax is orig
     assert grpo_mod.get_high_entropy_mask is S.get_high_entropy_mask
     assert core.masked_whiten is S.masked_whiten
     assert GRPOTrainer._compute_loss is S.compute_loss
