@@ -119,7 +119,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// B200TRL_K1_WAIT_HINT (ns): suspend-time hint of mbarrier.try_wait -- the warp sleeps in hardware until the phase
+// completes (or the hint expires) instead of re-issuing the probe every ~30 cycles.
+#ifndef B200TRL_K1_WAIT_HINT
+#define B200TRL_K1_WAIT_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if B200TRL_K1_WAIT_HINT > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(B200TRL_K1_WAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -131,6 +149,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -312,6 +331,29 @@ __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t 
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
+// ---- skewed rows (SKEW): the row does not start on a 16-byte boundary (vocab % 8 != 0, e.g. GPT-2's 50 257, or a
+// strided view).  The bulk copies fetch the 16-byte-aligned span that CONTAINS the slice, so the slice starts `h`
+// elements (0..7) into the first vector and the last vector may end early; the elements outside the slice belong to
+// the neighbouring rows (or lie past the tensor, inside the same 16-byte granule: never a fault) and are replaced by a
+// large negative logit before any arithmetic.  Only the first and the last vector of a slice are affected.
+constexpr uint32_t kNegBf = 0xF149u;  // bf16(-1e30): 2^(x c - m) == 0 and 0 * (x c - m) == -0 for any sane inv_T
+__device__ __forceinline__ uint4 mask_vec(const uint4& v, int lo, int hi) {  // keep elements [lo, hi) of the 8
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (2 * i < lo || 2 * i >= hi) w[i] = (w[i] & 0xffff0000u) | kNegBf;
+        if (2 * i + 1 < lo || 2 * i + 1 >= hi) w[i] = (w[i] & 0x0000ffffu) | (kNegBf << 16);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// elements [lo, hi) of one 16-byte vector, as 2-byte stores (the rest of the granule is not ours to write)
+__device__ __forceinline__ void st_global_edge(uint4* p, const uint4& v, int lo, int hi) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    unsigned short* q = reinterpret_cast<unsigned short*>(p);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (e >= lo && e < hi) q[e] = static_cast<unsigned short>((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+}
 // streaming 16-byte store: dlogits are not read again by this kernel
 __device__ __forceinline__ void st_global_cs(uint4* p, const uint4& v) {
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -341,6 +383,19 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+#if B200TRL_K1_WAIT_HINT > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_U:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE_U;\n\t"
+        "bra WAIT_LOOP_U;\n\t"
+        "WAIT_DONE_U:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(B200TRL_K1_WAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -352,6 +407,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
         "}" ::"r"(bar),
         "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -530,10 +586,11 @@ struct Cursor {
 };
 
 // FAST: 0 = generic consumer code; 1 = FusedConsumer
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST>
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST, bool SKEW>
 __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
     k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag, const int l2_prefetch) {
     static_assert(FAST == 0 || (HAS_FWD && HAS_BWD && DUAL && DIRECT), "the fast consumer is the fused pass");
+    static_assert(!SKEW || (FAST == 0 && (DIRECT || !HAS_BWD)), "skewed rows: generic consumers, dlogits from registers");
     constexpr int kConsumers = NC;
     constexpr int kWarps = NC / 32;
     // chunk geometry of this instantiation: 512 and 256 consumers use 16 KB chunks (2 / 4 vectors per thread),
@@ -558,8 +615,17 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
     const int64_t e_begin = static_cast<int64_t>(crank) * slice_elems;
     const int64_t e_end = min(a.vocab, e_begin + slice_elems);
     const int64_t my_elems = max(e_end - e_begin, (int64_t)0);
-    const int my_bytes = static_cast<int>(my_elems * 2);
+    // SKEW: the aligned span of a slice is up to 7 elements longer at either end; C covers the longest one and a
+    // row's last chunk may turn out empty (the DMA lane then completes its barrier without a copy)
+    const int my_bytes = SKEW ? static_cast<int>(((my_elems + 14) >> 3) << 4) : static_cast<int>(my_elems * 2);
     const int C = (my_bytes + kChunkBytes - 1) / kChunkBytes;  // chunks per row in this CTA
+    // head skew of a row's slice (elements between the 16-byte boundary below it and its first element) and the
+    // number of 16-byte vectors of its aligned span
+    const uint64_t base_elem = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(a.logits) >> 1);
+    auto row_head = [&](int64_t row) -> int {
+        return SKEW ? static_cast<int>((base_elem + static_cast<uint64_t>(logits_offset(a, row) + e_begin)) & 7u) : 0;
+    };
+    auto span_vecs = [&](int h) -> int { return SKEW ? static_cast<int>((h + my_elems + 7) >> 3) : (my_bytes >> 4); };
     const int n_my_rows =
         (a.n_rows > first_row) ? static_cast<int>((a.n_rows - first_row + row_step - 1) / row_step) : 0;
     const int spare = max(num_slots - C, 0);
@@ -605,7 +671,13 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             bool l_masked = masked_at(0), l_masked_next = masked_at(1);
             auto issue_load = [&]() {
                 const int64_t row = first_row + static_cast<int64_t>(l_row) * row_step;
-                const uint32_t bytes = static_cast<uint32_t>(l_c == C - 1 ? last_bytes : kChunkBytes);
+                uint32_t bytes = static_cast<uint32_t>(l_c == C - 1 ? last_bytes : kChunkBytes);
+                int l_h = 0;
+                if (SKEW) {  // this row's span: the chunk may be short or empty
+                    l_h = row_head(row);
+                    const int rest = span_vecs(l_h) * 16 - l_c * kChunkBytes;
+                    bytes = static_cast<uint32_t>(min(max(rest, 0), kChunkBytes));
+                }
                 if (l2_prefetch && l_c == 0 && l_row + 1 < n_my_rows && !(SKIP && l_masked_next)) {
                     // pull the NEXT row's slice into L2 now: its shared-memory slots only free up while this row is
                     // being written back, and a bulk load that hits L2 lands in a fraction of the HBM queueing time
@@ -614,13 +686,13 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         bulk_prefetch_l2(nxt + static_cast<int64_t>(cc) * kChunkElems,
                                          static_cast<uint32_t>(cc == C - 1 ? last_bytes : kChunkBytes));
                 }
-                if (SKIP && l_masked) {
+                if ((SKIP && l_masked) || (SKEW && bytes == 0)) {
                     mbar_arrive(&sm.full_bar[l_slot]);  // nothing to fetch: the slot is "full" right away
                 } else {
                     tr.ev(21, l_row, l_c);
                     mbar_expect_tx(&sm.full_bar[l_slot], bytes);
                     bulk_load(slots + static_cast<size_t>(l_slot) * kChunkBytes,
-                              logits + logits_offset(a, row) + e_begin + static_cast<int64_t>(l_c) * kChunkElems, bytes,
+                              logits + logits_offset(a, row) + e_begin - l_h + static_cast<int64_t>(l_c) * kChunkElems, bytes,
                               &sm.full_bar[l_slot], policy);
                 }
                 ++k_next;
@@ -756,12 +828,13 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         const float gp = token_grad(a, rs, st.logp) * a.inv_temp;
                         const int64_t e_id = rs.id - e_begin;
                         const bool mine = (e_id >= 0 && e_id < my_elems);
+                        const int64_t s_id = e_id + row_head(row);  // position inside the aligned span
                         RowResult rr;
                         rr.lse2 = st.lse2;
                         rr.ng = -gp;
                         rr.patch = fmaf(-expf(st.logp), gp, gp);  // g' * (1 - p_id)
-                        rr.id_chunk = mine ? static_cast<int>(e_id / kChunkElems) : -1;
-                        rr.id_elem = mine ? static_cast<int>(e_id % kChunkElems) : -1;
+                        rr.id_chunk = mine ? static_cast<int>(s_id / kChunkElems) : -1;
+                        rr.id_elem = mine ? static_cast<int>(s_id % kChunkElems) : -1;
                         rr.id_vec = mine ? (rr.id_elem >> 3) : -1;
                         rr.pad0 = rr.pad1 = 0;
                         sm.result[par] = rr;
@@ -865,6 +938,9 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         tr.init(a, &sm.trace, 0, tid == 0);
         int t_row = 0;  // row whose chunk the next fwd_chunk call folds (tracing only)
 
+        // SKEW: head skew / span of the row being folded (f_*) and of the row whose dlogits are being written (b_*)
+        int f_h = 0, f_nvec = 0;
+        const int tail_keep_of_h0 = static_cast<int>(my_elems & 7);  // (h + my_elems) & 7 with h added per row
         auto fwd_chunk = [&](Acc& acc, int cidx, bool skip) {
             tr.ev(1, t_row, cidx);
             mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
@@ -872,6 +948,35 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
             if (SKIP && skip) {
                 // masked row: nothing was loaded into this slot
+            } else if (SKEW) {
+                const int v0 = cidx * kChunkVecs;
+                const int n_here = min(max(f_nvec - v0, 0), kChunkVecs);
+                const int keep = (f_h + tail_keep_of_h0) & 7;  // valid elements of the span's last vector (0: all)
+                const bool edge = (cidx == 0 && f_h != 0) || (keep != 0 && f_nvec - 1 >= v0 && f_nvec - 1 < v0 + kChunkVecs);
+                if (n_here == kChunkVecs) {
+                    uint4 v[kVpt];
+#pragma unroll
+                    for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+                    if (edge) {  // a full chunk holding the span's first or last vector: only that vector is masked
+#pragma unroll
+                        for (int k = 0; k < kVpt; ++k) {
+                            const int gi = v0 + tid + k * kConsumers;
+                            const int lo = (gi == 0) ? f_h : 0;
+                            const int hi = (gi == f_nvec - 1 && keep != 0) ? keep : 8;
+                            if (lo != 0 || hi != 8) v[k] = mask_vec(v[k], lo, hi);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kVpt; k += 2) acc_vec2(acc, v[k], v[k + 1], c, c2);
+                } else {
+                    for (int v = tid; v < n_here; v += kConsumers) {
+                        uint4 x = sv[v];
+                        const int lo = (v0 + v == 0) ? f_h : 0;
+                        const int hi = (v0 + v == f_nvec - 1 && keep != 0) ? keep : 8;
+                        if (lo != 0 || hi != 8) x = mask_vec(x, lo, hi);
+                        acc_vec(acc, x, c, c2);
+                    }
+                }
             } else if (cidx != C - 1 || last_bytes == kChunkBytes) {
                 uint4 v[kVpt];
 #pragma unroll
@@ -902,6 +1007,10 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             return SKIP && r < n_my_rows && row_is_masked(a, first_row + static_cast<int64_t>(r) * row_step);
         };
         bool cur_masked = masked_at(0), nxt_masked = masked_at(1);
+        if (SKEW && n_my_rows > 0) {
+            f_h = row_head(first_row);
+            f_nvec = span_vecs(f_h);
+        }
         if (HAS_FWD && n_my_rows > 0) {
             for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, cur_masked);
         }
@@ -910,9 +1019,15 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             const int par = i & 1;
             const uint32_t rpar = static_cast<uint32_t>((i >> 1) & 1);
             const bool nn_masked = masked_at(i + 2);  // prefetched: consumed two iterations later
+            const int b_h = SKEW ? row_head(row) : 0;
+            const int b_nvec = span_vecs(b_h);
 
             if (HAS_FWD) {
                 t_row = i;
+                if (SKEW) {
+                    f_h = b_h;
+                    f_nvec = b_nvec;
+                }
                 for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx, cur_masked);
                 const Partial p = partial_warp_reduce_fast(acc_to_partial(acc));
                 tr.ev(4, i, 0);
@@ -925,6 +1040,10 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 acc = acc_empty();
                 t_row = i + 1;
                 if (i + 1 < n_my_rows) {
+                    if (SKEW) {
+                        f_h = row_head(row + row_step);
+                        f_nvec = span_vecs(f_h);
+                    }
                     for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, nxt_masked);
                 }
             }
@@ -946,12 +1065,13 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         const float gp = token_grad(a, rs, logp) * a.inv_temp;
                         const int64_t e_id = rs.id - e_begin;
                         const bool mine = (e_id >= 0 && e_id < my_elems);
+                        const int64_t s_id = e_id + row_head(row);
                         RowResult w;
                         w.lse2 = lse2;
                         w.ng = -gp;
                         w.patch = fmaf(-expf(logp), gp, gp);
-                        w.id_chunk = mine ? static_cast<int>(e_id / kChunkElems) : -1;
-                        w.id_elem = mine ? static_cast<int>(e_id % kChunkElems) : -1;
+                        w.id_chunk = mine ? static_cast<int>(s_id / kChunkElems) : -1;
+                        w.id_elem = mine ? static_cast<int>(s_id % kChunkElems) : -1;
                         w.id_vec = mine ? (w.id_elem >> 3) : -1;
                         w.pad0 = w.pad1 = 0;
                         sm.result[par] = w;
@@ -963,14 +1083,51 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 const uint64_t ng2 = pack2(rr.ng, rr.ng);
                 const bool zero_row = (rr.ng == 0.f);
                 const bool patch_mine = (rr.id_vec >= 0) && ((rr.id_vec % kConsumers) == tid);
-                __nv_bfloat16* grow = nullptr;  // DIRECT: this CTA's slice of the dlogits row
-                if (DIRECT) grow = dlogits + dlogits_offset(a, row) + e_begin;
+                __nv_bfloat16* grow = nullptr;  // DIRECT: this CTA's slice of the dlogits row (SKEW: its aligned span)
+                if (DIRECT) grow = dlogits + dlogits_offset(a, row) + e_begin - b_h;
+                const int b_keep = SKEW ? ((b_h + tail_keep_of_h0) & 7) : 0;
                 for (int cidx = 0; cidx < C; ++cidx) {
                     if (!HAS_FWD) mbar_wait(&sm.full_bar[bcur.slot], bcur.par);
                     uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(bcur.slot) * kChunkBytes);
-                    const bool full = (cidx != C - 1 || last_bytes == kChunkBytes);
-                    const int nvec = full ? kChunkVecs : (last_bytes >> 4);
-                    if (DIRECT) {
+                    bool full = (cidx != C - 1 || last_bytes == kChunkBytes);
+                    int nvec = full ? kChunkVecs : (last_bytes >> 4);
+                    if (SKEW) {
+                        const int v0 = cidx * kChunkVecs;
+                        nvec = min(max(b_nvec - v0, 0), kChunkVecs);
+                        const bool edge = (cidx == 0 && b_h != 0) ||
+                                          (b_keep != 0 && b_nvec - 1 >= v0 && b_nvec - 1 < v0 + kChunkVecs);
+                        full = (nvec == kChunkVecs) && !edge;
+                    }
+                    if (SKEW && DIRECT && !full) {
+                        // a chunk holding the first or the last vector of the span (or a short one): the edge vectors
+                        // leave element by element, everything else as whole vectors
+                        uint4* gv = reinterpret_cast<uint4*>(grow + static_cast<int64_t>(cidx) * kChunkElems);
+                        const int v0 = cidx * kChunkVecs;
+                        auto put = [&](int v, const uint4& o) {
+                            const int lo = (v0 + v == 0) ? b_h : 0;
+                            const int hi = (v0 + v == b_nvec - 1 && b_keep != 0) ? b_keep : 8;
+                            if (lo != 0 || hi != 8)
+                                st_global_edge(gv + v, o, lo, hi);
+                            else
+                                st_global_cs(gv + v, o);
+                        };
+                        if (nvec == kChunkVecs && !zero_row) {
+                            uint4 v[kVpt];
+#pragma unroll
+                            for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
+#pragma unroll
+                            for (int k = 0; k < kVpt; ++k) put(tid + k * kConsumers, grad_vec(v[k], c2, nl2, ng2));
+                        } else {
+                            for (int v = tid; v < nvec; v += kConsumers)
+                                put(v, zero_row ? make_uint4(0u, 0u, 0u, 0u) : grad_vec(sv[v], c2, nl2, ng2));
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
+                        }
+                        if (!zero_row && patch_mine && cidx == rr.id_chunk)
+                            reinterpret_cast<__nv_bfloat16*>(gv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                    } else if (DIRECT) {
                         // gradients go straight from registers to global memory (coalesced 16-byte stores); the slot is
                         // released as soon as every warp has READ it, so its refill overlaps this chunk's arithmetic
                         uint4* gv = reinterpret_cast<uint4*>(grow + static_cast<int64_t>(cidx) * kChunkElems);
@@ -1039,20 +1196,23 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// g_skew_extra: 16 when the rows are skewed (their aligned span is up to 14 bytes longer than the slice); set by
+// pick_geom for the duration of one decision (host side, under the caller's serial use of the API per thread)
+thread_local int g_skew_extra = 0;
 int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     static const int forced = env_int("B200TRL_K1_CLUSTER", 0);  // tuning knob: force a (larger) cluster size
     for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
         if (cs < forced) continue;
         const int64_t slice = ((vocab + cs - 1) / cs + 7) & ~int64_t(7);
-        const int64_t chunks = (slice * 2 + chunk_bytes - 1) / chunk_bytes;
+        const int64_t chunks = (slice * 2 + g_skew_extra + chunk_bytes - 1) / chunk_bytes;
         if (chunks <= num_slots - 1 || (chunks <= num_slots && cs == kMaxCluster)) return cs;
     }
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST>
+template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST, bool SKEW = false>
 int launch_mode_f(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP, FAST>;
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP, FAST, SKEW>;
     constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
     static_assert(chunk_bytes_for(NC) % (NC * 16) == 0, "a full chunk must give every consumer the same vector count");
     constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
@@ -1111,8 +1271,21 @@ int launch_mode_f(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
 }
 
 // The fused pass with direct stores and two chains runs on FusedConsumer (B200TRL_K1_FAST=0: generic consumer code).
+bool rows_skewed(const K1Args& a) {
+    return a.vocab % 8 != 0 || a.row_stride % 8 != 0 || a.batch_stride % 8 != 0 ||
+           (reinterpret_cast<uintptr_t>(a.logits) & 15) != 0;
+}
+
 template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP>
 int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+    // skewed rows (vocab % 8 != 0 ...): generic consumers with masked edge vectors, dlogits straight from registers
+    if constexpr (DUAL && (DIRECT || !Bk)) {
+        if (rows_skewed(a)) return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 0, true>(a, cs, num_slots, stream);
+    }
+    if (rows_skewed(a)) {
+        set_error("k1_resident: skewed rows need the dual-chain, direct-store variant");
+        return B200TRL_E_UNSUPPORTED;
+    }
 #ifndef B200TRL_K1_TRACE
     if constexpr (F && Bk && DUAL && DIRECT) {
         static const int fast = env_int("B200TRL_K1_FAST", 1);
@@ -1141,8 +1314,9 @@ Mode mode_of(const K1Args& a) {
     return (fwd && bwd) ? M_FUSED : (fwd ? M_FWD : M_BWD);
 }
 
-Geom pick_geom(int64_t vocab, Mode m) {
+Geom pick_geom(int64_t vocab, Mode m, bool skew = false) {
     static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense, 4 mid
+    g_skew_extra = skew ? 16 : 0;
     Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
     Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
     Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768)), kDenseSlots, 768};
@@ -1237,7 +1411,7 @@ template <bool F, bool Bk, bool DUAL, int NC>
 int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     if (!Bk) return launch_mode_p<F, Bk, DUAL, NC, false>(a, cs, num_slots, stream);
     static const int direct_env = env_int("B200TRL_K1_DIRECT", -1);
-    const bool direct = direct_env < 0 ? (F && Bk) : direct_env != 0;
+    const bool direct = rows_skewed(a) || (direct_env < 0 ? (F && Bk) : direct_env != 0);
     return direct ? launch_mode_p<F, Bk, DUAL, NC, Bk>(a, cs, num_slots, stream)
                   : launch_mode_p<F, Bk, DUAL, NC, false>(a, cs, num_slots, stream);
 }
@@ -1247,7 +1421,7 @@ int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
     // measured on B200 (tools/k1_sweep.sh): two accumulation chains with one reference-point check per vector pair
     // help every mode (forward-only +3 %, fused +2..4 %) now that the row hand-off no longer bounds the fused pass
     static const int dual_env = env_int("B200TRL_K1_DUAL", -1);
-    const bool dual = dual_env != 0;
+    const bool dual = dual_env != 0 || rows_skewed(a);
     if (g.nc == 256)
         return dual ? launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream)
                     : launch_mode_t<F, Bk, false, 256>(a, g.cs, g.slots, stream);
@@ -1265,14 +1439,20 @@ int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
 
 bool k1_resident_supported(const K1Args& a, int dtype) {
     if (dtype != B200TRL_BF16) return false;
-    if (a.vocab % 8 != 0 || a.row_stride % 8 != 0 || a.batch_stride % 8 != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(a.logits) & 15) != 0) return false;
-    if (a.dlogits && ((reinterpret_cast<uintptr_t>(a.dlogits) & 15) != 0 || a.dl_row_stride % 8 != 0 ||
-                      a.dl_batch_stride % 8 != 0))
-        return false;
+    static const int allow_skew = env_int("B200TRL_K1_SKEW", 1);  // 0: skewed rows go to the row kernel (A/B runs)
+    const bool skew = rows_skewed(a);
+    if (skew && !allow_skew) return false;
+    if ((reinterpret_cast<uintptr_t>(a.logits) & 1) != 0) return false;
+    if (a.dlogits) {
+        // every dlogits row must sit at the same offset inside its 16-byte granule as the logits row it mirrors
+        // (true for `empty_like(logits)` and for the in-place form): the interior vectors are then aligned stores
+        const uintptr_t la = reinterpret_cast<uintptr_t>(a.logits), da = reinterpret_cast<uintptr_t>(a.dlogits);
+        if (((la ^ da) & 15) != 0 || (a.dl_row_stride - a.row_stride) % 8 != 0) return false;
+        if (a.rows_per_batch != 0 && (a.dl_batch_stride - a.batch_stride) % 8 != 0) return false;
+    }
     if (a.vocab * 2 < 2 * kChunkBytes) return false;  // tiny rows: per-row overheads dominate, use the row kernel
     if (a.vocab * 2 > (int64_t(1) << 30)) return false;  // slice bytes are kept in 32-bit counters
-    return pick_geom(a.vocab, mode_of(a)).cs != 0;
+    return pick_geom(a.vocab, mode_of(a), skew).cs != 0;
 }
 
 // AUTO policy: whenever this kernel can take the call it is the faster one.  Measured fused / forward-only against
@@ -1284,8 +1464,8 @@ bool k1_resident_preferred(const K1Args& a, int dtype) { return k1_resident_supp
 // resident kernel cannot take the vocabulary in that mode (0 forward-only, 1 backward-only, 2 fused)
 void k1_resident_geometry(int64_t vocab, int mode, int32_t out[4]) {
     out[0] = out[1] = out[2] = out[3] = 0;
-    if (vocab <= 0 || vocab % 8 != 0 || vocab * 2 < 2 * kChunkBytes || mode < 0 || mode > 2) return;
-    const Geom g = pick_geom(vocab, mode == 0 ? M_FWD : (mode == 1 ? M_BWD : M_FUSED));
+    if (vocab <= 0 || vocab * 2 < 2 * kChunkBytes || mode < 0 || mode > 2) return;
+    const Geom g = pick_geom(vocab, mode == 0 ? M_FWD : (mode == 1 ? M_BWD : M_FUSED), vocab % 8 != 0);
     if (!g.cs) return;
     out[0] = g.nc;
     out[1] = g.cs;
@@ -1296,7 +1476,7 @@ void k1_resident_geometry(int64_t vocab, int mode, int32_t out[4]) {
 int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
     if (a.n_rows == 0) return B200TRL_OK;
     const Mode m = mode_of(a);
-    const Geom g = pick_geom(a.vocab, m);
+    const Geom g = pick_geom(a.vocab, m, rows_skewed(a));
     B200TRL_REQUIRE(g.cs != 0, B200TRL_E_UNSUPPORTED, "k1_resident: vocab %lld too large for an 8-CTA cluster",
                     (long long)a.vocab);
     if (m == M_FUSED) return launch_mode<true, true>(a, g, stream);

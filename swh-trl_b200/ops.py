@@ -140,6 +140,31 @@ def rows_view(logits: torch.Tensor, rows_per_batch: Optional[int] = None) -> Row
     return Rows(logits.contiguous(), n, V, V)
 
 
+def alloc_dlogits(r: Rows, shape):
+    """``(dlogits, dl_row_stride, dl_batch_stride)`` for logits addressed as ``r``.
+
+    Normally a contiguous tensor.  When the bf16 rows do not start on 16-byte boundaries (vocab % 8 != 0 as in GPT-2's
+    50 257, or a misaligned view) the resident kernel needs every dlogits row at the same offset inside its 16-byte
+    granule as the logits row it mirrors (its interior vectors are then aligned stores and only the two edge vectors of
+    a row go out element by element), so the buffer copies the logits' strides modulo 8 elements: at most 7 elements
+    of padding per row / per batch, returned as a strided view of the requested shape."""
+    x, V = r.t, r.V
+    skew = x.dtype == torch.bfloat16 and bool(V % 8 or r.row_stride % 8 or r.batch_stride % 8 or x.data_ptr() % 16)
+    if not skew or len(shape) not in (2, 3) or r.n == 0:
+        return torch.empty(shape, dtype=x.dtype, device=x.device), V, 0
+    e0 = (x.data_ptr() // 2) % 8
+    rs = V + ((r.row_stride - V) % 8)
+    if r.rows_per_batch:
+        nb = r.n // r.rows_per_batch
+        bs_min = r.rows_per_batch * rs
+        bs = bs_min + ((r.batch_stride - bs_min) % 8)
+        buf = torch.empty(e0 + nb * bs + 8, dtype=x.dtype, device=x.device)
+        return buf.as_strided(tuple(shape), (bs, rs, 1), e0), rs, bs
+    buf = torch.empty(e0 + r.n * rs + 8, dtype=x.dtype, device=x.device)
+    strides = (rs, 1) if len(shape) == 2 else (shape[1] * rs, rs, 1)
+    return buf.as_strided(tuple(shape), strides, e0), rs, 0
+
+
 def make_cfg(beta: float, epsilon_low: float, epsilon_high: float, delta: Optional[float], loss_type: str,
              importance_sampling_level: str, max_completion_length: int, grad_scale: float = 1.0) -> GrpoCfg:
     """Pack GRPO hyper-parameters; unknown enums raise the reference's ValueErrors (grpo_trainer.py:2106-2109, 2137)."""
@@ -214,11 +239,11 @@ def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: t
     r = rows_view(logits)
     x, n, V = r.t, r.n, r.V
     idx = ids.to(torch.int64).contiguous()
-    out = torch.empty(logits.shape, dtype=x.dtype, device=x.device)
+    out, dl_rs, dl_bs = alloc_dlogits(r, tuple(logits.shape))
     if n:
         check(lib.b200trl_logprob_bwd(_ptr(x), _DTYPES[x.dtype], n, V, r.row_stride, r.rows_per_batch, r.batch_stride,
                                       _ptr(idx), float(inv_temperature), k.f32(lse, "lse"), k.f32(g, "g"),
-                                      _ptr(out), V, 0, _stream(x)), "logprob_bwd")
+                                      _ptr(out), dl_rs, dl_bs, _stream(x)), "logprob_bwd")
         _count()
     return out
 
@@ -250,7 +275,7 @@ def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages
     lse = torch.empty(B, T, dtype=torch.float32, device=x.device)
     dl, dl_rs, dl_bs = None, V, 0
     if want_grad:
-        dl = dlogits_out if dlogits_out is not None else torch.empty((B, T, V), dtype=x.dtype, device=x.device)
+        dl = dlogits_out if dlogits_out is not None else alloc_dlogits(r, (B, T, V))[0]
         d = collapse_rows2(tuple(dl.shape), tuple(dl.stride()))
         if d is None or (d[1] not in (0, T)) or dl.dtype != x.dtype:
             raise ValueError("dlogits_out must be a [B,T,V] view with at most (batch, row) strides and the logits dtype")
@@ -384,11 +409,11 @@ def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advanta
     nlp = torch.empty(mb, T, dtype=torch.float32, device=dev)
     ent = torch.empty(mb, T, dtype=torch.float32, device=dev)
     lse = torch.empty(mb, T, dtype=torch.float32, device=dev)
-    dl = torch.empty((mb, T, V), dtype=x.dtype, device=dev) if want_grad else None
+    dl, dl_rs, dl_bs = alloc_dlogits(r, (mb, T, V)) if want_grad else (None, V, 0)
     check(lib.b200trl_ppo_fused_fwd_bwd(_ptr(x), _DTYPES[x.dtype], mb, T, V, r.row_stride, r.batch_stride, _ptr(idx),
                                         _ptr(sl), k.f32(old_logprobs, "old_logprobs"),
                                         k.f32(advantages, "advantages"), float(inv_temperature), float(cliprange),
-                                        float(grad_scale), _ptr(nlp), _ptr(ent), _ptr(lse), _ptr(dl), V, 0,
+                                        float(grad_scale), _ptr(nlp), _ptr(ent), _ptr(lse), _ptr(dl), dl_rs, dl_bs,
                                         _stream(x)), "ppo_fused_fwd_bwd")
     _count()
     return nlp, ent, lse, dl

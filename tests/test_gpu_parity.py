@@ -52,7 +52,7 @@ def _paths(S, logits):
     """K1 implementations applicable to this tensor."""
     out = [S.K1_ROW]
     V = logits.shape[-1]
-    if logits.dtype == torch.bfloat16 and V % 8 == 0 and V * 2 >= 32768:
+    if logits.dtype == torch.bfloat16 and V * 2 >= 32768:  # any alignment: skewed rows run with masked edge vectors
         out.append(S.K1_RESIDENT)
     return out
 
@@ -1301,3 +1301,93 @@ def test_patched_leaf_binding_keeps_reference_dtype(S):
     assert bound(logits.float().cpu(), ids.cpu()).dtype == torch.float32 and len(calls) == 2
     ent = P._ref_dtype_binding("entropy_from_logits", lambda x, chunk_size=1: None)(logits)
     assert ent.dtype == torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ skewed rows
+@pytest.mark.parametrize("V,layout", [
+    (50257, "contiguous"),   # GPT-2: row = 100 514 B, the head skew walks through all eight values; one 640-consumer CTA
+    (32003, "contiguous"),   # twin geometry (2 CTAs / SM)
+    (151937, "contiguous"),  # 2-CTA cluster: BOTH slices start and end inside a 16-byte granule
+    (151943, "offset"),      # base pointer 6 bytes past a 16-byte boundary, padded rows
+    (16391, "offset"),       # smallest rows the resident kernel takes
+    (65536, "offset"),       # vocab % 8 == 0 but a misaligned view: only the skew, no ragged tail
+])
+def test_skewed_rows_on_the_resident_kernel(S, V, layout):
+    """V % 8 != 0 (GPT-2's 50 257, the reference's tiny test models) and misaligned views: the resident kernel fetches the
+    16-byte-aligned span around every row slice and masks the neighbours' elements in the first / last vector
+    (k1_resident.cu, SKEW).  All three modes against the oracle and the row kernel; the logits and dlogits buffers
+    carry sentinels in every gap (margins, row padding) that must survive bit for bit."""
+    from swh_trl_b200 import ops
+    B, T = 2, 9
+    g = torch.Generator().manual_seed(V)
+    logits = (torch.randn(B, T, V, generator=g) * 2).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    ids[0, 0], ids[0, 1], ids[1, 0] = 0, V - 1, V // 2 + 1   # the edge elements of the row / of a cluster slice
+    sent = torch.tensor(-1.2345e30, dtype=torch.bfloat16).to(DEV)
+    margin = 4096
+    pad = 0 if layout == "contiguous" else 13
+    off = 0 if layout == "contiguous" else 3
+    stride = V + pad
+    n = B * T * stride
+
+    def boxed():
+        buf = torch.full((n + 2 * margin,), sent.item(), dtype=torch.bfloat16, device=DEV)
+        view = buf[margin + off:margin + off + n].view(B, T, stride)[:, :, :V]
+        return buf, view
+
+    def check_sentinels(buf, what):
+        assert bool((buf[:margin + off] == sent).all()) and bool((buf[margin + off + n:] == sent).all()), what
+        if pad:
+            assert bool((buf[margin + off:margin + off + n].view(B, T, stride)[:, :, V:] == sent).all()), what
+
+    src, x = boxed()
+    x.copy_(logits.to(DEV))
+    idx = ids.to(DEV)
+    mask = torch.ones(B, T, dtype=torch.int32, device=DEV)
+    mask[1, -3:] = 0
+    adv = torch.tensor([1.5, -0.7], device=DEV)
+    m32, rc, tot = ops.mask_stats(mask)
+    cfg = ops.make_cfg(0.04, 0.2, 0.2, None, "bnpo", "token", T)
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax(logits.float(), ids)
+    old = (lp0 + torch.randn(B, T, generator=g) * 0.3).to(DEV)
+    ref = (lp0 + torch.randn(B, T, generator=g) * 0.1).to(DEV)
+    gtok = (torch.randn(B, T, generator=g) * 1e-2)
+    gtok[0, 2] = 0.0  # a zero-gradient row: not read, its dlogits are zeros
+    gtok = gtok.to(DEV)
+    want_ent = O.entropy_from_logits(logits.double()).float()
+
+    res = {}
+    for name, path in (("row", S.K1_ROW), ("resident", S.K1_RESIDENT)):
+        prev = S.set_k1_path(path)
+        try:
+            lp, ent, lse = ops.logprob_entropy_fwd(x, idx, 1.0)                       # forward-only
+            dbuf1, dl1 = boxed()
+            flp, fent, flse, out1 = ops.grpo_fused_fwd_bwd(x, idx, m32, rc, tot, adv, old, ref, cfg, 1.0,
+                                                           dlogits_out=dl1)           # fused
+            dl2 = ops.logprob_bwd(x, idx, lse, gtok, 1.0)                            # backward-only
+        finally:
+            S.set_k1_path(prev)
+        torch.cuda.synchronize()
+        check_sentinels(src, f"{name}: logits buffer")
+        check_sentinels(dbuf1, f"{name}: fused dlogits buffer")
+        assert_logp(lp, logits, ids, where=f"{name} forward-only")
+        assert_logp(flp, logits, ids, where=f"{name} fused")
+        torch.testing.assert_close(ent.cpu(), want_ent, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(fent.cpu(), want_ent, rtol=1e-5, atol=1e-5)
+        res[name] = (lp.cpu(), dl1.float().cpu(), dl2.float().cpu())
+    # fp32 oracle gradients, rounded once to bf16: one bf16 ulp
+    xr = logits.float().requires_grad_(True)
+    cfgo = O.GRPOConfigLite(beta=0.04, loss_type="bnpo", importance_sampling_level="token", max_completion_length=T)
+    loss_r = O.grpo_compute_loss(xr, ids, mask.cpu(), adv.cpu(), cfgo, old.cpu(), ref.cpu())[0]
+    loss_r.backward()
+    want_fused = xr.grad.to(torch.bfloat16).float()
+    xr2 = logits.float().requires_grad_(True)
+    (O.selective_log_softmax(xr2, ids) * gtok.cpu()).sum().backward()
+    want_bwd = xr2.grad.to(torch.bfloat16).float()
+    for name in ("row", "resident"):
+        torch.testing.assert_close(res[name][1], want_fused, rtol=BF16_ULP, atol=1e-12, msg=lambda m: f"{name} fused: {m}")
+        torch.testing.assert_close(res[name][2], want_bwd, rtol=BF16_ULP, atol=1e-12, msg=lambda m: f"{name} bwd: {m}")
+        assert torch.count_nonzero(res[name][1][mask.cpu() == 0]) == 0
+        assert torch.count_nonzero(res[name][2][0, 2]) == 0
+    torch.testing.assert_close(res["resident"][0], res["row"][0], rtol=0, atol=4e-6)

@@ -106,5 +106,8 @@ def test_k1_geometry_policy():
     assert geom(49152, FUSED) == (0, (768, 1, 9, 24576))     # exactly four 24 KB chunks
     assert geom(32000, FUSED) == (0, (256, 1, 6, 16384))     # a whole row fits one twin CTA
     assert geom(262144, FUSED)[1][1] == 4 and geom(524288, FUSED)[1][1] == 8
-    assert geom(8192, FUSED)[0] == -2 and geom(32001, FWD)[0] == -2  # tiny / unaligned rows go to the row kernel
+    assert geom(8192, FUSED)[0] == -2                                # tiny rows go to the row kernel
+    # vocab % 8 != 0 (skewed rows): same shapes, with 16 bytes of the ring reserved for the aligned span of a slice
+    assert geom(32001, FWD) == (0, (256, 1, 6, 16384)) and geom(50257, FUSED) == (0, (640, 1, 11, 20480))
+    assert geom(151937, FUSED) == (0, (640, 2, 11, 20480)) and geom(50257, BWD)[1][0] == 768
     assert geom(1 << 23, FUSED)[0] == -2                             # 16 MB rows exceed an 8-CTA cluster
