@@ -8,8 +8,10 @@
 One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one batch of BASELINE config 2
 (B=16 sequences, T=1024, V=151936 bf16 logits, 8 completions per prompt) per GPU:
 
-    reward all-gather (N>1) -> K3 group advantages -> mask stats -> K1 fused log-prob/entropy/dlogits
-    -> K2 loss + metrics -> autograd hand-back of dlogits -> packed metric all-gather (N>1)
+    [once per generation batch of 4 steps, as the reference does at grpo_trainer.py:1497: reward all-gather (N>1)
+     -> K3 group advantages]  -> mask stats -> K1 fused log-prob / entropy / dlogits with the loss value and the metric
+    sums folded into the same launch -> autograd hand-back of dlogits -> packed metric rows kept in a device ring (N>1:
+    one all-gather per logging interval)
 
 * ``value``   whole-job logit-tokens/s with inputs resident in HBM (CUDA events, barrier both sides, max over ranks);
 * ``e2e``     same metric through the public API starting from PINNED HOST logits (H2D inside the timed region,
@@ -42,7 +44,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(B=16, T=1024, V=151936, G=8, beta=0.04, epsilon=0.2, loss_type="bnpo", level="token", temperature=1.0)
+CFG = dict(B=16, T=1024, V=151936, G=8, beta=0.04, epsilon=0.2, loss_type="bnpo", level="token", temperature=1.0,
+           steps_per_generation=4)
 WORKLOAD = "configs[1]: GRPO loss fwd+bwd, Qwen2.5 vocab V=151936, B=16 T=1024, 8 completions/prompt, per GPU"
 METRIC = "fwd+bwd logit-tokens/s for fused logprob+GRPO loss; % of HBM roofline"
 UNIT = "logit-tokens/s"
@@ -54,7 +57,7 @@ def static_config(n_gpus: int) -> dict:
     B, T, V, G = CFG["B"], CFG["T"], CFG["V"], CFG["G"]
     return {"workload": WORKLOAD, "loss_type": CFG["loss_type"], "importance_sampling_level": CFG["level"],
             "beta": CFG["beta"], "epsilon": CFG["epsilon"], "old_per_token_logps": True, "global_batch": B * n_gpus,
-            "seq_len": T, "vocab": V, "num_generations": G,
+            "seq_len": T, "vocab": V, "num_generations": G, "steps_per_generation": CFG["steps_per_generation"],
             "parallelism": f"sequence-sharded x{n_gpus}, no V-sized collective",
             "l2": "inputs 4.98 GB per GPU per step >> 126 MB L2, no flush needed"}
 
@@ -571,8 +574,13 @@ def run_b200(args):
         S.set_skip_masked(True)
     logits, ids, mask = synth_device(rank, B, T, V, dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    rewards_local = torch.randn(B, 1, generator=gen, device=dev)
+    # Rewards and advantages belong to a GENERATION batch, as in the reference: `_generate_and_score_completions` gathers
+    # the rewards of steps_per_generation loss steps at once (grpo_trainer.py:1497), normalises them per group (:1917-1938)
+    # and each loss step takes its slice.  So the reward all-gather + K3 run once per SPG steps, over SPG * B sequences.
+    SPG = CFG["steps_per_generation"]
+    rewards_local = torch.randn(SPG * B, 1, generator=gen, device=dev)
     weights = torch.ones(1, device=dev)
+    adv_gen, step_no = [None], [0]
     with torch.no_grad():
         lp0, _ = S.logprobs_and_entropy(logits, ids, CFG["temperature"], compute_entropy=False)
     old = lp0 + torch.randn(B, T, generator=gen, device=dev) * 0.3
@@ -595,22 +603,26 @@ def run_b200(args):
 
     def step(record=False):
         x.grad = None
-        adv = S.group_advantages(rewards_local, weights, G)["advantages"]  # all-gather (N>1) + K3
+        j = step_no[0] % SPG
+        step_no[0] += 1
+        if j == 0:  # a new generation batch: all-gather (N>1) + K3 over its SPG * B sequences per rank
+            adv_gen[0] = S.group_advantages(rewards_local, weights, G)["advantages"]
+        adv = adv_gen[0][j * B:(j + 1) * B]
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            orig = ops.grpo_fused_fwd_bwd
+            orig = ops.grpo_fused_step  # the K1 launch (log-probs, entropies, dlogits, loss + metrics sums)
 
             def timed(*a, **k):
                 e0.record()
                 r = orig(*a, **k)
                 e1.record()
                 return r
-            ops.grpo_fused_fwd_bwd = timed
+            ops.grpo_fused_step = timed
         try:
             out = loss_fn(x, ids, mask, adv, old, ref)
         finally:
             if record:
-                ops.grpo_fused_fwd_bwd = orig
+                ops.grpo_fused_step = orig
                 k1_events.append((e0, e1))
         out.loss.backward()
         if world > 1:
@@ -677,7 +689,7 @@ def run_b200(args):
             dev_logits.grad = None
             with torch.no_grad():
                 dev_logits.copy_(host_logits, non_blocking=True)
-            adv = S.group_advantages(rewards_local, weights, G)["advantages"]
+            adv = S.group_advantages(rewards_local[:B], weights, G)["advantages"]
             o = loss_fn(dev_logits, ids, mask, adv, old, ref)
             o.loss.backward()
             packed = torch.cat([o.metrics, o.loss.detach().reshape(1), o.per_token_logps.reshape(-1)])
@@ -708,10 +720,11 @@ def run_b200(args):
     from swh_trl_b200 import distributed as D
     res = S.group_advantages(rewards_local, weights, G)
     full_rewards = D.gather_rewards(rewards_local).cpu()
-    want_loc, want_all, _, want_std, _, _ = O.group_advantages(full_rewards, torch.ones(1), G, True, rank * B, B)
+    nloc = SPG * B  # this rank's sequences of one generation batch
+    want_loc, want_all, _, want_std, _, _ = O.group_advantages(full_rewards, torch.ones(1), G, True, rank * nloc, nloc)
     bound = 2e-5 * want_all.abs() + 3e-7 / (want_std.repeat_interleave(G) + 1e-4)
     adv_ok = bool(((res["all"].cpu() - want_all).abs() <= bound).all()) and \
-        torch.equal(res["advantages"].cpu(), res["all"].cpu()[rank * B:(rank + 1) * B])
+        torch.equal(res["advantages"].cpu(), res["all"].cpu()[rank * nloc:(rank + 1) * nloc])
     rows = slice(0, 64)
     lp_dev = out.per_token_logps[3, rows].cpu()
     lp_cpu = O.selective_log_softmax(logits.detach()[3:4, rows].float().cpu(), ids[3:4, rows].cpu())[0]
@@ -728,7 +741,7 @@ def run_b200(args):
     hbm_peak, peak_src = measured_peaks()
     extra, windows = {}, {}
     if not args.no_extras:
-        adv_now = res["advantages"]
+        adv_now = res["advantages"][:B]
         extra["two_phase_sequence_is"], windows["two_phase_sequence_is"] = extra_two_phase(S, x, ids, mask, adv_now, old,
                                                                                         ref, T, V, hbm_peak)
         extra["config5_strong_scaling"], windows["config5_strong_scaling"] = extra_config5(

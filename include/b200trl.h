@@ -166,6 +166,24 @@ int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t B, int64_t
                                const float* total_count, float* logp, float* entropy, float* lse, void* dlogits,
                                int64_t dl_row_stride, int64_t dl_batch_stride, b200trl_stream_t stream);
 
+/* The same pass PLUS the loss value and the logged metric means of grpo_trainer.py:2130-2135, 2139-2173 in the same
+ * call (what b200trl_grpo_loss would compute from the log-probs with ent_mask == NULL, g == NULL): on the resident
+ * kernel with dlogits != NULL every cluster keeps running sums of its rows' loss terms and the last cluster to finish
+ * folds them in cluster order (double accumulation, deterministic for a given GPU) -- no second launch; otherwise
+ * (row kernel, forward-only evaluation) K2 is launched right behind the pass.  `workspace`:
+ * b200trl_grpo_fused_step_workspace_bytes(B) bytes, zeroed once by the caller (the counter resets itself); it is
+ * in use until the call's work on `stream` has finished.  loss fp32 [1], metrics fp32 [B200TRL_NUM_GRPO_METRICS];
+ * entropy must be given.  row_count and total_count may BOTH be NULL: the call then counts the completion mask itself
+ * (grpo_trainer.py:2131,2133,2142) -- inside the resident kernel, by its consumer warps while the first chunks are in
+ * flight (B <= 256 sequences, B*T <= 131072 tokens), else with the mask_stats kernel into the workspace's tail. */
+int64_t b200trl_grpo_fused_step_workspace_bytes(int64_t B);
+int b200trl_grpo_fused_step(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab, int64_t row_stride,
+                            int64_t batch_stride, const int64_t* ids, const int32_t* mask, const float* advantages,
+                            const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
+                            float inv_temperature, const float* row_count, const float* total_count, float* logp,
+                            float* entropy, float* lse, void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
+                            void* workspace, float* loss, float* metrics, b200trl_stream_t stream);
+
 /* ---- K2: GRPO loss body + metrics (+ per-token d(loss)/d(logp)) --------------------------------
  * Replaces grpo_trainer.py:2084-2137 (loss) and :2139-2173 (local metric means).  All [B,T]
  * inputs fp32 row-major; ent_mask (uint8, from b200trl_entropy_quantile_mask) and entropy may be

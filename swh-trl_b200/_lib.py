@@ -60,6 +60,9 @@ PROTOTYPES = {
     "b200trl_mask_stats": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "b200trl_grpo_fused_fwd_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p,
                                              C.POINTER(GrpoCfg), _f, _p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "b200trl_grpo_fused_step_workspace_bytes": (_i64, [_i64]),
+    "b200trl_grpo_fused_step": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p,
+                                          C.POINTER(GrpoCfg), _f, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "b200trl_grpo_loss_workspace_bytes": (_i64, [_i64]),
     "b200trl_grpo_loss": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, C.POINTER(GrpoCfg), _p, _p, _p, _p, _p,
                                     _p, _p]),

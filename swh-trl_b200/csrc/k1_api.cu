@@ -1,5 +1,7 @@
 // C-ABI entry points of K1 (log-prob / entropy / dlogits) — argument checks and path selection.
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "k1_args.cuh"
 
@@ -12,6 +14,13 @@ std::atomic<int> g_skip_masked{0};
 std::atomic<unsigned long long*> g_trace{nullptr};
 std::atomic<int> g_trace_row0{0};
 
+// which implementation a call goes to (the in-kernel loss sums of b200trl_grpo_fused_step exist on the resident one)
+bool takes_resident(const K1Args& a, int dtype) {
+    const int path = g_k1_path.load();
+    if (path == B200TRL_K1_RESIDENT) return true;
+    return path == B200TRL_K1_AUTO && k1_resident_preferred(a, dtype);
+}
+
 int dispatch(K1Args a, int dtype, cudaStream_t stream) {
     a.trace = g_trace.load();
     a.trace_row0 = g_trace_row0.load();
@@ -19,10 +28,12 @@ int dispatch(K1Args a, int dtype, cudaStream_t stream) {
     const bool resident_ok = k1_resident_supported(a, dtype);
     if (path == B200TRL_K1_RESIDENT) {
         B200TRL_REQUIRE(resident_ok, B200TRL_E_UNSUPPORTED,
-                        "k1: resident path needs bf16 logits, vocab %% 8 == 0, 16-byte aligned rows and vocab >= 16384");
+                        "k1: resident path needs bf16 logits, rows of >= 16384 elements and a dlogits layout that mirrors "
+                        "the logits' 16-byte alignment");
         return launch_k1_resident(a, stream);
     }
     if (path == B200TRL_K1_AUTO && k1_resident_preferred(a, dtype)) return launch_k1_resident(a, stream);
+    a.step_ws = nullptr;  // the row kernel has no in-kernel loss sums
     return launch_k1_row(a, dtype, stream);
 }
 
@@ -162,6 +173,26 @@ extern "C" int b200trl_logprob_bwd(const void* logits, int dtype, int64_t n_rows
     return dispatch(a, dtype, as_stream(stream));
 }
 
+namespace {
+constexpr int64_t kStepMaxClusters = 1024;  // >= 2 CTAs / SM x 148 SMs with room to spare
+}
+
+// workspace of b200trl_grpo_fused_step: [counter | cluster partials or K2's row partials] [total_count | row_count[B]]
+static int64_t step_ws_main_bytes(int64_t B) {
+    const int64_t in_kernel = 16 + kStepMaxClusters * 8 * static_cast<int64_t>(sizeof(float));
+    return (std::max(in_kernel, b200trl_grpo_loss_workspace_bytes(B)) + 15) & ~int64_t(15);
+}
+extern "C" int64_t b200trl_grpo_fused_step_workspace_bytes(int64_t B) {
+    return step_ws_main_bytes(B) + 16 + (B > 0 ? B : 0) * static_cast<int64_t>(sizeof(float));
+}
+
+static int grpo_fused_impl(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab, int64_t row_stride,
+                           int64_t batch_stride, const int64_t* ids, const int32_t* mask, const float* advantages,
+                           const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
+                           float inv_temperature, const float* row_count, const float* total_count, float* logp,
+                           float* entropy, float* lse, void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
+                           void* step_workspace, float* step_loss, float* step_metrics, b200trl_stream_t stream);
+
 extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab,
                                           int64_t row_stride, int64_t batch_stride, const int64_t* ids,
                                           const int32_t* mask, const float* advantages, const float* old_logp,
@@ -169,13 +200,39 @@ extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t
                                           const float* row_count, const float* total_count, float* logp,
                                           float* entropy, float* lse, void* dlogits, int64_t dl_row_stride,
                                           int64_t dl_batch_stride, b200trl_stream_t stream) {
+    return grpo_fused_impl(logits, dtype, B, T, vocab, row_stride, batch_stride, ids, mask, advantages, old_logp, ref_logp,
+                           cfg, inv_temperature, row_count, total_count, logp, entropy, lse, dlogits, dl_row_stride,
+                           dl_batch_stride, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int b200trl_grpo_fused_step(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab,
+                                       int64_t row_stride, int64_t batch_stride, const int64_t* ids, const int32_t* mask,
+                                       const float* advantages, const float* old_logp, const float* ref_logp,
+                                       const b200trl_grpo_cfg* cfg, float inv_temperature, const float* row_count,
+                                       const float* total_count, float* logp, float* entropy, float* lse, void* dlogits,
+                                       int64_t dl_row_stride, int64_t dl_batch_stride, void* workspace, float* loss,
+                                       float* metrics, b200trl_stream_t stream) {
+    B200TRL_REQUIRE(workspace && loss && metrics && entropy, B200TRL_E_INVALID, "grpo_fused_step: null pointer");
+    return grpo_fused_impl(logits, dtype, B, T, vocab, row_stride, batch_stride, ids, mask, advantages, old_logp, ref_logp,
+                           cfg, inv_temperature, row_count, total_count, logp, entropy, lse, dlogits, dl_row_stride,
+                           dl_batch_stride, workspace, loss, metrics, stream);
+}
+
+static int grpo_fused_impl(const void* logits, int dtype, int64_t B, int64_t T, int64_t vocab, int64_t row_stride,
+                           int64_t batch_stride, const int64_t* ids, const int32_t* mask, const float* advantages,
+                           const float* old_logp, const float* ref_logp, const b200trl_grpo_cfg* cfg,
+                           float inv_temperature, const float* row_count, const float* total_count, float* logp,
+                           float* entropy, float* lse, void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
+                           void* step_workspace, float* step_loss, float* step_metrics, b200trl_stream_t stream) {
     K1Args a;
     B200TRL_REQUIRE(B > 0 && T > 0, B200TRL_E_INVALID, "grpo_fused: bad shape");
     const int rc = fill_common(a, logits, dtype, B * T, vocab, row_stride, T, batch_stride, ids, inv_temperature,
                                "grpo_fused");
     if (rc) return rc;
-    B200TRL_REQUIRE(mask && advantages && cfg && row_count && total_count && logp, B200TRL_E_INVALID,
-                    "grpo_fused: null pointer");
+    B200TRL_REQUIRE(mask && advantages && cfg && logp, B200TRL_E_INVALID, "grpo_fused: null pointer");
+    B200TRL_REQUIRE((row_count && total_count) || (step_workspace && !row_count && !total_count), B200TRL_E_INVALID,
+                    "grpo_fused: row_count / total_count must both be given (only b200trl_grpo_fused_step counts the mask "
+                    "itself when both are null)");
     B200TRL_REQUIRE(cfg->loss_type >= 0 && cfg->loss_type <= 2, B200TRL_E_INVALID, "grpo_fused: unknown loss type %d",
                     cfg->loss_type);
     B200TRL_REQUIRE(cfg->is_level == B200TRL_IS_TOKEN || (cfg->is_level == B200TRL_IS_SEQUENCE && old_logp == nullptr),
@@ -200,7 +257,42 @@ extern "C" int b200trl_grpo_fused_fwd_bwd(const void* logits, int dtype, int64_t
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
     if (dlogits && set_dl_layout(a, T, dl_batch_stride, "grpo_fused")) return B200TRL_E_INVALID;
-    return dispatch(a, dtype, as_stream(stream));
+    if (!step_workspace) return dispatch(a, dtype, as_stream(stream));
+    // loss value + logged metrics in the same call: inside the resident kernel's pass when it takes the call with a
+    // gradient, otherwise K2 right behind the pass (row kernel, forward-only evaluation)
+    const bool in_kernel = dlogits != nullptr && takes_resident(a, dtype);
+    if (!row_count) {
+        // the mask statistics are part of the step: counted by the resident kernel's idle consumer warps while the
+        // first chunks are in flight, or (row kernel, evaluation, very large batches) by the mask_stats kernel into
+        // the tail of the workspace
+        static const bool allow_count = []() {  // B200TRL_K1_COUNTMASK=0: always the mask_stats kernel (A/B runs)
+            const char* v = getenv("B200TRL_K1_COUNTMASK");
+            return !(v && atoi(v) == 0);
+        }();
+        if (allow_count && in_kernel && B <= 256 && B * T <= 131072) {
+            a.count_mask = 1;
+        } else {
+            float* stats = reinterpret_cast<float*>(static_cast<char*>(step_workspace) + step_ws_main_bytes(B));
+            const int rc0 = b200trl_mask_stats(mask, B, T, stats + 4, stats, stream);
+            if (rc0) return rc0;
+            row_count = stats + 4;
+            total_count = stats;
+            a.row_count = row_count;
+            a.total_count = total_count;
+        }
+    }
+    if (in_kernel) {
+        a.step_ws = static_cast<float*>(step_workspace);
+        a.step_loss = step_loss;
+        a.step_metrics = step_metrics;
+        return dispatch(a, dtype, as_stream(stream));
+    }
+    const int rc1 = dispatch(a, dtype, as_stream(stream));
+    if (rc1) return rc1;
+    b200trl_grpo_cfg c2 = *cfg;
+    c2.grad_scale = 1.f;
+    return b200trl_grpo_loss(logp, old_logp, a.ref_lp, advantages, mask, nullptr, entropy, B, T, &c2, row_count, total_count,
+                             step_workspace, step_loss, step_metrics, nullptr, stream);
 }
 
 extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab,

@@ -48,6 +48,13 @@ struct K1Args {
     // fused modes only: rows whose loss weight is zero (completion_mask == 0 / PPO padding) are not read from HBM;
     // their dlogits are zeros and their logp / entropy / lse outputs are 0.  Opt-in (b200trl_set_skip_masked).
     int skip_masked;
+    // G_GRPO, resident kernel only (b200trl_grpo_fused_step): the loss value and the logged metric sums are folded
+    // into the same pass -- every cluster leader keeps running sums of its rows' terms, leaves them in step_ws and the
+    // last one to finish adds the partials in cluster order (double) and writes loss[1] / metrics[8].  Null: off.
+    int count_mask;  // 1: row_count / total_count are null, the kernel counts `mask` itself (B <= 256 sequences)
+    float* step_ws;  // [1 counter word + 3 pad][max clusters][8]
+    float* step_loss;
+    float* step_metrics;
     // diagnostics (b200trl_k1_set_trace, trace builds only): phase timestamps of the first 4 CTAs of the resident kernel
     unsigned long long* trace;
     int trace_row0;  // first traced row (per-CTA row counter)
@@ -93,16 +100,19 @@ struct RowScalars {
     float aux1;    // G_GRPO: ref
     float adv;
     float weight;  // mask * normalisation * grad_scale (0 => dlogits row is zero)
+    float norm;    // G_GRPO: mask * normalisation (the token's weight in the loss VALUE)
     float pad;     // G_PPO: 1 if the position is padding
 };
 
 // Split in two so that a caller can software-pipeline the dependent pair (ids[row] -> logits[row, id]):
-// everything addressed by the row alone ...
-__device__ __forceinline__ RowScalars load_row_scalars_direct(const K1Args& a, int64_t row, float ppo_count) {
+// everything addressed by the row alone ...  (`row_count` / `total_count`: where the mask statistics live -- the
+// arguments' global arrays, or the resident kernel's shared-memory copy when it counted the mask itself)
+__device__ __forceinline__ RowScalars load_row_scalars_direct(const K1Args& a, int64_t row, float ppo_count,
+                                                              const float* row_count, const float* total_count) {
     RowScalars s;
     s.id = a.ids[row];
     s.x_sel = 0.f;
-    s.aux0 = s.aux1 = s.adv = s.weight = s.pad = 0.f;
+    s.aux0 = s.aux1 = s.adv = s.weight = s.pad = s.norm = 0.f;
     if (a.gmode == G_GIVEN) {
         s.aux0 = a.g[row];
         s.weight = 1.f;
@@ -112,7 +122,8 @@ __device__ __forceinline__ RowScalars load_row_scalars_direct(const K1Args& a, i
         s.adv = a.adv[b];
         if (a.old_lp) s.aux0 = a.old_lp[row];
         if (a.ref_lp) s.aux1 = a.ref_lp[row];
-        s.weight = m * grpo_norm(a.cfg, a.row_count[b], a.total_count[0], static_cast<float>(a.B)) * a.cfg.grad_scale;
+        s.norm = m * grpo_norm(a.cfg, row_count[b], total_count[0], static_cast<float>(a.B));
+        s.weight = s.norm * a.cfg.grad_scale;
     } else if (a.gmode == G_PPO) {
         const int64_t b = row / a.T, t = row % a.T;
         s.pad = (t > a.seq_len[b]) ? 1.f : 0.f;
@@ -129,6 +140,10 @@ __device__ __forceinline__ float load_selected_logit(const K1Args& a, int64_t ro
     return (id >= 0 && id < a.vocab) ? ElemTraits<T>::load(base + id) : __int_as_float(0x7fc00000);
 }
 
+__device__ __forceinline__ RowScalars load_row_scalars_direct(const K1Args& a, int64_t row, float ppo_count) {
+    return load_row_scalars_direct(a, row, ppo_count, a.row_count, a.total_count);
+}
+
 template <typename T>
 __device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t row, float ppo_count) {
     RowScalars s = load_row_scalars_direct(a, row, ppo_count);
@@ -137,13 +152,17 @@ __device__ __forceinline__ RowScalars load_row_scalars(const K1Args& a, int64_t 
 }
 
 // d(loss)/d(logp) of this token, including mask, normalisation and the upstream scale
-__device__ __forceinline__ float token_grad(const K1Args& a, const RowScalars& s, float logp) {
+// `tok` (G_GRPO, optional): the token's loss terms for the in-kernel loss / metric sums; `tok->loss` etc. are left
+// untouched for a token the loss ignores (s.norm == 0)
+__device__ __forceinline__ float token_grad(const K1Args& a, const RowScalars& s, float logp, GrpoTok* tok = nullptr) {
     if (a.gmode == G_GIVEN) return s.aux0;
-    if (s.weight == 0.f) return 0.f;
     if (a.gmode == G_GRPO) {
+        if (s.norm == 0.f) return 0.f;
         const GrpoTok t = grpo_token(logp, a.old_lp != nullptr, s.aux0, a.ref_lp != nullptr, s.aux1, s.adv, 1.f, a.cfg);
+        if (tok) *tok = t;
         return s.weight * (t.dl + t.dkl);
     }
+    if (s.weight == 0.f) return 0.f;
     if (a.gmode == G_PPO) {
         float pg, dpg, clipped, ratio, diff;
         ppo_policy(logp, s.aux0, s.adv, a.clip_lo, a.clip_hi, pg, dpg, clipped, ratio, diff);

@@ -31,9 +31,12 @@ constexpr int kMaxConsumers = 768;  // consumer threads per CTA: 768 / 640 / 512
 constexpr int kChunkBytes = 16384;  // default chunk; per-geometry value: chunk_bytes_for()
 constexpr int kMaxSlots = 13;
 __host__ __device__ constexpr int chunk_bytes_for(int consumers) {
-    return (consumers == 768 || consumers == 640) ? consumers * 32 : 16384;
+    // 320 / 384 consumers ("lean" shapes): the 640 / 768 chunk with FOUR vectors per thread instead of two
+    return (consumers == 768 || consumers == 640) ? consumers * 32
+                                                  : ((consumers == 320 || consumers == 384) ? consumers * 64 : 16384);
 }
 constexpr int kMaxCluster = 8;
+constexpr int kMaxCountSeqs = 256;  // in-kernel mask statistics (K1Args::count_mask): sequences per batch
 constexpr float kSlack = 6.0f;   // reference point may trail the running max by 2^6
 
 struct __align__(16) Part4 {
@@ -104,6 +107,8 @@ struct Smem {
     Part4 warp_part[2][kMaxConsumers / 32];
     RowResult result[2];
     float ppo_count;
+    float total_cnt;               // count_mask: number of unmasked tokens of the batch ...
+    float row_cnt[kMaxCountSeqs];  // ... and per sequence, counted by the consumer warps while the first chunks fly
     TraceLog trace;
 };
 
@@ -564,6 +569,31 @@ struct FusedConsumer {
     }
 };
 
+// In-kernel mask statistics (K1Args::count_mask): the consumer warps have nothing to do until the first chunk lands
+// (~2 us), so they count the completion mask -- warp w the sequences w, w + n_warps, ... -- into shared memory; the
+// reducer warp joins the named barrier before it reads them.  Replaces the mask_stats launch (+ its memset node) of a
+// step.  Integer-valued fp32 sums: exact below 2^24 tokens, order-independent.
+template <int NC>
+__device__ __forceinline__ void count_mask_consumers(const K1Args& a, float* row_cnt, float* total_cnt, int warp, int lane) {
+    constexpr int kWarps = NC / 32;
+    const int B = static_cast<int>(a.B), T = static_cast<int>(a.T);
+    for (int b = warp; b < B; b += kWarps) {
+        const int32_t* m = a.mask + static_cast<int64_t>(b) * T;
+        int n = 0;
+        for (int t = lane; t < T; t += 32) n += m[t];
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0) row_cnt[b] = static_cast<float>(n);
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(NC) : "memory");  // consumers only: every row_cnt is written
+    if (warp == 0) {
+        float tot = 0.f;
+        for (int b = lane; b < B; b += 32) tot += row_cnt[b];
+        tot = warp_sum(tot);
+        if (lane == 0) *total_cnt = tot;
+    }
+    asm volatile("bar.arrive 3, %0;" ::"n"(NC + 32) : "memory");  // hand over to the reducer warp (bar.sync 3)
+}
+
 // ------------------------------------------------------------------ the kernel
 // Warp roles: 0..15 consumers, 16 DMA (one lane), 17 reducer (row statistics + cluster exchange).
 //
@@ -755,10 +785,18 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             const float ppo_count = (a.gmode == G_PPO) ? sm.ppo_count : 1.f;
             Tracer tr;
             tr.init(a, &sm.trace, 1, lane == 0);
+            // in-kernel loss / metric sums of this cluster's rows (leader CTA, lane 0): loss, kl, entropy, low, high, region
+            const bool step_sums = HAS_BWD && a.step_ws != nullptr && a.gmode == G_GRPO && crank == 0;
+            float sums[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const bool counted = HAS_BWD && a.count_mask != 0;
+            if (counted) asm volatile("bar.sync 3, %0;" ::"n"(NC + 32) : "memory");  // the consumers counted the mask
+            const float* row_count = counted ? sm.row_cnt : a.row_count;
+            const float* total_count = counted ? &sm.total_cnt : a.total_count;
             RowScalars rs{}, rs_next{};
             if (lane == 0 && n_my_rows > 0) {
-                rs = load_row_scalars<__nv_bfloat16>(a, first_row, ppo_count);
-                if (n_my_rows > 1) rs_next = load_row_scalars_direct(a, first_row + row_step, ppo_count);
+                rs = load_row_scalars_direct(a, first_row, ppo_count, row_count, total_count);
+                rs.x_sel = load_selected_logit<__nv_bfloat16>(a, first_row, rs.id);
+                if (n_my_rows > 1) rs_next = load_row_scalars_direct(a, first_row + row_step, ppo_count, row_count, total_count);
             }
             for (int i = 0; i < n_my_rows; ++i) {
                 const int64_t row = first_row + static_cast<int64_t>(i) * row_step;
@@ -769,7 +807,8 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 RowScalars rs_after{};
                 if (lane == 0) {
                     if (i + 1 < n_my_rows) x_next = load_selected_logit<__nv_bfloat16>(a, row + row_step, rs_next.id);
-                    if (i + 2 < n_my_rows) rs_after = load_row_scalars_direct(a, row + 2 * row_step, ppo_count);
+                    if (i + 2 < n_my_rows)
+                        rs_after = load_row_scalars_direct(a, row + 2 * row_step, ppo_count, row_count, total_count);
                 }
                 tr.ev(10, i, 0);
                 mbar_wait(&sm.part_bar[par], rpar);
@@ -825,7 +864,17 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                     }
                     const RowStats st = finish_row(q, rs.x_sel, c);
                     if (HAS_BWD) {
-                        const float gp = token_grad(a, rs, st.logp) * a.inv_temp;
+                        GrpoTok tok;
+                        tok.loss = tok.kl = tok.low = tok.high = 0.f;
+                        const float gp = token_grad(a, rs, st.logp, &tok) * a.inv_temp;
+                        if (step_sums && rs.norm != 0.f) {  // a token the loss sees (mask == 1), in this CTA's row order
+                            sums[0] = fmaf(tok.loss, rs.norm, sums[0]);
+                            sums[1] += tok.kl;
+                            sums[2] += st.entropy;
+                            sums[3] += tok.low;
+                            sums[4] += tok.high;
+                            sums[5] += fmaxf(tok.low, tok.high);
+                        }
                         const int64_t e_id = rs.id - e_begin;
                         const bool mine = (e_id >= 0 && e_id < my_elems);
                         const int64_t s_id = e_id + row_head(row);  // position inside the aligned span
@@ -853,11 +902,53 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 rs.x_sel = x_next;
                 rs_next = rs_after;
             }
+            if (HAS_BWD && a.step_ws != nullptr && a.gmode == G_GRPO && crank == 0) {
+                // leave this cluster's sums; the last cluster to arrive folds all of them in cluster order (double):
+                // deterministic for a given grid, one launch
+                unsigned int* counter = reinterpret_cast<unsigned int*>(a.step_ws);
+                volatile float* part = a.step_ws + 4;
+                const unsigned int n_cl = num_clusters_x();
+                bool last = false;
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) part[static_cast<size_t>(cluster_id_x()) * 8 + k] = sums[k];
+                    __threadfence();
+                    const unsigned int prev = atomicAdd(counter, 1u);
+                    last = (prev == n_cl - 1);
+                    if (last) {
+                        *counter = 0u;  // ready for the next launch
+                        __threadfence();
+                    }
+                }
+                last = __shfl_sync(0xffffffffu, last ? 1 : 0, 0) != 0;
+                if (last) {
+                    double acc[6] = {0, 0, 0, 0, 0, 0};
+                    for (unsigned int cl = lane; cl < n_cl; cl += 32)
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc[k] += static_cast<double>(part[static_cast<size_t>(cl) * 8 + k]);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+                    if (lane == 0) {
+                        const float total = total_count[0];
+                        const double ntok = fmax(static_cast<double>(total), 1.0);
+                        a.step_loss[0] = static_cast<float>(acc[0]);
+                        a.step_metrics[B200TRL_M_LOSS] = static_cast<float>(acc[0]);
+                        a.step_metrics[B200TRL_M_KL] = static_cast<float>(acc[1] / ntok);
+                        a.step_metrics[B200TRL_M_ENTROPY] = static_cast<float>(acc[2] / ntok);
+                        a.step_metrics[B200TRL_M_CLIP_LOW] = static_cast<float>(acc[3] / ntok);
+                        a.step_metrics[B200TRL_M_CLIP_HIGH] = static_cast<float>(acc[4] / ntok);
+                        a.step_metrics[B200TRL_M_CLIP_REGION] = static_cast<float>(acc[5] / ntok);
+                        a.step_metrics[B200TRL_M_TOKENS] = total;
+                        a.step_metrics[B200TRL_M_RESERVED] = 0.f;
+                    }
+                }
+            }
             tr.finish();
         }
     } else if (FAST != 0) {
         // =========================== consumers, fused pass (FusedConsumer) ===========================
         using FC = FusedConsumer<NC>;
+        if (a.count_mask != 0) count_mask_consumers<NC>(a, sm.row_cnt, &sm.total_cnt, warp, lane);
         FC fc;
         fc.slots_u32 = smem_u32(slots);
         fc.full0 = smem_u32(&sm.full_bar[0]);
@@ -931,6 +1022,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         }
     } else {
         // =========================== consumers ===========================
+        if (HAS_FWD && HAS_BWD && a.count_mask != 0) count_mask_consumers<NC>(a, sm.row_cnt, &sm.total_cnt, warp, lane);
         const float c = a.c;
         const uint64_t c2 = pack2(c, c);
         Cursor fcur{0, 0u}, bcur{0, 0u};
@@ -939,8 +1031,16 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
         int t_row = 0;  // row whose chunk the next fwd_chunk call folds (tracing only)
 
         // SKEW: head skew / span of the row being folded (f_*) and of the row whose dlogits are being written (b_*)
-        int f_h = 0, f_nvec = 0;
+        // per row (hoisted out of the chunk loops): chunk holding the span's last vector and the valid elements of that
+        // vector (0: all eight)
+        int f_h = 0, f_nvec = 0, f_last = 0, f_keep = 0;
         const int tail_keep_of_h0 = static_cast<int>(my_elems & 7);  // (h + my_elems) & 7 with h added per row
+        auto set_fwd_row = [&](int64_t r) {
+            f_h = row_head(r);
+            f_nvec = span_vecs(f_h);
+            f_last = (f_nvec - 1) / kChunkVecs;
+            f_keep = (f_h + tail_keep_of_h0) & 7;
+        };
         auto fwd_chunk = [&](Acc& acc, int cidx, bool skip) {
             tr.ev(1, t_row, cidx);
             mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
@@ -948,11 +1048,17 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             const uint4* sv = reinterpret_cast<const uint4*>(slots + static_cast<size_t>(fcur.slot) * kChunkBytes);
             if (SKIP && skip) {
                 // masked row: nothing was loaded into this slot
+            } else if (SKEW && cidx < f_last && (cidx != 0 || f_h == 0)) {  // an interior chunk: nothing to mask
+                uint4 v[kVpt];
+#pragma unroll
+                for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+#pragma unroll
+                for (int k = 0; k < kVpt; k += 2) acc_vec2(acc, v[k], v[k + 1], c, c2);
             } else if (SKEW) {
                 const int v0 = cidx * kChunkVecs;
                 const int n_here = min(max(f_nvec - v0, 0), kChunkVecs);
-                const int keep = (f_h + tail_keep_of_h0) & 7;  // valid elements of the span's last vector (0: all)
-                const bool edge = (cidx == 0 && f_h != 0) || (keep != 0 && f_nvec - 1 >= v0 && f_nvec - 1 < v0 + kChunkVecs);
+                const int keep = f_keep;
+                const bool edge = (cidx == 0 && f_h != 0) || (keep != 0 && cidx == f_last);
                 if (n_here == kChunkVecs) {
                     uint4 v[kVpt];
 #pragma unroll
@@ -1007,10 +1113,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             return SKIP && r < n_my_rows && row_is_masked(a, first_row + static_cast<int64_t>(r) * row_step);
         };
         bool cur_masked = masked_at(0), nxt_masked = masked_at(1);
-        if (SKEW && n_my_rows > 0) {
-            f_h = row_head(first_row);
-            f_nvec = span_vecs(f_h);
-        }
+        if (SKEW && n_my_rows > 0) set_fwd_row(first_row);
         if (HAS_FWD && n_my_rows > 0) {
             for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, cur_masked);
         }
@@ -1024,10 +1127,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
 
             if (HAS_FWD) {
                 t_row = i;
-                if (SKEW) {
-                    f_h = b_h;
-                    f_nvec = b_nvec;
-                }
+                if (SKEW) set_fwd_row(row);
                 for (int cidx = k_pre; cidx < C; ++cidx) fwd_chunk(acc, cidx, cur_masked);
                 const Partial p = partial_warp_reduce_fast(acc_to_partial(acc));
                 tr.ev(4, i, 0);
@@ -1040,10 +1140,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 acc = acc_empty();
                 t_row = i + 1;
                 if (i + 1 < n_my_rows) {
-                    if (SKEW) {
-                        f_h = row_head(row + row_step);
-                        f_nvec = span_vecs(f_h);
-                    }
+                    if (SKEW) set_fwd_row(row + row_step);
                     for (int cidx = 0; cidx < k_pre; ++cidx) fwd_chunk(acc, cidx, nxt_masked);
                 }
             }
@@ -1086,17 +1183,17 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 __nv_bfloat16* grow = nullptr;  // DIRECT: this CTA's slice of the dlogits row (SKEW: its aligned span)
                 if (DIRECT) grow = dlogits + dlogits_offset(a, row) + e_begin - b_h;
                 const int b_keep = SKEW ? ((b_h + tail_keep_of_h0) & 7) : 0;
+                const int b_last = SKEW ? (b_nvec - 1) / kChunkVecs : 0;
                 for (int cidx = 0; cidx < C; ++cidx) {
                     if (!HAS_FWD) mbar_wait(&sm.full_bar[bcur.slot], bcur.par);
                     uint4* sv = reinterpret_cast<uint4*>(slots + static_cast<size_t>(bcur.slot) * kChunkBytes);
                     bool full = (cidx != C - 1 || last_bytes == kChunkBytes);
                     int nvec = full ? kChunkVecs : (last_bytes >> 4);
                     if (SKEW) {
-                        const int v0 = cidx * kChunkVecs;
-                        nvec = min(max(b_nvec - v0, 0), kChunkVecs);
-                        const bool edge = (cidx == 0 && b_h != 0) ||
-                                          (b_keep != 0 && b_nvec - 1 >= v0 && b_nvec - 1 < v0 + kChunkVecs);
-                        full = (nvec == kChunkVecs) && !edge;
+                        full = cidx < b_last && (cidx != 0 || b_h == 0);  // interior chunk: whole vectors only
+                        nvec = full ? kChunkVecs : min(max(b_nvec - cidx * kChunkVecs, 0), kChunkVecs);
+                        if (!full && nvec == kChunkVecs && !(cidx == 0 && b_h != 0) && !(b_keep != 0 && cidx == b_last))
+                            full = true;  // the last chunk happens to be complete and to end on a vector boundary
                     }
                     if (SKEW && DIRECT && !full) {
                         // a chunk holding the first or the last vector of the span (or a short one): the edge vectors
@@ -1352,6 +1449,8 @@ Geom pick_geom(int64_t vocab, Mode m, bool skew = false) {
         return m == M_FWD ? twin : dense;
     }
     if (mode == 4 && mid.cs) return mid;
+    if (mode == 5 && mid.cs) return Geom{mid.cs, kMidSlots, 320};    // lean mid: half the warps, twice the work per wait
+    if (mode == 6 && dense.cs) return Geom{dense.cs, kDenseSlots, 384};
     if (mode == 3 && dense.cs && dense.cs <= wide.cs) return dense;
     if (mode == 2 && twin.cs) return twin;
     if (mode == 1) return wide;
@@ -1431,6 +1530,10 @@ int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
     if (g.nc == 768)
         return dual ? launch_mode_t<F, Bk, true, 768>(a, g.cs, g.slots, stream)
                     : launch_mode_t<F, Bk, false, 768>(a, g.cs, g.slots, stream);
+    if constexpr (F && Bk) {  // lean shapes: fused pass only
+        if (g.nc == 320) return launch_mode_t<F, Bk, true, 320>(a, g.cs, g.slots, stream);
+        if (g.nc == 384) return launch_mode_t<F, Bk, true, 384>(a, g.cs, g.slots, stream);
+    }
     return dual ? launch_mode_t<F, Bk, true, 512>(a, g.cs, g.slots, stream)
                 : launch_mode_t<F, Bk, false, 512>(a, g.cs, g.slots, stream);
 }

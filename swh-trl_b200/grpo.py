@@ -60,14 +60,14 @@ class _FusedGRPO(torch.autograd.Function):
                 dl[:, :lo].zero_()
                 dl[:, lo + T:].zero_()
                 dl_view = dl[:, lo:lo + T]
-        logp, ent, lse, dl_out = ops.grpo_fused_fwd_bwd(x, ids, mask_i32, row_count, total_count, advantages, old_lp,
-                                                        ref_lp, cfg, inv_temp, want_grad=want_grad,
-                                                        dlogits_out=dl_view)
+        # one C call: log-probs, entropies, dlogits AND the loss value / logged metric means (summed inside the
+        # resident kernel's pass; K2 behind the pass on the row kernel or without a gradient)
+        logp, ent, lse, dl_out, loss, metrics = ops.grpo_fused_step(x, ids, mask_i32, row_count, total_count, advantages,
+                                                                    old_lp, ref_lp, cfg, inv_temp, want_grad=want_grad,
+                                                                    dlogits_out=dl_view)
         if dl is None:
             dl = dl_out
         cfg.grad_scale = 1.0
-        loss, metrics, _ = ops.grpo_loss(logp, old_lp, ref_lp, advantages, mask_i32, row_count, total_count, cfg,
-                                         ent_mask=None, entropy=ent, want_g=False)
         ctx.grad_scale = grad_scale
         ctx.dl = dl
         ctx.logits_shape = logits.shape
@@ -166,17 +166,20 @@ class GRPOLoss:
             raise KeyError("ref_per_token_logps")  # the reference indexes inputs[...] (grpo_trainer.py:2086)
         cfg = ops.make_cfg(self.beta, self.epsilon_low, self.epsilon_high, self.delta, self.loss_type,
                            self.importance_sampling_level, self.max_completion_length)
-        mask_i32, row_count, total = ops.mask_stats(completion_mask)
         inv_temp = 1.0 / float(self.temperature)
         ref = ref_per_token_logps if self.beta != 0.0 else None
         sched = schedule or self.schedule(old_per_token_logps is not None)
         if sched == "fused":
             if self.schedule(old_per_token_logps is not None) != "fused":
                 raise NotImplementedError("the fused schedule needs a per-token gradient (see GRPOLoss.schedule)")
+            # the completion-mask statistics (:2131, 2133, 2142) are counted inside the fused call
+            ops._need_cuda(completion_mask, "completion_mask")
+            mask_i32, row_count, total = completion_mask.to(torch.int32).contiguous(), None, None
             loss, metrics, logp, ent = _FusedGRPO.apply(logits, completion_ids, mask_i32, row_count, total, advantages,
                                                         old_per_token_logps, ref, cfg, inv_temp, float(grad_scale),
                                                         logits_to_keep)
         else:
+            mask_i32, row_count, total = ops.mask_stats(completion_mask)
             loss, metrics, logp, ent = _TwoPhaseGRPO.apply(logits, completion_ids, mask_i32, row_count, total,
                                                            advantages, old_per_token_logps, ref, cfg, inv_temp,
                                                            float(self.top_entropy_quantile), logits_to_keep)

@@ -290,6 +290,42 @@ def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages
     return logp, ent, lse, dl
 
 
+def grpo_fused_step(logits, ids, mask_i32, row_count, total_count, advantages, old_logp, ref_logp, cfg: GrpoCfg,
+                    inv_temperature: float, want_grad: bool = True, dlogits_out: Optional[torch.Tensor] = None):
+    """``(logp, entropy, lse, dlogits|None, loss[1], metrics[8])`` — ``b200trl_grpo_fused_step``: the fused pass with the
+    loss value and the logged metric means produced by the same launch (resident kernel with a gradient; otherwise K2
+    runs right behind the pass inside the C call).  ``cfg.grad_scale`` scales ``dlogits`` only, never the loss value.
+    ``row_count`` / ``total_count`` may both be ``None``: the call counts ``mask_i32`` itself (no ``mask_stats`` launch)."""
+    k = _Keep()
+    B, T = mask_i32.shape
+    r = rows_view(logits, rows_per_batch=T)
+    x, n, V = r.t, r.n, r.V
+    if n != B * T:
+        raise ValueError(f"logits rows {n} != B*T {B * T}")
+    idx = ids.to(torch.int64).contiguous()
+    dev = x.device
+    logp = torch.empty(B, T, dtype=torch.float32, device=dev)
+    ent = torch.empty(B, T, dtype=torch.float32, device=dev)
+    lse = torch.empty(B, T, dtype=torch.float32, device=dev)
+    out = torch.empty(1 + _lib.NUM_GRPO_METRICS, dtype=torch.float32, device=dev)  # loss | metrics, one allocation
+    dl, dl_rs, dl_bs = None, V, 0
+    if want_grad:
+        dl = dlogits_out if dlogits_out is not None else alloc_dlogits(r, (B, T, V))[0]
+        d = collapse_rows2(tuple(dl.shape), tuple(dl.stride()))
+        if d is None or (d[1] not in (0, T)) or dl.dtype != x.dtype:
+            raise ValueError("dlogits_out must be a [B,T,V] view with at most (batch, row) strides and the logits dtype")
+        dl_rs, dl_bs = d[0], d[2]
+    ws = _workspace(dev, lib.b200trl_grpo_fused_step_workspace_bytes(B), "grpo_fused_step", zero=True)
+    check(lib.b200trl_grpo_fused_step(
+        _ptr(x), _DTYPES[x.dtype], B, T, V, r.row_stride, r.batch_stride, _ptr(idx), _ptr(mask_i32),
+        k.f32(advantages, "advantages"), k.f32(old_logp, "old_per_token_logps"),
+        k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg), float(inv_temperature), _ptr(row_count),
+        _ptr(total_count), _ptr(logp), _ptr(ent), _ptr(lse), _ptr(dl), dl_rs, dl_bs, _ptr(ws), _ptr(out),
+        out.data_ptr() + 4, _stream(x)), "grpo_fused_step")
+    _count()
+    return logp, ent, lse, dl, out[:1], out[1:]
+
+
 # ------------------------------------------------------------------------------------------------ K2
 _ws_cache = {}
 
@@ -359,13 +395,13 @@ def group_advantages(rewards_per_func: torch.Tensor, weights: torch.Tensor, num_
     ng = Bg // num_generations
     mean = torch.empty(ng, dtype=torch.float32, device=dev)
     std = torch.empty(ng, dtype=torch.float32, device=dev)
-    zero = torch.empty(ng, dtype=torch.uint8, device=dev)
+    zero = torch.empty(ng, dtype=torch.bool, device=dev)  # the kernel writes 0 / 1 bytes: a bool's storage, no cast kernel
     check(lib.b200trl_group_advantages(_ptr(r), _ptr(w), Bg, F, num_generations, int(bool(scale_rewards)),
                                        int(local_offset), int(local_count), _ptr(rewards), _ptr(adv_all),
                                        _ptr(adv_loc), _ptr(mean), _ptr(std), _ptr(zero), _stream(r)),
           "group_advantages")
     _count()
-    return dict(advantages=adv_loc, all=adv_all, rewards=rewards, mean=mean, std=std, is_std_zero=zero.bool())
+    return dict(advantages=adv_loc, all=adv_all, rewards=rewards, mean=mean, std=std, is_std_zero=zero)
 
 
 # ------------------------------------------------------------------------------------------------ K4 / PPO

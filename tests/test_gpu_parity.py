@@ -1391,3 +1391,69 @@ def test_skewed_rows_on_the_resident_kernel(S, V, layout):
         assert torch.count_nonzero(res[name][1][mask.cpu() == 0]) == 0
         assert torch.count_nonzero(res[name][2][0, 2]) == 0
     torch.testing.assert_close(res["resident"][0], res["row"][0], rtol=0, atol=4e-6)
+
+
+# ------------------------------------------------------------------------------------------------ one-launch step
+@pytest.mark.parametrize("V", [32000, 50257, 151936])   # twin CTAs, skewed rows, 2-CTA clusters
+@pytest.mark.parametrize("loss_type,beta,with_old", [("bnpo", 0.04, True), ("grpo", 0.0, False), ("dr_grpo", 0.1, True)])
+def test_loss_and_metrics_inside_the_fused_pass(S, V, loss_type, beta, with_old):
+    """b200trl_grpo_fused_step: on the resident kernel the loss value and the logged metric means are summed inside
+    the pass (cluster partials, folded by the last cluster in cluster order).  Against K2 fed with the same
+    log-probs (the row-kernel route of the same entry point), against the oracle (1e-4, grpo_trainer.py:2130-2173),
+    bit-for-bit reproducible over repeated launches (the workspace counter resets itself)."""
+    from swh_trl_b200 import ops
+    from swh_trl_b200.grpo import METRIC_INDEX
+    B, T = 4, 37
+    logits, ids, mask = O.synth_batch(B, T, V, seed=V % 97, edge_rows=True)
+    g = torch.Generator().manual_seed(5)
+    adv = torch.randn(B, generator=g)
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax(logits.float(), ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.4 if with_old else None
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.2
+    x, idx, m = logits.to(DEV), ids.to(DEV), mask.to(DEV)
+    m32, rc, tot = ops.mask_stats(m)
+    cfg = ops.make_cfg(beta, 0.2, 0.25, None, loss_type, "token", T, grad_scale=0.5)
+    args = (x, idx, m32, rc, tot, adv.to(DEV), None if old is None else old.to(DEV), ref.to(DEV), cfg, 1.0)
+    runs = {}
+    for name, path in (("row", S.K1_ROW), ("resident", S.K1_RESIDENT)):
+        prev = S.set_k1_path(path)
+        try:
+            outs = [ops.grpo_fused_step(*args) for _ in range(3)]
+        finally:
+            S.set_k1_path(prev)
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            assert torch.equal(o[4], outs[0][4]) and torch.equal(o[5], outs[0][5]), f"{name}: not reproducible"
+        runs[name] = outs[0]
+    cfgo = O.GRPOConfigLite(beta=beta, epsilon_low=0.2, epsilon_high=0.25, loss_type=loss_type,
+                            importance_sampling_level="token", max_completion_length=T)
+    loss_r, met_r, _, _ = O.grpo_compute_loss(logits.float(), ids, mask, adv, cfgo, old, ref)
+    for name, o in runs.items():
+        loss, met = o[4].cpu(), o[5].cpu()
+        assert loss.item() == pytest.approx(loss_r.item(), rel=1e-4, abs=1e-7), name
+        assert met[METRIC_INDEX["kl"]].item() == pytest.approx(float(met_r.get("kl", 0.0)), rel=1e-4, abs=1e-7), name
+        assert met[METRIC_INDEX["entropy"]].item() == pytest.approx(float(met_r["entropy"]), rel=1e-4), name
+        for key in ("clip_ratio/low", "clip_ratio/high", "clip_ratio/region"):
+            assert met[METRIC_INDEX[key]].item() == pytest.approx(float(met_r[key]), abs=1e-6), (name, key)
+    # the two routes differ only in the order of the fp32 partial sums
+    torch.testing.assert_close(runs["resident"][4], runs["row"][4], rtol=2e-6, atol=1e-9)
+    torch.testing.assert_close(runs["resident"][5], runs["row"][5], rtol=2e-6, atol=1e-9)
+    # mask statistics counted by the call itself (row_count = total_count = None): inside the resident kernel by the
+    # consumer warps, through the mask_stats kernel on the row route -- the same integers, so the same bits
+    for name, path in (("row", S.K1_ROW), ("resident", S.K1_RESIDENT)):
+        prev = S.set_k1_path(path)
+        try:
+            own = ops.grpo_fused_step(x, idx, m32, None, None, *args[5:])
+        finally:
+            S.set_k1_path(prev)
+        for k in (0, 1, 3, 4, 5):
+            assert torch.equal(own[k], runs[name][k]), (name, k)
+    # forward-only evaluation (no gradient): K2 behind the pass, same numbers
+    prev = S.set_k1_path(S.K1_RESIDENT)
+    try:
+        ev = ops.grpo_fused_step(*args, want_grad=False)
+    finally:
+        S.set_k1_path(prev)
+    assert ev[3] is None
+    torch.testing.assert_close(ev[4], runs["row"][4], rtol=2e-6, atol=1e-9)
