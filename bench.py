@@ -562,8 +562,15 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
+        # stdout carries exactly one JSON line: NCCL writes its version banner (and, with NCCL_DEBUG set, its log) to
+        # file descriptor 1 from C, so everything written to fd 1 during the run is sent to stderr and the line goes
+        # out through a duplicate of the original descriptor
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     import swh_trl_b200 as S
@@ -807,7 +814,10 @@ def run_b200(args):
                                     "sample": f"{cpu_steps} timed steps of 1 sequence each (T={T}, V={V}; {nb} distinct "
                                               f"sequences of the same batch in turn), fp32 torch path fwd+bwd, "
                                               f"{ms:.0f} ms/step"}
-        print(json.dumps(line), flush=True)
+        if json_fd is not None:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
