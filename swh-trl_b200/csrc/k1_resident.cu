@@ -421,8 +421,28 @@ __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
 constexpr uint32_t kNegInf2 = 0xff80ff80u;  // bf16x2 (-inf, -inf)
 
 // fold one vector
+#ifndef B200TRL_K1_TREE
+#define B200TRL_K1_TREE 0
+#endif
 __device__ __forceinline__ void fold_words(uint64_t& s2, uint64_t& u2, const uint4& v, uint64_t c2, uint64_t nm2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#if B200TRL_K1_TREE
+    // A/B variant: the four pairs of a vector are summed as a tree, so the loop-carried accumulators see ONE dependent
+    // add / fma per vector instead of four
+    uint64_t e2[4], d2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+        d2[i] = ffma2(x2, c2, nm2);
+        float d0, d1;
+        unpack2(d2[i], d0, d1);
+        e2[i] = pack2(ex2(d0), ex2(d1));
+    }
+    s2 = fadd2(s2, fadd2(fadd2(e2[0], e2[1]), fadd2(e2[2], e2[3])));
+    const uint64_t ua = ffma2(e2[1], d2[1], fmul2(e2[0], d2[0]));
+    const uint64_t ub = ffma2(e2[3], d2[3], fmul2(e2[2], d2[2]));
+    u2 = fadd2(u2, fadd2(ua, ub));
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
@@ -434,7 +454,63 @@ __device__ __forceinline__ void fold_words(uint64_t& s2, uint64_t& u2, const uin
         s2 = fadd2(s2, e2);
         u2 = ffma2(e2, d2, u2);
     }
+#endif
 }
+// ---- exponentials on the FMA pipe (backward sweep of the fused pass) ----------------------------------------------
+// Under the power cap the fused pass is bound by the SFU (one MUFU.EX2 per element and sweep, 16 per clock and SM),
+// while the FMA pipe idles at 20 %.  B200TRL_K1_BWD_POLY8 of every 8 bf16 pairs of the BACKWARD sweep therefore take
+// 2^d from a Cody-Waite split + cubic instead: n = round(d) by the 1.5 * 2^23 trick, r = d - n in [-0.5, 0.5],
+// p(r) ~ 2^r (max rel. error 1.2e-4, a 30th of a bf16 half-ulp; the result is rounded to bf16 right after), and n is
+// added into p's exponent field.  d <= 0 here (lse >= max); the logits are clamped from below (packed bf16 max, NaN
+// propagating) so that d >= -125.5 and the exponent cannot wrap -- 2^-125 g is zero in bf16 anyway.  The forward sweep
+// keeps MUFU: its sums need fp32-accurate terms.
+#ifndef B200TRL_K1_BWD_POLY8
+#define B200TRL_K1_BWD_POLY8 0
+#endif
+__device__ __forceinline__ uint32_t bf16x2_max_nan(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t d2) {
+    const uint64_t magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f);
+    const uint64_t t2 = fadd2(d2, magic2);                            // low mantissa bits: round(d)
+    const uint64_t r2 = fadd2(d2, fadd2(nmagic2, t2) ^ 0x8000000080000000ull);  // d - round(d)
+    uint64_t p2 = ffma2(pack2(0.05507577f, 0.05507577f), r2, pack2(0.24237224f, 0.24237224f));
+    p2 = ffma2(p2, r2, pack2(0.69325519f, 0.69325519f));
+    p2 = ffma2(p2, r2, pack2(0.99994314f, 0.99994314f));
+    float t0, t1, p0, p1;
+    unpack2(t2, t0, t1);
+    unpack2(p2, p0, p1);
+    return pack2(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
+                 __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
+}
+// one vector of dlogits with NP of its 4 pairs on the FMA pipe; xmin2: packed bf16 lower clamp of the row
+template <int NP>
+__device__ __forceinline__ uint4 grad_vec_mix(const uint4& v, uint64_t c2, uint64_t nl2, uint64_t ng2, uint32_t xmin2) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool poly = i < NP;
+        const uint32_t wi = poly ? bf16x2_max_nan(w[i], xmin2) : w[i];
+        const uint64_t x2 = pack2(__uint_as_float(wi << 16), __uint_as_float(wi & 0xffff0000u));
+        const uint64_t d2 = ffma2(x2, c2, nl2);
+        uint64_t e2;
+        if (poly) {
+            e2 = exp2_poly2(d2);
+        } else {
+            float d0, d1;
+            unpack2(d2, d0, d1);
+            e2 = pack2(ex2(d0), ex2(d1));
+        }
+        float o0, o1;
+        unpack2(fmul2(e2, ng2), o0, o1);
+        o[i] = cvt_bf16x2(o0, o1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <int NC>
 struct FusedConsumer {
     static constexpr int kChunkBytes = chunk_bytes_for(NC);
@@ -543,7 +619,8 @@ struct FusedConsumer {
     }
     // one chunk of dlogits: gv = this CTA's slice of the row at this chunk
     template <bool FULL>
-    __device__ __forceinline__ void bwd(uint4* gv, uint64_t nl2, uint64_t ng2) {
+    __device__ __forceinline__ void bwd(uint4* gv, uint64_t nl2, uint64_t ng2, uint32_t xmin2) {
+        constexpr int kPolyEven = (B200TRL_K1_BWD_POLY8 + 1) / 2, kPolyOdd = B200TRL_K1_BWD_POLY8 / 2;
         const uint32_t base = slots_u32 + static_cast<uint32_t>(bslot) * kChunkBytes + my_off;
         uint4 v[kVpt];
 #pragma unroll
@@ -556,7 +633,8 @@ struct FusedConsumer {
 #pragma unroll
         for (int k = 0; k < kVpt; ++k)
             if (FULL || (tid + k * NC < tail_vecs))
-                st_global_cs(gv + tid + k * NC, grad_vec(v[k], c2, nl2, ng2));
+                st_global_cs(gv + tid + k * NC, (k & 1) ? grad_vec_mix<kPolyOdd>(v[k], c2, nl2, ng2, xmin2)
+                                                        : grad_vec_mix<kPolyEven>(v[k], c2, nl2, ng2, xmin2));
         if (++bslot == num_slots) bslot = 0;
     }
     template <bool FULL>
@@ -1011,9 +1089,13 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 for (int cidx = 0; cidx < n_full; ++cidx) fc.template bwd_zero<true>(gv + static_cast<int64_t>(cidx) * (kChunkBytes / 16));
                 if (n_full < C) fc.template bwd_zero<false>(gv + static_cast<int64_t>(n_full) * (kChunkBytes / 16));
             } else {
+                // lower clamp of the logits for the FMA-pipe exponentials: x c - lse2 >= -125.5 (bf16 rounding included)
+                const uint32_t xm = __float_as_uint((rr.lse2 - 125.f) / fc.c) >> 16;
+                const uint32_t xmin2 = xm | (xm << 16);
                 for (int cidx = 0; cidx < n_full; ++cidx)
-                    fc.template bwd<true>(gv + static_cast<int64_t>(cidx) * (kChunkBytes / 16), nl2, ng2);
-                if (n_full < C) fc.template bwd<false>(gv + static_cast<int64_t>(n_full) * (kChunkBytes / 16), nl2, ng2);
+                    fc.template bwd<true>(gv + static_cast<int64_t>(cidx) * (kChunkBytes / 16), nl2, ng2, xmin2);
+                if (n_full < C)
+                    fc.template bwd<false>(gv + static_cast<int64_t>(n_full) * (kChunkBytes / 16), nl2, ng2, xmin2);
                 // the selected id: g' * (1 - p_id); the thread that wrote the vector holding it patches it
                 if (rr.id_vec >= 0 && (rr.id_vec % kConsumers) == tid)
                     reinterpret_cast<__nv_bfloat16*>(gv + static_cast<int64_t>(rr.id_chunk) * (kChunkBytes / 16))[rr.id_elem] =
