@@ -31,7 +31,7 @@ from typing import Optional, Sequence, Sized, Union
 import torch
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("REF_ROOT", "/root/reference")
+REF_ROOT = "/root/reference"  # the read-only mount; deliberately not overridable (this module exec()s source read from it)
 
 _BASE_NS = {
     "torch": torch,

@@ -22,3 +22,23 @@ def nvtx_range(name: str):
             torch.cuda.nvtx.range_pop()
     else:
         yield
+
+
+def nvtx_op(name: str):
+    """Decorator form: the wrapped operator runs inside a ``b200trl.<name>`` range."""
+    def deco(fn):
+        if not _ENABLED:
+            return fn
+        import functools
+
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            if not torch.cuda.is_available():
+                return fn(*args, **kwargs)
+            torch.cuda.nvtx.range_push("b200trl." + name)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco

@@ -12,6 +12,7 @@ from typing import Optional, Tuple
 
 import torch
 
+from ._nvtx import nvtx_op
 from . import ops
 from ._lib import check, lib
 
@@ -23,6 +24,7 @@ def _ids(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.to(torch.int64).contiguous()
 
 
+@nvtx_op("first_true_indices")
 def first_true_indices(bools: torch.Tensor, dtype: torch.dtype = torch.long) -> torch.Tensor:
     """Position of the first True along the last dim, the row length if there is none (utils.py:877-897)."""
     ops._need_cuda(bools, "bools")
@@ -40,6 +42,7 @@ def first_true_indices(bools: torch.Tensor, dtype: torch.dtype = torch.long) -> 
     return out.to(dtype)
 
 
+@nvtx_op("completion_mask_from_eos")
 def completion_mask_from_eos(completion_ids: torch.Tensor, eos_token_id: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """``(completion_mask int32 [B,T], eos_idx int64 [B])`` — grpo_trainer.py:1812-1817 in one launch."""
     ids = _ids(completion_ids, "completion_ids")
@@ -53,6 +56,7 @@ def completion_mask_from_eos(completion_ids: torch.Tensor, eos_token_id: int) ->
     return mask, eos_idx
 
 
+@nvtx_op("truncate_response_with_lengths")
 def truncate_response_with_lengths(stop_token_id: Optional[int], pad_token_id: int,
                                    responses: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """``(postprocessed_response, sequence_length)`` as ppo_trainer.py:455-464 / rloo_trainer.py:347-355 compute

@@ -672,3 +672,19 @@ def set_seam_gemm_mask(mask: int) -> int:
     """Bit 0 / 1 / 2 = logits / dH / dW GEMM of ``fused_linear_grpo`` on the tcgen05 kernel (clear = cuBLASLt);
     returns the previous mask, ``mask < 0`` only queries."""
     return int(lib.b200trl_set_seam_gemm_mask(int(mask)))
+
+
+# ------------------------------------------------------------------------------------------------ tracing
+# Every operator that reaches the library runs inside an NVTX range ``b200trl.<op>`` (SURVEY §5 tracing / profiling);
+# B200TRL_NVTX=0 leaves the functions unwrapped.
+from ._nvtx import nvtx_op as _nvtx_op  # noqa: E402
+
+for _name in ("logprob_entropy_fwd", "masked_logprob_fwd", "logprob_bwd", "mask_stats", "grpo_fused_fwd_bwd",
+              "grpo_fused_step", "grpo_loss", "entropy_quantile_mask", "group_advantages", "ppo_rewards_gae",
+              "ppo_fused_fwd_bwd", "ppo_loss", "masked_whiten", "rloo_rewards_advantages", "rloo_loss",
+              "fused_linear_logprob_fwd", "fused_linear_grpo", "tc_gemm", "rescale_if_needed", "completion_mask",
+              "first_true_indices", "truncate_response"):
+    if _name in globals():
+        globals()[_name] = _nvtx_op(_name)(globals()[_name])
+del _name
+

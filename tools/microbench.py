@@ -162,7 +162,7 @@ def main():
     ms, n = timeit(lambda: ops.grpo_loss(lp0, old, ref, adv, m32, rc, tot, cfg, entropy=ent0, want_g=True), flush=flush)
     add("K2 grpo_loss (+g) C2", ms, n, 40 * N, "latency-bound: 16K tokens, ~40 B/token")
     ms, n = timeit(lambda: ops.entropy_quantile_mask(ent0, mask, 0.8), flush=flush)
-    add("entropy quantile mask C2 (16K tokens)", ms, n, None, "single-CTA radix select")
+    add("entropy quantile mask C2 (16K tokens)", ms, n, None, "radix select in one 8-CTA cluster (DSMEM histograms)")
     ms, n = timeit(lambda: ops.mask_stats(mask), flush=flush)
     add("mask_stats C2", ms, n, None, "memset + kernel")
     del logits, x, dl
