@@ -22,6 +22,7 @@ bool takes_resident(const K1Args& a, int dtype) {
 }
 
 int dispatch(K1Args a, int dtype, cudaStream_t stream) {
+    a.elem_f16 = (dtype == B200TRL_F16) ? 1 : 0;
     a.trace = g_trace.load();
     a.trace_row0 = g_trace_row0.load();
     const int path = g_k1_path.load();

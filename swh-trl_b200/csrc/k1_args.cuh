@@ -51,6 +51,7 @@ struct K1Args {
     // G_GRPO, resident kernel only (b200trl_grpo_fused_step): the loss value and the logged metric sums are folded
     // into the same pass -- every cluster leader keeps running sums of its rows' terms, leaves them in step_ws and the
     // last one to finish adds the partials in cluster order (double) and writes loss[1] / metrics[8].  Null: off.
+    int elem_f16;    // resident kernel: the 16-bit logits are fp16 (0: bf16); set by the dispatcher
     int count_mask;  // 1: row_count / total_count are null, the kernel counts `mask` itself (B <= 256 sequences)
     float* step_ws;  // [1 counter word + 3 pad][max clusters][8]
     float* step_loss;

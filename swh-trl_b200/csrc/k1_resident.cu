@@ -19,8 +19,15 @@
 // Persistent grid: clusters (or single CTAs) loop over rows with a static stride.  Replaces
 // trl/trainer/utils.py:1430-1490 + grpo_trainer.py:1258 + the autograd backward down to the logits
 // (see include/b200trl.h).  Measured behaviour, the phase trace and what was tried: DESIGN.md §3.
+// Two translation units are built from this file so that the ~170 kernel instantiations compile in parallel:
+// k1_resident.cu itself (bf16, K1_UNIT_F16 = 0: every variant plus the host-side policy and the public entry points)
+// and k1_resident_f16.cu (defines K1_UNIT_F16 = 1 and includes this file: the fp16 instantiations only).
+#ifndef K1_UNIT_F16
+#define K1_UNIT_F16 0
+#endif
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "k1_args.cuh"
 
@@ -259,6 +266,56 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
     return d;
 }
 
+// ------------------------------------------------------------------ element type (bf16, or fp16 when F16)
+// Only four things depend on the 16-bit element type: the packed maximum, the unpack to fp32 pairs, the pack of a
+// gradient pair, and the "very negative" stand-in of a masked element.  fp16 runs on the generic consumer code.
+template <bool F16>
+__device__ __forceinline__ uint32_t el_max2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    if (F16)
+        asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    else
+        asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint64_t el_unpack(uint32_t w) {  // packed pair -> (lo, hi) as f32x2
+    if (F16) {
+        float lo, hi;
+        asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+            : "=f"(lo), "=f"(hi)
+            : "r"(w));
+        return pack2(lo, hi);
+    }
+    return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <bool F16>
+__device__ __forceinline__ float el_pair_max(uint32_t mx) {  // max of the two halves of a packed pair, as fp32
+    float lo, hi;
+    unpack2(el_unpack<F16>(mx), lo, hi);
+    return fmaxf(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t el_pack(float lo, float hi) {
+    uint32_t d;
+    if (F16)
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <bool F16>
+__device__ __forceinline__ void el_store(void* base, int64_t idx, float v) {
+    if (F16)
+        reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+    else
+        reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+// stand-in of a masked element: bf16(-1e30) / the most negative finite fp16 (-65504): 2^(x c - m) == 0 and
+// 0 * (x c - m) == -0 for any sane inv_T
+template <bool F16>
+constexpr uint32_t kNegEl = F16 ? 0xFBFFu : 0xF149u;
+
 // ------------------------------------------------------------------ consumer state
 struct Acc {
     float m;       // reference point (log2 units)
@@ -272,8 +329,9 @@ __device__ __forceinline__ Acc acc_empty() {
     return Acc{kNegBig, 0ull, 0ull, 0ull, 0ull};  // bit pattern 0 == (0.f, 0.f)
 }
 
+template <bool F16 = false>
 __device__ __forceinline__ uint32_t vec_max(const uint4& v) {
-    return bf16x2_max(bf16x2_max(v.x, v.y), bf16x2_max(v.z, v.w));
+    return el_max2<F16>(el_max2<F16>(v.x, v.y), el_max2<F16>(v.z, v.w));
 }
 
 // move the reference point to cm (rare after the first chunk)
@@ -288,11 +346,12 @@ __device__ __forceinline__ void acc_rescale(Acc& a, float cm) {
     a.m = cm;
 }
 
+template <bool F16 = false>
 __device__ __forceinline__ void acc_words(uint64_t& s2, uint64_t& u2, const uint4& v, uint64_t c2, uint64_t nm2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+        const uint64_t x2 = el_unpack<F16>(w[i]);
         const uint64_t d2 = ffma2(x2, c2, nm2);
         float d0, d1;
         unpack2(d2, d0, d1);
@@ -303,36 +362,37 @@ __device__ __forceinline__ void acc_words(uint64_t& s2, uint64_t& u2, const uint
 }
 
 // fold one 16-byte vector
+template <bool F16 = false>
 __device__ __forceinline__ void acc_vec(Acc& a, const uint4& v, float c, uint64_t c2) {
-    const uint32_t mx = vec_max(v);
-    const float cm = fmaxf(__uint_as_float(mx << 16), __uint_as_float(mx & 0xffff0000u)) * c;
+    const float cm = el_pair_max<F16>(vec_max<F16>(v)) * c;
     if (cm > a.m + kSlack) acc_rescale(a, cm);
-    acc_words(a.s2, a.u2, v, c2, pack2(-a.m, -a.m));
+    acc_words<F16>(a.s2, a.u2, v, c2, pack2(-a.m, -a.m));
 }
 
 // fold two vectors with ONE reference-point check and two independent accumulation chains
+template <bool F16 = false>
 __device__ __forceinline__ void acc_vec2(Acc& a, const uint4& v0, const uint4& v1, float c, uint64_t c2) {
-    const uint32_t mx = bf16x2_max(vec_max(v0), vec_max(v1));
-    const float cm = fmaxf(__uint_as_float(mx << 16), __uint_as_float(mx & 0xffff0000u)) * c;
+    const float cm = el_pair_max<F16>(el_max2<F16>(vec_max<F16>(v0), vec_max<F16>(v1))) * c;
     if (cm > a.m + kSlack) acc_rescale(a, cm);
     const uint64_t nm2 = pack2(-a.m, -a.m);
-    acc_words(a.s2, a.u2, v0, c2, nm2);
-    acc_words(a.t2, a.v2, v1, c2, nm2);
+    acc_words<F16>(a.s2, a.u2, v0, c2, nm2);
+    acc_words<F16>(a.t2, a.v2, v1, c2, nm2);
 }
 
+template <bool F16 = false>
 __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t nl2, uint64_t ng2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const uint64_t x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+        const uint64_t x2 = el_unpack<F16>(w[i]);
         const uint64_t d2 = ffma2(x2, c2, nl2);
         float d0, d1;
         unpack2(d2, d0, d1);
         const uint64_t e2 = pack2(ex2(d0), ex2(d1));
         float o0, o1;
         unpack2(fmul2(e2, ng2), o0, o1);
-        o[i] = cvt_bf16x2(o0, o1);
+        o[i] = el_pack<F16>(o0, o1);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -341,13 +401,13 @@ __device__ __forceinline__ uint4 grad_vec(const uint4& v, uint64_t c2, uint64_t 
 // elements (0..7) into the first vector and the last vector may end early; the elements outside the slice belong to
 // the neighbouring rows (or lie past the tensor, inside the same 16-byte granule: never a fault) and are replaced by a
 // large negative logit before any arithmetic.  Only the first and the last vector of a slice are affected.
-constexpr uint32_t kNegBf = 0xF149u;  // bf16(-1e30): 2^(x c - m) == 0 and 0 * (x c - m) == -0 for any sane inv_T
+template <bool F16 = false>
 __device__ __forceinline__ uint4 mask_vec(const uint4& v, int lo, int hi) {  // keep elements [lo, hi) of the 8
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (2 * i < lo || 2 * i >= hi) w[i] = (w[i] & 0xffff0000u) | kNegBf;
-        if (2 * i + 1 < lo || 2 * i + 1 >= hi) w[i] = (w[i] & 0x0000ffffu) | (kNegBf << 16);
+        if (2 * i < lo || 2 * i >= hi) w[i] = (w[i] & 0xffff0000u) | kNegEl<F16>;
+        if (2 * i + 1 < lo || 2 * i + 1 >= hi) w[i] = (w[i] & 0x0000ffffu) | (kNegEl<F16> << 16);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -694,9 +754,11 @@ struct Cursor {
 };
 
 // FAST: 0 = generic consumer code; 1 = FusedConsumer
-template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST, bool SKEW>
+template <bool HAS_FWD, bool HAS_BWD, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST, bool SKEW, bool F16>
 __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumers: <= 78 registers
     k1_resident_kernel(const K1Args a, const int num_slots, const int max_lag, const int l2_prefetch) {
+    static_assert(!F16 || FAST == 0, "fp16 logits run on the generic consumer code");
+    using ElemT = typename std::conditional<F16, __half, __nv_bfloat16>::type;
     static_assert(FAST == 0 || (HAS_FWD && HAS_BWD && DUAL && DIRECT), "the fast consumer is the fused pass");
     static_assert(!SKEW || (FAST == 0 && (DIRECT || !HAS_BWD)), "skewed rows: generic consumers, dlogits from registers");
     constexpr int kConsumers = NC;
@@ -759,6 +821,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
     __syncthreads();
     if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
 
+    // 16-bit elements either way: the pointer arithmetic (element offsets) is the same for bf16 and fp16
     const __nv_bfloat16* logits = reinterpret_cast<const __nv_bfloat16*>(a.logits);
     __nv_bfloat16* dlogits = reinterpret_cast<__nv_bfloat16*>(a.dlogits);
 
@@ -873,7 +936,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             RowScalars rs{}, rs_next{};
             if (lane == 0 && n_my_rows > 0) {
                 rs = load_row_scalars_direct(a, first_row, ppo_count, row_count, total_count);
-                rs.x_sel = load_selected_logit<__nv_bfloat16>(a, first_row, rs.id);
+                rs.x_sel = load_selected_logit<ElemT>(a, first_row, rs.id);
                 if (n_my_rows > 1) rs_next = load_row_scalars_direct(a, first_row + row_step, ppo_count, row_count, total_count);
             }
             for (int i = 0; i < n_my_rows; ++i) {
@@ -884,7 +947,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 float x_next = 0.f;
                 RowScalars rs_after{};
                 if (lane == 0) {
-                    if (i + 1 < n_my_rows) x_next = load_selected_logit<__nv_bfloat16>(a, row + row_step, rs_next.id);
+                    if (i + 1 < n_my_rows) x_next = load_selected_logit<ElemT>(a, row + row_step, rs_next.id);
                     if (i + 2 < n_my_rows)
                         rs_after = load_row_scalars_direct(a, row + 2 * row_step, ppo_count, row_count, total_count);
                 }
@@ -1135,7 +1198,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
 #pragma unroll
                 for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
 #pragma unroll
-                for (int k = 0; k < kVpt; k += 2) acc_vec2(acc, v[k], v[k + 1], c, c2);
+                for (int k = 0; k < kVpt; k += 2) acc_vec2<F16>(acc, v[k], v[k + 1], c, c2);
             } else if (SKEW) {
                 const int v0 = cidx * kChunkVecs;
                 const int n_here = min(max(f_nvec - v0, 0), kChunkVecs);
@@ -1151,18 +1214,18 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                             const int gi = v0 + tid + k * kConsumers;
                             const int lo = (gi == 0) ? f_h : 0;
                             const int hi = (gi == f_nvec - 1 && keep != 0) ? keep : 8;
-                            if (lo != 0 || hi != 8) v[k] = mask_vec(v[k], lo, hi);
+                            if (lo != 0 || hi != 8) v[k] = mask_vec<F16>(v[k], lo, hi);
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < kVpt; k += 2) acc_vec2(acc, v[k], v[k + 1], c, c2);
+                    for (int k = 0; k < kVpt; k += 2) acc_vec2<F16>(acc, v[k], v[k + 1], c, c2);
                 } else {
                     for (int v = tid; v < n_here; v += kConsumers) {
                         uint4 x = sv[v];
                         const int lo = (v0 + v == 0) ? f_h : 0;
                         const int hi = (v0 + v == f_nvec - 1 && keep != 0) ? keep : 8;
-                        if (lo != 0 || hi != 8) x = mask_vec(x, lo, hi);
-                        acc_vec(acc, x, c, c2);
+                        if (lo != 0 || hi != 8) x = mask_vec<F16>(x, lo, hi);
+                        acc_vec<F16>(acc, x, c, c2);
                     }
                 }
             } else if (cidx != C - 1 || last_bytes == kChunkBytes) {
@@ -1172,15 +1235,15 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
 #pragma unroll
                 for (int k = 0; k < kVpt; k += 2) {
                     if (DUAL) {
-                        acc_vec2(acc, v[k], v[k + 1], c, c2);
+                        acc_vec2<F16>(acc, v[k], v[k + 1], c, c2);
                     } else {
-                        acc_vec(acc, v[k], c, c2);
-                        acc_vec(acc, v[k + 1], c, c2);
+                        acc_vec<F16>(acc, v[k], c, c2);
+                        acc_vec<F16>(acc, v[k + 1], c, c2);
                     }
                 }
             } else {
                 const int nvec = last_bytes >> 4;
-                for (int v = tid; v < nvec; v += kConsumers) acc_vec(acc, sv[v], c, c2);
+                for (int v = tid; v < nvec; v += kConsumers) acc_vec<F16>(acc, sv[v], c, c2);
             }
             if (!HAS_BWD) {  // forward only: the slot can be refilled as soon as every warp has read it
                 __syncwarp();
@@ -1238,7 +1301,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                     rr = sm.result[par];
                 } else {
                     if (tid == 0) {
-                        const RowScalars rs = load_row_scalars<__nv_bfloat16>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
+                        const RowScalars rs = load_row_scalars<ElemT>(a, row, a.gmode == G_PPO ? sm.ppo_count : 1.f);
                         const float lse2 = a.lse_in[row] * kLog2e;
                         const float logp = fmaf(rs.x_sel, c, -lse2) * kLn2;
                         const float gp = token_grad(a, rs, logp) * a.inv_temp;
@@ -1297,15 +1360,15 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
 #pragma unroll
-                            for (int k = 0; k < kVpt; ++k) put(tid + k * kConsumers, grad_vec(v[k], c2, nl2, ng2));
+                            for (int k = 0; k < kVpt; ++k) put(tid + k * kConsumers, grad_vec<F16>(v[k], c2, nl2, ng2));
                         } else {
                             for (int v = tid; v < nvec; v += kConsumers)
-                                put(v, zero_row ? make_uint4(0u, 0u, 0u, 0u) : grad_vec(sv[v], c2, nl2, ng2));
+                                put(v, zero_row ? make_uint4(0u, 0u, 0u, 0u) : grad_vec<F16>(sv[v], c2, nl2, ng2));
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
                         }
                         if (!zero_row && patch_mine && cidx == rr.id_chunk)
-                            reinterpret_cast<__nv_bfloat16*>(gv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                            el_store<F16>(gv, rr.id_elem, rr.patch);
                     } else if (DIRECT) {
                         // gradients go straight from registers to global memory (coalesced 16-byte stores); the slot is
                         // released as soon as every warp has READ it, so its refill overlaps this chunk's arithmetic
@@ -1320,14 +1383,14 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
 #pragma unroll
-                            for (int k = 0; k < kVpt; ++k) st_global_cs(gv + tid + k * kConsumers, grad_vec(v[k], c2, nl2, ng2));
+                            for (int k = 0; k < kVpt; ++k) st_global_cs(gv + tid + k * kConsumers, grad_vec<F16>(v[k], c2, nl2, ng2));
                         } else {
-                            for (int v = tid; v < nvec; v += kConsumers) st_global_cs(gv + v, grad_vec(sv[v], c2, nl2, ng2));
+                            for (int v = tid; v < nvec; v += kConsumers) st_global_cs(gv + v, grad_vec<F16>(sv[v], c2, nl2, ng2));
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&sm.done_bar[bcur.slot]);
                         }
                         if (!zero_row && patch_mine && cidx == rr.id_chunk)  // same thread wrote the vector holding it
-                            reinterpret_cast<__nv_bfloat16*>(gv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                            el_store<F16>(gv, rr.id_elem, rr.patch);
                     } else {
                         if (zero_row) {
                             for (int v = tid; v < nvec; v += kConsumers) sv[v] = make_uint4(0u, 0u, 0u, 0u);
@@ -1337,12 +1400,12 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
 #pragma unroll
                                 for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
 #pragma unroll
-                                for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec(v[k], c2, nl2, ng2);
+                                for (int k = 0; k < kVpt; ++k) sv[tid + k * kConsumers] = grad_vec<F16>(v[k], c2, nl2, ng2);
                             } else {
-                                for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec(sv[v], c2, nl2, ng2);
+                                for (int v = tid; v < nvec; v += kConsumers) sv[v] = grad_vec<F16>(sv[v], c2, nl2, ng2);
                             }
                             if (patch_mine && cidx == rr.id_chunk)
-                                reinterpret_cast<__nv_bfloat16*>(sv)[rr.id_elem] = __float2bfloat16_rn(rr.patch);
+                                el_store<F16>(sv, rr.id_elem, rr.patch);
                         }
                         fence_proxy_async();  // generic-proxy writes -> visible to the bulk store
                         __syncwarp();
@@ -1380,6 +1443,11 @@ int env_int(const char* name, int dflt) {
 thread_local int g_skew_extra = 0;
 int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     static const int forced = env_int("B200TRL_K1_CLUSTER", 0);  // tuning knob: force a (larger) cluster size
+    if (forced == 3 || forced == 5 || forced == 6 || forced == 7) {  // experiments: any size the hardware takes
+        const int64_t slice = ((vocab + forced - 1) / forced + 7) & ~int64_t(7);
+        const int64_t chunks = (slice * 2 + g_skew_extra + chunk_bytes - 1) / chunk_bytes;
+        if (chunks <= num_slots - 1) return forced;
+    }
     for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
         if (cs < forced) continue;
         const int64_t slice = ((vocab + cs - 1) / cs + 7) & ~int64_t(7);
@@ -1389,9 +1457,9 @@ int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
     return 0;
 }
 
-template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST, bool SKEW = false>
+template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP, int FAST, bool SKEW = false, bool F16 = false>
 int launch_mode_f(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
-    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP, FAST, SKEW>;
+    auto kern = k1_resident_kernel<F, Bk, DUAL, NC, DIRECT, SKIP, FAST, SKEW, F16>;
     constexpr int kThreads = NC + 64;  // + DMA warp + reducer warp
     static_assert(chunk_bytes_for(NC) % (NC * 16) == 0, "a full chunk must give every consumer the same vector count");
     constexpr int kCtasPerSm = (NC <= 256) ? 2 : 1;
@@ -1457,6 +1525,17 @@ bool rows_skewed(const K1Args& a) {
 
 template <bool F, bool Bk, bool DUAL, int NC, bool DIRECT, bool SKIP>
 int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
+#if K1_UNIT_F16
+    // fp16 logits: the generic consumer code with the fp16 unpack / pack / max (dual chains; lean shapes excluded)
+    if constexpr (DUAL && NC != 320 && NC != 384) {
+        if constexpr (DIRECT || !Bk) {
+            if (rows_skewed(a)) return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 0, true, true>(a, cs, num_slots, stream);
+        }
+        if (!rows_skewed(a)) return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 0, false, true>(a, cs, num_slots, stream);
+    }
+    set_error("k1_resident: no fp16 instantiation for this variant");
+    return B200TRL_E_UNSUPPORTED;
+#else
     // skewed rows (vocab % 8 != 0 ...): generic consumers with masked edge vectors, dlogits straight from registers
     if constexpr (DUAL && (DIRECT || !Bk)) {
         if (rows_skewed(a)) return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 0, true>(a, cs, num_slots, stream);
@@ -1472,6 +1551,7 @@ int launch_mode_s(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
     }
 #endif
     return launch_mode_f<F, Bk, DUAL, NC, DIRECT, SKIP, 0>(a, cs, num_slots, stream);
+#endif  // K1_UNIT_F16
 }
 
 // Four CTA geometries (which one serves a call: pick_geom below):
@@ -1599,31 +1679,27 @@ int launch_mode_t(const K1Args& a, int cs, int num_slots, cudaStream_t stream) {
 
 template <bool F, bool Bk>
 int launch_mode(const K1Args& a, const Geom& g, cudaStream_t stream) {
-    // measured on B200 (tools/k1_sweep.sh): two accumulation chains with one reference-point check per vector pair
-    // help every mode (forward-only +3 %, fused +2..4 %) now that the row hand-off no longer bounds the fused pass
-    static const int dual_env = env_int("B200TRL_K1_DUAL", -1);
-    const bool dual = dual_env != 0 || rows_skewed(a);
-    if (g.nc == 256)
-        return dual ? launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream)
-                    : launch_mode_t<F, Bk, false, 256>(a, g.cs, g.slots, stream);
+    // Two accumulation chains with one reference-point check per vector pair: measured on B200 (tools/k1_sweep.sh)
+    // they help every mode (forward-only +3 %, fused +2..4 %), so the single-chain form is no longer instantiated
+    // (the DUAL template parameter stays for the record; it halves the number of kernels to compile).
+    if (g.nc == 256) return launch_mode_t<F, Bk, true, 256>(a, g.cs, g.slots, stream);
     if (g.nc == 640)  // fused pass only (pick_geom); the other modes never ask for it
-        return dual ? launch_mode_t<F, Bk, true, (F && Bk) ? 640 : 512>(a, g.cs, g.slots, stream)
-                    : launch_mode_t<F, Bk, false, (F && Bk) ? 640 : 512>(a, g.cs, g.slots, stream);
-    if (g.nc == 768)
-        return dual ? launch_mode_t<F, Bk, true, 768>(a, g.cs, g.slots, stream)
-                    : launch_mode_t<F, Bk, false, 768>(a, g.cs, g.slots, stream);
+        return launch_mode_t<F, Bk, true, (F && Bk) ? 640 : 512>(a, g.cs, g.slots, stream);
+    if (g.nc == 768) return launch_mode_t<F, Bk, true, 768>(a, g.cs, g.slots, stream);
     if constexpr (F && Bk) {  // lean shapes: fused pass only
         if (g.nc == 320) return launch_mode_t<F, Bk, true, 320>(a, g.cs, g.slots, stream);
         if (g.nc == 384) return launch_mode_t<F, Bk, true, 384>(a, g.cs, g.slots, stream);
     }
-    return dual ? launch_mode_t<F, Bk, true, 512>(a, g.cs, g.slots, stream)
-                : launch_mode_t<F, Bk, false, 512>(a, g.cs, g.slots, stream);
+    return launch_mode_t<F, Bk, true, 512>(a, g.cs, g.slots, stream);
 }
 
 }  // namespace
 
+#if !K1_UNIT_F16
 bool k1_resident_supported(const K1Args& a, int dtype) {
-    if (dtype != B200TRL_BF16) return false;
+    if (dtype != B200TRL_BF16 && dtype != B200TRL_F16) return false;
+    static const int allow_f16 = env_int("B200TRL_K1_F16", 1);  // 0: fp16 logits go to the row kernel (A/B runs)
+    if (dtype == B200TRL_F16 && !allow_f16) return false;
     static const int allow_skew = env_int("B200TRL_K1_SKEW", 1);  // 0: skewed rows go to the row kernel (A/B runs)
     const bool skew = rows_skewed(a);
     if (skew && !allow_skew) return false;
@@ -1658,7 +1734,15 @@ void k1_resident_geometry(int64_t vocab, int mode, int32_t out[4]) {
     out[3] = chunk_bytes_for(g.nc);
 }
 
+#endif  // !K1_UNIT_F16
+
+#if K1_UNIT_F16
+int launch_k1_resident_f16(const K1Args& a, cudaStream_t stream) {
+#else
+int launch_k1_resident_f16(const K1Args& a, cudaStream_t stream);  // k1_resident_f16.cu
 int launch_k1_resident(const K1Args& a, cudaStream_t stream) {
+    if (a.elem_f16) return launch_k1_resident_f16(a, stream);
+#endif
     if (a.n_rows == 0) return B200TRL_OK;
     const Mode m = mode_of(a);
     const Geom g = pick_geom(a.vocab, m, rows_skewed(a));

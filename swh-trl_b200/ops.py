@@ -149,7 +149,7 @@ def alloc_dlogits(r: Rows, shape):
     a row go out element by element), so the buffer copies the logits' strides modulo 8 elements: at most 7 elements
     of padding per row / per batch, returned as a strided view of the requested shape."""
     x, V = r.t, r.V
-    skew = x.dtype == torch.bfloat16 and bool(V % 8 or r.row_stride % 8 or r.batch_stride % 8 or x.data_ptr() % 16)
+    skew = x.dtype in (torch.bfloat16, torch.float16) and bool(V % 8 or r.row_stride % 8 or r.batch_stride % 8 or x.data_ptr() % 16)
     if not skew or len(shape) not in (2, 3) or r.n == 0:
         return torch.empty(shape, dtype=x.dtype, device=x.device), V, 0
     e0 = (x.data_ptr() // 2) % 8

@@ -52,7 +52,7 @@ def _paths(S, logits):
     """K1 implementations applicable to this tensor."""
     out = [S.K1_ROW]
     V = logits.shape[-1]
-    if logits.dtype == torch.bfloat16 and V * 2 >= 32768:  # any alignment: skewed rows run with masked edge vectors
+    if logits.dtype in (torch.bfloat16, torch.float16) and V * 2 >= 32768:  # any alignment (skewed rows); fp16 too
         out.append(S.K1_RESIDENT)
     return out
 
@@ -1457,3 +1457,120 @@ def test_loss_and_metrics_inside_the_fused_pass(S, V, loss_type, beta, with_old)
         S.set_k1_path(prev)
     assert ev[3] is None
     torch.testing.assert_close(ev[4], runs["row"][4], rtol=2e-6, atol=1e-9)
+
+
+def test_one_launch_step_in_a_graph_and_on_two_streams(S):
+    """b200trl_grpo_fused_step neither allocates nor synchronises: the whole GRPO loss step (mask statistics, log-probs,
+    dlogits, loss, metrics -- one kernel) is captured in a CUDA graph and replayed on new data; and two streams running
+    the step at the same time do not share its workspace (the cluster partials and the arrival counter live there)."""
+    from swh_trl_b200 import ops
+    B, T, V = 3, 40, 151936
+    cfg = ops.make_cfg(0.04, 0.2, 0.2, None, "bnpo", "token", T)
+    data = []
+    for seed in (21, 22):
+        logits, ids, mask = O.synth_batch(B, T, V, seed=seed, edge_rows=False)
+        g = torch.Generator().manual_seed(seed)
+        adv = torch.randn(B, generator=g)
+        with torch.no_grad():
+            lp0 = O.selective_log_softmax(logits.float(), ids)
+        old, ref = lp0 + torch.randn(B, T, generator=g) * 0.3, lp0 + torch.randn(B, T, generator=g) * 0.1
+        cfgo = O.GRPOConfigLite(beta=0.04, loss_type="bnpo", importance_sampling_level="token", max_completion_length=T)
+        want = O.grpo_compute_loss(logits.float(), ids, mask, adv, cfgo, old, ref)[0].item()
+        data.append(([t.to(DEV) for t in (logits, ids, mask, adv, old, ref)], want))
+    bufs = [t.clone() for t in data[0][0]]
+    dl = torch.empty_like(bufs[0])
+
+    def step(t, out_dl):
+        return ops.grpo_fused_step(t[0], t[1], t[2], None, None, t[3], t[4], t[5], cfg, 1.0, dlogits_out=out_dl)
+
+    eager = step(bufs, dl)  # warm-up outside capture (workspace allocation, kernel attributes)
+    torch.cuda.synchronize()
+    assert eager[4].item() == pytest.approx(data[0][1], rel=1e-4)
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            cap = step(bufs, dl)
+    torch.cuda.current_stream().wait_stream(side)
+    for b, t in zip(bufs, data[1][0]):
+        b.copy_(t)
+    for _ in range(3):  # the arrival counter resets itself: replays reproduce each other
+        graph.replay()
+    torch.cuda.synchronize()
+    assert cap[4].item() == pytest.approx(data[1][1], rel=1e-4)
+    ref_run = step(data[1][0], torch.empty_like(dl))
+    assert torch.equal(cap[4], ref_run[4]) and torch.equal(cap[5], ref_run[5]) and torch.equal(cap[0], ref_run[0])
+    assert torch.equal(dl, ref_run[3])
+    # two streams, different data, interleaved launches
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for s in (s1, s2):
+        s.wait_stream(torch.cuda.current_stream())
+    outs = {1: [], 2: []}
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            outs[1].append(step(data[0][0], torch.empty_like(dl)))
+        with torch.cuda.stream(s2):
+            outs[2].append(step(data[1][0], torch.empty_like(dl)))
+    torch.cuda.synchronize()
+    for k, want in ((1, data[0][1]), (2, data[1][1])):
+        for o in outs[k]:
+            assert o[4].item() == pytest.approx(want, rel=1e-4)
+            assert torch.equal(o[4], outs[k][0][4]) and torch.equal(o[5], outs[k][0][5])
+
+
+# ------------------------------------------------------------------------------------------------ fp16 logits
+@pytest.mark.parametrize("V", [32768, 50257, 151936])   # twin CTAs / skewed rows / 2-CTA clusters
+def test_fp16_logits_on_the_resident_kernel(S, V):
+    """fp16 logits take the TMA kernel too (generic consumer code with the fp16 unpack / pack / max): forward-only,
+    fused GRPO and backward-only against the oracle on the same fp16 inputs and against the row kernel.  Bars as for
+    bf16 with fp16's ulp: log-probs 1e-5, dlogits within one fp16 ulp of the fp32 oracle gradient rounded to fp16
+    (plus one fp16 subnormal step, 6e-8, where the gradient underflows)."""
+    from swh_trl_b200 import ops
+    B, T = 2, 7
+    g = torch.Generator().manual_seed(V + 1)
+    logits = (torch.randn(B, T, V, generator=g) * 2).to(torch.float16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    ids[0, 0], ids[0, 1] = 0, V - 1
+    mask = torch.ones(B, T, dtype=torch.int32)
+    mask[1, -2:] = 0
+    adv = torch.tensor([1.5, -0.7])
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax(logits.float(), ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.3
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1
+    gtok = torch.randn(B, T, generator=g) * 0.5
+    gtok[0, 2] = 0.0
+    want_ent = O.entropy_from_logits(logits.double()).float()
+    x, idx, m = logits.to(DEV), ids.to(DEV), mask.to(DEV)
+    cfg = ops.make_cfg(0.04, 0.2, 0.2, None, "bnpo", "token", T, grad_scale=64.0)  # fp16 training scales the loss
+    res = {}
+    for name, path in (("row", S.K1_ROW), ("resident", S.K1_RESIDENT)):
+        prev = S.set_k1_path(path)
+        try:
+            lp, ent, lse = ops.logprob_entropy_fwd(x, idx, 1.0)
+            flp, fent, _, dl1, loss, met = ops.grpo_fused_step(x, idx, m, None, None, adv.to(DEV), old.to(DEV),
+                                                               ref.to(DEV), cfg, 1.0)
+            dl2 = ops.logprob_bwd(x, idx, lse, gtok.to(DEV), 1.0)
+        finally:
+            S.set_k1_path(prev)
+        torch.cuda.synchronize()
+        assert dl1.dtype == torch.float16 and dl2.dtype == torch.float16
+        assert_logp(lp, logits, ids, where=f"{name} forward-only")
+        assert_logp(flp, logits, ids, where=f"{name} fused")
+        torch.testing.assert_close(ent.cpu(), want_ent, rtol=1e-5, atol=1e-5)
+        res[name] = (lp.cpu(), dl1.float().cpu(), dl2.float().cpu(), loss.cpu())
+    xr = logits.float().requires_grad_(True)
+    cfgo = O.GRPOConfigLite(beta=0.04, loss_type="bnpo", importance_sampling_level="token", max_completion_length=T)
+    loss_r = O.grpo_compute_loss(xr, ids, mask, adv, cfgo, old, ref)[0]
+    (loss_r * 64.0).backward()
+    want_fused = xr.grad.to(torch.float16).float()
+    xr2 = logits.float().requires_grad_(True)
+    (O.selective_log_softmax(xr2, ids) * gtok).sum().backward()
+    want_bwd = xr2.grad.to(torch.float16).float()
+    ulp = 2.0 ** -10
+    for name in ("row", "resident"):
+        assert res[name][3].item() == pytest.approx(loss_r.item(), rel=1e-4)
+        torch.testing.assert_close(res[name][1], want_fused, rtol=ulp, atol=6e-8, msg=lambda t: f"{name} fused: {t}")
+        torch.testing.assert_close(res[name][2], want_bwd, rtol=ulp, atol=6e-8, msg=lambda t: f"{name} bwd: {t}")
+        assert torch.count_nonzero(res[name][1][mask == 0]) == 0 and torch.count_nonzero(res[name][2][0, 2]) == 0
+    torch.testing.assert_close(res["resident"][0], res["row"][0], rtol=0, atol=4e-6)

@@ -16,7 +16,6 @@ for s in 9 5 4; do run KV_TAG=bwd_slots$s B200TRL_K1_BWD_SLOTS=$s; done
 # 3. streaming vs clustered forward-only / backward-only, accumulation chains, dlogits via TMA stores vs registers
 run KV_TAG=fwd_cluster2 B200TRL_K1_FWD_CS=2 B200TRL_K1_GEOM=3
 run KV_TAG=bwd_cluster2 B200TRL_K1_BWD_CS=2
-run KV_TAG=single_chain B200TRL_K1_DUAL=0
 run KV_TAG=fused_bulk_stores B200TRL_K1_DIRECT=0
 # 4. large vocabularies: 4- and 8-CTA clusters against the row kernel
 for v in 200000 262144 524288; do
