@@ -248,11 +248,14 @@ __device__ __forceinline__ void cluster_sum2(double (*xch)[2], float a, float b,
     }
 }
 
-// masked_whiten of x[0, n_loc) (shared memory) with statistics over the whole cluster; keep(i) takes the LOCAL index
-template <typename KeepFn>
-__device__ __forceinline__ void cluster_whiten(double (*xch)[kClusterCtas][2], int slot0, float* x, int n_loc, KeepFn keep,
+// masked_whiten of x[0, n_loc) (shared memory) with statistics over the whole cluster.  Every pass of the kernel
+// walks the CTA's elements with the same stride, so element tid + j * kClBlock always belongs to thread tid: its mask
+// is bit j of `bits` (computed once in phase 1, where the sequence length is loaded anyway -- the per-element i / T,
+// i % T and seq_len loads of a mask functor were a measurable part of a 13 us kernel).
+__device__ __forceinline__ void cluster_whiten(double (*xch)[kClusterCtas][2], int slot0, float* x, int n_loc, uint32_t bits,
                                                bool shift_mean, float* red) {
     const int tid = threadIdx.x;
+    auto keep = [bits, tid](int i) { return ((bits >> ((i - tid) / kClBlock)) & 1u) != 0u; };
     float s = 0.f, c = 0.f;
     for (int i = tid; i < n_loc; i += kClBlock) {
         const float k = keep(i) ? 1.f : 0.f;
@@ -296,15 +299,21 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClBlock,
     const int64_t g0 = row0 * T;                                  // global index of local element 0
 
     // ---- phase 1: pad fills, KL reward, score at actual_end  (:500-516)
-    for (int i = tid; i < n_loc; i += kClBlock) {
+    uint32_t keep_p0 = 0u, keep_p1 = 0u;  // bit j: element tid + j * kClBlock is not padding / not padding shifted by one
+    for (int i = tid, j = 0; i < n_loc; i += kClBlock, ++j) {
         const int rl = i / T, t = i - rl * T;
         const int64_t b = row0 + rl, gi = g0 + i;
         const int64_t len = a.seq_len[b];
         const int64_t end = (len + 1 < T) ? len + 1 : len;  // :515
         const bool pad = t > len, pad1 = t > len + 1;
-        const float lp = pad ? 1.0f : a.lp[gi];      // INVALID_LOGPROB (:502)
-        const float rlp = pad ? 1.0f : a.rlp[gi];    // :503
-        const float v = pad1 ? 0.f : a.values[gi];   // :506
+        keep_p0 |= pad ? 0u : (1u << j);
+        keep_p1 |= pad1 ? 0u : (1u << j);
+        // the three tensors are full [B, T]: load unconditionally (the loads then fly together with the seq_len load
+        // instead of behind it) and select afterwards
+        const float lp_raw = a.lp[gi], rlp_raw = a.rlp[gi], v_raw = a.values[gi];
+        const float lp = pad ? 1.0f : lp_raw;        // INVALID_LOGPROB (:502)
+        const float rlp = pad ? 1.0f : rlp_raw;      // :503
+        const float v = pad1 ? 0.f : v_raw;          // :506
         const float logr = rlp - lp;                 // :510
         const float kl = (a.estimator == B200TRL_KL_K1) ? -logr : (expf(logr) - 1.f) - logr;  // :511
         float r = -a.kl_coef * kl;                   // :512
@@ -316,15 +325,68 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClBlock,
         if (a.val_f) a.val_f[gi] = v;
     }
     __syncthreads();
-    const int64_t* sl = a.seq_len;
-    auto keep_p1 = [sl, T, row0](int i) { return (i % T) <= sl[row0 + i / T] + 1; };  // ~padding_mask_p1
-    auto keep_p0 = [sl, T, row0](int i) { return (i % T) <= sl[row0 + i / T]; };      // ~padding_mask
-    if (a.whiten_rewards)  // :519-521
+    if (a.whiten_rewards)  // :519-521   (keep_p1 = ~padding_mask_p1, keep_p0 = ~padding_mask)
         cluster_whiten(xch, 0, r_s, n_loc, keep_p1, /*shift_mean=*/false, red);
     for (int i = tid; i < n_loc; i += kClBlock) a.rewards[g0 + i] = r_s[i];
 
     // ---- phase 2: reverse GAE, one warp per row, 32 steps per round  (:523-533)
-    {
+    // With few rows per CTA (config 3: 8 rows, 32 warps) a row is cut into W segments of whole 32-step chunks, one warp
+    // each: every warp scans its segment with a zero carry-in, then the carries are chained over the W segments (A at a
+    // segment's first step = its zero-carry value + k^len * carry-in) and added back as k^(steps to the segment's end)
+    // * carry-in.  The serial part of a row drops from T / 32 chunk scans to T / (32 W) + W.
+    const int n_chunks = (T + 31) / 32;
+    int W = 1;
+    while (W * 2 * rows <= kClBlock / 32 && W * 2 <= n_chunks && W < 8) W *= 2;
+    if (W > 1) {
+        const float k = a.gamma * a.lam;
+        const float log2k = log2f(k);  // k in (0, 1]; k == 0 -> -inf -> powers are 0, as they should be
+        const int seg_chunks = (n_chunks + W - 1) / W;
+        float* seg_first = red;  // [rows * W] zero-carry advantage at each segment's first step (red: 64 floats, >= 32)
+        const int rl = warp / W, sg = warp - rl * W;
+        const bool active = rl < rows;
+        const int c_lo = sg * seg_chunks, c_hi = min(c_lo + seg_chunks, n_chunks);  // chunks [c_lo, c_hi) of the row
+        if (active) {
+            const float* r = r_s + rl * T;
+            const float* v = v_s + rl * T;
+            float carry = 0.f;
+            for (int c = c_hi - 1; c >= c_lo; --c) {
+                const int t = c * 32 + lane;
+                float Q = 0.f, P = 1.f;
+                if (t < T) {
+                    const float nv = (t + 1 < T) ? v[t + 1] : 0.f;
+                    Q = r[t] + a.gamma * nv - v[t];
+                    P = k;
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float nQ = __shfl_down_sync(0xffffffffu, Q, o);
+                    const float nP = __shfl_down_sync(0xffffffffu, P, o);
+                    if (lane + o < 32) {
+                        Q = Q + P * nQ;
+                        P = P * nP;
+                    }
+                }
+                const float A = Q + P * carry;
+                if (t < T) a_s[rl * T + t] = A;
+                carry = __shfl_sync(0xffffffffu, A, 0);
+            }
+            if (lane == 0) seg_first[rl * W + sg] = (c_lo < c_hi) ? carry : 0.f;
+        }
+        __syncthreads();
+        if (active && sg < W - 1 && c_lo < c_hi) {
+            // carry into this segment = true advantage at the first step of the next segment
+            float cin = 0.f;
+            for (int q = W - 1; q > sg; --q) {
+                const int q_lo = q * seg_chunks, q_hi = min(q_lo + seg_chunks, n_chunks);
+                if (q_lo >= q_hi) continue;
+                const int steps = min(q_hi * 32, T) - q_lo * 32;  // real steps of segment q
+                cin = seg_first[rl * W + q] + exp2f(log2k * static_cast<float>(steps)) * cin;
+            }
+            const int end = min(c_hi * 32, T);  // one past the segment's last real step
+            for (int t = c_lo * 32 + lane; t < end; t += 32)
+                a_s[rl * T + t] += exp2f(log2k * static_cast<float>(end - t)) * cin;
+        }
+    } else {
         const float k = a.gamma * a.lam;
         for (int rl = warp; rl < rows; rl += kClBlock / 32) {
             const float* r = r_s + rl * T;
