@@ -213,6 +213,18 @@ int b200trl_group_advantages(const float* rewards_per_func, const float* weights
                              float* adv_all, float* adv_local, float* mean, float* std, uint8_t* is_std_zero,
                              b200trl_stream_t stream);
 
+/* ---- f-4: the logging block of GRPOTrainer._generate_and_score_completions (grpo_trainer.py:1942-1972) -----------
+ * Three gathers + ~13 .item() host syncs (+ 2 per reward function) become ONE gather of a packed int64 vector, this ONE
+ * launch and ONE device->host read.  packed: the all-gathered vector, rank-major [world][1 + 2*b_local] =
+ * {sum(attention_mask), completion_lengths[b_local], terminated_with_eos[b_local]}; rewards_per_func: gathered fp32
+ * [world*b_local, n_funcs] (NaN = not applicable); mean / std / is_std_zero: per group, from b200trl_group_advantages.
+ * out: fp64 [12 + 2*n_funcs] = {num_input_tokens, completions/mean_length, min_length, max_length, clipped_ratio,
+ * mean_terminated_length, min_terminated_length, max_terminated_length (0 when nothing terminated, :1956-1957),
+ * reward, reward_std, frac_reward_zero_std, 0, then (nanmean, nanstd) per reward function (:196-211, :1961-1965)}. */
+int b200trl_generation_stats(const int64_t* packed, int64_t world, int64_t b_local, const float* rewards_per_func,
+                             int64_t n_funcs, const float* mean_grouped, const float* std_grouped,
+                             const uint8_t* is_std_zero, int64_t n_groups, double* out, b200trl_stream_t stream);
+
 /* ---- K4: PPO KL reward + score + whitening + reverse GAE (ppo_trainer.py:500-535) ------------
  * logprobs/ref_logprobs/values: raw fp32 [B,T] (pads filled here as :500-506 does); scores [B];
  * sequence_lengths int64 [B].  Outputs fp32 [B,T]: rewards, advantages (whitened, pads 0), returns;

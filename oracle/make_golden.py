@@ -167,6 +167,31 @@ def gold_advantages():
 
 
 # ----------------------------------------------------------------------------
+def gold_generation_metrics():
+    """grpo_trainer.py:1940-1970 executed from the reference's source on gathered tensors (incl. a NaN reward column,
+    a zero-std group, a batch where nothing terminated and one where everything did)."""
+    cases = []
+    # (B_global, n_funcs, G, world, P+T, T, terminated fraction, seed)
+    for Bg, F_, G, world, L, T, frac, seed in [(16, 1, 8, 1, 48, 32, 0.6, 1), (24, 3, 4, 2, 96, 64, 0.5, 2),
+                                               (12, 2, 3, 4, 40, 24, 0.0, 3), (256, 1, 8, 8, 160, 128, 1.0, 4)]:
+        g = torch.Generator().manual_seed(100 + seed)
+        rewards = O.synth_rewards(Bg, G, F_, seed)
+        w = torch.linspace(1.0, 0.5, F_)
+        adv = R.ref_group_advantages(rewards, w, G, True, 0, Bg)
+        lengths = torch.randint(1, T + 1, (Bg,), generator=g)
+        terminated = torch.rand(Bg, generator=g) < frac
+        lengths = torch.where(terminated, lengths, torch.full_like(lengths, T))
+        attention_mask = (torch.rand(Bg, L, generator=g) < 0.8).long()
+        names = [f"f{i}" for i in range(F_)]
+        metrics, seen = R.ref_generation_metrics(attention_mask, lengths, terminated, rewards, adv["mean_grouped_rewards"],
+                                                 adv["std_grouped_rewards"], adv["is_std_zero"], names)
+        cases.append(dict(B_global=Bg, n_funcs=F_, G=G, world=world, rewards_per_func=rewards, weights=w,
+                          completion_lengths=lengths, terminated=terminated, attention_mask=attention_mask.bool(),
+                          names=names, metrics={k: v[0] for k, v in metrics.items()}, num_input_tokens_seen=seen))
+    save("generation_metrics.pt", cases)
+
+
+# ----------------------------------------------------------------------------
 def gold_ppo():
     cases = []
     grid = list(itertools.product([(8, 32, 1), (5, 77, 2)], ["k1", "k3"], [False, True], [(1.0, 0.95), (0.99, 0.9)]))
@@ -333,6 +358,7 @@ if __name__ == "__main__":
     gold_grpo_loss()
     gold_grpo_c1()
     gold_advantages()
+    gold_generation_metrics()
     gold_ppo()
     gold_misc()
     gold_rloo()

@@ -333,3 +333,29 @@ def ref_rloo_loss(logits, responses, old_logprobs, advantages, padding_mask, *, 
         run_lines("trl/trainer/rloo_trainer.py", 497, 500, ns, anchor_first="pg_clipfrac = (pg_losses2",
                   anchor_last="approxkl = 0.5")
     return {k: ns[k] for k in ("loss", "pg_clipfrac", "approxkl", "entropy", "new_ratio", "ratio")}
+
+def ref_generation_metrics(attention_mask, completion_lengths, is_eos_any, rewards_per_func, mean_grouped_rewards,
+                           std_grouped_rewards, is_std_zero, reward_func_names):
+    """Exec grpo_trainer.py:1940-1970 (the logging block of _generate_and_score_completions) with the GLOBAL tensors
+    and an identity ``gather`` — the block only ever sees gathered tensors.  ``is_eos_any``: ``is_eos.any(dim=1)``.
+    Returns ``(metrics dict of lists, num_input_tokens_seen)``."""
+    import collections
+    ns = dict(_BASE_NS)
+    ns.update(load_defs("trl/trainer/grpo_trainer.py", ["nanstd"]))
+
+    class _IsEos:  # the block only calls is_eos.any(dim=1)
+        def any(self, dim):
+            return is_eos_any
+
+    metrics = {"train": collections.defaultdict(list)}
+    fake = types.SimpleNamespace(
+        state=types.SimpleNamespace(num_input_tokens_seen=0),
+        accelerator=types.SimpleNamespace(gather=lambda t: t),
+        _metrics=metrics, reward_func_names=list(reward_func_names))
+    ns.update(self=fake, mode="train", attention_mask=attention_mask, completion_lengths=completion_lengths,
+              is_eos=_IsEos(), device=torch.device("cpu"), rewards_per_func=rewards_per_func,
+              mean_grouped_rewards=mean_grouped_rewards, std_grouped_rewards=std_grouped_rewards, is_std_zero=is_std_zero)
+    run_lines("trl/trainer/grpo_trainer.py", 1940, 1970, ns, anchor_first="# Log the metrics",
+              anchor_last='self._metrics[mode]["frac_reward_zero_std"]')
+    return dict(metrics["train"]), fake.state.num_input_tokens_seen
+

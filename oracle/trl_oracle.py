@@ -305,6 +305,39 @@ def group_advantages(rewards_per_func, reward_weights, num_generations, scale_re
     return adv[lo : lo + local_batch], adv, mean, std, is_std_zero, rewards
 
 
+def nanstd(x):
+    """grpo_trainer.py:196-211."""
+    variance = torch.nanmean((x - torch.nanmean(x, keepdim=True)) ** 2)
+    count = torch.sum(~torch.isnan(x))
+    variance = variance * (count / (count - 1))
+    return torch.sqrt(variance)
+
+
+def generation_metrics(attention_mask_sums, completion_lengths, terminated, rewards_per_func, mean_grouped, std_grouped,
+                       is_std_zero, reward_func_names):
+    """The logged scalars of grpo_trainer.py:1942-1968 from the GATHERED tensors (``attention_mask_sums``: one sum per
+    rank).  ``mean_grouped`` / ``std_grouped`` / ``is_std_zero`` per group or repeated per sample (same means)."""
+    out = {"num_tokens": int(attention_mask_sums.sum().item())}  # :1943
+    lens = completion_lengths.float()
+    out["completions/mean_length"] = lens.mean().item()  # :1947-1949
+    out["completions/min_length"] = lens.min().item()
+    out["completions/max_length"] = lens.max().item()
+    term = completion_lengths[terminated.bool()]  # :1952-1953
+    out["completions/clipped_ratio"] = 1 - len(term) / len(completion_lengths)  # :1954
+    if len(term) == 0:  # :1956-1957
+        term = torch.zeros(1)
+    out["completions/mean_terminated_length"] = term.float().mean().item()
+    out["completions/min_terminated_length"] = term.float().min().item()
+    out["completions/max_terminated_length"] = term.float().max().item()
+    for i, name in enumerate(reward_func_names):  # :1961-1965
+        out[f"rewards/{name}/mean"] = torch.nanmean(rewards_per_func[:, i]).item()
+        out[f"rewards/{name}/std"] = nanstd(rewards_per_func[:, i]).item()
+    out["reward"] = mean_grouped.mean().item()  # :1966-1968
+    out["reward_std"] = std_grouped.mean().item()
+    out["frac_reward_zero_std"] = is_std_zero.float().mean().item()
+    return out
+
+
 # --------------------------------------------------------------------------
 # completion / padding masks (grpo_trainer.py:1812-1817; utils.py:877-897)
 # --------------------------------------------------------------------------

@@ -7,7 +7,7 @@ library raises.
 
 from . import _lib  # noqa: F401  (raises ImportError if libb200trl.so is missing)
 from ._lib import K1_AUTO, K1_RESIDENT, K1_ROW, B200TRLError, set_k1_path, set_skip_masked  # noqa: F401
-from .advantages import group_advantages  # noqa: F401
+from .advantages import generation_metrics, group_advantages  # noqa: F401
 from .functional import (  # noqa: F401
     entropy_from_logits,
     fused_linear_logprobs,

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "b200trl_entropy_quantile_workspace_bytes": (_i64, [_i64]),
     "b200trl_entropy_quantile_mask": (C.c_int, [_p, _p, _i64, _f, _p, _p, _p, _p]),
     "b200trl_group_advantages": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "b200trl_generation_stats": (C.c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p]),
     "b200trl_ppo_gae_workspace_bytes": (_i64, [_i64, _i64]),
     "b200trl_ppo_rewards_gae": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _f, _i32, _f, _f, _i32, _p, _p, _p, _p, _p,
                                           _p, _p, _p]),

@@ -404,6 +404,28 @@ def group_advantages(rewards_per_func: torch.Tensor, weights: torch.Tensor, num_
     return dict(advantages=adv_loc, all=adv_all, rewards=rewards, mean=mean, std=std, is_std_zero=zero)
 
 
+def generation_stats(packed: torch.Tensor, world: int, b_local: int, rewards_per_func: torch.Tensor,
+                     mean_grouped: torch.Tensor, std_grouped: torch.Tensor, is_std_zero: torch.Tensor) -> torch.Tensor:
+    """fp64 ``[12 + 2 * n_funcs]`` on the device — ``b200trl_generation_stats`` (layout in include/b200trl.h)."""
+    k = _Keep()
+    _need_cuda(packed, "packed")
+    pk = packed.to(torch.int64).contiguous()
+    if pk.numel() != world * (1 + 2 * b_local):
+        raise ValueError(f"packed has {pk.numel()} elements, expected world * (1 + 2 * B_local) = {world * (1 + 2 * b_local)}")
+    r = _f32(rewards_per_func, "rewards_per_func")
+    if r.dim() == 1:
+        r = r.unsqueeze(1)
+    if r.shape[0] != world * b_local:
+        raise ValueError(f"rewards_per_func has {r.shape[0]} rows, expected world * B_local = {world * b_local}")
+    z = is_std_zero.to(torch.bool).contiguous()
+    out = torch.empty(12 + 2 * r.shape[1], dtype=torch.float64, device=pk.device)
+    check(lib.b200trl_generation_stats(_ptr(pk), int(world), int(b_local), _ptr(r), int(r.shape[1]),
+                                       k.f32(mean_grouped, "mean"), k.f32(std_grouped, "std"), _ptr(z),
+                                       int(mean_grouped.numel()), _ptr(out), _stream(pk)), "generation_stats")
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ K4 / PPO
 def ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl_coef, kl_estimator, gamma, lam,
                     whiten_rewards, want_filled: bool = True):
@@ -683,6 +705,7 @@ for _name in ("logprob_entropy_fwd", "masked_logprob_fwd", "logprob_bwd", "mask_
               "grpo_fused_step", "grpo_loss", "entropy_quantile_mask", "group_advantages", "ppo_rewards_gae",
               "ppo_fused_fwd_bwd", "ppo_loss", "masked_whiten", "rloo_rewards_advantages", "rloo_loss",
               "fused_linear_logprob_fwd", "fused_linear_grpo", "tc_gemm", "rescale_if_needed", "completion_mask",
+              "generation_stats",
               "first_true_indices", "truncate_response"):
     if _name in globals():
         globals()[_name] = _nvtx_op(_name)(globals()[_name])

@@ -68,6 +68,11 @@ def patch_module(mod: types.ModuleType) -> list:
         if isinstance(cls, type) and train_patch.patch_trainer_class(cls, blocks):
             done.append(cls_name + ".train")
     trainer = ns.get("GRPOTrainer")
+    if isinstance(trainer, type) and "_generate_and_score_completions" in trainer.__dict__:
+        # the EOS mask, the group advantages and the logging block are inline in a 500-line method (generation, vLLM,
+        # reward functions): its source is edited like PPO's train()
+        if train_patch.patch_trainer_class(trainer, train_patch.GRPO_GENERATE_BLOCKS, "_generate_and_score_completions"):
+            done.append("GRPOTrainer._generate_and_score_completions")
     if isinstance(trainer, type) and "_compute_loss" in trainer.__dict__:
         if trainer.__dict__["_compute_loss"] is not grpo.compute_loss:  # the class may be reachable from several modules
             trainer._trl_original_compute_loss = trainer._compute_loss

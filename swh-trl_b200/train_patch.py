@@ -132,6 +132,46 @@ RLOO_BLOCKS: List[Block] = [
 ]
 
 
+# GRPOTrainer._generate_and_score_completions: generation, vLLM plumbing and reward functions stay the reference's;
+# three inline blocks of the scope table move to the library
+GRPO_GENERATE_BLOCKS: List[Block] = [
+    ("completion mask from the first EOS (grpo_trainer.py:1812-1817): eight [B, T] kernels -> one launch",
+     "is_eos = completion_ids == self.eos_token_id",
+     "completion_mask = (sequence_indices <= eos_idx.unsqueeze(1)).int()",
+     ["is_eos = completion_ids == self.eos_token_id  # still named by the mask_truncated_completions option below",
+      "completion_mask, eos_idx = _b200_masks.completion_mask_from_eos(completion_ids, self.eos_token_id)",
+      "sequence_indices = None"]),
+    ("group-relative advantages (grpo_trainer.py:1917-1938) on the gathered rewards: one launch",
+     "rewards = (rewards_per_func * self.reward_weights.to(device).unsqueeze(0)).nansum(dim=1)",
+     "advantages = advantages[process_slice]",
+     ["_b200_adv = _b200_adv_mod.group_advantages(rewards_per_func, self.reward_weights.to(device), self.num_generations,",
+      "                                           scale_rewards=self.scale_rewards,",
+      "                                           process_index=self.accelerator.process_index,",
+      "                                           local_batch=len(prompts), gathered=True)",
+      "rewards, advantages, all_process_advantages = _b200_adv['rewards'], _b200_adv['advantages'], _b200_adv['all']",
+      "mean_grouped_rewards, std_grouped_rewards = _b200_adv['mean'], _b200_adv['std']  # per group (not repeated)",
+      "is_std_zero = _b200_adv['is_std_zero']",
+      "process_slice = slice(self.accelerator.process_index * len(prompts),",
+      "                      (self.accelerator.process_index + 1) * len(prompts))"]),
+    ("logged metrics (grpo_trainer.py:1940-1970): 3 gathers + ~13 .item() -> one packed gather, one launch, one read",
+     "# Log the metrics",
+     'self._metrics[mode]["frac_reward_zero_std"].append(is_std_zero.float().mean().item())',
+     ["_b200_gm = _b200_adv_mod.generation_metrics(attention_mask, completion_lengths, is_eos.any(dim=1),",
+      "                                            rewards_per_func, mean_grouped_rewards, std_grouped_rewards,",
+      "                                            is_std_zero, self.reward_func_names, accelerator=self.accelerator)",
+      "if mode == \"train\":",
+      "    self.state.num_input_tokens_seen += _b200_gm['num_tokens']",
+      "self._metrics[mode][\"num_tokens\"] = [self.state.num_input_tokens_seen]",
+      "for _b200_key in _b200_adv_mod.GENERATION_KEYS:",
+      "    self._metrics[mode][_b200_key].append(_b200_gm[_b200_key])",
+      "for reward_func_name in self.reward_func_names:",
+      "    self._metrics[mode][f\"rewards/{reward_func_name}/mean\"].append(_b200_gm[f\"rewards/{reward_func_name}/mean\"])",
+      "    self._metrics[mode][f\"rewards/{reward_func_name}/std\"].append(_b200_gm[f\"rewards/{reward_func_name}/std\"])",
+      "for _b200_key in (\"reward\", \"reward_std\", \"frac_reward_zero_std\"):",
+      "    self._metrics[mode][_b200_key].append(_b200_gm[_b200_key])"]),
+]
+
+
 def _swap(lines: List[str], block: Block) -> List[str]:
     what, first, last, new = block
     starts = [i for i, l in enumerate(lines) if l.strip() == first]
@@ -163,30 +203,35 @@ def rewrite_rloo_train(src: str) -> str:
     return rewrite_train(src, RLOO_BLOCKS)
 
 
-def compile_train(src: str, namespace: Dict, filename: str) -> types.FunctionType:
-    """Compile a rewritten ``def train(self): ...`` inside ``namespace`` (the reference module's globals, extended with
-    the two helper modules the replacement lines name) and return the function."""
+def compile_train(src: str, namespace: Dict, filename: str, method: str = "train") -> types.FunctionType:
+    """Compile a rewritten ``def <method>(self, ...): ...`` inside ``namespace`` (the reference module's globals, extended
+    with the helper modules the replacement lines name) and return the function."""
+    from . import advantages as _adv_mod
+    from . import masks as _masks
     namespace.setdefault("_b200_ppo", _ppo)
     namespace.setdefault("_b200_rloo", _rloo)
+    namespace.setdefault("_b200_adv_mod", _adv_mod)
+    namespace.setdefault("_b200_masks", _masks)
     local: Dict = {}
     exec(compile(src, filename, "exec"), namespace, local)  # noqa: S102 - source of the imported trainer, edited above
-    fn = local.get("train")
+    fn = local.get(method)
     if not isinstance(fn, types.FunctionType):
-        raise TrainPatchError("the rewritten source does not define train()")
+        raise TrainPatchError(f"the rewritten source does not define {method}()")
     return fn
 
 
-def patch_trainer_class(cls: type, blocks: Sequence[Block]) -> bool:
-    """Replace ``cls.train`` by its rewritten form (the original stays at ``cls._trl_original_train``)."""
-    if "train" not in cls.__dict__ or getattr(cls, "_b200_train_patched", False):
+def patch_trainer_class(cls: type, blocks: Sequence[Block], method: str = "train") -> bool:
+    """Replace ``cls.<method>`` by its rewritten form (the original stays at ``cls._trl_original_<method>``)."""
+    flag = f"_b200_{method}_patched"
+    if method not in cls.__dict__ or getattr(cls, flag, False):
         return False
-    original = cls.__dict__["train"]
+    original = cls.__dict__[method]
     src = rewrite_train(inspect.getsource(original), blocks)
     module_globals = original.__globals__
-    fn = compile_train(src, module_globals, f"<swh_trl_b200 patched {cls.__name__}.train>")
-    fn.__qualname__ = f"{cls.__name__}.train"
+    fn = compile_train(src, module_globals, f"<swh_trl_b200 patched {cls.__name__}.{method}>", method)
+    fn.__qualname__ = f"{cls.__name__}.{method}"
     fn.__doc__ = (original.__doc__ or "") + "\n[swh_trl_b200: hot blocks replaced, see swh_trl_b200.train_patch]"
-    cls._trl_original_train = original
-    cls.train = fn
-    cls._b200_train_patched = True
+    setattr(cls, f"_trl_original_{method}", original)
+    setattr(cls, method, fn)
+    setattr(cls, flag, True)
     return True

@@ -38,6 +38,9 @@ out = {
     "ppo_original_kept": inspect.getsource(ppo.PPOTrainer._trl_original_train) == before["PPOTrainer"],
     "ppo_co_names": sorted(set(ppo.PPOTrainer.train.__code__.co_names) & {"_b200_ppo", "masked_whiten", "masked_mean"}),
     "rloo_co_names": sorted(set(rloo.RLOOTrainer.train.__code__.co_names) & {"_b200_rloo", "_b200_ppo"}),
+    "grpo_generate_patched": bool(getattr(grpo_mod.GRPOTrainer, "_b200__generate_and_score_completions_patched", False)),
+    "grpo_generate_co_names": sorted(set(grpo_mod.GRPOTrainer._generate_and_score_completions.__code__.co_names)
+                                     & {"_b200_adv_mod", "_b200_masks", "nanstd"}),
     "second_patch_is_noop": S.patch_trl() == {},
 }
 print("RESULT " + json.dumps(out))

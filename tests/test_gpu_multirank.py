@@ -64,6 +64,21 @@ def _worker(rank, world, port, case_idx, q):
         gathered = D.gather_rewards(local).cpu()
         assert torch.equal(gathered.nan_to_num(7.0), c["rewards_per_func"].nan_to_num(7.0)), "rank-major gather"
 
+        # ---- the logging block behind the advantages (grpo_trainer.py:1942-1970): one packed NCCL gather + one launch
+        gm_cases = [g for g in load_golden("generation_metrics.pt") if g["world"] == world]
+        for gc in gm_cases:
+            nl = gc["B_global"] // world
+            sl = slice(rank * nl, (rank + 1) * nl)
+            a2 = S.group_advantages(gc["rewards_per_func"][sl].clone().to(dev), gc["weights"].to(dev), gc["G"], True)
+            full = D.gather_rewards(gc["rewards_per_func"][sl].clone().to(dev))
+            gm = S.generation_metrics(gc["attention_mask"][sl].long().to(dev), gc["completion_lengths"][sl].to(dev),
+                                      gc["terminated"][sl].to(dev), full, a2["mean"], a2["std"], a2["is_std_zero"],
+                                      gc["names"])
+            assert gm["num_tokens"] == gc["metrics"]["num_tokens"]
+            for k, w in gc["metrics"].items():
+                if k != "num_tokens":
+                    assert (gm[k] != gm[k] and w != w) or gm[k] == pytest.approx(w, rel=2e-6, abs=1e-6), (k, gm[k], w)
+
         # ---- packed metric exchange: each rank runs the loss on its own shard, one [world, 8] all-gather
         B, T, V, G = 4, 32, 4096, 2
         logits, ids, mask = O.synth_batch(B, T, V, seed=100 + rank, edge_rows=False)

@@ -1574,3 +1574,41 @@ def test_fp16_logits_on_the_resident_kernel(S, V):
         torch.testing.assert_close(res[name][2], want_bwd, rtol=ulp, atol=6e-8, msg=lambda t: f"{name} bwd: {t}")
         assert torch.count_nonzero(res[name][1][mask == 0]) == 0 and torch.count_nonzero(res[name][2][0, 2]) == 0
     torch.testing.assert_close(res["resident"][0], res["row"][0], rtol=0, atol=4e-6)
+
+
+# ------------------------------------------------------------------------------------------------ f-4: GRPO logging block
+@pytest.mark.parametrize("i", range(4))
+def test_generation_metrics_golden(S, i):
+    """grpo_trainer.py:1942-1970 (three gathers + ~13 .item() syncs + 2 per reward function) as one packed gather, one
+    launch, one host read — against the block executed from the reference's own source.  Integer-valued entries
+    (token count, min / max lengths, clipped ratio) exact; fp32 means within fp32 round-off of torch's reduction."""
+    from swh_trl_b200 import ops
+    c = load_golden("generation_metrics.pt")[i]
+    world, Bg = c["world"], c["B_global"]
+    n_local = Bg // world
+    adv = S.group_advantages(c["rewards_per_func"].to(DEV), c["weights"].to(DEV), c["G"], True, 0, Bg, gathered=True)
+    am = c["attention_mask"].long()
+    # what `world` ranks would have gathered: [world][1 + 2 * n_local] = {sum(attention_mask), lengths, terminated}
+    packed = torch.cat([torch.cat([am[r * n_local:(r + 1) * n_local].sum().reshape(1),
+                                   c["completion_lengths"][r * n_local:(r + 1) * n_local],
+                                   c["terminated"][r * n_local:(r + 1) * n_local].long()]) for r in range(world)])
+    raw = ops.generation_stats(packed.to(DEV), world, n_local, c["rewards_per_func"].to(DEV), adv["mean"], adv["std"],
+                               adv["is_std_zero"]).cpu()
+    want = c["metrics"]
+    assert int(raw[0]) == c["num_input_tokens_seen"]
+    assert raw[2].item() == want["completions/min_length"] and raw[3].item() == want["completions/max_length"]
+    assert raw[4].item() == want["completions/clipped_ratio"]
+    assert raw[6].item() == want["completions/min_terminated_length"]
+    assert raw[7].item() == want["completions/max_terminated_length"]
+    # the public call (this process is the only rank: it passes the global tensors)
+    got = S.generation_metrics(am.to(DEV), c["completion_lengths"].to(DEV), c["terminated"].to(DEV),
+                               c["rewards_per_func"].to(DEV), adv["mean"], adv["std"], adv["is_std_zero"], c["names"])
+    assert got["num_tokens"] == want["num_tokens"]
+    for k, w in want.items():
+        if k == "num_tokens":
+            continue
+        if w != w:
+            assert got[k] != got[k], k
+        else:
+            assert got[k] == pytest.approx(w, rel=2e-6, abs=1e-6), (k, got[k], w)
+

@@ -231,3 +231,23 @@ def test_dpo_sequence_logps_vs_reference(i):
     assert torch.equal(all_logps.detach(), c["all_logps"]) and torch.equal(per_token.detach(), c["per_token_logps"])
     (all_logps * c["w"]).sum().backward()
     torch.testing.assert_close(x.grad, c["grad_logits"], rtol=1e-6, atol=1e-7)
+
+
+def test_generation_metrics_restatement_vs_reference_block():
+    """oracle.generation_metrics against grpo_trainer.py:1940-1970 executed from the reference's own source (goldens):
+    same torch ops on the gathered tensors, so the values are equal to the last bit."""
+    for c in load_golden("generation_metrics.pt"):
+        adv = O.group_advantages(c["rewards_per_func"], c["weights"], c["G"], True, 0, c["B_global"])
+        n_local = c["B_global"] // c["world"]
+        sums = c["attention_mask"].long().view(c["world"], n_local, -1).sum(dim=(1, 2))
+        got = O.generation_metrics(sums, c["completion_lengths"], c["terminated"], c["rewards_per_func"], adv[2], adv[3],
+                                   adv[4], c["names"])
+        assert got["num_tokens"] == c["num_input_tokens_seen"] == c["metrics"]["num_tokens"]
+        for k, want in c["metrics"].items():
+            if k == "num_tokens":
+                continue
+            if k in ("reward", "reward_std"):  # the reference averages the per-sample REPEATED vector: same value,
+                assert got[k] == pytest.approx(want, rel=2e-6, abs=1e-7), k  # another fp32 summation order
+            else:
+                assert got[k] == want or (got[k] != got[k] and want != want), (k, got[k], want)
+

@@ -25,12 +25,36 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 needs_lifted = pytest.mark.skipif(not H.available(), reason="oracle/_ref not built (python oracle/build_ref.py)")
 
 
-def _lifted_train(cls_name):
+def _lifted_train(cls_name, method="train"):
     src = open(H.LOOPS).read()
     tree = ast.parse(src)
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name)
-    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "train")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == method)
     return "\n".join(src.splitlines()[fn.lineno - 1:fn.end_lineno])
+
+
+@needs_lifted
+def test_rewrite_of_the_lifted_generate_and_score():
+    """GRPOTrainer._generate_and_score_completions: the EOS mask (:1812-1817), the group advantages (:1917-1938) and the
+    logging block (:1940-1970) are found in the reference's text, replaced, and the method still compiles; generation,
+    vLLM plumbing and the reward functions are untouched."""
+    from swh_trl_b200 import train_patch as TP
+    src = _lifted_train("GRPOTrainer", "_generate_and_score_completions")
+    out = TP.rewrite_train(src, TP.GRPO_GENERATE_BLOCKS)
+    compile(out, "<rewritten>", "exec")
+    assert out.count("# ---- swh_trl_b200:") == 3
+    for text in ("eos_idx[is_eos.any(dim=1)] = is_eos.int().argmax(dim=1)[is_eos.any(dim=1)]",
+                 "std_grouped_rewards = rewards.view(-1, self.num_generations).std(dim=1)",
+                 "agg_completion_lengths = self.accelerator.gather(completion_lengths)",
+                 "std_rewards = nanstd(rewards_per_func[:, i]).item()"):
+        assert text in src and text not in out
+    for text in ("rewards_per_func = self._calculate_rewards(inputs, original_prompts, completions, completion_ids_list)",
+                 "completion_lengths = completion_mask.sum(1)", "if self.mask_truncated_completions:",
+                 'self._logs["advantages"].extend(all_process_advantages.tolist())', '"advantages": advantages,'):
+        assert text in out
+    with pytest.raises(TP.TrainPatchError):
+        TP.rewrite_train(src.replace("advantages = advantages[process_slice]", "advantages = advantages[sl]"),
+                         TP.GRPO_GENERATE_BLOCKS)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/trl"), reason="the reference tree is not on this box")
@@ -44,8 +68,9 @@ def test_patch_trl_on_the_real_reference_modules():
     assert "PPOTrainer.train" in rep["trl.trainer.ppo_trainer"] and "RLOOTrainer.train" in rep["trl.trainer.rloo_trainer"]
     assert {"selective_log_softmax", "masked_mean", "masked_whiten", "first_true_indices",
             "truncate_response"} <= set(rep["trl.trainer.ppo_trainer"])
-    assert {"GRPOTrainer._compute_loss", "LigerFusedLinearGRPOLoss", "get_high_entropy_mask"} <= set(
-        rep["trl.trainer.grpo_trainer"])
+    assert {"GRPOTrainer._compute_loss", "LigerFusedLinearGRPOLoss", "get_high_entropy_mask",
+            "GRPOTrainer._generate_and_score_completions"} <= set(rep["trl.trainer.grpo_trainer"])
+    assert d["grpo_generate_patched"] is True and d["grpo_generate_co_names"] == ["_b200_adv_mod", "_b200_masks"]
     assert set(rep["trl.core"]) == {"masked_mean", "masked_var", "masked_whiten"}
     for key in ("ppo_sls_is_ours", "ppo_masked_whiten_is_ours", "ppo_first_true_is_ours", "rloo_sls_is_ours",
                 "grpo_compute_loss_is_ours", "grpo_liger_is_ours", "ppo_train_patched", "rloo_train_patched",

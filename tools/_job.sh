@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python tools/latency_kernels.py > gpurun_out/s18_latency.json 2> gpurun_out/s18_err.log; echo rc=$?
-cat gpurun_out/s18_latency.json
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "ppo_gae or masked_stats or cuda_graph" 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_train_patch.py -q -x -m gpu 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "generation_metrics or group_advantages" > gpurun_out/s20_new_tests.log 2>&1; echo "new tests rc=$?"
+tail -30 gpurun_out/s20_new_tests.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s20_gputest.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/s20_gputest.log
