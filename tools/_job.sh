@@ -1,7 +1,11 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "generation_metrics or group_advantages" > gpurun_out/s20_new_tests.log 2>&1; echo "new tests rc=$?"
-tail -30 gpurun_out/s20_new_tests.log
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s20_gputest.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/s20_gputest.log
+O=gpurun_out/s21_sustained.jsonl
+: > $O
+KS_SECS=3 KS_ONLY=fwd timeout 300 python tools/k1_sustained.py >> $O 2>gpurun_out/s21_err.log
+B200TRL_K1_GEOM=1 KS_SECS=3 KS_ONLY=fwd timeout 300 python tools/k1_sustained.py >> $O 2>>gpurun_out/s21_err.log
+B200TRL_K1_GEOM=3 KS_SECS=3 KS_ONLY=fwd timeout 300 python tools/k1_sustained.py >> $O 2>>gpurun_out/s21_err.log
+B200TRL_K1_FWD_CS=2 KS_SECS=3 KS_ONLY=fwd timeout 300 python tools/k1_sustained.py >> $O 2>>gpurun_out/s21_err.log
+KS_SECS=3 KS_ONLY=fwd timeout 300 python tools/k1_sustained.py >> $O 2>>gpurun_out/s21_err.log
+cat $O
