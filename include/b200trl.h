@@ -254,6 +254,21 @@ int b200trl_ppo_loss(const float* new_logprobs, const float* old_logprobs, const
                      float vf_coef, float grad_scale, void* workspace, float* stats, float* dvpred,
                      b200trl_stream_t stream);
 
+/* The PPO micro-batch in ONE call: b200trl_ppo_fused_fwd_bwd plus everything b200trl_ppo_loss computes from its
+ * outputs (the clipped policy / value losses, the seven statistics and d loss / d vpred, ppo_trainer.py:564-605).  On
+ * the resident kernel with dlogits != NULL the per-token terms are summed inside the pass (cluster partials, folded by
+ * the last cluster in cluster order, double) -- no second launch; otherwise (row kernel, evaluation) K2p is launched
+ * right behind the pass.  workspace: b200trl_ppo_fused_step_workspace_bytes(mb) bytes, zeroed once (the counter resets
+ * itself).  dvpred (fp32 [mb,T]) may be NULL; entropy must be given. */
+int64_t b200trl_ppo_fused_step_workspace_bytes(int64_t mb);
+int b200trl_ppo_fused_step(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab, int64_t row_stride,
+                           int64_t batch_stride, const int64_t* responses, const int64_t* sequence_lengths,
+                           const float* old_logprobs, const float* advantages, const float* returns, const float* values,
+                           const float* vpred, float inv_temperature, float cliprange, float cliprange_value,
+                           float vf_coef, float grad_scale, float* new_logprobs, float* entropy, float* lse,
+                           void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride, float* dvpred, void* workspace,
+                           float* stats, b200trl_stream_t stream);
+
 /* ---- RLOO ---------------------------------------------------------------------
  * rewards + leave-one-out advantages, trl/trainer/rloo_trainer.py:397-441.  logprobs/ref_logprobs raw fp32 [B,T]
  * (pads filled here), scores [B], sequence_lengths int64 [B]; sample i of prompt p is row i * (B / rloo_k) + p.

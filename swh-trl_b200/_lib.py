@@ -75,6 +75,9 @@ PROTOTYPES = {
                                           _p, _p, _p]),
     "b200trl_ppo_fused_fwd_bwd": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _f, _f, _f, _p,
                                             _p, _p, _p, _i64, _i64, _p]),
+    "b200trl_ppo_fused_step_workspace_bytes": (_i64, [_i64]),
+    "b200trl_ppo_fused_step": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f,
+                                         _f, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "b200trl_ppo_loss": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _f, _f, _f, _f, _p, _p, _p, _p]),
     "b200trl_rloo_rewards_advantages": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _f, _i64, _i32, _f, _i32, _i32, _p, _p, _p,
                                                   _p, _p, _p]),

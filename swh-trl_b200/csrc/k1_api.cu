@@ -296,13 +296,13 @@ static int grpo_fused_impl(const void* logits, int dtype, int64_t B, int64_t T, 
                              step_workspace, step_loss, step_metrics, nullptr, stream);
 }
 
-extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab,
-                                         int64_t row_stride, int64_t batch_stride, const int64_t* responses,
-                                         const int64_t* sequence_lengths, const float* old_logprobs,
-                                         const float* advantages, float inv_temperature, float cliprange,
-                                         float grad_scale, float* new_logprobs, float* entropy, float* lse,
-                                         void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
-                                         b200trl_stream_t stream) {
+static int ppo_fused_impl(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab, int64_t row_stride,
+                          int64_t batch_stride, const int64_t* responses, const int64_t* sequence_lengths,
+                          const float* old_logprobs, const float* advantages, float inv_temperature, float cliprange,
+                          float grad_scale, float* new_logprobs, float* entropy, float* lse, void* dlogits,
+                          int64_t dl_row_stride, int64_t dl_batch_stride, const float* returns, const float* values,
+                          const float* vpred, float cliprange_value, float vf_coef, float* dvpred, void* workspace,
+                          float* stats, b200trl_stream_t stream) {
     K1Args a;
     B200TRL_REQUIRE(mb > 0 && T > 0, B200TRL_E_INVALID, "ppo_fused: bad shape");
     const int rc = fill_common(a, logits, dtype, mb * T, vocab, row_stride, T, batch_stride, responses,
@@ -327,5 +327,53 @@ extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t 
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
     if (dlogits && set_dl_layout(a, T, dl_batch_stride, "ppo_fused")) return B200TRL_E_INVALID;
-    return dispatch(a, dtype, as_stream(stream));
+    if (!workspace) return dispatch(a, dtype, as_stream(stream));
+    // the clipped losses, their statistics and d loss / d vpred in the same call: inside the resident kernel's pass
+    // when it takes the call with a gradient, otherwise K2p right behind the pass
+    if (dlogits != nullptr && takes_resident(a, dtype)) {
+        a.step_ws = static_cast<float*>(workspace);
+        a.step_metrics = stats;
+        a.ppo_vpred = vpred;
+        a.ppo_values = values;
+        a.ppo_returns = returns;
+        a.ppo_dvpred = dvpred;
+        a.cliprange_value = cliprange_value;
+        a.vf_coef = vf_coef;
+        return dispatch(a, dtype, as_stream(stream));
+    }
+    const int rc1 = dispatch(a, dtype, as_stream(stream));
+    if (rc1) return rc1;
+    return b200trl_ppo_loss(new_logprobs, old_logprobs, advantages, returns, values, vpred, entropy, sequence_lengths, mb, T,
+                            cliprange, cliprange_value, vf_coef, grad_scale, workspace, stats, dvpred, stream);
+}
+
+extern "C" int b200trl_ppo_fused_fwd_bwd(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab,
+                                         int64_t row_stride, int64_t batch_stride, const int64_t* responses,
+                                         const int64_t* sequence_lengths, const float* old_logprobs,
+                                         const float* advantages, float inv_temperature, float cliprange,
+                                         float grad_scale, float* new_logprobs, float* entropy, float* lse,
+                                         void* dlogits, int64_t dl_row_stride, int64_t dl_batch_stride,
+                                         b200trl_stream_t stream) {
+    return ppo_fused_impl(logits, dtype, mb, T, vocab, row_stride, batch_stride, responses, sequence_lengths, old_logprobs,
+                          advantages, inv_temperature, cliprange, grad_scale, new_logprobs, entropy, lse, dlogits,
+                          dl_row_stride, dl_batch_stride, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr,
+                          stream);
+}
+
+extern "C" int64_t b200trl_ppo_fused_step_workspace_bytes(int64_t mb) { return step_ws_main_bytes(mb); }
+
+extern "C" int b200trl_ppo_fused_step(const void* logits, int dtype, int64_t mb, int64_t T, int64_t vocab,
+                                      int64_t row_stride, int64_t batch_stride, const int64_t* responses,
+                                      const int64_t* sequence_lengths, const float* old_logprobs, const float* advantages,
+                                      const float* returns, const float* values, const float* vpred, float inv_temperature,
+                                      float cliprange, float cliprange_value, float vf_coef, float grad_scale,
+                                      float* new_logprobs, float* entropy, float* lse, void* dlogits,
+                                      int64_t dl_row_stride, int64_t dl_batch_stride, float* dvpred, void* workspace,
+                                      float* stats, b200trl_stream_t stream) {
+    B200TRL_REQUIRE(returns && values && vpred && entropy && workspace && stats, B200TRL_E_INVALID,
+                    "ppo_fused_step: null pointer");
+    return ppo_fused_impl(logits, dtype, mb, T, vocab, row_stride, batch_stride, responses, sequence_lengths, old_logprobs,
+                          advantages, inv_temperature, cliprange, grad_scale, new_logprobs, entropy, lse, dlogits,
+                          dl_row_stride, dl_batch_stride, returns, values, vpred, cliprange_value, vf_coef, dvpred, workspace,
+                          stats, stream);
 }

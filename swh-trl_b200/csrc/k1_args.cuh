@@ -53,6 +53,13 @@ struct K1Args {
     // last one to finish adds the partials in cluster order (double) and writes loss[1] / metrics[8].  Null: off.
     int elem_f16;    // resident kernel: the 16-bit logits are fp16 (0: bf16); set by the dispatcher
     int count_mask;  // 1: row_count / total_count are null, the kernel counts `mask` itself (B <= 256 sequences)
+    // G_PPO, resident kernel only (b200trl_ppo_fused_step): the clipped policy / value losses, their statistics and
+    // d loss / d vpred (ppo_trainer.py:564-605) are produced by the same pass, like the GRPO sums below
+    const float* ppo_vpred;
+    const float* ppo_values;
+    const float* ppo_returns;
+    float* ppo_dvpred;  // nullable
+    float cliprange_value, vf_coef;
     float* step_ws;  // [1 counter word + 3 pad][max clusters][8]
     float* step_loss;
     float* step_metrics;
@@ -83,14 +90,42 @@ __device__ __forceinline__ bool row_is_masked(const K1Args& a, int64_t row) {
     return false;
 }
 
-// Number of non-pad positions sum_b min(len_b + 1, T) (ppo_trainer.py:501: pad = idx > len); warp-cooperative.
-__device__ __forceinline__ float ppo_unpadded_count(const K1Args& a, int lane) {
+// Number of non-pad positions sum_b min(len_b + 1 + shift, T) (ppo_trainer.py:501: pad = idx > len; :505: the mask
+// shifted by one, shift = 1); warp-cooperative.
+__device__ __forceinline__ float ppo_unpadded_count(const K1Args& a, int lane, int shift = 0) {
     float n = 0.f;
     for (int64_t b = lane; b < a.B; b += 32) {
         const int64_t len = a.seq_len[b];
-        n += static_cast<float>(min(max(len + 1, (int64_t)0), a.T));
+        n += static_cast<float>(min(max(len + 1 + shift, (int64_t)0), a.T));
     }
     return warp_sum(n);
+}
+
+// One token's terms of the PPO micro-batch statistics (ppo_trainer.py:564-605), shared by K2p and the in-kernel sums of
+// the resident K1 kernel.  v: 0 pg, 1 vf, 2 pg_clip, 3 vf_clip, 4 diff^2, 5 entropy, 6 ratio.  Returns d(loss)/d(vpred)
+// without the 0.5 * vf_coef * grad_scale / n_p1 factor.
+__device__ __forceinline__ float ppo_token_stats(float nlp, float old_lp, float adv, float vpred_raw, float val, float ret,
+                                                 float entropy, bool pad, bool pad1, float clip_lo, float clip_hi,
+                                                 float cliprange_value, float (&v)[7]) {
+    float pg, dpg, clipped, ratio, diff;
+    ppo_policy(pad ? 1.0f : nlp, old_lp, adv, clip_lo, clip_hi, pg, dpg, clipped, ratio, diff);  // :561-563 fill
+    const float vp = pad1 ? 0.f : vpred_raw;  // :565
+    const float lo = val - cliprange_value, hi = val + cliprange_value;
+    const float vc = fminf(fmaxf(vp, lo), hi);  // :566-570
+    const float e1 = vp - ret, e2 = vc - ret;
+    const float vf1 = e1 * e1, vf2 = e2 * e2;  // :571-572
+    const float keep = pad ? 0.f : 1.f, keep1 = pad1 ? 0.f : 1.f;
+    v[0] += pg * keep;
+    v[1] += fmaxf(vf1, vf2) * keep1;
+    v[2] += clipped * keep;
+    v[3] += (vf2 > vf1 ? 1.f : 0.f) * keep1;
+    v[4] += diff * diff;  // unmasked mean (:594)
+    v[5] += entropy;
+    v[6] += ratio;
+    const float d1 = 2.f * e1;
+    const float d2 = (vp >= lo && vp <= hi) ? 2.f * e2 : 0.f;
+    const float dmax = (vf1 > vf2) ? d1 : ((vf2 > vf1) ? d2 : 0.5f * (d1 + d2));
+    return keep1 * dmax;
 }
 
 // Row scalars fetched early (latency hidden behind the streaming pass).

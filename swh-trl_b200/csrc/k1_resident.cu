@@ -114,6 +114,7 @@ struct Smem {
     Part4 warp_part[2][kMaxConsumers / 32];
     RowResult result[2];
     float ppo_count;
+    float ppo_count_p1;            // G_PPO step sums: positions with t <= len + 1 (ppo_trainer.py:505)
     float total_cnt;               // count_mask: number of unmasked tokens of the batch ...
     float row_cnt[kMaxCountSeqs];  // ... and per sequence, counted by the consumer warps while the first chunks fly
     TraceLog trace;
@@ -816,7 +817,11 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
     }
     if (a.gmode == G_PPO && warp == kWarps) {
         const float n = ppo_unpadded_count(a, lane);
-        if (lane == 0) sm.ppo_count = n;
+        const float n1 = a.step_ws ? ppo_unpadded_count(a, lane, 1) : 0.f;
+        if (lane == 0) {
+            sm.ppo_count = n;
+            sm.ppo_count_p1 = n1;
+        }
     }
     __syncthreads();
     if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -929,6 +934,17 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             // in-kernel loss / metric sums of this cluster's rows (leader CTA, lane 0): loss, kl, entropy, low, high, region
             const bool step_sums = HAS_BWD && a.step_ws != nullptr && a.gmode == G_GRPO && crank == 0;
             float sums[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            // same for the PPO micro-batch statistics (+ d loss / d vpred, one float per row)
+            const bool ppo_sums = HAS_BWD && a.step_ws != nullptr && a.gmode == G_PPO && crank == 0;
+            float psums[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            auto ppo_row = [&](int64_t row, const RowScalars& r, float logp, float entropy) {  // lane 0, after the publish
+                const int64_t b = row / a.T, t = row - b * a.T;
+                const bool pad1 = t > a.seq_len[b] + 1;
+                const float dv = ppo_token_stats(logp, r.aux0, r.adv, a.ppo_vpred[row], a.ppo_values[row],
+                                                 a.ppo_returns[row], entropy, r.pad != 0.f, pad1, a.clip_lo, a.clip_hi,
+                                                 a.cliprange_value, psums);
+                if (a.ppo_dvpred) a.ppo_dvpred[row] = dv * (0.5f * a.vf_coef * a.grad_scale / sm.ppo_count_p1);
+            };
             const bool counted = HAS_BWD && a.count_mask != 0;
             if (counted) asm volatile("bar.sync 3, %0;" ::"n"(NC + 32) : "memory");  // the consumers counted the mask
             const float* row_count = counted ? sm.row_cnt : a.row_count;
@@ -969,6 +985,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         rr.pad0 = rr.pad1 = 0;
                         sm.result[par] = rr;
                         mbar_arrive(&sm.res_bar[par]);
+                        if (ppo_sums) ppo_row(row, rs, 1.0f, 0.f);  // a skipped row is a pad row: INVALID_LOGPROB, entropy 0
                     }
                     __syncwarp();
                     rs = rs_next;
@@ -1036,12 +1053,52 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                         if (a.logp) a.logp[row] = pad ? 1.0f : st.logp;
                         if (a.entropy) a.entropy[row] = st.entropy;
                         if (a.lse) a.lse[row] = st.lse;
+                        if (ppo_sums) ppo_row(row, rs, st.logp, st.entropy);
                     }
                 }
                 __syncwarp();
                 rs = rs_next;
                 rs.x_sel = x_next;
                 rs_next = rs_after;
+            }
+            if (HAS_BWD && a.step_ws != nullptr && a.gmode == G_PPO && crank == 0) {
+                unsigned int* counter = reinterpret_cast<unsigned int*>(a.step_ws);
+                volatile float* part = a.step_ws + 4;
+                const unsigned int n_cl = num_clusters_x();
+                bool last = false;
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) part[static_cast<size_t>(cluster_id_x()) * 8 + k] = psums[k];
+                    __threadfence();
+                    const unsigned int prev = atomicAdd(counter, 1u);
+                    last = (prev == n_cl - 1);
+                    if (last) {
+                        *counter = 0u;
+                        __threadfence();
+                    }
+                }
+                last = __shfl_sync(0xffffffffu, last ? 1 : 0, 0) != 0;
+                if (last) {
+                    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                    for (unsigned int cl = lane; cl < n_cl; cl += 32)
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) acc[k] += static_cast<double>(part[static_cast<size_t>(cl) * 8 + k]);
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
+                    if (lane == 0) {  // ppo_trainer.py:573-605, as b200trl_ppo_loss writes them
+                        const double n_pad = sm.ppo_count, n_p1 = sm.ppo_count_p1;
+                        const double n_all = static_cast<double>(a.B) * static_cast<double>(a.T);
+                        const double pg_loss = acc[0] / n_pad, vf_loss = 0.5 * acc[1] / n_p1;
+                        a.step_metrics[B200TRL_P_LOSS] = static_cast<float>(pg_loss + a.vf_coef * vf_loss);
+                        a.step_metrics[B200TRL_P_PG_LOSS] = static_cast<float>(pg_loss);
+                        a.step_metrics[B200TRL_P_VF_LOSS] = static_cast<float>(vf_loss);
+                        a.step_metrics[B200TRL_P_PG_CLIPFRAC] = static_cast<float>(acc[2] / n_pad);
+                        a.step_metrics[B200TRL_P_VF_CLIPFRAC] = static_cast<float>(acc[3] / n_p1);
+                        a.step_metrics[B200TRL_P_APPROXKL] = static_cast<float>(0.5 * acc[4] / n_all);
+                        a.step_metrics[B200TRL_P_ENTROPY] = static_cast<float>(acc[5] / n_all);
+                        a.step_metrics[B200TRL_P_RATIO] = static_cast<float>(acc[6] / n_all);
+                    }
+                }
             }
             if (HAS_BWD && a.step_ws != nullptr && a.gmode == G_GRPO && crank == 0) {
                 // leave this cluster's sums; the last cluster to arrive folds all of them in cluster order (double):

@@ -4,7 +4,7 @@
 //   b200trl_ppo_loss     ppo_trainer.py:564-605
 // One CTA per sequence; row partials go to a workspace and the last CTA to finish folds them in row
 // order (double accumulation), so results are run-to-run deterministic without a second launch.
-#include "token_math.cuh"
+#include "k1_args.cuh"
 
 namespace b200trl {
 namespace {
@@ -233,29 +233,10 @@ __global__ void __launch_bounds__(kBlock) ppo_loss_kernel(const PpoLossArgs a) {
     for (int64_t t = tid; t < a.T; t += kBlock) {
         const int64_t i = base + t;
         const bool pad = t > len, pad1 = t > len + 1;
-        const float nlp = pad ? 1.0f : a.new_lp[i];  // :561-563
-        float pg, dpg, clipped, ratio, diff;
-        ppo_policy(nlp, a.old_lp[i], a.adv[i], a.clip_lo, a.clip_hi, pg, dpg, clipped, ratio, diff);
-        const float vp = pad1 ? 0.f : a.vpred[i];  // :565
-        const float val = a.values[i], ret = a.returns[i];
-        const float lo = val - a.cliprange_value, hi = val + a.cliprange_value;
-        const float vc = fminf(fmaxf(vp, lo), hi);  // :566-570
-        const float e1 = vp - ret, e2 = vc - ret;
-        const float vf1 = e1 * e1, vf2 = e2 * e2;  // :571-572
-        const float keep = pad ? 0.f : 1.f, keep1 = pad1 ? 0.f : 1.f;
-        v[0] += pg * keep;
-        v[1] += fmaxf(vf1, vf2) * keep1;
-        v[2] += clipped * keep;
-        v[3] += (vf2 > vf1 ? 1.f : 0.f) * keep1;
-        v[4] += diff * diff;  // unmasked mean (:594)
-        if (a.entropy) v[5] += a.entropy[i];
-        v[6] += ratio;
-        if (a.dvpred) {
-            const float d1 = 2.f * e1;
-            const float d2 = (vp >= lo && vp <= hi) ? 2.f * e2 : 0.f;
-            const float dmax = (vf1 > vf2) ? d1 : ((vf2 > vf1) ? d2 : 0.5f * (d1 + d2));
-            a.dvpred[i] = keep1 * dmax * (0.5f * a.vf_coef * a.grad_scale / n_p1);
-        }
+        const float dv = ppo_token_stats(pad ? 1.0f : a.new_lp[i], a.old_lp[i], a.adv[i], pad1 ? 0.f : a.vpred[i],
+                                         a.values[i], a.returns[i], a.entropy ? a.entropy[i] : 0.f, pad, pad1, a.clip_lo,
+                                         a.clip_hi, a.cliprange_value, v);
+        if (a.dvpred) a.dvpred[i] = dv * (0.5f * a.vf_coef * a.grad_scale / n_p1);
     }
     block_sum<7, kBlock>(v, red);
     if (tid == 0) {

@@ -477,6 +477,37 @@ def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advanta
     return nlp, ent, lse, dl
 
 
+def ppo_fused_step(logits, responses, sequence_lengths, old_logprobs, advantages, returns, values, vpred,
+                   inv_temperature, cliprange, cliprange_value, vf_coef, grad_scale: float = 1.0, want_grad: bool = True,
+                   want_dvpred: bool = True):
+    """``(new_logprobs, entropy, dlogits|None, stats[8], dvpred|None)`` — ``b200trl_ppo_fused_step``: the fused PPO pass
+    with the clipped losses, their statistics and ``d loss / d vpred`` produced by the same launch (resident kernel
+    with a gradient; otherwise K2p runs right behind the pass inside the C call)."""
+    k = _Keep()
+    mb, T = responses.shape
+    r = rows_view(logits, rows_per_batch=T)
+    x, n, V = r.t, r.n, r.V
+    if n != mb * T:
+        raise ValueError(f"logits rows {n} != mb*T {mb * T}")
+    idx = responses.to(torch.int64).contiguous()
+    sl = sequence_lengths.to(torch.int64).contiguous()
+    dev = x.device
+    nlp = torch.empty(mb, T, dtype=torch.float32, device=dev)
+    ent = torch.empty(mb, T, dtype=torch.float32, device=dev)
+    dl, dl_rs, dl_bs = alloc_dlogits(r, (mb, T, V)) if want_grad else (None, V, 0)
+    dvp = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_dvpred else None
+    stats = torch.empty(_lib.NUM_PPO_STATS, dtype=torch.float32, device=dev)
+    ws = _workspace(dev, lib.b200trl_ppo_fused_step_workspace_bytes(mb), "ppo_fused_step", zero=True)
+    check(lib.b200trl_ppo_fused_step(_ptr(x), _DTYPES[x.dtype], mb, T, V, r.row_stride, r.batch_stride, _ptr(idx), _ptr(sl),
+                                     k.f32(old_logprobs, "old_logprobs"), k.f32(advantages, "advantages"),
+                                     k.f32(returns, "returns"), k.f32(values, "values"), k.f32(vpred, "vpred"),
+                                     float(inv_temperature), float(cliprange), float(cliprange_value), float(vf_coef),
+                                     float(grad_scale), _ptr(nlp), _ptr(ent), None, _ptr(dl), dl_rs, dl_bs, _ptr(dvp),
+                                     _ptr(ws), _ptr(stats), _stream(x)), "ppo_fused_step")
+    _count()
+    return nlp, ent, dl, stats, dvp
+
+
 def ppo_loss(new_logprobs, old_logprobs, advantages, returns, values, vpred, entropy, sequence_lengths, cliprange,
              cliprange_value, vf_coef, grad_scale: float = 1.0, want_dvpred: bool = True):
     """``(stats[8], dvpred|None)`` — ``b200trl_ppo_loss``."""
@@ -703,7 +734,7 @@ from ._nvtx import nvtx_op as _nvtx_op  # noqa: E402
 
 for _name in ("logprob_entropy_fwd", "masked_logprob_fwd", "logprob_bwd", "mask_stats", "grpo_fused_fwd_bwd",
               "grpo_fused_step", "grpo_loss", "entropy_quantile_mask", "group_advantages", "ppo_rewards_gae",
-              "ppo_fused_fwd_bwd", "ppo_loss", "masked_whiten", "rloo_rewards_advantages", "rloo_loss",
+              "ppo_fused_fwd_bwd", "ppo_fused_step", "ppo_loss", "masked_whiten", "rloo_rewards_advantages", "rloo_loss",
               "fused_linear_logprob_fwd", "fused_linear_grpo", "tc_gemm", "rescale_if_needed", "completion_mask",
               "generation_stats",
               "first_true_indices", "truncate_response"):

@@ -41,10 +41,11 @@ class _PPOLoss(torch.autograd.Function):
                 inv_temp, cliprange, cliprange_value, vf_coef, grad_scale):
         ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         need_dl, need_dv = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
-        nlp, ent, _lse, dl = ops.ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advantages,
-                                                   inv_temp, cliprange, grad_scale, want_grad=need_dl)
-        stats, dvp = ops.ppo_loss(nlp, old_logprobs, advantages, returns, values, vpred, ent, sequence_lengths,
-                                  cliprange, cliprange_value, vf_coef, grad_scale, want_dvpred=need_dv)
+        # one C call (and, for bf16 / fp16 logits, one launch): new log-probs, entropy, dlogits, the clipped losses,
+        # their statistics and d loss / d vpred
+        nlp, _ent, dl, stats, dvp = ops.ppo_fused_step(logits, responses, sequence_lengths, old_logprobs, advantages,
+                                                       returns, values, vpred, inv_temp, cliprange, cliprange_value,
+                                                       vf_coef, grad_scale, want_grad=need_dl, want_dvpred=need_dv)
         ctx.dl, ctx.dvp, ctx.grad_scale = dl, dvp, grad_scale
         ctx.shapes = (logits.shape, vpred.shape)
         ctx.mark_non_differentiable(stats, nlp)

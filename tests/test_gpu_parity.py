@@ -1612,3 +1612,52 @@ def test_generation_metrics_golden(S, i):
         else:
             assert got[k] == pytest.approx(w, rel=2e-6, abs=1e-6), (k, got[k], w)
 
+
+
+@pytest.mark.parametrize("V", [32768, 50257, 151936])  # twin CTAs / skewed rows / 2-CTA clusters
+@pytest.mark.parametrize("skip", [False, True])
+def test_ppo_losses_and_stats_inside_the_fused_pass(S, V, skip):
+    """b200trl_ppo_fused_step: on the resident kernel the clipped policy / value losses, the seven statistics and
+    d loss / d vpred (ppo_trainer.py:564-605) come out of the K1 launch; against the row-kernel route of the same entry
+    point (K1 + K2p: the same per-token function, another summation order), against the oracle, reproducible bit for
+    bit; with masked-row skipping (pads are not read) the two routes still agree."""
+    from swh_trl_b200 import ops
+    mb, T = 4, 11
+    g = torch.Generator().manual_seed(V % 89)
+    logits = (torch.randn(mb, T, V, generator=g) * 2).to(torch.bfloat16)
+    responses = torch.randint(0, V, (mb, T), generator=g)
+    lens = torch.tensor([10, 4, 6, 0])
+    adv, ret, val = (torch.randn(mb, T, generator=g) for _ in range(3))
+    vpred = val + torch.randn(mb, T, generator=g) * 0.3
+    base = O.selective_log_softmax(logits.float() / (0.7 + 1e-7), responses)
+    pad = torch.arange(T).unsqueeze(0) > lens.unsqueeze(1)
+    old = (base + torch.randn(mb, T, generator=g) * 0.3).masked_fill(pad, 1.0)
+    dev = [t.to(DEV) for t in (logits, responses, lens, old, adv, ret, val, vpred)]
+    inv_temp = 1.0 / (0.7 + 1e-7)
+    prev_skip = S.set_skip_masked(skip)
+    runs = {}
+    try:
+        for name, path in (("row", S.K1_ROW), ("resident", S.K1_RESIDENT)):
+            prev = S.set_k1_path(path)
+            try:
+                outs = [ops.ppo_fused_step(*dev, inv_temp, 0.2, 0.2, 0.1, grad_scale=0.5) for _ in range(3)]
+            finally:
+                S.set_k1_path(prev)
+            torch.cuda.synchronize()
+            for o in outs[1:]:
+                assert torch.equal(o[3], outs[0][3]) and torch.equal(o[4], outs[0][4]), f"{name}: not reproducible"
+            runs[name] = outs[0]
+    finally:
+        S.set_skip_masked(prev_skip)
+    torch.testing.assert_close(runs["resident"][3], runs["row"][3], rtol=3e-6, atol=1e-8)   # stats
+    torch.testing.assert_close(runs["resident"][4], runs["row"][4], rtol=1e-6, atol=1e-9)   # dvpred: same formula
+    torch.testing.assert_close(runs["resident"][0], runs["row"][0], rtol=0, atol=4e-6)      # new log-probs
+    if not skip:  # with skipping the entropy statistic leaves out the pads the reference averages over
+        xr = logits.float().requires_grad_(True)
+        vr = vpred.clone().requires_grad_(True)
+        loss_r, stats_r, _ = O.ppo_loss(xr, responses, old, adv, ret, val, vr, lens)
+        (loss_r * 0.5).backward()
+        for name, o in runs.items():
+            assert o[3][0].item() == pytest.approx(loss_r.item(), rel=1e-4), name
+            torch.testing.assert_close(o[4].cpu(), vr.grad, rtol=1e-4, atol=1e-8, msg=lambda m: f"{name} dvpred: {m}")
+            torch.testing.assert_close(o[2].float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)

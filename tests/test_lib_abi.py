@@ -62,6 +62,24 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"null" in lib.b200trl_last_error()
     rc = lib.b200trl_completion_mask(None, 2, 4, 0, None, None, None)
     assert rc == -1
+    # the one-launch step: its outputs and workspace are mandatory, the mask statistics may be left to the call (both
+    # pointers null) but not half-given; the plain fused entry point still needs them
+    cfg = _lib.GrpoCfg()
+    assert lib.b200trl_grpo_fused_step_workspace_bytes(16) >= 16 + 1024 * 32 + 16 + 64
+    assert lib.b200trl_grpo_fused_step_workspace_bytes(5000) >= lib.b200trl_grpo_loss_workspace_bytes(5000) + 16 + 20000
+    rc = lib.b200trl_grpo_fused_step(p, 0, 2, 4, 32768, 32768, 0, p, p, p, None, None, ctypes.byref(cfg), 1.0, None, None,
+                                     p, p, p, None, 32768, 0, None, p, p, None)
+    assert rc == -1 and b"null" in lib.b200trl_last_error()
+    rc = lib.b200trl_grpo_fused_step(p, 0, 2, 4, 32768, 32768, 0, p, p, p, None, None, ctypes.byref(cfg), 1.0, p, None,
+                                     p, p, p, None, 32768, 0, p, p, p, None)
+    assert rc == -1 and b"row_count" in lib.b200trl_last_error()
+    rc = lib.b200trl_grpo_fused_fwd_bwd(p, 0, 2, 4, 32768, 32768, 0, p, p, p, None, None, ctypes.byref(cfg), 1.0, None,
+                                        None, p, p, p, None, 32768, 0, None)
+    assert rc == -1 and b"row_count" in lib.b200trl_last_error()
+    rc = lib.b200trl_generation_stats(None, 1, 4, p, 1, p, p, p, 1, p, None)
+    assert rc == -1 and b"null" in lib.b200trl_last_error()
+    rc = lib.b200trl_generation_stats(p, 0, 4, p, 1, p, p, p, 1, p, None)
+    assert rc == -1 and b"sizes" in lib.b200trl_last_error()
     assert lib.b200trl_completion_mask(None, 0, 4, 0, None, None, None) == 0  # empty batch: nothing to launch
 
 
