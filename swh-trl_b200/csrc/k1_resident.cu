@@ -1495,20 +1495,18 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-// g_skew_extra: 16 when the rows are skewed (their aligned span is up to 14 bytes longer than the slice); set by
-// pick_geom for the duration of one decision (host side, under the caller's serial use of the API per thread)
-thread_local int g_skew_extra = 0;
-int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes = kChunkBytes) {
+// extra_bytes: 16 when the rows are skewed (their aligned span is up to 14 bytes longer than the slice)
+int pick_cluster(int64_t vocab, int num_slots, int chunk_bytes, int extra_bytes) {
     static const int forced = env_int("B200TRL_K1_CLUSTER", 0);  // tuning knob: force a (larger) cluster size
     if (forced == 3 || forced == 5 || forced == 6 || forced == 7) {  // experiments: any size the hardware takes
         const int64_t slice = ((vocab + forced - 1) / forced + 7) & ~int64_t(7);
-        const int64_t chunks = (slice * 2 + g_skew_extra + chunk_bytes - 1) / chunk_bytes;
+        const int64_t chunks = (slice * 2 + extra_bytes + chunk_bytes - 1) / chunk_bytes;
         if (chunks <= num_slots - 1) return forced;
     }
     for (int cs = 1; cs <= kMaxCluster; cs *= 2) {
         if (cs < forced) continue;
         const int64_t slice = ((vocab + cs - 1) / cs + 7) & ~int64_t(7);
-        const int64_t chunks = (slice * 2 + g_skew_extra + chunk_bytes - 1) / chunk_bytes;
+        const int64_t chunks = (slice * 2 + extra_bytes + chunk_bytes - 1) / chunk_bytes;
         if (chunks <= num_slots - 1 || (chunks <= num_slots && cs == kMaxCluster)) return cs;
     }
     return 0;
@@ -1632,11 +1630,11 @@ Mode mode_of(const K1Args& a) {
 
 Geom pick_geom(int64_t vocab, Mode m, bool skew = false) {
     static const int mode = env_int("B200TRL_K1_GEOM", 0);  // 0 auto, 1 wide, 2 twin, 3 dense, 4 mid
-    g_skew_extra = skew ? 16 : 0;
-    Geom wide{pick_cluster(vocab, kMaxSlots), kMaxSlots, 512};
-    Geom twin{pick_cluster(vocab, kTwinSlots), kTwinSlots, 256};
-    Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768)), kDenseSlots, 768};
-    const Geom mid{pick_cluster(vocab, kMidSlots, chunk_bytes_for(640)), kMidSlots, 640};
+    const int extra = skew ? 16 : 0;
+    Geom wide{pick_cluster(vocab, kMaxSlots, kChunkBytes, extra), kMaxSlots, 512};
+    Geom twin{pick_cluster(vocab, kTwinSlots, kChunkBytes, extra), kTwinSlots, 256};
+    Geom dense{pick_cluster(vocab, kDenseSlots, chunk_bytes_for(768), extra), kDenseSlots, 768};
+    const Geom mid{pick_cluster(vocab, kMidSlots, chunk_bytes_for(640), extra), kMidSlots, 640};
     if (m != M_FUSED) {
         // forward-only / backward-only: nothing has to stay resident between two sweeps, so a row simply STREAMS
         // through the ring of one CTA -- no cluster, no DSMEM exchange, any vocabulary.  Measured at config 2
