@@ -1661,3 +1661,37 @@ def test_ppo_losses_and_stats_inside_the_fused_pass(S, V, skip):
             assert o[3][0].item() == pytest.approx(loss_r.item(), rel=1e-4), name
             torch.testing.assert_close(o[4].cpu(), vr.grad, rtol=1e-4, atol=1e-8, msg=lambda m: f"{name} dvpred: {m}")
             torch.testing.assert_close(o[2].float().cpu(), xr.grad.to(torch.bfloat16).float(), rtol=BF16_ULP, atol=1e-12)
+
+
+def test_one_launch_step_edge_batches(S):
+    """The one-launch GRPO step on the batches its in-kernel bookkeeping could get wrong: a fully masked batch (token
+    count 0: loss 0, dlogits 0, nothing NaN), more sequences than the in-kernel mask counter holds (B = 300 > 256: the
+    call falls back to the mask_stats kernel inside the C function), and a single row."""
+    from swh_trl_b200 import ops
+    V = 32768
+    for B, T, all_masked in ((3, 5, True), (300, 2, False), (1, 1, False)):
+        logits, ids, mask = O.synth_batch(B, T, V, seed=B + T, edge_rows=False)
+        if all_masked:
+            mask = torch.zeros_like(mask)
+        g = torch.Generator().manual_seed(B)
+        adv = torch.randn(B, generator=g)
+        cfg = ops.make_cfg(0.0, 0.2, 0.2, None, "grpo", "token", T)
+        x, idx, m = logits.to(DEV), ids.to(DEV), mask.to(DEV)
+        outs = {}
+        for name, path in (("row", S.K1_ROW), ("resident", S.K1_RESIDENT)):
+            prev = S.set_k1_path(path)
+            try:
+                outs[name] = ops.grpo_fused_step(x, idx, m, None, None, adv.to(DEV), None, None, cfg, 1.0)
+            finally:
+                S.set_k1_path(prev)
+        torch.cuda.synchronize()
+        lo, me = outs["resident"][4], outs["resident"][5]
+        assert bool(torch.isfinite(lo).all()) and bool(torch.isfinite(me).all())
+        torch.testing.assert_close(lo, outs["row"][4], rtol=2e-6, atol=1e-9)
+        torch.testing.assert_close(me, outs["row"][5], rtol=2e-6, atol=1e-9)
+        cfgo = O.GRPOConfigLite(beta=0.0, loss_type="grpo", importance_sampling_level="token", max_completion_length=T)
+        want = O.grpo_compute_loss(logits.float(), ids, mask, adv, cfgo, None, None)[0]
+        if all_masked:
+            assert lo.item() == 0.0 and torch.count_nonzero(outs["resident"][3]) == 0
+        else:
+            assert lo.item() == pytest.approx(want.item(), rel=1e-4, abs=1e-7)
