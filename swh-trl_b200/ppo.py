@@ -85,6 +85,17 @@ def ppo_loss(logits, mb_responses, mb_logprobs, mb_advantage, mb_return, mb_valu
 # ------------------------------------------------------------------------------------------------------------------
 # Helpers named by the rewritten ``PPOTrainer.train`` / ``RLOOTrainer.train`` (train_patch.py)
 # ------------------------------------------------------------------------------------------------------------------
+def rollout_logprobs(logits: torch.Tensor, responses: torch.Tensor, temperature: float) -> torch.Tensor:
+    """``selective_log_softmax(logits / temperature, responses)`` of the rollout phase (ppo_trainer.py:448-451,
+    rloo_trainer.py:339-342) in ONE read of the logits: the reference divides the ``[b, T, V]`` slice in place first (a
+    V-sized read + write) and then runs the log-softmax over it.  The strided slice ``logits[:, ctx - 1 : -1]`` is read
+    where it lies; the result has the logits' dtype, as the reference's (utils.py:1455-1461)."""
+    from .functional import logprobs_and_entropy
+    with torch.no_grad():
+        lp, _ = logprobs_and_entropy(logits, responses, float(temperature), compute_entropy=False)
+    return lp if lp.dtype == logits.dtype or logits.dtype == torch.float64 else lp.to(logits.dtype)
+
+
 def kl_terms(logprobs, ref_logprobs, kl_coef: float, kl_estimator: str = "k1"):
     """``(kl, non_score_reward)`` as ppo_trainer.py:510-512 defines them on the pad-filled log-probs: only the two
     logged row sums (``objective/kl``, ``objective/non_score_reward``, :618-620) still need these ``[B, T]`` tensors

@@ -35,6 +35,11 @@ Block = Tuple[str, str, str, Sequence[str]]  # (what, first line, last line, rep
 _STATS_IDX = "[ppo_epoch_idx, minibatch_idx, gradient_accumulation_idx]"
 
 PPO_BLOCKS: List[Block] = [
+    ("rollout reference log-probs (ppo_trainer.py:448-451): the in-place temperature division + log-softmax -> one read",
+     "ref_logits = ref_output.logits[:, context_length - 1 : -1]",
+     "ref_logprob = selective_log_softmax(ref_logits, response)",
+     ["ref_logits = ref_output.logits[:, context_length - 1 : -1]",
+      "ref_logprob = _b200_ppo.rollout_logprobs(ref_logits, response, args.temperature + 1e-7)"]),
     ("reward shaping + GAE + whitening (ppo_trainer.py:500-535)",
      "response_idxs = torch.arange(responses.shape[1], device=responses.device).repeat(responses.shape[0], 1)",
      "advantages = torch.masked_fill(advantages, padding_mask, 0)",
@@ -85,6 +90,11 @@ PPO_BLOCKS: List[Block] = [
 ]
 
 RLOO_BLOCKS: List[Block] = [
+    ("rollout reference log-probs (rloo_trainer.py:339-342): the in-place temperature division + log-softmax -> one read",
+     "ref_logits = ref_output.logits[:, context_length - 1 : -1]",
+     "ref_logprob = selective_log_softmax(ref_logits, response)",
+     ["ref_logits = ref_output.logits[:, context_length - 1 : -1]",
+      "ref_logprob = _b200_ppo.rollout_logprobs(ref_logits, response, args.temperature + 1e-7)"]),
     ("rewards + leave-one-out advantages (rloo_trainer.py:397-441)",
      "response_idxs = torch.arange(responses.shape[1], device=responses.device).repeat(responses.shape[0], 1)",
      "advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)",

@@ -91,6 +91,7 @@ def test_rewrite_of_the_lifted_train(cls_name):
     assert out.count("# ---- swh_trl_b200:") == len(blocks)
     gone = ["for t in reversed(range(gen_length))", "prob_dist = torch.nn.functional.softmax(logits, dim=-1)",
             "gather_for_metrics(approxkl_stats)"]
+    assert "ref_logits /= args.temperature + 1e-7" in src and "ref_logits /= args.temperature + 1e-7" not in out
     if cls_name == "RLOOTrainer":
         gone = ["baseline = (rlhf_reward.sum(0) - rlhf_reward) / (args.rloo_k - 1)", gone[1], gone[2]]
     for text in gone:
