@@ -7,7 +7,9 @@ Same names, argument meaning and error behaviour as ``trl/trainer/utils.py`` (``
 * results are computed in fp32 from the logits' own dtype in ONE pass over the logits; for half inputs the
   returned log-probs are fp32 (the reference's bf16 branch returns bf16 rounded values that differ from its
   own fp32 path by up to 4.7e-2).  Pass ``out_dtype=logits.dtype`` for the reference's dtype behaviour.
-* there is no CPU path: CPU tensors raise.
+* there is no CPU path: CPU tensors raise; fp64 logits are accepted but computed in fp32 and cast up (the reference
+  computes fp64 natively) — the bindings ``patch_trl()`` installs send CPU and fp64 tensors to the reference's own
+  function instead (``patch._ref_dtype_binding``).
 """
 
 from __future__ import annotations

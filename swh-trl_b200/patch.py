@@ -77,7 +77,11 @@ def patch_module(mod: types.ModuleType) -> list:
         if trainer.__dict__["_compute_loss"] is not grpo.compute_loss:  # the class may be reachable from several modules
             trainer._trl_original_compute_loss = trainer._compute_loss
             trainer._compute_loss = grpo.compute_loss
-            trainer._get_per_token_logps_and_entropies = grpo.get_per_token_logps_and_entropies
+            # the reference profiles this method (`@profiling_decorator`, grpo_trainer.py:1205-1206: the
+            # "profiling/Time taken: GRPOTrainer._get_per_token_logps_and_entropies" metric): keep the decoration
+            deco = ns.get("profiling_decorator")
+            trainer._get_per_token_logps_and_entropies = (deco(grpo.get_per_token_logps_and_entropies)
+                                                          if callable(deco) else grpo.get_per_token_logps_and_entropies)
             done.append("GRPOTrainer._compute_loss")
         # the operator seam: GRPOTrainer.__init__ builds `LigerFusedLinearGRPOLoss(beta=..., ...)` from ITS module's
         # global (grpo_trainer.py:82-83, 878-886) behind `is_liger_kernel_available()` (:871); rebinding both there

@@ -41,6 +41,8 @@ out = {
     "grpo_generate_patched": bool(getattr(grpo_mod.GRPOTrainer, "_b200__generate_and_score_completions_patched", False)),
     "grpo_generate_co_names": sorted(set(grpo_mod.GRPOTrainer._generate_and_score_completions.__code__.co_names)
                                      & {"_b200_adv_mod", "_b200_masks", "nanstd"}),
+    "grpo_logps_keeps_profiling": getattr(grpo_mod.GRPOTrainer._get_per_token_logps_and_entropies, "__wrapped__", None)
+    is grpo.get_per_token_logps_and_entropies,
     "second_patch_is_noop": S.patch_trl() == {},
 }
 print("RESULT " + json.dumps(out))

@@ -74,7 +74,7 @@ def test_patch_trl_on_the_real_reference_modules():
     assert set(rep["trl.core"]) == {"masked_mean", "masked_var", "masked_whiten"}
     for key in ("ppo_sls_is_ours", "ppo_masked_whiten_is_ours", "ppo_first_true_is_ours", "rloo_sls_is_ours",
                 "grpo_compute_loss_is_ours", "grpo_liger_is_ours", "ppo_train_patched", "rloo_train_patched",
-                "ppo_train_globals_are_module", "ppo_original_kept", "second_patch_is_noop"):
+                "ppo_train_globals_are_module", "ppo_original_kept", "second_patch_is_noop", "grpo_logps_keeps_profiling"):
         assert d[key] is True, key
     # the rewritten PPO train() no longer names the leaf reductions of the inline blocks; it names our helper module
     assert d["ppo_co_names"] == ["_b200_ppo"] and d["rloo_co_names"] == ["_b200_ppo", "_b200_rloo"]

@@ -1,5 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_train_patch.py -q -x -m gpu > gpurun_out/s26_train_patch.log 2>&1; echo "train patch rc=$?"
-tail -8 gpurun_out/s26_train_patch.log
+which compute-sanitizer
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q -k "skewed_rows and 50257" > gpurun_out/s27_sanitizer.log 2>&1; echo "sanitizer rc=$?"
+tail -15 gpurun_out/s27_sanitizer.log
