@@ -174,7 +174,7 @@ class GRPOLoss:
                 raise NotImplementedError("the fused schedule needs a per-token gradient (see GRPOLoss.schedule)")
             # the completion-mask statistics (:2131, 2133, 2142) are counted inside the fused call
             ops._need_cuda(completion_mask, "completion_mask")
-            mask_i32, row_count, total = completion_mask.to(torch.int32).contiguous(), None, None
+            mask_i32, row_count, total = ops._as(completion_mask, torch.int32), None, None
             loss, metrics, logp, ent = _FusedGRPO.apply(logits, completion_ids, mask_i32, row_count, total, advantages,
                                                         old_per_token_logps, ref, cfg, inv_temp, float(grad_scale),
                                                         logits_to_keep)

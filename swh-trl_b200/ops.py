@@ -26,11 +26,20 @@ def _count(n: int = 1) -> None:
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    # a plain int: ctypes converts it for a c_void_p parameter itself (every prototype in _lib.PROTOTYPES is typed)
+    return None if t is None else t.data_ptr()
+
+
+def _raw_stream(device: torch.device) -> int:
+    """The current stream's ``cudaStream_t`` of ``device`` as an int: the raw getter costs ~0.3 us where
+    ``torch.cuda.current_stream(device).cuda_stream`` costs ~8 us (it builds a Stream object) -- three of those per step
+    were a fifth of a config-1 step's host time."""
+    idx = device.index
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if idx is None else idx)
 
 
 def _stream(t: torch.Tensor):
-    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return _raw_stream(t.device)
 
 
 def _need_cuda(t: torch.Tensor, name: str) -> None:
@@ -42,7 +51,14 @@ def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     if t is None:
         return None
     _need_cuda(t, name)
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t.detach() if t.requires_grad else t
     return t.detach().to(torch.float32).contiguous()
+
+
+def _as(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """``t.to(dtype).contiguous()`` without the two no-op dispatcher trips when ``t`` already is both."""
+    return t if (t.dtype is dtype and t.is_contiguous()) else t.to(dtype).contiguous()
 
 
 class _Keep:
@@ -194,7 +210,7 @@ def logprob_entropy_fwd(logits: torch.Tensor, ids: torch.Tensor, inv_temperature
     r = rows_view(logits)
     x, n, V = r.t, r.n, r.V
     _need_cuda(ids, "index")
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     if idx.numel() != n:
         raise ValueError(f"index has {idx.numel()} elements, logits has {n} rows")
     shape = tuple(logits.shape[:-1])
@@ -216,7 +232,7 @@ def masked_logprob_fwd(logits: torch.Tensor, ids: torch.Tensor, row_mask: torch.
     r = rows_view(logits)
     x, n, V = r.t, r.n, r.V
     _need_cuda(ids, "index")
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     m = row_mask.to(torch.bool).contiguous().view(torch.uint8)
     if idx.numel() != n or m.numel() != n:
         raise ValueError(f"index / mask have {idx.numel()} / {m.numel()} elements, logits has {n} rows")
@@ -238,7 +254,7 @@ def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: t
     k = _Keep()
     r = rows_view(logits)
     x, n, V = r.t, r.n, r.V
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     out, dl_rs, dl_bs = alloc_dlogits(r, tuple(logits.shape))
     if n:
         check(lib.b200trl_logprob_bwd(_ptr(x), _DTYPES[x.dtype], n, V, r.row_stride, r.rows_per_batch, r.batch_stride,
@@ -251,7 +267,7 @@ def logprob_bwd(logits: torch.Tensor, ids: torch.Tensor, lse: torch.Tensor, g: t
 def mask_stats(mask: torch.Tensor):
     """``(mask_i32, row_count[B], total[1])`` for a ``[B,T]`` completion mask."""
     _need_cuda(mask, "completion_mask")
-    m = mask.to(torch.int32).contiguous()
+    m = _as(mask, torch.int32)
     B, T = m.shape
     row = torch.empty(B, dtype=torch.float32, device=m.device)
     tot = torch.empty(1, dtype=torch.float32, device=m.device)
@@ -269,7 +285,7 @@ def grpo_fused_fwd_bwd(logits, ids, mask_i32, row_count, total_count, advantages
     x, n, V = r.t, r.n, r.V
     if n != B * T:
         raise ValueError(f"logits rows {n} != B*T {B * T}")
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     logp = torch.empty(B, T, dtype=torch.float32, device=x.device)
     ent = torch.empty(B, T, dtype=torch.float32, device=x.device)
     lse = torch.empty(B, T, dtype=torch.float32, device=x.device)
@@ -302,7 +318,7 @@ def grpo_fused_step(logits, ids, mask_i32, row_count, total_count, advantages, o
     x, n, V = r.t, r.n, r.V
     if n != B * T:
         raise ValueError(f"logits rows {n} != B*T {B * T}")
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     dev = x.device
     logp = torch.empty(B, T, dtype=torch.float32, device=dev)
     ent = torch.empty(B, T, dtype=torch.float32, device=dev)
@@ -332,7 +348,7 @@ _ws_cache = {}
 
 def _workspace(device, nbytes: int, key: str, zero: bool) -> torch.Tensor:
     # one workspace per (device, stream, kernel family): kernels of different streams never share scratch memory
-    k = (device, torch.cuda.current_stream(device).cuda_stream, key)
+    k = (device, _raw_stream(device), key)
     ws = _ws_cache.get(k)
     if ws is None or ws.numel() < nbytes:
         ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
@@ -364,7 +380,7 @@ def entropy_quantile_mask(entropies: torch.Tensor, mask: torch.Tensor, threshold
     """``(bool mask, threshold[1])`` — ``b200trl_entropy_quantile_mask``."""
     _need_cuda(entropies, "entropies")
     e = _f32(entropies, "entropies")
-    m = mask.to(torch.int32).contiguous()
+    m = _as(mask, torch.int32)
     out = torch.empty(e.shape, dtype=torch.bool, device=e.device)  # the kernel writes 0 / 1 bytes: a bool's storage
     thr = torch.empty(1, dtype=torch.float32, device=e.device)
     if e.numel():
@@ -434,7 +450,7 @@ def ppo_rewards_gae(logprobs, ref_logprobs, values, scores, sequence_lengths, kl
         raise ValueError(f"Unknown kl_estimator: {kl_estimator}")
     lp, rlp, val = _f32(logprobs, "logprobs"), _f32(ref_logprobs, "ref_logprobs"), _f32(values, "values")
     sc = _f32(scores, "scores")
-    sl = sequence_lengths.to(torch.int64).contiguous()
+    sl = _as(sequence_lengths, torch.int64)
     B, T = lp.shape
     dev = lp.device
     ws = _workspace(dev, lib.b200trl_ppo_gae_workspace_bytes(B, T), "ppo_gae", zero=False)
@@ -461,8 +477,8 @@ def ppo_fused_fwd_bwd(logits, responses, sequence_lengths, old_logprobs, advanta
     x, n, V = r.t, r.n, r.V
     if n != mb * T:
         raise ValueError(f"logits rows {n} != mb*T {mb * T}")
-    idx = responses.to(torch.int64).contiguous()
-    sl = sequence_lengths.to(torch.int64).contiguous()
+    idx = _as(responses, torch.int64)
+    sl = _as(sequence_lengths, torch.int64)
     dev = x.device
     nlp = torch.empty(mb, T, dtype=torch.float32, device=dev)
     ent = torch.empty(mb, T, dtype=torch.float32, device=dev)
@@ -489,8 +505,8 @@ def ppo_fused_step(logits, responses, sequence_lengths, old_logprobs, advantages
     x, n, V = r.t, r.n, r.V
     if n != mb * T:
         raise ValueError(f"logits rows {n} != mb*T {mb * T}")
-    idx = responses.to(torch.int64).contiguous()
-    sl = sequence_lengths.to(torch.int64).contiguous()
+    idx = _as(responses, torch.int64)
+    sl = _as(sequence_lengths, torch.int64)
     dev = x.device
     nlp = torch.empty(mb, T, dtype=torch.float32, device=dev)
     ent = torch.empty(mb, T, dtype=torch.float32, device=dev)
@@ -515,7 +531,7 @@ def ppo_loss(new_logprobs, old_logprobs, advantages, returns, values, vpred, ent
     nlp = _f32(new_logprobs, "new_logprobs")
     mb, T = nlp.shape
     dev = nlp.device
-    sl = sequence_lengths.to(torch.int64).contiguous()
+    sl = _as(sequence_lengths, torch.int64)
     ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(mb), "ppo_loss", zero=True)
     stats = torch.empty(_lib.NUM_PPO_STATS, dtype=torch.float32, device=dev)
     dvp = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_dvpred else None
@@ -549,7 +565,9 @@ def rescale_if_needed(buf: torch.Tensor, actual: torch.Tensor, expected: float) 
     if row_stride is None:
         raise ValueError("rescale_if_needed needs a buffer with one uniform row stride")
     V = buf.shape[-1]
-    a = actual.detach().to(torch.float32).reshape(1)
+    a = actual.detach()
+    if a.dtype is not torch.float32:
+        a = a.to(torch.float32)
     check(lib.b200trl_rescale_if_needed(_ptr(buf), _DTYPES[buf.dtype], buf.numel() // V, V, row_stride, _ptr(a),
                                         float(expected), _stream(buf)), "rescale_if_needed")
     _count()
@@ -561,7 +579,7 @@ def rloo_rewards_advantages(logprobs, ref_logprobs, scores, sequence_lengths, kl
     """``dict(advantages, rlhf_reward, non_score_reward[, logprobs, ref_logprobs])`` — rloo_trainer.py:397-441."""
     lp, rlp = _f32(logprobs, "logprobs"), _f32(ref_logprobs, "ref_logprobs")
     sc = _f32(scores, "scores")
-    sl = sequence_lengths.to(torch.int64).contiguous()
+    sl = _as(sequence_lengths, torch.int64)
     B, T = lp.shape
     dev = lp.device
     adv = torch.empty(B, dtype=torch.float32, device=dev)
@@ -588,7 +606,7 @@ def rloo_loss(new_logprobs, old_logprobs, advantages, entropy, sequence_lengths,
     nlp = _f32(new_logprobs, "new_logprobs")
     mb, T = nlp.shape
     dev = nlp.device
-    sl = sequence_lengths.to(torch.int64).contiguous()
+    sl = _as(sequence_lengths, torch.int64)
     ws = _workspace(dev, lib.b200trl_grpo_loss_workspace_bytes(mb), "rloo_loss", zero=True)
     stats = torch.empty(8, dtype=torch.float32, device=dev)
     g = torch.empty(mb, T, dtype=torch.float32, device=dev) if want_g else None
@@ -613,7 +631,7 @@ def fused_linear_logprob_fwd(hidden: torch.Tensor, weight: torch.Tensor, ids: to
         h2 = h2.contiguous()
     w = weight if weight.stride(-1) == 1 else weight.contiguous()
     n, V = h2.shape[0], w.shape[0]
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     if idx.numel() != n:
         raise ValueError(f"index has {idx.numel()} elements, hidden has {n} rows")
     shape = tuple(hidden.shape[:-1])
@@ -648,7 +666,7 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     h = hidden.contiguous()
     w = weight.contiguous()
     b = None if bias is None else bias.to(torch.bfloat16).contiguous()
-    idx = ids.to(torch.int64).contiguous()
+    idx = _as(ids, torch.int64)
     logp = torch.empty(B, T, dtype=torch.float32, device=dev)
     ent = torch.empty(B, T, dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
