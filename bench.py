@@ -495,6 +495,27 @@ def extra_two_phase(S, x, ids, mask, adv, old, ref, T, V, hbm_peak):
             "ceiling": "0.667 of the 4V roofline: the logits are read twice"}, win
 
 
+def extra_dropin_skip(S, x, ids, mask, adv, old, ref, T, V, hbm_peak):
+    """NOT the headline: the same config-2 step the way the trainer drop-in (``compute_loss``) runs it -- with
+    ``skip_masked_rows=True``, because its per-token tensors never leave the call, the rows with completion_mask == 0 are
+    not read (loss, metrics and gradients bit-identical, tests/test_gpu_parity.py::test_per_call_masked_row_skipping).
+    The headline ``value`` reads and writes every row, as the reference does."""
+    fn = S.GRPOLoss(beta=CFG["beta"], epsilon_low=CFG["epsilon"], epsilon_high=CFG["epsilon"], loss_type=CFG["loss_type"],
+                    importance_sampling_level=CFG["level"], max_completion_length=T, temperature=CFG["temperature"],
+                    skip_masked_rows=True)
+
+    def step():
+        x.grad = None
+        fn(x, ids, mask, adv, old, ref).loss.backward()
+    ms, win = event_ms(step, 20)
+    n = ids.numel()
+    masked = 1.0 - float(mask.float().mean())
+    return {"workload": "config-2 tensors through GRPOLoss(skip_masked_rows=True), the trainer drop-in's setting; NOT the "
+                        "headline (masked rows are not read; they are still written as zeros)",
+            "masked_token_fraction": masked, "ms_per_step": ms, "logit_tokens_per_s": n / (ms * 1e-3),
+            "bytes_moved_per_step": int((4 - 2 * masked) * V * n)}, win
+
+
 def extra_config5(S, ops, dist, world, rank, dev, x, ids, mask, old, ref, hbm_peak):
     """BASELINE configs[4]: B=256, T=4096, V=151936, G=8 over the N ranks -- STRONG scaling.  Rank r owns 256/N
     sequences and streams them as micro-batches of 4 sequences (16 384 logit-tokens; the config-2 buffer viewed as
@@ -751,6 +772,8 @@ def run_b200(args):
         adv_now = res["advantages"][:B]
         extra["two_phase_sequence_is"], windows["two_phase_sequence_is"] = extra_two_phase(S, x, ids, mask, adv_now, old,
                                                                                         ref, T, V, hbm_peak)
+        extra["trainer_dropin_masked_rows_skipped"], windows["trainer_dropin_masked_rows_skipped"] = extra_dropin_skip(
+            S, x, ids, mask, adv_now, old, ref, T, V, hbm_peak)
         extra["config5_strong_scaling"], windows["config5_strong_scaling"] = extra_config5(
             S, ops, dist, world, rank, dev, x, ids, mask, old, ref, hbm_peak)
         if rank == 0:

@@ -62,6 +62,9 @@ typedef struct b200trl_grpo_cfg {
     int32_t is_level;            /* enum b200trl_is_level                                           */
     float max_completion_length; /* dr_grpo denominator (grpo_trainer.py:2135)                      */
     float grad_scale;            /* upstream d(loss) known a priori (1/grad_accum, AMP scale)       */
+    int32_t skip_masked;         /* fused passes: per-call form of b200trl_set_skip_masked -- rows with
+                                    completion_mask == 0 are not read (their dlogits are zeros, their
+                                    per-token outputs 0); loss, metrics and gradients are unchanged    */
 } b200trl_grpo_cfg;
 
 /* metrics[] layout written by b200trl_grpo_loss (grpo_trainer.py:2150-2172, local means) */

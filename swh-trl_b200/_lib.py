@@ -33,6 +33,7 @@ class GrpoCfg(C.Structure):
         ("is_level", C.c_int32),
         ("max_completion_length", C.c_float),
         ("grad_scale", C.c_float),
+        ("skip_masked", C.c_int32),
     ]
 
 

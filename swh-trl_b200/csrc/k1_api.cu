@@ -254,7 +254,7 @@ static int grpo_fused_impl(const void* logits, int dtype, int64_t B, int64_t T, 
     a.total_count = total_count;
     a.cfg = *cfg;
     a.gmode = dlogits ? G_GRPO : G_NONE;
-    a.skip_masked = g_skip_masked.load();
+    a.skip_masked = (g_skip_masked.load() != 0 || cfg->skip_masked != 0) ? 1 : 0;
     a.dlogits = dlogits;
     a.dl_row_stride = dl_row_stride;
     if (dlogits && set_dl_layout(a, T, dl_batch_stride, "grpo_fused")) return B200TRL_E_INVALID;

@@ -97,7 +97,10 @@ class _TwoPhaseGRPO(torch.autograd.Function):
             ctx.full_shape, ctx.lo = logits_full.shape, lo
         else:
             ctx.full_shape = None
-        logp, ent, lse = ops.logprob_entropy_fwd(logits, ids, inv_temp)
+        if cfg.skip_masked:  # the forward pass does not read the rows the loss ignores either (their outputs are 0)
+            logp, ent, lse = ops.masked_logprob_fwd(logits, ids, mask_i32, inv_temp, want_entropy=True)
+        else:
+            logp, ent, lse = ops.logprob_entropy_fwd(logits, ids, inv_temp)
         B, T = mask_i32.shape
         logp, ent, lse = logp.view(B, T), ent.view(B, T), lse.view(B, T)
         ent_mask = None
@@ -128,7 +131,8 @@ class GRPOLoss:
 
     def __init__(self, beta: float = 0.0, epsilon_low: float = 0.2, epsilon_high: float = 0.2,
                  delta: Optional[float] = None, loss_type: str = "bnpo", importance_sampling_level: str = "token",
-                 max_completion_length: int = 256, temperature: float = 1.0, top_entropy_quantile: float = 1.0):
+                 max_completion_length: int = 256, temperature: float = 1.0, top_entropy_quantile: float = 1.0,
+                 skip_masked_rows: bool = False):
         if loss_type not in _lib.LOSS_TYPES:
             raise ValueError(f"Unknown loss type: {loss_type}")
         if importance_sampling_level not in _lib.IS_LEVELS:
@@ -139,6 +143,11 @@ class GRPOLoss:
         self.loss_type, self.importance_sampling_level = loss_type, importance_sampling_level
         self.max_completion_length, self.temperature = max_completion_length, temperature
         self.top_entropy_quantile = top_entropy_quantile
+        # rows with completion_mask == 0 are not read from HBM: loss, metrics and gradients are bit-identical, only
+        # the returned per-token log-probs / entropies at masked positions become 0 (the reference computes and then
+        # discards them).  Off by default; the trainer drop-in (compute_loss), whose per-token tensors never leave the
+        # call, turns it on.
+        self.skip_masked_rows = bool(skip_masked_rows)
 
     def schedule(self, has_old: bool) -> str:
         if self.top_entropy_quantile < 1.0:
@@ -165,7 +174,8 @@ class GRPOLoss:
         if self.beta != 0.0 and ref_per_token_logps is None:
             raise KeyError("ref_per_token_logps")  # the reference indexes inputs[...] (grpo_trainer.py:2086)
         cfg = ops.make_cfg(self.beta, self.epsilon_low, self.epsilon_high, self.delta, self.loss_type,
-                           self.importance_sampling_level, self.max_completion_length)
+                           self.importance_sampling_level, self.max_completion_length,
+                           skip_masked=self.skip_masked_rows)
         inv_temp = 1.0 / float(self.temperature)
         ref = ref_per_token_logps if self.beta != 0.0 else None
         sched = schedule or self.schedule(old_per_token_logps is not None)
@@ -259,7 +269,10 @@ def compute_loss(self, model, inputs):
 
     loss_fn = GRPOLoss(self.beta, self.epsilon_low, self.epsilon_high, getattr(self.args, "delta", None),
                        self.loss_type, self.importance_sampling_level, self.max_completion_length, self.temperature,
-                       self.top_entropy_quantile)
+                       self.top_entropy_quantile,
+                       # the per-token log-probs / entropies never leave this call (only the loss and the masked metric
+                       # means do), so the padded rows need not be read at all; `_b200_skip_masked = False` reads them
+                       skip_masked_rows=bool(getattr(self, "_b200_skip_masked", True)))
     # HF Trainer.training_step divides the loss by `current_gradient_accumulation_steps` before backward (GRPOTrainer
     # sets `model_accepts_loss_kwargs = False`, grpo_trainer.py:1018-1019), so that is the upstream gradient the fused
     # pass folds in; any other upstream value (fp16 GradScaler ...) is fixed on the device by `rescale_if_needed`.

@@ -182,7 +182,8 @@ def alloc_dlogits(r: Rows, shape):
 
 
 def make_cfg(beta: float, epsilon_low: float, epsilon_high: float, delta: Optional[float], loss_type: str,
-             importance_sampling_level: str, max_completion_length: int, grad_scale: float = 1.0) -> GrpoCfg:
+             importance_sampling_level: str, max_completion_length: int, grad_scale: float = 1.0,
+             skip_masked: bool = False) -> GrpoCfg:
     """Pack GRPO hyper-parameters; unknown enums raise the reference's ValueErrors (grpo_trainer.py:2106-2109, 2137)."""
     if loss_type not in _lib.LOSS_TYPES:
         raise ValueError(f"Unknown loss type: {loss_type}")
@@ -200,6 +201,7 @@ def make_cfg(beta: float, epsilon_low: float, epsilon_high: float, delta: Option
     cfg.is_level = _lib.IS_LEVELS[importance_sampling_level]
     cfg.max_completion_length = float(max_completion_length)
     cfg.grad_scale = float(grad_scale)
+    cfg.skip_masked = int(bool(skip_masked))
     return cfg
 
 

@@ -1713,3 +1713,36 @@ def test_randomised_agreement_of_the_two_k1_implementations():
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
     assert r.returncode == 0, line or r.stderr[-2000:]
     assert json.loads(line)["agree"] is True
+
+
+@pytest.mark.parametrize("level", ["token", "sequence"])
+@pytest.mark.parametrize("V", [32768, 151936])
+def test_per_call_masked_row_skipping(S, V, level):
+    """GRPOLoss(skip_masked_rows=True) -- what the trainer drop-in (compute_loss) uses, since its per-token tensors never
+    leave the call: the rows with completion_mask == 0 are not read in either schedule; the loss, the packed metrics
+    and the gradient are bit-identical, the per-token outputs agree where the mask is 1 and are 0 elsewhere."""
+    B, T = 4, 24
+    logits, ids, mask = O.synth_batch(B, T, V, seed=33, edge_rows=True)
+    g = torch.Generator().manual_seed(3)
+    adv = torch.randn(B, generator=g)
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax(logits.float(), ids)
+    old, ref = lp0 + torch.randn(B, T, generator=g) * 0.3, lp0 + torch.randn(B, T, generator=g) * 0.1
+    res = {}
+    for skip in (False, True):
+        x = logits.to(DEV).requires_grad_(True)
+        fn = S.GRPOLoss(beta=0.04, loss_type="grpo", importance_sampling_level=level, max_completion_length=T,
+                        skip_masked_rows=skip)
+        out = fn(x, ids.to(DEV), mask.to(DEV), adv.to(DEV), old.to(DEV), ref.to(DEV))
+        out.loss.backward()
+        torch.cuda.synchronize()
+        res[skip] = (out.loss.detach().clone(), out.metrics.clone(), x.grad.clone(), out.per_token_logps.clone(),
+                     out.entropies.clone(), out.schedule)
+    assert res[True][5] == res[False][5] == ("fused" if level == "token" else "two-phase")
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    assert torch.equal(res[True][2], res[False][2])
+    m = mask.to(DEV).bool()
+    for k in (3, 4):
+        assert torch.equal(res[True][k][m], res[False][k][m])
+        assert torch.count_nonzero(res[True][k][~m]) == 0
+    assert int((~m).sum()) > 0
