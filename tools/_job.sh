@@ -1,7 +1,13 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "per_call_masked or skip_masked or trainer_surface" > gpurun_out/s36_new_tests.log 2>&1; echo "new tests rc=$?"
-tail -20 gpurun_out/s36_new_tests.log
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/s36_gputest.log 2>&1; echo "pytest rc=$?"
-tail -4 gpurun_out/s36_gputest.log
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/s37_bench.json 2> gpurun_out/s37_bench.err; echo "bench rc=$?"
+tail -3 gpurun_out/s37_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/s37_bench.json'))
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['roofline']['kernel_ms'], d['roofline']['frac'])
+print(json.dumps(d['extra']['trainer_dropin_masked_rows_skipped']))
+print(d['extra']['two_phase_sequence_is']['ms_per_step'])
+PY
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/s37_bench_ref.json 2> gpurun_out/s37_bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/s37_bench_ref.json
