@@ -455,7 +455,9 @@ def extra_config4(S, ops, dev):
     ref = lp0 + torch.randn(B, T, generator=g, device=dev) * 0.1
     h = hidden.clone().requires_grad_(True)
     w = W.clone().requires_grad_(True)
-    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=2)
+    # the config-4 figure does the DENSE work (every row of the padded batch goes through the three GEMMs, as in the
+    # reference's Liger operator); the operator's default -- padding trimmed -- is reported separately below
+    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=2, trim_padding=False)
 
     def seam():
         h.grad = None
@@ -472,7 +474,23 @@ def extra_config4(S, ops, dev):
     out["fwd_bwd"] = {"ms": ms, "tokens_per_s": B * T / (ms * 1e-3), "tflops": fl3 / ms / 1e9,
                       "frac_of_bf16_sustained_peak": fl3 / ms / 1e9 / sustained, "peak_source": src,
                       "gemms": {"logits": names[m & 1], "dH": names[(m >> 1) & 1], "dW": names[(m >> 2) & 1]},
-                      "our_launches": launches, "chunk_sequences": 2}
+                      "our_launches": launches, "chunk_sequences": 2, "padding": "computed (trim_padding=False)"}
+    fn_t = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T)  # default: trim_padding=True
+
+    def seam_trimmed():
+        h.grad = None
+        w.grad = None
+        loss, _ = fn_t(h, w, ids, mask, adv, None, old, ref)
+        loss.backward()
+    ms_t, win3 = event_ms(seam_trimmed, 5, warmup=1)
+    kept = float(lens.sum()) / (B * T)
+    out["fwd_bwd_padding_trimmed"] = {
+        "ms": ms_t, "tokens_per_s_of_the_padded_batch": B * T / (ms_t * 1e-3), "unmasked_row_fraction": kept,
+        "tflops_on_the_rows_computed": fl3 * kept / ms_t / 1e9,
+        "what": "NOT the config-4 figure: the operator's default leaves the rows behind each sequence's last unmasked "
+                "token out of the three contractions (one chunk per sequence, one D2H read of B lengths per call); "
+                "same loss / metrics / gradients"}
+    win2 = (win2[0], win3[1])
     del h, w, hidden, W
     torch.cuda.empty_cache()
     return out, (win[0], win2[1])

@@ -348,6 +348,20 @@ int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void
                               float* loss, float* metrics, void* dhidden, float* dweight, void* dweight_bf16,
                               float* dbias, b200trl_stream_t stream);
 
+/* The same operator with the PADDING TRIMMED.  seq_rows_host: HOST memory, B entries; seq_rows_host[b] = number of
+ * leading rows of sequence b that can carry a non-zero mask (index of its last unmasked token + 1; 0 for a fully masked
+ * sequence).  Every sequence becomes its own chunk of seq_rows_host[b] rows, so the three contractions do
+ * sum(seq_rows) / (B*T) of the dense work (a batch padded to T = 2048 with lengths in [T/2, T]: 0.75).  Loss, metrics,
+ * dW, dbias as the dense call (order of fp32 sums aside); dhidden rows, logp and entropy behind seq_rows_host[b] are
+ * zeros.  The caller needs the lengths on the host (one device->host read of B integers per call). */
+int b200trl_fused_linear_grpo_trimmed(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
+                                      int64_t H, int64_t V, const int64_t* ids, const int32_t* mask,
+                                      const float* advantages, const float* old_logp, const float* ref_logp,
+                                      const b200trl_grpo_cfg* cfg, float inv_temperature, const int64_t* seq_rows_host,
+                                      void* workspace, float* logp, float* entropy, float* loss, float* metrics,
+                                      void* dhidden, float* dweight, void* dweight_bf16, float* dbias,
+                                      b200trl_stream_t stream);
+
 /* ---- a-12: masked_mean / masked_var / masked_whiten (trl/core.py:43-76) ------------------------
  * stats fp32 [3] = {mean, unbiased var, count}; out (whitened, fp32 [n]) may be NULL.
  * workspace >= b200trl_masked_workspace_bytes(n), any contents. */

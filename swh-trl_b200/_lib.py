@@ -92,6 +92,9 @@ PROTOTYPES = {
     "b200trl_fused_linear_grpo_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "b200trl_fused_linear_grpo": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, C.POINTER(GrpoCfg),
                                             _f, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200trl_fused_linear_grpo_trimmed": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p,
+                                                    C.POINTER(GrpoCfg), _f, C.POINTER(C.c_int64), _p, _p, _p, _p, _p, _p,
+                                                    _p, _p, _p, _p]),
     "b200trl_masked_workspace_bytes": (_i64, [_i64]),
     "b200trl_masked_whiten": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p]),
     "b200trl_first_true_indices": (C.c_int, [_p, _i64, _i64, _p, _p]),

@@ -248,6 +248,12 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
     reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<uint4*>(r);
 }
 
+static int seam_impl(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T, int64_t H, int64_t V,
+                     const int64_t* ids, const int32_t* mask, const float* advantages, const float* old_logp,
+                     const float* ref_logp, const b200trl_grpo_cfg* cfg, float inv_temperature, int64_t chunk_seqs,
+                     void* workspace, float* logp, float* entropy, float* loss, float* metrics, void* dhidden,
+                     float* dweight, void* dweight_bf16, float* dbias, const int64_t* seq_rows, b200trl_stream_t stream_);
+
 extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T,
                                          int64_t H, int64_t V, const int64_t* ids, const int32_t* mask,
                                          const float* advantages, const float* old_logp, const float* ref_logp,
@@ -255,6 +261,37 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
                                          void* workspace, float* logp, float* entropy, float* loss, float* metrics,
                                          void* dhidden, float* dweight, void* dweight_bf16, float* dbias,
                                          b200trl_stream_t stream_) {
+    return seam_impl(hidden, weight, bias, B, T, H, V, ids, mask, advantages, old_logp, ref_logp, cfg, inv_temperature,
+                     chunk_seqs, workspace, logp, entropy, loss, metrics, dhidden, dweight, dweight_bf16, dbias, nullptr,
+                     stream_);
+}
+
+// The same operator with the padding trimmed: seq_rows_host[b] (HOST memory, B entries, 0 <= value <= T) is the number of
+// leading rows of sequence b that can carry a non-zero mask (index of its last unmasked token + 1).  The rows behind it
+// take part in none of the three contractions: every sequence is its own chunk of seq_rows[b] rows, so the GEMMs do
+// sum(seq_rows) / (B T) of the dense work.  Results are those of the dense call: loss, metrics, dW, db identical up to
+// the order of the fp32 sums, dH rows behind seq_rows[b] are zeros (as their dlogits are), logp / entropy there are 0.
+extern "C" int b200trl_fused_linear_grpo_trimmed(const void* hidden, const void* weight, const void* bias, int64_t B,
+                                                 int64_t T, int64_t H, int64_t V, const int64_t* ids, const int32_t* mask,
+                                                 const float* advantages, const float* old_logp, const float* ref_logp,
+                                                 const b200trl_grpo_cfg* cfg, float inv_temperature,
+                                                 const int64_t* seq_rows_host, void* workspace, float* logp, float* entropy,
+                                                 float* loss, float* metrics, void* dhidden, float* dweight,
+                                                 void* dweight_bf16, float* dbias, b200trl_stream_t stream_) {
+    B200TRL_REQUIRE(seq_rows_host != nullptr, B200TRL_E_INVALID, "fused_linear_grpo_trimmed: null seq_rows");
+    for (int64_t b = 0; b < B; ++b)
+        B200TRL_REQUIRE(seq_rows_host[b] >= 0 && seq_rows_host[b] <= T, B200TRL_E_INVALID,
+                        "fused_linear_grpo_trimmed: seq_rows[%lld] = %lld outside [0, T]", (long long)b,
+                        (long long)seq_rows_host[b]);
+    return seam_impl(hidden, weight, bias, B, T, H, V, ids, mask, advantages, old_logp, ref_logp, cfg, inv_temperature, 1,
+                     workspace, logp, entropy, loss, metrics, dhidden, dweight, dweight_bf16, dbias, seq_rows_host, stream_);
+}
+
+static int seam_impl(const void* hidden, const void* weight, const void* bias, int64_t B, int64_t T, int64_t H, int64_t V,
+                     const int64_t* ids, const int32_t* mask, const float* advantages, const float* old_logp,
+                     const float* ref_logp, const b200trl_grpo_cfg* cfg, float inv_temperature, int64_t chunk_seqs,
+                     void* workspace, float* logp, float* entropy, float* loss, float* metrics, void* dhidden,
+                     float* dweight, void* dweight_bf16, float* dbias, const int64_t* seq_rows, b200trl_stream_t stream_) {
     B200TRL_REQUIRE(hidden && weight && ids && mask && advantages && cfg && workspace && logp && entropy && loss && metrics,
                     B200TRL_E_INVALID, "fused_linear_grpo: null pointer");
     B200TRL_REQUIRE(B > 0 && T > 0 && H > 0 && V > 0 && chunk_seqs > 0, B200TRL_E_INVALID, "fused_linear_grpo: bad shape");
@@ -265,7 +302,11 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
                     "fused_linear_grpo: sequence-level importance sampling with old_logp needs the two-phase path");
     B200TRL_REQUIRE(cfg->beta == 0.f || ref_logp, B200TRL_E_INVALID, "fused_linear_grpo: beta != 0 needs ref_logp");
     chunk_seqs = std::min(chunk_seqs, B);
-    const int64_t n_chunks = (B + chunk_seqs - 1) / chunk_seqs;
+    int64_t n_chunks = (B + chunk_seqs - 1) / chunk_seqs;
+    if (seq_rows) {  // one chunk per sequence that has rows at all
+        n_chunks = 0;
+        for (int64_t b = 0; b < B; ++b) n_chunks += seq_rows[b] > 0 ? 1 : 0;
+    }
     B200TRL_REQUIRE(!dweight_bf16 || dweight || n_chunks == 1, B200TRL_E_INVALID,
                     "fused_linear_grpo: dweight_bf16 over several chunks needs the fp32 dweight accumulator as well");
     const bool want_dw = dweight || dweight_bf16;
@@ -296,10 +337,29 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
 
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dh = static_cast<__nv_bfloat16*>(dhidden);
+    if (seq_rows && n_chunks == 0) {  // nothing unmasked anywhere: every gradient is zero
+        if (dweight && cudaMemsetAsync(dweight, 0, static_cast<size_t>(V) * H * 4, stream) != cudaSuccess)
+            return check_launch("fused_linear_grpo memset");
+        if (dweight_bf16 && cudaMemsetAsync(dweight_bf16, 0, static_cast<size_t>(V) * H * 2, stream) != cudaSuccess)
+            return check_launch("fused_linear_grpo memset");
+    }
     int64_t chunk = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk_seqs, ++chunk) {
-        const int64_t nb = std::min(chunk_seqs, B - b0), rows = nb * T, r0 = b0 * T;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk_seqs) {
+        const int64_t nb = std::min(chunk_seqs, B - b0), r0 = b0 * T;
+        int64_t rows = nb * T;
+        if (seq_rows) {  // trimmed: this sequence's leading rows only; what lies behind them is defined here
+            rows = seq_rows[b0];
+            const size_t tail = static_cast<size_t>(T - rows);
+            if (tail) {
+                if (cudaMemsetAsync(logp + r0 + rows, 0, tail * 4, stream) != cudaSuccess ||
+                    cudaMemsetAsync(entropy + r0 + rows, 0, tail * 4, stream) != cudaSuccess ||
+                    (dh && cudaMemsetAsync(dh + (r0 + rows) * H, 0, tail * H * 2, stream) != cudaSuccess))
+                    return check_launch("fused_linear_grpo memset");
+            }
+            if (rows == 0) continue;
+        }
         const bool first = chunk == 0, last = chunk == n_chunks - 1;
+        ++chunk;
         // row-major logits[rows, V] = hidden_c[rows, H] W[V, H]^T  <=>  column-major D[V, rows] = W^T(T) x hidden_c(N)
         if (mask_tc & 1) {  // hidden_c and W both K-major; all row blocks of one W tile run at the same time
             TcGemmParams p;
@@ -316,7 +376,8 @@ extern "C" int b200trl_fused_linear_grpo(const void* hidden, const void* weight,
         b200trl_grpo_cfg c = *cfg;
         c.grad_scale = cfg->grad_scale * (cfg->loss_type == B200TRL_LOSS_BNPO ? 1.f
                                                                               : static_cast<float>(nb) / static_cast<float>(B));
-        rc = b200trl_grpo_fused_fwd_bwd(logits, B200TRL_BF16, nb, T, V, V, 0, ids + r0, mask + r0, advantages + b0,
+        rc = b200trl_grpo_fused_fwd_bwd(logits, B200TRL_BF16, nb, seq_rows ? rows : T, V, V, 0, ids + r0, mask + r0,
+                                        advantages + b0,
                                         old_logp ? old_logp + r0 : nullptr, ref_logp ? ref_logp + r0 : nullptr, &c,
                                         inv_temperature, row_count + b0, total, logp + r0, entropy + r0, nullptr,
                                         want_grad ? logits : nullptr, V, 0, stream_);  // in place: dlogits overwrite logits

@@ -75,7 +75,7 @@ def _chunked_with_torch_gemms(hidden, weight, bias, ids, mask_i32, advantages, o
 
 class _FusedLinearGRPO(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight, bias, ids, mask, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs):
+    def forward(ctx, hidden, weight, bias, ids, mask, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs, trim):
         ctx.set_materialize_grads(False)  # no zero-fill kernels for the non-differentiable outputs
         need_dh, need_dw = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
         need_db = bias is not None and bool(ctx.needs_input_grad[2])
@@ -84,9 +84,16 @@ class _FusedLinearGRPO(torch.autograd.Function):
             # the product path: ONE C-ABI call (GEMMs + K1 in place + K2); dW is accumulated in fp32 inside the GEMM
             # and comes back already rounded to bf16
             cfg.grad_scale = 1.0
+            seq_rows = None
+            if trim and not torch.cuda.is_current_stream_capturing():
+                # the rows behind a sequence's last unmasked token take part in nothing: one device->host read of B
+                # integers (the reference syncs several times per step anyway) buys sum(len) / (B T) of the GEMM work
+                T_ = mask_i32.shape[1]
+                pos = torch.arange(1, T_ + 1, device=mask_i32.device, dtype=torch.int32)
+                seq_rows = ((mask_i32 != 0) * pos).amax(dim=1).tolist()
             loss, metrics, logp, ent, dh, dw, db = ops.fused_linear_grpo(
                 hidden, weight, bias, ids, mask_i32, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs, need_dh,
-                need_dw, need_db)
+                need_dw, need_db, seq_rows=seq_rows)
         else:
             loss, metrics, logp, ent, dh, dw, db = _chunked_with_torch_gemms(
                 hidden, weight, bias, ids, mask_i32, advantages, old_lp, ref_lp, cfg, inv_temp, chunk_seqs, need_dh,
@@ -98,7 +105,7 @@ class _FusedLinearGRPO(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, *_):
         if g_loss is None:
-            return (None,) * 11
+            return (None,) * 12
         dh, dw, db = ctx.grads
         ctx.grads = None
         # the gradients were produced in the forward pass for an upstream gradient of 1 (what `loss.backward()` and
@@ -107,7 +114,7 @@ class _FusedLinearGRPO(torch.autograd.Function):
         for g in (dh, dw, db):
             if g is not None:
                 ops.rescale_if_needed(g, g_loss, 1.0)
-        return (dh, dw, db) + (None,) * 8
+        return (dh, dw, db) + (None,) * 9
 
 
 class B200FusedLinearGRPOLoss:
@@ -117,11 +124,15 @@ class B200FusedLinearGRPOLoss:
     def __init__(self, beta: float = 0.04, epsilon_low: float = 0.2, epsilon_high: float = 0.2,
                  temperature: float = 1.0, use_ref_model: bool = True, loss_type: str = "bnpo",
                  max_completion_length: Optional[int] = None, importance_sampling_level: str = "token",
-                 delta: Optional[float] = None, chunk_size: int = 2):
+                 delta: Optional[float] = None, chunk_size: int = 2, trim_padding: bool = True):
         self.beta, self.epsilon_low, self.epsilon_high = beta, epsilon_low, epsilon_high
         self.temperature, self.use_ref_model, self.loss_type = temperature, use_ref_model, loss_type
         self.max_completion_length = max_completion_length
         self.importance_sampling_level, self.delta = importance_sampling_level, delta
+        # bf16 path: leave the rows behind every sequence's last unmasked token out of the three contractions (one
+        # device->host read of B lengths per call; skipped while a CUDA graph is being captured).  Same loss / metrics /
+        # gradients; `last_per_token_logps` / `last_entropies` are 0 behind the trim.
+        self.trim_padding = bool(trim_padding)
         self.chunk_size = max(1, int(chunk_size))  # sequences per logits chunk (config 4: 1 / 2 / 4 -> 43.6 / 42.0 / 42.5 ms)
         ops.make_cfg(beta, epsilon_low, epsilon_high, delta, loss_type, importance_sampling_level,
                      max_completion_length or 1)  # validates enums like the reference (ValueError)
@@ -152,7 +163,7 @@ class B200FusedLinearGRPOLoss:
             return loss.reshape(()), ([m[1]] if self.beta != 0.0 else []) + [m[5]]
         loss, m, logp, ent = _FusedLinearGRPO.apply(_input, lin_weight, bias, selected_token_ids, attention_mask,
                                                     advantages, old_per_token_logps, ref, cfg,
-                                                    1.0 / float(self.temperature), self.chunk_size)
+                                                    1.0 / float(self.temperature), self.chunk_size, self.trim_padding)
         self.last_per_token_logps, self.last_entropies, self.last_metrics = logp, ent, m
         metrics = []
         if self.beta != 0.0:

@@ -654,10 +654,12 @@ def fused_linear_logprob_fwd(hidden: torch.Tensor, weight: torch.Tensor, ids: to
 def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], ids: torch.Tensor,
                       mask_i32: torch.Tensor, advantages: torch.Tensor, old_logp: Optional[torch.Tensor],
                       ref_logp: Optional[torch.Tensor], cfg: GrpoCfg, inv_temperature: float, chunk_seqs: int,
-                      need_dh: bool, need_dw: bool, need_db: bool):
+                      need_dh: bool, need_dw: bool, need_db: bool, seq_rows=None):
     """``(loss[1], metrics[8], logp, entropy, dH|None, dW bf16|None, db fp32|None)`` — ``b200trl_fused_linear_grpo``:
     the whole chunked lm_head + GRPO loss forward/backward in one C call (GEMMs + K1 in place + K2).  ``dW`` is
-    accumulated over the chunks in fp32 and handed back rounded once to the weight's dtype."""
+    accumulated over the chunks in fp32 and handed back rounded once to the weight's dtype.  ``seq_rows`` (a HOST
+    sequence of B ints: index of each sequence's last unmasked token + 1) selects ``b200trl_fused_linear_grpo_trimmed``:
+    the rows behind it take part in none of the contractions."""
     k = _Keep()
     _need_cuda(hidden, "_input")
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -675,16 +677,29 @@ def fused_linear_grpo(hidden: torch.Tensor, weight: torch.Tensor, bias: Optional
     metrics = torch.empty(_lib.NUM_GRPO_METRICS, dtype=torch.float32, device=dev)
     dh = torch.empty_like(h) if need_dh else None
     n_chunks = -(-B // max(1, min(int(chunk_seqs), B)))
+    if seq_rows is not None:
+        seq_rows = [int(v) for v in seq_rows]
+        if len(seq_rows) != B:
+            raise ValueError(f"seq_rows has {len(seq_rows)} entries for {B} sequences")
+        n_chunks = max(1, sum(1 for v in seq_rows if v > 0))
     dw = torch.empty(V, H, dtype=torch.bfloat16, device=dev) if need_dw else None
     dw_acc = torch.empty(V, H, dtype=torch.float32, device=dev) if need_dw and n_chunks > 1 else None
     db = torch.empty(V, dtype=torch.float32, device=dev) if need_db else None
     ws = _workspace(dev, lib.b200trl_fused_linear_grpo_workspace_bytes(B, T, H, V, int(chunk_seqs)), "fused_linear_grpo",
                     zero=False)
-    check(lib.b200trl_fused_linear_grpo(
-        _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), k.f32(advantages, "advantages"),
-        k.f32(old_logp, "old_per_token_logps"), k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg),
-        float(inv_temperature), int(chunk_seqs), _ptr(ws), _ptr(logp), _ptr(ent), _ptr(loss), _ptr(metrics), _ptr(dh),
-        _ptr(dw_acc), _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo")
+    if seq_rows is not None:
+        rows_host = (C.c_int64 * B)(*seq_rows)
+        check(lib.b200trl_fused_linear_grpo_trimmed(
+            _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), k.f32(advantages, "advantages"),
+            k.f32(old_logp, "old_per_token_logps"), k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg),
+            float(inv_temperature), rows_host, _ptr(ws), _ptr(logp), _ptr(ent), _ptr(loss), _ptr(metrics), _ptr(dh),
+            _ptr(dw_acc), _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo_trimmed")
+    else:
+        check(lib.b200trl_fused_linear_grpo(
+            _ptr(h), _ptr(w), _ptr(b), B, T, H, V, _ptr(idx), _ptr(mask_i32), k.f32(advantages, "advantages"),
+            k.f32(old_logp, "old_per_token_logps"), k.f32(ref_logp, "ref_per_token_logps"), C.byref(cfg),
+            float(inv_temperature), int(chunk_seqs), _ptr(ws), _ptr(logp), _ptr(ent), _ptr(loss), _ptr(metrics), _ptr(dh),
+            _ptr(dw_acc), _ptr(dw), _ptr(db), _stream(h)), "fused_linear_grpo")
     _count(2 + n_chunks + 1)  # mask stats (memset + kernel), K1 per chunk, K2; the GEMMs are library launches
     return loss, metrics, logp, ent, dh, dw, db
 

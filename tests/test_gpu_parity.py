@@ -543,7 +543,7 @@ def test_fused_linear_grpo_seam(S, dtype, V, H, loss_type, beta, with_old, level
 
     fn = S.B200FusedLinearGRPOLoss(beta=beta, epsilon_low=0.2, epsilon_high=0.2, temperature=temp, use_ref_model=True,
                                    loss_type=loss_type, max_completion_length=T, importance_sampling_level=level,
-                                   delta=3.0, chunk_size=3)
+                                   delta=3.0, chunk_size=3, trim_padding=False)
     h = hidden.to(DEV).requires_grad_(True)
     w = W.to(DEV).requires_grad_(True)
     loss, metrics = fn(_input=h, lin_weight=w, selected_token_ids=ids.to(DEV), attention_mask=mask.to(DEV),
@@ -598,7 +598,8 @@ def _check_seam_against_bf16_oracle(S, B, T, H, V, chunk, seed, wscale):
     ref = lp0 + torch.randn(B, T, generator=g) * 0.1
     loss_r, met_r, lp_r, ent_r, dH_r, dW_r, logits_r = _seam_bf16_oracle(hidden, W, ids, mask, adv, old, ref, cfg)
 
-    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
+    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk,
+                                   trim_padding=False)  # the per-token outputs are compared at every position below
     h = hidden.to(DEV).requires_grad_(True)
     w = W.to(DEV).requires_grad_(True)
     loss, metrics = fn(h, w, ids.to(DEV), mask.to(DEV), adv.to(DEV), None, old.to(DEV), ref.to(DEV))
@@ -1746,3 +1747,49 @@ def test_per_call_masked_row_skipping(S, V, level):
         assert torch.equal(res[True][k][m], res[False][k][m])
         assert torch.count_nonzero(res[True][k][~m]) == 0
     assert int((~m).sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------ seam: trimmed padding
+@pytest.mark.parametrize("loss_type,beta", [("bnpo", 0.04), ("grpo", 0.0), ("dr_grpo", 0.04)])
+def test_seam_with_trimmed_padding(S, loss_type, beta):
+    """B200FusedLinearGRPOLoss(trim_padding=True), the default: the rows behind every sequence's last unmasked token are
+    left out of the three contractions (b200trl_fused_linear_grpo_trimmed, one chunk per sequence).  Against the dense
+    operator on the same inputs: loss and metrics (sum order aside), dH on the kept rows within one bf16 ulp and exactly
+    zero behind the trim, dW within the bf16 rounding of an fp32 sum taken in another chunk order.  The batch has a fully
+    masked sequence, a full one, and a mask with a hole (not a prefix)."""
+    B, T, H, V = 5, 48, 128, 32768
+    g = torch.Generator().manual_seed(17)
+    hidden = torch.randn(B, T, H, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g) * 0.1).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    lens = torch.tensor([T, 0, 17, 33, 40])
+    mask = (torch.arange(T).unsqueeze(0) < lens.unsqueeze(1)).int()
+    mask[3, 5:9] = 0  # a hole: the trim goes by the LAST unmasked token
+    adv = torch.randn(B, generator=g)
+    with torch.no_grad():
+        lp0 = O.selective_log_softmax((hidden.float() @ W.float().t()).to(torch.bfloat16).float(), ids)
+    old = lp0 + torch.randn(B, T, generator=g) * 0.3
+    ref = lp0 + torch.randn(B, T, generator=g) * 0.1
+    out = {}
+    for trim in (False, True):
+        fn = S.B200FusedLinearGRPOLoss(beta=beta, loss_type=loss_type, max_completion_length=T, chunk_size=2,
+                                       trim_padding=trim)
+        h = hidden.to(DEV).requires_grad_(True)
+        w = W.to(DEV).requires_grad_(True)
+        loss, _ = fn(h, w, ids.to(DEV), mask.to(DEV), adv.to(DEV), None, old.to(DEV), ref.to(DEV) if beta else None)
+        loss.backward()
+        torch.cuda.synchronize()
+        out[trim] = (loss.detach().cpu(), fn.last_metrics.cpu(), h.grad.float().cpu(), w.grad.float().cpu(),
+                     fn.last_per_token_logps.cpu())
+    d, t = out[False], out[True]
+    assert t[0].item() == pytest.approx(d[0].item(), rel=2e-6, abs=1e-8)
+    torch.testing.assert_close(t[1], d[1], rtol=2e-6, atol=1e-8)
+    m = mask.bool()
+    torch.testing.assert_close(t[4][m], d[4][m], rtol=0, atol=0)           # same kernels on the kept rows
+    last = ((mask != 0) * torch.arange(1, T + 1)).amax(1)
+    behind = torch.arange(T).unsqueeze(0) >= last.unsqueeze(1)
+    assert torch.count_nonzero(t[2][behind]) == 0 and torch.count_nonzero(t[4][behind]) == 0
+    torch.testing.assert_close(t[2][~behind], d[2][~behind], rtol=BF16_ULP, atol=1e-9)
+    err = (t[3] - d[3]).norm() / d[3].norm().clamp_min(1e-20)
+    assert float(err) < 3e-3, float(err)   # both are bf16 roundings of fp32 sums over the same rows, chunked differently
+    torch.testing.assert_close(t[3], d[3], rtol=2 * BF16_ULP, atol=4e-3 * float(d[3].abs().max()))
