@@ -63,7 +63,7 @@ def main():
     chunks = [int(c) for c in os.environ.get("SEAM_CHUNKS", "2,4").split(",")]
     for gemm_mask, chunk in [(m, c) for m in masks for c in chunks]:
         ops.set_seam_gemm_mask(gemm_mask)
-        fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
+        fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk, trim_padding=False)
 
         def ours():
             h.grad = None

@@ -20,7 +20,7 @@ old = -torch.rand(B, T, generator=g, device=DEV) * 12
 ref = old + torch.randn(B, T, generator=g, device=DEV) * 0.1
 out = {}
 for chunk in [int(c) for c in os.environ.get("SEAM_CHUNKS", "1,2,4,8").split(",")]:
-    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
+    fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk, trim_padding=False)
 
     def step():
         hidden.grad = None

@@ -25,7 +25,8 @@ mask = (torch.arange(T, device=DEV).unsqueeze(0) < lens.unsqueeze(1)).int()
 adv = torch.randn(B, generator=g, device=DEV)
 old = -torch.rand(B, T, generator=g, device=DEV) * 12
 ref = old + torch.randn(B, T, generator=g, device=DEV) * 0.1
-fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=int(os.environ.get("SEAM_CHUNK", 2)))
+fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=int(os.environ.get("SEAM_CHUNK", 2)),
+                               trim_padding=bool(int(os.environ.get("SEAM_TRIM", 0))))  # dense by default: the profile is of the chunked GEMMs
 
 
 def step():

@@ -27,7 +27,7 @@ adv = torch.randn(B, generator=g, device=DEV)
 old = -torch.rand(B, T, generator=g, device=DEV) * 12
 ref = old + torch.randn(B, T, generator=g, device=DEV) * 0.1
 chunk = int(os.environ.get("SEAM_CHUNK", 2))
-fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk)
+fn = S.B200FusedLinearGRPOLoss(beta=0.04, loss_type="bnpo", max_completion_length=T, chunk_size=chunk, trim_padding=False)
 
 
 def step():
