@@ -80,7 +80,8 @@ class _FusedLinearGRPO(torch.autograd.Function):
         need_dh, need_dw = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
         need_db = bias is not None and bool(ctx.needs_input_grad[2])
         mask_i32 = mask.to(torch.int32).contiguous()
-        if hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16:
+        if (hidden.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and hidden.shape[-1] % 8 == 0
+                and weight.shape[0] % 8 == 0):  # the tensor maps need 16-byte rows: H % 8 == 0 and V % 8 == 0
             # the product path: ONE C-ABI call (GEMMs + K1 in place + K2); dW is accumulated in fp32 inside the GEMM
             # and comes back already rounded to bf16
             cfg.grad_scale = 1.0

@@ -1793,3 +1793,29 @@ def test_seam_with_trimmed_padding(S, loss_type, beta):
     err = (t[3] - d[3]).norm() / d[3].norm().clamp_min(1e-20)
     assert float(err) < 3e-3, float(err)   # both are bf16 roundings of fp32 sums over the same rows, chunked differently
     torch.testing.assert_close(t[3], d[3], rtol=2 * BF16_ULP, atol=4e-3 * float(d[3].abs().max()))
+
+
+def test_seam_with_a_vocabulary_the_tensor_maps_cannot_take(S):
+    """V % 8 != 0 (GPT-2's 50 257): the one-call tcgen05 route needs 16-byte rows, so the operator runs the same chunked
+    schedule with the library GEMM (torch.matmul) and K1 on the skewed logits rows -- same results, no error."""
+    B, T, H, V = 2, 12, 64, 50257
+    g = torch.Generator().manual_seed(9)
+    hidden = torch.randn(B, T, H, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, H, generator=g) * 0.1).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, T), generator=g)
+    mask = (torch.arange(T).unsqueeze(0) < torch.tensor([[12], [7]])).int()
+    adv = torch.tensor([0.7, -1.1])
+    hr, Wr = hidden.float().requires_grad_(True), W.float().requires_grad_(True)
+    logits_r = hr @ Wr.t()
+    logits_r = logits_r.detach().to(torch.bfloat16).float() + (logits_r - logits_r.detach())
+    cfg = O.GRPOConfigLite(beta=0.0, loss_type="bnpo", max_completion_length=T)
+    loss_r = O.grpo_compute_loss(logits_r, ids, mask, adv, cfg, None, None)[0]
+    loss_r.backward()
+    fn = S.B200FusedLinearGRPOLoss(beta=0.0, loss_type="bnpo", max_completion_length=T)
+    h, w = hidden.to(DEV).requires_grad_(True), W.to(DEV).requires_grad_(True)
+    loss, _ = fn(h, w, ids.to(DEV), mask.to(DEV), adv.to(DEV))
+    loss.backward()
+    assert loss.item() == pytest.approx(loss_r.item(), rel=2e-3, abs=1e-6)
+    for got, want in ((h.grad, hr.grad), (w.grad, Wr.grad)):
+        err = (got.float().cpu() - want).norm() / want.norm().clamp(min=1e-12)
+        assert float(err) < 2e-2, float(err)

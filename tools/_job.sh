@@ -1,5 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s40_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/s40_smoke.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/s40_smoke_launches.csv python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s40_ncu_smoke.log 2>&1; echo "ncu smoke rc=$?"
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "tensor_maps_cannot_take or seam" > gpurun_out/s41_tests.log 2>&1; echo "tests rc=$?"
+tail -15 gpurun_out/s41_tests.log
