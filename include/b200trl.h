@@ -389,6 +389,11 @@ int b200trl_truncate_response(const int64_t* responses, int64_t B, int64_t T, in
  * the grad_scale assumed in the fused forward.  No host sync. */
 int b200trl_rescale_if_needed(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
                               const float* actual, float expected, b200trl_stream_t stream);
+/* The same for a two-level layout: row r = (b, t) at b * batch_stride + t * row_stride with rows_per_batch rows per
+ * batch (a dlogits buffer that mirrors a strided view of the model output); rows_per_batch == 0: flat. */
+int b200trl_rescale_if_needed_batched(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                                      int64_t rows_per_batch, int64_t batch_stride, const float* actual, float expected,
+                                      b200trl_stream_t stream);
 
 #ifdef __cplusplus
 }

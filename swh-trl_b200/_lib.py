@@ -101,6 +101,7 @@ PROTOTYPES = {
     "b200trl_completion_mask": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "b200trl_truncate_response": (C.c_int, [_p, _i64, _i64, _i32, _i64, _i64, _p, _p, _p]),
     "b200trl_rescale_if_needed": (C.c_int, [_p, _i32, _i64, _i64, _i64, _p, _f, _p]),
+    "b200trl_rescale_if_needed_batched": (C.c_int, [_p, _i32, _i64, _i64, _i64, _i64, _i64, _p, _f, _p]),
 }
 
 

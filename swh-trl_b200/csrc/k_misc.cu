@@ -362,9 +362,11 @@ __global__ void __cluster_dims__(kQCtas, 1, 1) __launch_bounds__(kSelBlock, 1)
     cluster.sync();  // the leader's histogram stays mapped until every CTA has read it
 }
 
+// rows_per_batch == 0: row r at r * row_stride; else row r = (b, t) at b * batch_stride + t * row_stride (a dlogits buffer
+// that mirrors a strided logits view, ops.alloc_dlogits)
 template <typename T>
-__global__ void rescale_kernel(T* buf, int64_t n_rows, int64_t vocab, int64_t row_stride, const float* actual,
-                               float expected) {
+__global__ void rescale_kernel(T* buf, int64_t n_rows, int64_t vocab, int64_t row_stride, int64_t rows_per_batch,
+                               int64_t batch_stride, const float* actual, float expected) {
     const float a = actual[0];
     if (a == expected) return;  // the common case: nothing to do, the launch costs a few microseconds
     const float f = a / expected;
@@ -372,7 +374,12 @@ __global__ void rescale_kernel(T* buf, int64_t n_rows, int64_t vocab, int64_t ro
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int64_t r = i / vocab, c = i - r * vocab;
-        T* p = buf + r * row_stride + c;
+        int64_t off = r * row_stride;
+        if (rows_per_batch > 0) {
+            const int64_t b = r / rows_per_batch;
+            off = b * batch_stride + (r - b * rows_per_batch) * row_stride;
+        }
+        T* p = buf + off + c;
         ElemTraits<T>::store(p, ElemTraits<T>::load(p) * f);
     }
 }
@@ -419,8 +426,25 @@ extern "C" int b200trl_entropy_quantile_mask(const float* entropies, const int32
     return check_launch("entropy_quantile_kernel");
 }
 
+static int rescale_impl(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride, int64_t rows_per_batch,
+                        int64_t batch_stride, const float* actual, float expected, b200trl_stream_t stream);
+
 extern "C" int b200trl_rescale_if_needed(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
                                          const float* actual, float expected, b200trl_stream_t stream) {
+    return rescale_impl(buf, dtype, n_rows, vocab, row_stride, 0, 0, actual, expected, stream);
+}
+
+extern "C" int b200trl_rescale_if_needed_batched(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride,
+                                                 int64_t rows_per_batch, int64_t batch_stride, const float* actual,
+                                                 float expected, b200trl_stream_t stream) {
+    B200TRL_REQUIRE(rows_per_batch >= 0 && (rows_per_batch == 0 || n_rows % rows_per_batch == 0), B200TRL_E_INVALID,
+                    "rescale_if_needed: rows_per_batch %lld does not divide n_rows %lld", (long long)rows_per_batch,
+                    (long long)n_rows);
+    return rescale_impl(buf, dtype, n_rows, vocab, row_stride, rows_per_batch, batch_stride, actual, expected, stream);
+}
+
+static int rescale_impl(void* buf, int dtype, int64_t n_rows, int64_t vocab, int64_t row_stride, int64_t rows_per_batch,
+                        int64_t batch_stride, const float* actual, float expected, b200trl_stream_t stream) {
     B200TRL_REQUIRE(buf && actual, B200TRL_E_INVALID, "rescale_if_needed: null pointer");
     B200TRL_REQUIRE(expected != 0.f, B200TRL_E_INVALID, "rescale_if_needed: expected scale is zero");
     const int block = 256;
@@ -428,17 +452,20 @@ extern "C" int b200trl_rescale_if_needed(void* buf, int dtype, int64_t n_rows, i
     cudaStream_t s = as_stream(stream);
     switch (dtype) {
         case B200TRL_BF16:
-            rescale_kernel<<<grid, block, 0, s>>>(static_cast<__nv_bfloat16*>(buf), n_rows, vocab, row_stride, actual,
-                                                  expected);
+            rescale_kernel<<<grid, block, 0, s>>>(static_cast<__nv_bfloat16*>(buf), n_rows, vocab, row_stride, rows_per_batch,
+                                                  batch_stride, actual, expected);
             break;
         case B200TRL_F16:
-            rescale_kernel<<<grid, block, 0, s>>>(static_cast<__half*>(buf), n_rows, vocab, row_stride, actual, expected);
+            rescale_kernel<<<grid, block, 0, s>>>(static_cast<__half*>(buf), n_rows, vocab, row_stride, rows_per_batch,
+                                                  batch_stride, actual, expected);
             break;
         case B200TRL_F32:
-            rescale_kernel<<<grid, block, 0, s>>>(static_cast<float*>(buf), n_rows, vocab, row_stride, actual, expected);
+            rescale_kernel<<<grid, block, 0, s>>>(static_cast<float*>(buf), n_rows, vocab, row_stride, rows_per_batch,
+                                                  batch_stride, actual, expected);
             break;
         case B200TRL_F64:
-            rescale_kernel<<<grid, block, 0, s>>>(static_cast<double*>(buf), n_rows, vocab, row_stride, actual, expected);
+            rescale_kernel<<<grid, block, 0, s>>>(static_cast<double*>(buf), n_rows, vocab, row_stride, rows_per_batch,
+                                                  batch_stride, actual, expected);
             break;
         default: set_error("rescale_if_needed: unknown dtype %d", dtype); return B200TRL_E_UNSUPPORTED;
     }

@@ -563,15 +563,16 @@ def masked_whiten(values: torch.Tensor, mask: torch.Tensor, shift_mean: bool = T
 
 def rescale_if_needed(buf: torch.Tensor, actual: torch.Tensor, expected: float) -> None:
     """``buf *= actual / expected`` on the device, skipped when equal (no host sync)."""
-    row_stride = collapse_rows(tuple(buf.shape), tuple(buf.stride()))
-    if row_stride is None:
-        raise ValueError("rescale_if_needed needs a buffer with one uniform row stride")
+    lay = collapse_rows2(tuple(buf.shape), tuple(buf.stride()))
+    if lay is None:
+        raise ValueError("rescale_if_needed needs a buffer with at most (batch, row) strides")
+    row_stride, rpb, bs = lay
     V = buf.shape[-1]
     a = actual.detach()
     if a.dtype is not torch.float32:
         a = a.to(torch.float32)
-    check(lib.b200trl_rescale_if_needed(_ptr(buf), _DTYPES[buf.dtype], buf.numel() // V, V, row_stride, _ptr(a),
-                                        float(expected), _stream(buf)), "rescale_if_needed")
+    check(lib.b200trl_rescale_if_needed_batched(_ptr(buf), _DTYPES[buf.dtype], buf.numel() // V, V, row_stride, rpb, bs,
+                                                _ptr(a), float(expected), _stream(buf)), "rescale_if_needed")
     _count()
 
 
