@@ -94,13 +94,44 @@ for case in range(N):
         assert ulps(d_r, d_k, dtype) <= 1.01, "backward-only"
         vals = [torch.randn(B, T, generator=g, device=DEV) for _ in range(4)]
         pl = torch.clamp(lens - 1, min=0)
-        p_r, p_k = both(lambda: ops.ppo_fused_step(x, ids, pl, lp_r + 0.2 * vals[0], vals[1], vals[2], vals[3],
+        pad_p = torch.arange(T, device=DEV).unsqueeze(0) > pl.unsqueeze(1)
+        old_p = (lp_r + 0.2 * vals[0]).masked_fill(pad_p, 1.0)  # INVALID_LOGPROB at the pads, as the trainers store it
+        p_r, p_k = both(lambda: ops.ppo_fused_step(x, ids, pl, old_p, vals[1], vals[2], vals[3],
                                                    vals[3] + 0.3 * vals[0], 1.0 / (temp + 1e-7), 0.2, 0.2, 0.1))
         worst["dl_ulp"] = max(worst["dl_ulp"], ulps(p_r[2], p_k[2], dtype))
         assert ulps(p_r[2], p_k[2], dtype) <= 1.01, "PPO step dlogits"
         tol = 1e-5 * torch.maximum(p_r[3].abs(), torch.full_like(p_r[3], max(1.0, float(vals[1].abs().max()))))
         assert bool(((p_r[3] - p_k[3]).abs() <= tol).all()), f"PPO stats {p_r[3].tolist()} vs {p_k[3].tolist()}"
         assert float((p_r[4] - p_k[4]).abs().max()) <= 1e-6 * max(1.0, float(p_r[4].abs().max())), "PPO dvpred"
+        # ---- the same through the autograd-level API (leaf = the padded / offset storage, the view goes in): GRPOLoss in
+        # both schedules, the plain op, PPO and RLOO losses; gradients land in the leaf through autograd's view backward
+        if case % 3 == 0:
+            def api(kind):
+                leaf = buf.detach().clone().requires_grad_(True)
+                xv = leaf[off:off + B * T * stride].view(B, T, stride)[:, :, :V]
+                if kind == "grpo_token" or kind == "grpo_seq":
+                    fn = S.GRPOLoss(beta=beta, epsilon_low=0.2, epsilon_high=0.25, delta=delta, loss_type=loss_type,
+                                    importance_sampling_level="token" if kind == "grpo_token" else "sequence",
+                                    max_completion_length=T, temperature=temp)
+                    loss = fn(xv, ids, mask, adv, old, ref if beta else None, grad_scale=1.0).loss
+                elif kind == "sls":
+                    loss = (S.selective_log_softmax(xv, ids) * gtok).sum()
+                elif kind == "ppo":
+                    loss = S.ppo_loss(xv, ids, old_p, vals[1], vals[2], vals[3], vals[3] + 0.3 * vals[0], pl,
+                                      temperature=temp).loss
+                else:
+                    loss = S.rloo_loss(xv, ids, old_p, vals[1][:, 0].contiguous(), pl, temperature=temp).loss
+                (loss * 0.5).backward()
+                return loss.detach().float(), leaf.grad
+            for kind in ("grpo_token", "grpo_seq", "sls", "ppo", "rloo"):
+                (l_r, g_r), (l_k, g_k) = both(lambda: api(kind))
+                assert torch.isfinite(l_k).all() and abs(float(l_r - l_k)) <= 1e-5 * max(1.0, abs(float(l_r))), f"api {kind} loss"
+                u = ulps(g_r, g_k, dtype)
+                if kind in ("sls", "ppo"):  # no cancelling gradient terms: one ulp
+                    assert u <= 1.01, f"api {kind} gradient"
+                else:                       # see the sensitivity note above: a relative bar on the whole tensor
+                    assert float((g_r.float() - g_k.float()).abs().max()) <= 2e-2 * float(g_r.float().abs().max()) + 1e-12, \
+                        f"api {kind} gradient"
     except AssertionError as e:
         info = {"failed": str(e), **desc, "worst": worst}
         if "dlogits" in str(e) or "backward" in str(e):  # locate the worst element and show the fp64 value next to it
