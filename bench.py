@@ -8,8 +8,9 @@
 One JSON line on stdout (rank 0).  A *step* is one pass of the hot path over one batch of BASELINE config 2
 (B=16 sequences, T=1024, V=151936 bf16 logits, 8 completions per prompt) per GPU:
 
-    [once per generation batch of 4 steps, as the reference does at grpo_trainer.py:1497: reward all-gather (N>1)
-     -> K3 group advantages]  -> mask stats -> K1 fused log-prob / entropy / dlogits with the loss value and the metric
+    [once per generation batch -- 16 loss steps with the fork's own script settings (steps_per_generation 8 x
+     num_iterations 2, examples/scripts/grpo_train.py:493-496), as the reference does at grpo_trainer.py:1497:
+     reward all-gather (N>1) -> K3 group advantages]  -> mask stats -> K1 fused log-prob / entropy / dlogits with the loss value and the metric
     sums folded into the same launch -> autograd hand-back of dlogits -> packed metric rows kept in a device ring (N>1:
     one all-gather per logging interval)
 
@@ -44,8 +45,10 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# steps_per_generation / num_iterations: the fork's own training script (examples/scripts/grpo_train.py:493-496:
+# gradient_accumulation_steps=8 -> steps_per_generation=8, num_iterations=2): a generation batch feeds 16 loss steps
 CFG = dict(B=16, T=1024, V=151936, G=8, beta=0.04, epsilon=0.2, loss_type="bnpo", level="token", temperature=1.0,
-           steps_per_generation=4)
+           steps_per_generation=8, num_iterations=2)
 WORKLOAD = "configs[1]: GRPO loss fwd+bwd, Qwen2.5 vocab V=151936, B=16 T=1024, 8 completions/prompt, per GPU"
 METRIC = "fwd+bwd logit-tokens/s for fused logprob+GRPO loss; % of HBM roofline"
 UNIT = "logit-tokens/s"
@@ -58,6 +61,7 @@ def static_config(n_gpus: int) -> dict:
     return {"workload": WORKLOAD, "loss_type": CFG["loss_type"], "importance_sampling_level": CFG["level"],
             "beta": CFG["beta"], "epsilon": CFG["epsilon"], "old_per_token_logps": True, "global_batch": B * n_gpus,
             "seq_len": T, "vocab": V, "num_generations": G, "steps_per_generation": CFG["steps_per_generation"],
+            "num_iterations": CFG["num_iterations"],
             "parallelism": f"sequence-sharded x{n_gpus}, no V-sized collective",
             "l2": "inputs 4.98 GB per GPU per step >> 126 MB L2, no flush needed"}
 
@@ -621,9 +625,11 @@ def run_b200(args):
     logits, ids, mask = synth_device(rank, B, T, V, dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # Rewards and advantages belong to a GENERATION batch, as in the reference: `_generate_and_score_completions` gathers
-    # the rewards of steps_per_generation loss steps at once (grpo_trainer.py:1497), normalises them per group (:1917-1938)
-    # and each loss step takes its slice.  So the reward all-gather + K3 run once per SPG steps, over SPG * B sequences.
-    SPG = CFG["steps_per_generation"]
+    # the rewards of steps_per_generation loss steps at once (grpo_trainer.py:1497), normalises them per group (:1917-1938),
+    # each loss step takes its slice, and the buffered batch is walked num_iterations times before the next generation
+    # (`generate_every = steps_per_generation * num_iterations`, :1430-1431).  So the reward all-gather + K3 run once per
+    # SPG * NIT loss steps, over SPG * B sequences per rank.
+    SPG, NIT = CFG["steps_per_generation"], CFG["num_iterations"]
     rewards_local = torch.randn(SPG * B, 1, generator=gen, device=dev)
     weights = torch.ones(1, device=dev)
     adv_gen, step_no = [None], [0]
@@ -649,10 +655,11 @@ def run_b200(args):
 
     def step(record=False):
         x.grad = None
-        j = step_no[0] % SPG
+        j = step_no[0] % (SPG * NIT)
         step_no[0] += 1
         if j == 0:  # a new generation batch: all-gather (N>1) + K3 over its SPG * B sequences per rank
             adv_gen[0] = S.group_advantages(rewards_local, weights, G)["advantages"]
+        j %= SPG    # the second iteration walks the same buffered slices again
         adv = adv_gen[0][j * B:(j + 1) * B]
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
