@@ -347,7 +347,9 @@ __device__ __forceinline__ void acc_rescale(Acc& a, float cm) {
     a.m = cm;
 }
 
-template <bool F16 = false>
+// ENT = false: the caller wants no entropy (the no-grad old / ref log-prob passes), so the sum of 2^(y-m) (y-m) is not
+// accumulated -- one packed FMA per pair less in a pass whose speed under the power cap is set by the energy it spends
+template <bool F16 = false, bool ENT = true>
 __device__ __forceinline__ void acc_words(uint64_t& s2, uint64_t& u2, const uint4& v, uint64_t c2, uint64_t nm2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -358,26 +360,26 @@ __device__ __forceinline__ void acc_words(uint64_t& s2, uint64_t& u2, const uint
         unpack2(d2, d0, d1);
         const uint64_t e2 = pack2(ex2(d0), ex2(d1));
         s2 = fadd2(s2, e2);
-        u2 = ffma2(e2, d2, u2);
+        if (ENT) u2 = ffma2(e2, d2, u2);
     }
 }
 
 // fold one 16-byte vector
-template <bool F16 = false>
+template <bool F16 = false, bool ENT = true>
 __device__ __forceinline__ void acc_vec(Acc& a, const uint4& v, float c, uint64_t c2) {
     const float cm = el_pair_max<F16>(vec_max<F16>(v)) * c;
     if (cm > a.m + kSlack) acc_rescale(a, cm);
-    acc_words<F16>(a.s2, a.u2, v, c2, pack2(-a.m, -a.m));
+    acc_words<F16, ENT>(a.s2, a.u2, v, c2, pack2(-a.m, -a.m));
 }
 
 // fold two vectors with ONE reference-point check and two independent accumulation chains
-template <bool F16 = false>
+template <bool F16 = false, bool ENT = true>
 __device__ __forceinline__ void acc_vec2(Acc& a, const uint4& v0, const uint4& v1, float c, uint64_t c2) {
     const float cm = el_pair_max<F16>(el_max2<F16>(vec_max<F16>(v0), vec_max<F16>(v1))) * c;
     if (cm > a.m + kSlack) acc_rescale(a, cm);
     const uint64_t nm2 = pack2(-a.m, -a.m);
-    acc_words<F16>(a.s2, a.u2, v0, c2, nm2);
-    acc_words<F16>(a.t2, a.v2, v1, c2, nm2);
+    acc_words<F16, ENT>(a.s2, a.u2, v0, c2, nm2);
+    acc_words<F16, ENT>(a.t2, a.v2, v1, c2, nm2);
 }
 
 template <bool F16 = false>
@@ -1243,6 +1245,7 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
             f_last = (f_nvec - 1) / kChunkVecs;
             f_keep = (f_h + tail_keep_of_h0) & 7;
         };
+        const bool want_ent = a.entropy != nullptr;  // forward-only: the full chunks skip the entropy sum when nobody reads it
         auto fwd_chunk = [&](Acc& acc, int cidx, bool skip) {
             tr.ev(1, t_row, cidx);
             mbar_wait(&sm.full_bar[fcur.slot], fcur.par);
@@ -1254,8 +1257,13 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 uint4 v[kVpt];
 #pragma unroll
                 for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
+                if (!HAS_BWD && !want_ent) {
 #pragma unroll
-                for (int k = 0; k < kVpt; k += 2) acc_vec2<F16>(acc, v[k], v[k + 1], c, c2);
+                    for (int k = 0; k < kVpt; k += 2) acc_vec2<F16, false>(acc, v[k], v[k + 1], c, c2);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kVpt; k += 2) acc_vec2<F16>(acc, v[k], v[k + 1], c, c2);
+                }
             } else if (SKEW) {
                 const int v0 = cidx * kChunkVecs;
                 const int n_here = min(max(f_nvec - v0, 0), kChunkVecs);
@@ -1291,7 +1299,9 @@ __global__ void __launch_bounds__(NC + 64, (NC <= 256) ? 2 : 1)  // 768 consumer
                 for (int k = 0; k < kVpt; ++k) v[k] = sv[tid + k * kConsumers];
 #pragma unroll
                 for (int k = 0; k < kVpt; k += 2) {
-                    if (DUAL) {
+                    if (DUAL && !HAS_BWD && !want_ent) {  // forward-only pass without entropies: no U accumulation
+                        acc_vec2<F16, false>(acc, v[k], v[k + 1], c, c2);
+                    } else if (DUAL) {
                         acc_vec2<F16>(acc, v[k], v[k + 1], c, c2);
                     } else {
                         acc_vec<F16>(acc, v[k], c, c2);

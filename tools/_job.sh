@@ -1,6 +1,9 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python tools/microbench.py > gpurun_out/s46_microbench.json 2> gpurun_out/s46_microbench.err; echo "microbench rc=$?"
-tail -c 600 gpurun_out/s46_microbench.err
-timeout 300 python tools/latency_kernels.py > gpurun_out/s46_latency.json 2>/dev/null; cat gpurun_out/s46_latency.json
+O=gpurun_out/s47_sustained.jsonl
+: > $O
+KS_SECS=3 KS_ONLY=fwd,fwd_noent timeout 300 python tools/k1_sustained.py >> $O 2>gpurun_out/s47_err.log
+KS_SECS=3 KS_ONLY=fwd_noent,fwd timeout 300 python tools/k1_sustained.py >> $O 2>>gpurun_out/s47_err.log
+cat $O
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "k1_forward or golden or skewed or fp16 or randomised" 2>&1 | tail -3

@@ -2,7 +2,7 @@
 """K1 under SUSTAINED load: each mode looped back to back for a few seconds while NVML is polled -> ms per launch,
 SM clock and power once the 1 kW cap has settled.  The sweeps of k1_variants.py time single launches with a
 synchronise in between (burst clocks); this says what the power cap makes of each variant.  The knobs are the
-B200TRL_K1_* variables of the environment; KS_ONLY picks modes (comma list of: copy,fused,fwd,bwd)."""
+B200TRL_K1_* variables of the environment; KS_ONLY picks modes (comma list of: copy,fused,fwd,fwd_noent,bwd)."""
 import json, os, statistics, sys, threading, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -80,6 +80,7 @@ cases = {
     "copy": (lambda: dl.copy_(logits), 2 * nbytes),
     "fused": (lambda: ops.grpo_fused_fwd_bwd(logits, ids, m32, rc, tot, adv, old, ref, cfg, 1.0, dlogits_out=dl), 2 * nbytes),
     "fwd": (lambda: ops.logprob_entropy_fwd(logits, ids, 1.0), nbytes),
+    "fwd_noent": (lambda: ops.logprob_entropy_fwd(logits, ids, 1.0, want_entropy=False), nbytes),
     "bwd": (lambda: ops.logprob_bwd(logits, ids, lse0, gtok, 1.0), 2 * nbytes),
 }
 only = os.environ.get("KS_ONLY")
