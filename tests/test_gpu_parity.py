@@ -101,6 +101,26 @@ def test_k1_forward_vs_oracle(S, V, temp, peaked):
         torch.testing.assert_close(ent.cpu(), ref32_ent, rtol=1e-4, atol=5e-4, msg=lambda m: f"path {path}: {m}")
 
 
+@pytest.mark.parametrize("V", [32000, 50257, 151936, 151937, 262144])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_k1_forward_without_entropy_is_the_same_pass(S, V, dtype):
+    """The old / ref log-prob passes ask for no entropies and take the forward sweep without the entropy sum: the
+    log-probs and the log-sum-exp must be the ones of the full pass, bit for bit, and agree with the oracle."""
+    from swh_trl_b200 import ops
+    logits, ids, _ = O.synth_batch(3, 7, V, seed=V % 97, sigma=3.0)
+    x, idx = logits.to(dtype).to(DEV), ids.to(DEV)
+    for path in _paths(S, x):
+        prev = S.set_k1_path(path)
+        try:
+            lp_full, ent, lse_full = ops.logprob_entropy_fwd(x, idx, 0.8, want_entropy=True)
+            lp, none, lse = ops.logprob_entropy_fwd(x, idx, 0.8, want_entropy=False)
+        finally:
+            S.set_k1_path(prev)
+        assert none is None and ent is not None
+        assert torch.equal(lp, lp_full) and torch.equal(lse, lse_full), f"path {path}"
+        assert_logp(lp, x.cpu(), ids, 1.0 / 0.8, where=f"path {path}")
+
+
 def test_k1_extreme_values(S):
     """+-60 logits (online-softmax stability) and a strided row view."""
     V = 32768
