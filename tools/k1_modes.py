@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""One launch each of the K1 streaming modes at config 2 (forward-only, backward-only) inside a profiler range, for
+"""One launch each of the K1 streaming modes at config 2 (forward-only, forward-only without entropies, backward-only)
+inside a profiler range, for
 `ncu --profile-from-start off --set full`; prints CUDA-event timings when run without ncu.
 
     python tools/k1_modes.py && ncu --profile-from-start off --set full --clock-control none --import-source on \\
@@ -42,8 +43,10 @@ for _ in range(3):
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 t_fwd = timed(lambda: ops.logprob_entropy_fwd(logits, ids, 1.0))
+t_noent = timed(lambda: ops.logprob_entropy_fwd(logits, ids, 1.0, want_entropy=False))
 t_bwd = timed(lambda: ops.logprob_bwd(logits, ids, lse, gtok, 1.0))
 torch.cuda.profiler.stop()
 n = B * T
-print(json.dumps({"fwd_only_ms": t_fwd, "fwd_only_gbs": 2 * V * n / t_fwd / 1e6, "bwd_only_ms": t_bwd,
+print(json.dumps({"fwd_only_ms": t_fwd, "fwd_only_gbs": 2 * V * n / t_fwd / 1e6, "fwd_no_entropy_ms": t_noent,
+                  "fwd_no_entropy_gbs": 2 * V * n / t_noent / 1e6, "bwd_only_ms": t_bwd,
                   "bwd_only_gbs": 4 * V * n / t_bwd / 1e6}))
