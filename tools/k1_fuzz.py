@@ -63,6 +63,12 @@ for case in range(N):
         worst["logp"] = max(worst["logp"], float((lp_r - lp_k).abs().max()))
         worst["entropy"] = max(worst["entropy"], float((en_r - en_k).abs().max()))
         assert float((lp_r - lp_k).abs().max()) <= 6e-6 and float((en_r - en_k).abs().max()) <= 2e-5, "forward-only"
+        prev = S.set_k1_path(S.K1_RESIDENT)  # the pass without entropies (old / ref log-probs) is the same pass
+        try:
+            lp_n, en_n, ls_n = ops.logprob_entropy_fwd(x, ids, 1.0 / temp, want_entropy=False)
+        finally:
+            S.set_k1_path(prev)
+        assert en_n is None and torch.equal(lp_n, lp_k) and torch.equal(ls_n, ls_k), "forward-only without entropies"
         old = lp_r + torch.randn(B, T, generator=g, device=DEV) * 0.3 if with_old else None
         ref = lp_r + torch.randn(B, T, generator=g, device=DEV) * 0.1
         cfg = ops.make_cfg(beta, 0.2, 0.25, delta, loss_type, "token", T, grad_scale=rnd.choice([1.0, 0.25]))
