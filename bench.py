@@ -288,6 +288,30 @@ def event_ms(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters, (t0, time.time())
 
 
+def graph_replay(body, iters, flush=None, ms_flush=0.0):
+    """``body`` (an autograd-level step: forward + backward) captured once in a CUDA graph and replayed ``iters`` times:
+    what the device needs when the host is out of the way.  Returns a dict for the bench line; never raises."""
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+
+        def replay():
+            if flush is not None:
+                flush.add_(1.0)
+            graph.replay()
+        ms, _ = event_ms(replay, iters)
+        return {"us_per_step": (ms - ms_flush) * 1e3,
+                "what": "the same autograd-level step (forward + backward) captured once in a CUDA graph and replayed"}
+    except Exception as e:  # noqa: BLE001 -- an extra must not take the bench line down
+        torch.cuda.synchronize()
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 def gpu_affinity(local_rank):
     """CPUs and NUMA node next to this rank's GPU (sysfs of its PCI function); (None, None) if the box does not say."""
     try:
@@ -369,9 +393,18 @@ def extra_config1(S, ops, dev, hbm_peak):
     ms_all, win = event_ms(step, 30)
     ms_flush, _ = event_ms(flush_only, 30)
     ms = ms_all - ms_flush
-    return {"workload": "configs[0]: B=4 T=256 V=32000 G=4, fused logprob + GRPO loss fwd+bwd", "us_per_step": ms * 1e3,
-            "logit_tokens_per_s": B * T / (ms * 1e-3), "frac_of_hbm_roofline": 4 * V * B * T / (ms * 1e-3) / 1e9 / hbm_peak,
-            "l2": "256 MB flush write between steps (its own time, measured alone, subtracted)"}, win
+    out = {"workload": "configs[0]: B=4 T=256 V=32000 G=4, fused logprob + GRPO loss fwd+bwd", "us_per_step": ms * 1e3,
+           "logit_tokens_per_s": B * T / (ms * 1e-3), "frac_of_hbm_roofline": 4 * V * B * T / (ms * 1e-3) / 1e9 / hbm_peak,
+           "l2": "256 MB flush write between steps (its own time, measured alone, subtracted)"}
+    # The eager step above is bound by the host (autograd + ctypes, one launch); the same step captured in a CUDA graph
+    # and replayed shows what the device needs.  Same flush between replays.
+    def body():
+        x.grad = None
+        fn(x, ids, mask, adv, old, None).loss.backward()
+    out["graph_replay"] = graph_replay(body, 30, flush, ms_flush)
+    if "us_per_step" in out["graph_replay"]:
+        out["graph_replay"]["frac_of_hbm_roofline"] = 4 * V * B * T / (out["graph_replay"]["us_per_step"] * 1e-6) / 1e9 / hbm_peak
+    return out, win
 
 
 def extra_config3(S, ops, dev):
@@ -428,6 +461,7 @@ def extra_config3(S, ops, dev):
     out["microbatch_step_launches"] = ops.launch_count - n0
     ms_s, _ = event_ms(ppo_step, 20)
     out["microbatch_step_us"] = ms_s * 1e3
+    out["microbatch_step_graph_replay"] = graph_replay(ppo_step, 20)
     out["microbatch_step_shape"] = f"mb={mb} T={T} V={V} bf16 (412 MB logits > L2)"
     out["workload"] = "configs[2]: PPO per-token KL reward + GAE (gamma=1, lam=0.95) + whitening, clipped policy/value loss, B=64 T=512"
     out["l2"] = "256 MB flush write before each small-kernel call (its own time subtracted)"

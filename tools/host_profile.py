@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Host-side cost of one GRPO loss step at BASELINE config 1 (B=4, T=256, V=32000: the kernel takes ~30 us, so the
-Python path around it is what a step costs): cProfile over 3000 steps, top functions by cumulative time."""
+Python path around it is what a step costs): cProfile over 3000 steps, top functions by cumulative time.
+``HP_MODE=ppo``: the PPO micro-batch step of config 3 instead (mb=8, T=512, V=50304; the kernel takes ~150 us)."""
 import cProfile, io, os, pstats, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,6 +24,21 @@ def step():
     logits.grad = None
     out = fn(logits, ids, mask, adv, old, ref)
     out.loss.backward()
+
+
+if os.environ.get("HP_MODE") == "ppo":
+    mb, T, V = 8, 512, 50304
+    logits = (torch.randn(mb, T, V, generator=g, device=DEV) * 2).to(torch.bfloat16).requires_grad_(True)
+    rsp = torch.randint(0, V, (mb, T), generator=g, device=DEV)
+    oldp = -torch.rand(mb, T, generator=g, device=DEV) * 5
+    advp, ret, val = (torch.randn(mb, T, generator=g, device=DEV) for _ in range(3))
+    vp = (val + 0.1).requires_grad_(True)
+    ln = torch.randint(T // 2, T, (mb,), generator=g, device=DEV)
+
+    def step():  # noqa: F811
+        logits.grad = None
+        vp.grad = None
+        S.ppo_loss(logits, rsp, oldp, advp, ret, val, vp, ln).loss.backward()
 
 
 for _ in range(200):
