@@ -459,9 +459,9 @@ def extra_config3(S, ops, dev):
     n0 = ops.launch_count
     ppo_step()
     out["microbatch_step_launches"] = ops.launch_count - n0
-    ms_s, _ = event_ms(ppo_step, 20)
+    ms_s, _ = event_ms(ppo_step, 100, warmup=10)
     out["microbatch_step_us"] = ms_s * 1e3
-    out["microbatch_step_graph_replay"] = graph_replay(ppo_step, 20)
+    out["microbatch_step_graph_replay"] = graph_replay(ppo_step, 100)
     out["microbatch_step_shape"] = f"mb={mb} T={T} V={V} bf16 (412 MB logits > L2)"
     out["workload"] = "configs[2]: PPO per-token KL reward + GAE (gamma=1, lam=0.95) + whitening, clipped policy/value loss, B=64 T=512"
     out["l2"] = "256 MB flush write before each small-kernel call (its own time subtracted)"
