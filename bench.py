@@ -288,25 +288,21 @@ def event_ms(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters, (t0, time.time())
 
 
-def graph_replay(body, iters, flush=None, ms_flush=0.0):
-    """``body`` (an autograd-level step: forward + backward) captured once in a CUDA graph and replayed ``iters`` times:
-    what the device needs when the host is out of the way.  Returns a dict for the bench line; never raises."""
+def graph_replay(S, body, static, iters, flush=None, ms_flush=0.0):
+    """``body`` (an autograd-level step: forward + backward) captured once through the package's public
+    ``swh_trl_b200.GraphedStep`` (``static`` = the step's input buffers) and replayed ``iters`` times: what the device
+    needs when the host is out of the way.  Returns a dict for the bench line; never raises."""
     try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(graph, stream=side):
-                body()
-        torch.cuda.current_stream().wait_stream(side)
+        step = S.GraphedStep(lambda s: (body(), {})[1], static, warmup=1)
 
         def replay():
             if flush is not None:
                 flush.add_(1.0)
-            graph.replay()
+            step.replay()
         ms, _ = event_ms(replay, iters)
         return {"us_per_step": (ms - ms_flush) * 1e3,
-                "what": "the same autograd-level step (forward + backward) captured once in a CUDA graph and replayed"}
+                "what": "the same autograd-level step (forward + backward) captured once in a CUDA graph "
+                        "(swh_trl_b200.GraphedStep) and replayed"}
     except Exception as e:  # noqa: BLE001 -- an extra must not take the bench line down
         torch.cuda.synchronize()
         return {"error": f"{type(e).__name__}: {e}"[:200]}
@@ -401,7 +397,7 @@ def extra_config1(S, ops, dev, hbm_peak):
     def body():
         x.grad = None
         fn(x, ids, mask, adv, old, None).loss.backward()
-    out["graph_replay"] = graph_replay(body, 30, flush, ms_flush)
+    out["graph_replay"] = graph_replay(S, body, {"logits": x}, 30, flush, ms_flush)
     if "us_per_step" in out["graph_replay"]:
         out["graph_replay"]["frac_of_hbm_roofline"] = 4 * V * B * T / (out["graph_replay"]["us_per_step"] * 1e-6) / 1e9 / hbm_peak
     return out, win
@@ -461,7 +457,7 @@ def extra_config3(S, ops, dev):
     out["microbatch_step_launches"] = ops.launch_count - n0
     ms_s, _ = event_ms(ppo_step, 100, warmup=10)
     out["microbatch_step_us"] = ms_s * 1e3
-    out["microbatch_step_graph_replay"] = graph_replay(ppo_step, 100)
+    out["microbatch_step_graph_replay"] = graph_replay(S, ppo_step, {"logits": x, "vpred": vp}, 100)
     out["microbatch_step_shape"] = f"mb={mb} T={T} V={V} bf16 (412 MB logits > L2)"
     out["workload"] = "configs[2]: PPO per-token KL reward + GAE (gamma=1, lam=0.95) + whitening, clipped policy/value loss, B=64 T=512"
     out["l2"] = "256 MB flush write before each small-kernel call (its own time subtracted)"

@@ -20,6 +20,7 @@ from .functional import (  # noqa: F401
     selective_log_softmax,
     sequence_logps,
 )
+from .graphs import GraphedStep  # noqa: F401
 from .grpo import GRPOLoss, GRPOLossOutput, compute_loss, get_per_token_logps_and_entropies  # noqa: F401
 from .liger_seam import B200FusedLinearGRPOLoss  # noqa: F401
 from .masks import (  # noqa: F401

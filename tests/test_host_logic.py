@@ -104,3 +104,14 @@ def test_patch_trl_rebinds_every_importer():
     assert ppo_mod._trl_original_truncate_response is orig
     assert "faketrl.other" not in report and set(report) == {"faketrl.trainer.utils", "faketrl.trainer.grpo_trainer",
                                                               "faketrl.core", "faketrl.trainer.ppo_trainer"}
+
+
+def test_graphed_step_has_no_cpu_path():
+    """GraphedStep validates its static buffers before touching CUDA: CPU tensors raise (no fallback)."""
+    import swh_trl_b200 as S
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        S.GraphedStep(lambda s: {"y": s["x"]}, {"x": torch.zeros(4)})
+    with pytest.raises(ValueError):
+        S.GraphedStep(lambda s: {}, {})
+    with pytest.raises(TypeError):
+        S.GraphedStep(lambda s: {}, {"x": 3})
