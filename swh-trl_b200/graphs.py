@@ -30,7 +30,7 @@ from typing import Callable, Dict, Mapping
 
 import torch
 
-from . import _nvtx
+from . import _nvtx, ops
 
 
 class GraphedStep:
@@ -57,7 +57,10 @@ class GraphedStep:
         self.device = next(iter(static_inputs.values())).device
         self.graph = torch.cuda.CUDAGraph()
         self.replays = 0
-        with torch.cuda.device(self.device):
+        # the operators' scratch buffers (loss / metric accumulators, GAE exchange rows ...) are baked into the graph by
+        # address: this step owns its own set instead of borrowing the per-stream ones (ops.private_workspaces)
+        self._workspaces = {}
+        with torch.cuda.device(self.device), ops.private_workspaces(self._workspaces):
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)

@@ -6,6 +6,7 @@ kernel in ``libb200trl.so``.  All wrappers are asynchronous and never synchronis
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional
 
@@ -346,15 +347,39 @@ def grpo_fused_step(logits, ids, mask_i32, row_count, total_count, advantages, o
 
 # ------------------------------------------------------------------------------------------------ K2
 _ws_cache = {}
+# a private {(device, family): tensor} while a GraphedStep warms up / captures.  A plain global, not a thread-local:
+# autograd runs the backward operators on its own device thread, and they must see the same scope (stream capture is
+# process-wide state anyway -- no other thread may issue CUDA work during it)
+_ws_private = None
+
+
+@contextlib.contextmanager
+def private_workspaces(store: dict):
+    """Scratch buffers requested inside the block live in ``store`` instead of the per-stream cache.
+
+    A captured CUDA graph bakes its workspace POINTERS in: were they the shared per-stream buffers, a later eager call
+    that needs a larger one would replace (and free) the buffer under the graph, and a second graph captured on a
+    recycled pool stream could run concurrently on the same scratch memory.  ``graphs.GraphedStep`` therefore owns
+    its workspaces for as long as the graph lives."""
+    global _ws_private
+    prev, _ws_private = _ws_private, store
+    try:
+        yield store
+    finally:
+        _ws_private = prev
 
 
 def _workspace(device, nbytes: int, key: str, zero: bool) -> torch.Tensor:
     # one workspace per (device, stream, kernel family): kernels of different streams never share scratch memory
-    k = (device, _raw_stream(device), key)
-    ws = _ws_cache.get(k)
+    store = _ws_private
+    if store is not None:
+        cache, k = store, (device, key)
+    else:
+        cache, k = _ws_cache, (device, _raw_stream(device), key)
+    ws = cache.get(k)
     if ws is None or ws.numel() < nbytes:
         ws = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
-        _ws_cache[k] = ws
+        cache[k] = ws
     return ws
 
 

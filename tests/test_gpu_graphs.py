@@ -112,3 +112,30 @@ def test_graphed_step_rejects_other_shapes(S):
         step.replay(x=torch.zeros(2, 8, 32000, dtype=torch.float16, device=DEV))
     with pytest.raises(KeyError):
         step.replay(nope=x)
+
+
+def test_graphed_step_owns_its_workspaces(S):
+    """The accumulators a captured step uses are its own: an eager call on the same stream that needs (and
+    re-allocates) a larger shared workspace afterwards must not disturb the graph."""
+    B, T, V = 4, 64, 32000
+    fn = S.GRPOLoss(beta=0.0, max_completion_length=T)
+    a = _grpo_inputs(B, T, V, 8)
+    static = {k: v.clone() for k, v in a.items()}
+    static["logits"].requires_grad_(True)
+
+    def body(s):
+        s["logits"].grad = None
+        out = fn(s["logits"], s["ids"], s["mask"], s["adv"], s["old"])
+        out.loss.backward()
+        return {"loss": out.loss, "dlogits": s["logits"].grad}
+
+    step = S.GraphedStep(body, static)
+    assert step._workspaces, "the fused step's accumulators should have been taken from the step's own store"
+    first = {k: v.detach().clone() for k, v in step.replay().items()}
+    big = _grpo_inputs(96, 16, V, 9)  # more sequences -> a larger shared workspace is allocated by this eager call
+    x = big["logits"].requires_grad_(True)
+    S.GRPOLoss(beta=0.0, max_completion_length=16)(x, big["ids"], big["mask"], big["adv"], big["old"]).loss.backward()
+    again = step.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(again["dlogits"], first["dlogits"])
+    torch.testing.assert_close(again["loss"].detach(), first["loss"], rtol=1e-6, atol=1e-9)

@@ -115,3 +115,27 @@ def test_graphed_step_has_no_cpu_path():
         S.GraphedStep(lambda s: {}, {})
     with pytest.raises(TypeError):
         S.GraphedStep(lambda s: {}, {"x": 3})
+
+
+def test_private_workspaces_scope():
+    """Inside ops.private_workspaces the operators' scratch buffers live in the caller's dict (a GraphedStep's), keyed
+    by kernel family, grow on demand, and the scope unwinds on exit -- also when the body raises."""
+    cpu = torch.device("cpu")
+    store = {}
+    with ops.private_workspaces(store) as s:
+        assert s is store
+        a = ops._workspace(cpu, 100, "family_a", zero=True)
+        assert a.numel() == 256 and int(a.sum()) == 0
+        assert ops._workspace(cpu, 200, "family_a", zero=True) is a          # fits: the same buffer
+        b = ops._workspace(cpu, 1000, "family_a", zero=False)                # grows: replaced inside the store only
+        assert b.numel() == 1000 and store[(cpu, "family_a")] is b
+        with ops.private_workspaces({}) as inner:                             # nests
+            ops._workspace(cpu, 10, "family_b", zero=False)
+            assert (cpu, "family_b") in inner and (cpu, "family_b") not in store
+        assert ops._ws_private is store
+    assert ops._ws_private is None
+    with pytest.raises(RuntimeError):
+        with ops.private_workspaces({}):
+            raise RuntimeError("boom")
+    assert ops._ws_private is None
+    assert not any(k[-1] in ("family_a", "family_b") for k in ops._ws_cache)   # nothing leaked into the shared cache
